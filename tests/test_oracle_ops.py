@@ -1,0 +1,184 @@
+"""Pins the CPU oracle (oracle/) against Python big-integer ground truth and the known answers in
+SURVEY.md §8(c)-4.  The reference's own tests hold no golden vector at this boundary,
+so these uniqueness checks are what the oracle stands on: parity unpinned."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import orc
+from tests import pyref
+from tests.pyref import R_MOD, P_MOD
+
+
+def rnd_fr(rng, n):
+    return [rng.randrange(R_MOD) for _ in range(n)]
+
+
+def test_field_constants():
+    assert pow(pyref.ROOT_OF_UNITY, 1 << 28, R_MOD) == 1 and pow(pyref.ROOT_OF_UNITY, 1 << 27, R_MOD) != 1
+    assert pyref.ROOT_OF_UNITY == pow(7, (R_MOD - 1) >> 28, R_MOD)
+    assert pyref.DELTA == pow(7, 1 << 28, R_MOD)
+    assert pow(pyref.ZETA, 3, R_MOD) == 1 and pyref.ZETA != 1
+    # SURVEY §8a a5 omega prefixes/suffixes
+    for k, hi, lo in [(17, 0x304cd1e7, 0x79c2c3ea), (19, 0x0cf1526a, 0x568fc082), (22, 0x18c95f1a, 0x8326bede)]:
+        w = pyref.omega_for(k)
+        assert w >> 224 == hi and w & 0xFFFFFFFF == lo
+
+
+@pytest.mark.parametrize("which,mod", [("fr", R_MOD), ("fq", P_MOD)])
+def test_field_ops(which, mod):
+    rng = random.Random(1)
+    edge = [0, 1, 2, mod - 1, mod - 2, (1 << 253), (1 << 64) - 1, 1 << 64]
+    a = edge + [rng.randrange(mod) for _ in range(200)]
+    b = list(reversed(edge)) + [rng.randrange(mod) for _ in range(200)]
+    conv = orc.fr_from_ints if which == "fr" else orc.fq_from_ints
+    back = orc.fr_to_ints if which == "fr" else orc.fq_to_ints
+    A, B = conv(a), conv(b)
+    assert back(orc.field_op(which, "add", A, B)) == [(x + y) % mod for x, y in zip(a, b)]
+    assert back(orc.field_op(which, "sub", A, B)) == [(x - y) % mod for x, y in zip(a, b)]
+    assert back(orc.field_op(which, "mul", A, B)) == [(x * y) % mod for x, y in zip(a, b)]
+    assert back(orc.field_op(which, "neg", A)) == [(-x) % mod for x in a]
+    assert back(orc.field_op(which, "inv", A)) == [pow(x, -1, mod) if x else 0 for x in a]
+    # Montgomery conversion done by the C code agrees with the Python one
+    assert np.array_equal(orc.field_op(which, "from_canonical", orc.ints_to_limbs(a)), A)
+    assert orc.limbs_to_ints(orc.field_op(which, "to_canonical", A)) == a
+
+
+def test_from_u512():
+    rng = random.Random(2)
+    vals = [0, 1, (1 << 512) - 1, R_MOD << 256] + [rng.getrandbits(512) for _ in range(50)]
+    got = orc.fr_to_ints(orc.field_op("fr", "from_u512", orc.ints_to_limbs(vals, 8)))
+    assert got == [v % R_MOD for v in vals]
+
+
+def test_chacha_known_answers():
+    # ChaCha20 zero-key keystream and the gen_srs secret s
+    ks = pyref.ChaChaRng(bytes(32), 20)
+    stream = b"".join(ks.next_u32().to_bytes(4, "little") for _ in range(16))
+    assert stream.hex() == ("76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7"
+                            "da41597c5157488d7724e03fb8d84a376a43b8f41518a11cc387b669b2ee6586")
+    s = pyref.ChaChaRng(bytes(32), 20).fr_random()
+    assert s == 0x1c59a59b6cff4308740943526ade1d8c09f71b337a67269cc89586bcdd6dfcba
+    assert pyref.seed_from_u64(0).hex() == "ecf273f981b5cd4587f0467306ad6cadd0d0a3e33317e767f29bea72d78a7dfe"
+    # independent ChaCha20: `cryptography` (IETF layout: 32-bit counter + 96-bit nonce, same block 0..)
+    from cryptography.hazmat.primitives.ciphers import Cipher, algorithms
+    enc = Cipher(algorithms.ChaCha20(bytes(32), bytes(16)), mode=None).encryptor()
+    assert enc.update(bytes(64)) == stream
+
+
+def test_g1_ops():
+    rng = random.Random(3)
+    G = orc.g1_generator()
+    assert orc.g1_to_ints(G) == [pyref.G1_GEN]
+    for s in [0, 1, 2, 3, R_MOD - 1, rng.randrange(R_MOD), rng.randrange(R_MOD)]:
+        got = orc.g1_to_ints(orc.g1_mul(G, orc.fr_from_ints([s])))[0]
+        assert got == pyref.ec_mul(pyref.G1_GEN, s)
+    P = pyref.ec_mul(pyref.G1_GEN, 12345)
+    Q = pyref.ec_mul(pyref.G1_GEN, 99999)
+    for a, b in [(P, Q), (P, P), (P, pyref.ec_neg(P)), (P, None), (None, Q), (None, None)]:
+        got = orc.g1_to_ints(orc.g1_add(orc.g1_from_ints([a]), orc.g1_from_ints([b])))[0]
+        assert got == pyref.ec_add(a, b)
+    assert orc.g1_on_curve(orc.g1_from_ints([P]))
+    assert not orc.g1_on_curve(orc.g1_from_ints([(P[0], P[1] + 1)]))
+
+
+def _points(n, seed):
+    rng = random.Random(seed)
+    ks = [rng.randrange(1, R_MOD) for _ in range(n)]
+    arr = orc.fixed_base_batch(orc.fr_from_ints(ks))
+    return ks, arr
+
+
+def test_fixed_base_and_msm_small():
+    ks, bases = _points(40, 4)
+    pts = orc.g1_to_ints(bases)
+    assert pts[:5] == [pyref.ec_mul(pyref.G1_GEN, k) for k in ks[:5]]
+    rng = random.Random(5)
+    for n in [0, 1, 3, 4, 31, 32, 40]:
+        sc = [rng.randrange(R_MOD) for _ in range(n)]
+        if n >= 4:
+            sc[0] = 0; sc[1] = 1; sc[2] = R_MOD - 1
+        want = pyref.ec_msm(sc, pts[:n])
+        S = orc.fr_from_ints(sc) if n else np.zeros((0, 4), dtype=np.uint64)
+        assert orc.g1_to_ints(orc.msm_naive(S, bases[:n]))[0] == want
+        for threads in (1, 3, 8):
+            assert orc.g1_to_ints(orc.best_multiexp(S, bases[:n], threads))[0] == want
+
+
+def test_best_multiexp_matches_naive_2k():
+    ks, bases = _points(2048, 6)
+    rng = random.Random(7)
+    sc = [rng.randrange(R_MOD) for _ in range(2048)]
+    for i in range(0, 2048, 7):
+        sc[i] = rng.randrange(2)          # bit-valued witness cells
+    for i in range(3, 2048, 11):
+        sc[i] = rng.randrange(1 << 64)    # limb-valued cells
+    bases[5] = 0                           # an identity base
+    S = orc.fr_from_ints(sc)
+    want = orc.msm_naive(S, bases)
+    assert np.array_equal(orc.best_multiexp(S, bases, 1), want)
+    assert np.array_equal(orc.best_multiexp(S, bases, 8), want)
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 5, 8])
+def test_best_fft_vs_naive_dft(log_n):
+    rng = random.Random(8 + log_n)
+    n = 1 << log_n
+    a = rnd_fr(rng, n)
+    w = pyref.omega_for(log_n)
+    want = pyref.dft(a, w)
+    for threads in (1, 4):
+        got = orc.fr_to_ints(orc.best_fft(orc.fr_from_ints(a), orc.fr_from_ints([w]), log_n, threads))
+        assert got == want
+
+
+def test_fft_roundtrip_and_domain():
+    rng = random.Random(20)
+    j, k = 4, 9
+    n = 1 << k
+    d = orc.domain_constants(j, k)
+    assert d["extended_k"] == k + 2
+    assert orc.fr_to_ints(d["omega"])[0] == pyref.omega_for(k)
+    assert orc.fr_to_ints(d["extended_omega"])[0] == pyref.omega_for(k + 2)
+    assert orc.fr_to_ints(d["g_coset"])[0] == pyref.ZETA
+    assert orc.fr_to_ints(d["g_coset_inv"])[0] == pow(pyref.ZETA, 2, R_MOD)
+    coeffs = rnd_fr(rng, n)
+    A = orc.fr_from_ints(coeffs)
+    lag = orc.coeff_to_lagrange(j, k, A)
+    w = pyref.omega_for(k)
+    lag_i = orc.fr_to_ints(lag)
+    for i in (0, 1, 5, n - 1):
+        assert lag_i[i] == pyref.poly_eval(coeffs, pow(w, i, R_MOD))
+    assert np.array_equal(orc.lagrange_to_coeff(j, k, lag), A)
+    # coeff_to_extended evaluates on zeta * extended_omega^i
+    ext = orc.coeff_to_extended(j, k, A)
+    we = pyref.omega_for(k + 2)
+    ext_i = orc.fr_to_ints(ext)
+    for i in (0, 1, 2, 3, 777, 4 * n - 1):
+        assert ext_i[i] == pyref.poly_eval(coeffs, pyref.ZETA * pow(we, i, R_MOD) % R_MOD)
+    back = orc.extended_to_coeff(j, k, ext)
+    assert np.array_equal(back[:n], A) and not back[n:].any()
+    # divide_by_vanishing_poly multiplies row i by 1 / ((zeta*we^i)^n - 1)
+    dv = orc.fr_to_ints(orc.divide_by_vanishing(j, k, ext))
+    for i in (0, 1, 2, 3, 4, 1001):
+        x = pyref.ZETA * pow(we, i, R_MOD) % R_MOD
+        assert dv[i] == ext_i[i] * pow(pow(x, n, R_MOD) - 1, -1, R_MOD) % R_MOD
+
+
+def test_srs_setup_small():
+    k = 5
+    n = 1 << k
+    s = pyref.ChaChaRng(bytes(32), 20).fr_random()   # the gen_srs secret
+    g, gl = orc.srs_setup(k, orc.fr_from_ints([s]))
+    gi = orc.g1_to_ints(g)
+    assert gi[0] == pyref.G1_GEN and gi[3] == pyref.ec_mul(pyref.G1_GEN, pow(s, 3, R_MOD))
+    # commit(coeff) == commit_lagrange(lagrange) for the same polynomial
+    rng = random.Random(9)
+    coeffs = rnd_fr(rng, n)
+    A = orc.fr_from_ints(coeffs)
+    lag = orc.coeff_to_lagrange(2, k, A)
+    c1 = orc.best_multiexp(A, g, 2)
+    c2 = orc.best_multiexp(lag, gl, 2)
+    assert np.array_equal(c1, c2)
+    assert orc.g1_to_ints(c1)[0] == pyref.ec_mul(pyref.G1_GEN, pyref.poly_eval(coeffs, s))
