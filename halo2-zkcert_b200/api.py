@@ -1,0 +1,298 @@
+"""ctypes binding + host-side mirror of the reference operator surface.
+
+Host field elements are numpy uint64 arrays of shape (n, 4) — the bytes of halo2curves `Fr`/`Fq`
+(little-endian Montgomery limbs); G1Affine is (n, 8); G1 (Jacobian) is (n, 12).  Device-resident
+data are torch CUDA tensors of dtype int64 with the same trailing shape (torch is only the
+allocator / stream provider here).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libzkcert_cuda.so")
+_lib = None
+
+STATUS = {0: "OK", 1: "BAD_ARG", 2: "CUDA", 3: "OOM", 10: "InvalidInstances", 11: "ConstraintSystemFailure",
+          12: "BoundsFailure", 13: "Opening", 14: "Synthesis", 15: "NotEnoughRowsAvailable", 16: "Transcript"}
+
+
+class ZkcError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__("zkcert_cuda error %s (%d): %s" % (STATUS.get(code, "?"), code, msg))
+        self.code = code
+
+
+class DomainInfo(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("extended_k", C.c_uint32), ("j", C.c_uint32)] + \
+        [(n, C.c_uint64 * 4) for n in ("omega", "omega_inv", "extended_omega", "extended_omega_inv", "g_coset", "g_coset_inv",
+                                       "ifft_divisor", "extended_ifft_divisor")]
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def lib():
+    """Load libzkcert_cuda.so (building it first if the sources are newer).  Never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            from . import build as _b
+            _b.build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.zkc_last_error.restype = C.c_char_p
+        _lib.zkc_version.restype = C.c_char_p
+        _lib.zkc_ctx_launch_count.restype = C.c_uint64
+        _lib.zkc_ctx_destroy.restype = None
+        _lib.zkc_domain_free.restype = None
+        if hasattr(_lib, "zkc_srs_free"):
+            _lib.zkc_srs_free.restype = None
+    return _lib
+
+
+def _np(a, cols):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.ndim != 2 or a.shape[1] != cols:
+        raise ValueError("expected array of shape (n, %d), got %r" % (cols, a.shape))
+    return a
+
+
+def _hp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dp(t):
+    """device pointer of a torch CUDA tensor"""
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError("expected a contiguous CUDA tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """One per GPU (zkc_ctx).  `use_torch_stream()` makes kernels run on torch's current stream so
+    torch.cuda.Event timing brackets them."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        st = lib().zkc_ctx_create(C.c_int(device), C.byref(self._h))
+        if st != 0:
+            raise ZkcError(st, "zkc_ctx_create failed: no CUDA device %d (this library has no CPU fallback)" % device)
+        self.device = device
+
+    def check(self, st):
+        if st != 0:
+            raise ZkcError(st, lib().zkc_last_error(self._h).decode())
+
+    def use_torch_stream(self):
+        import torch
+        self.check(lib().zkc_ctx_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def sync(self):
+        self.check(lib().zkc_ctx_sync(self._h))
+
+    @property
+    def launches(self):
+        return int(lib().zkc_ctx_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().zkc_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- field vectors -------------------------------------------------------------------
+    def field_vec_op_dev(self, field, op, a, b, out):
+        ops = {"add": 0, "sub": 1, "mul": 2, "inv": 3, "from_canonical": 4, "to_canonical": 5, "neg": 6}
+        n = a.shape[0]
+        self.check(lib().zkc_field_vec_op_dev(self._h, C.c_int(0 if field == "fr" else 1), C.c_int(ops[op]), _dp(a),
+                                              None if b is None else _dp(b), _dp(out), C.c_size_t(n)))
+        return out
+
+    # ---- best_fft ------------------------------------------------------------------------------
+    def fft(self, a, omega, log_n):
+        """best_fft(a, omega, log_n) on a host array; returns the transformed copy."""
+        a = np.array(_np(a, 4), copy=True)
+        omega = _np(omega, 4)
+        assert a.shape[0] == 1 << log_n
+        self.check(lib().zkc_fft_fr(self._h, _hp(a), _hp(omega), C.c_uint32(log_n)))
+        return a
+
+    def fft_dev(self, a_dev, omega, log_n, ncols=1):
+        omega = _np(omega, 4)
+        self.check(lib().zkc_fft_fr_dev(self._h, _dp(a_dev), _hp(omega), C.c_uint32(log_n), C.c_uint32(ncols)))
+        return a_dev
+
+    # ---- best_multiexp -------------------------------------------------------------------------
+    def msm(self, scalars, bases):
+        scalars, bases = _np(scalars, 4), _np(bases, 8)
+        assert scalars.shape[0] == bases.shape[0]
+        out = np.zeros((1, 12), dtype=np.uint64)
+        self.check(lib().zkc_msm_g1(self._h, _hp(scalars), _hp(bases), C.c_size_t(scalars.shape[0]), _hp(out)))
+        return out
+
+    def msm_dev(self, scalars_dev, bases_dev, n, ncols=1):
+        out = np.zeros((ncols, 12), dtype=np.uint64)
+        self.check(lib().zkc_msm_g1_dev(self._h, _dp(scalars_dev), _dp(bases_dev), C.c_size_t(n), C.c_uint32(ncols), _hp(out)))
+        return out
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def best_fft(a, omega, log_n, ctx=None):
+    """halo2_proofs::arithmetic::best_fft — natural order in/out; returns a new array."""
+    return (ctx or default_context()).fft(a, omega, log_n)
+
+
+def best_multiexp(coeffs, bases, ctx=None):
+    """halo2_proofs::arithmetic::best_multiexp — returns the Jacobian result (1, 12), normalised."""
+    return (ctx or default_context()).msm(coeffs, bases)
+
+
+def jac_to_affine(j):
+    """normalised Jacobian (z = 1 or 0) -> affine (x, y); identity -> (0, 0)"""
+    j = np.asarray(j, dtype=np.uint64).reshape(-1, 12)
+    out = j[:, :8].copy()
+    ident = ~j[:, 8:].any(axis=1)
+    out[ident] = 0
+    return out
+
+
+class EvaluationDomain:
+    """halo2_proofs::poly::EvaluationDomain::new(j, k) and its conversions."""
+
+    def __init__(self, j, k, ctx=None, zeta_choice=0):
+        self.ctx = ctx or default_context()
+        self._h = C.c_void_p()
+        self.ctx.check(lib().zkc_domain_create(self.ctx._h, C.c_uint32(j), C.c_uint32(k), C.c_int(zeta_choice), C.byref(self._h)))
+        info = DomainInfo()
+        self.ctx.check(lib().zkc_domain_get_info(self._h, C.byref(info)))
+        self.k, self.extended_k, self.j = info.k, info.extended_k, info.j
+        self.n, self.extended_n = 1 << info.k, 1 << info.extended_k
+        for name in ("omega", "omega_inv", "extended_omega", "extended_omega_inv", "g_coset", "g_coset_inv", "ifft_divisor",
+                     "extended_ifft_divisor"):
+            setattr(self, name, np.array([list(getattr(info, name))], dtype=np.uint64))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().zkc_domain_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def get_omega(self):
+        return self.omega
+
+    def get_extended_omega(self):
+        return self.extended_omega
+
+    def lagrange_to_coeff(self, a):
+        a = np.array(_np(a, 4), copy=True)
+        assert a.shape[0] == self.n
+        self.ctx.check(lib().zkc_lagrange_to_coeff(self.ctx._h, self._h, _hp(a)))
+        return a
+
+    def coeff_to_lagrange(self, a):
+        a = np.array(_np(a, 4), copy=True)
+        assert a.shape[0] == self.n
+        self.ctx.check(lib().zkc_coeff_to_lagrange(self.ctx._h, self._h, _hp(a)))
+        return a
+
+    def coeff_to_extended(self, a):
+        a = _np(a, 4)
+        assert a.shape[0] == self.n
+        out = np.empty((self.extended_n, 4), dtype=np.uint64)
+        self.ctx.check(lib().zkc_coeff_to_extended(self.ctx._h, self._h, _hp(a), _hp(out)))
+        return out
+
+    def extended_to_coeff(self, a):
+        a = np.array(_np(a, 4), copy=True)
+        assert a.shape[0] == self.extended_n
+        self.ctx.check(lib().zkc_extended_to_coeff(self.ctx._h, self._h, _hp(a)))
+        return a
+
+    # device-resident, batched
+    def lagrange_to_coeff_dev(self, t, ncols=1):
+        self.ctx.check(lib().zkc_lagrange_to_coeff_dev(self.ctx._h, self._h, _dp(t), C.c_uint32(ncols)))
+        return t
+
+    def coeff_to_lagrange_dev(self, t, ncols=1):
+        self.ctx.check(lib().zkc_coeff_to_lagrange_dev(self.ctx._h, self._h, _dp(t), C.c_uint32(ncols)))
+        return t
+
+    def coeff_to_extended_dev(self, src, dst, ncols=1):
+        self.ctx.check(lib().zkc_coeff_to_extended_dev(self.ctx._h, self._h, _dp(src), _dp(dst), C.c_uint32(ncols)))
+        return dst
+
+    def extended_to_coeff_dev(self, t, ncols=1):
+        self.ctx.check(lib().zkc_extended_to_coeff_dev(self.ctx._h, self._h, _dp(t), C.c_uint32(ncols)))
+        return t
+
+    def divide_by_vanishing_poly_dev(self, t):
+        self.ctx.check(lib().zkc_divide_by_vanishing_dev(self.ctx._h, self._h, _dp(t)))
+        return t
+
+
+class ParamsKZG:
+    """halo2_proofs::poly::kzg::commitment::ParamsKZG<Bn256> with g / g_lagrange resident in HBM."""
+
+    def __init__(self, k, g=None, g_lagrange=None, s=None, ctx=None):
+        self.ctx = ctx or default_context()
+        self.k, self.n = k, 1 << k
+        self._h = C.c_void_p()
+        if g is not None:
+            g, gl = _np(g, 8), _np(g_lagrange, 8)
+            assert g.shape[0] == self.n and gl.shape[0] == self.n
+            self.ctx.check(lib().zkc_srs_load(self.ctx._h, C.c_uint32(k), _hp(g), _hp(gl), C.byref(self._h)))
+        else:
+            s = _np(s, 4)
+            self.ctx.check(lib().zkc_srs_setup(self.ctx._h, C.c_uint32(k), _hp(s), C.byref(self._h)))
+
+    @classmethod
+    def setup(cls, k, s, ctx=None):
+        """ParamsKZG::setup(k, rng) with the secret s = Fr::random(rng) supplied by the caller."""
+        return cls(k, s=s, ctx=ctx)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().zkc_srs_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def get_g(self, basis=0):
+        out = np.empty((self.n, 8), dtype=np.uint64)
+        self.ctx.check(lib().zkc_srs_get(self.ctx._h, self._h, C.c_int(basis), _hp(out)))
+        return out
+
+    def commit(self, poly):
+        poly = _np(poly, 4)
+        out = np.zeros((1, 12), dtype=np.uint64)
+        self.ctx.check(lib().zkc_commit(self.ctx._h, self._h, C.c_int(0), _hp(poly), C.c_size_t(poly.shape[0]), _hp(out)))
+        return out
+
+    def commit_lagrange(self, poly):
+        poly = _np(poly, 4)
+        out = np.zeros((1, 12), dtype=np.uint64)
+        self.ctx.check(lib().zkc_commit(self.ctx._h, self._h, C.c_int(1), _hp(poly), C.c_size_t(poly.shape[0]), _hp(out)))
+        return out
+
+    def commit_dev(self, polys_dev, length, ncols=1, basis=0):
+        out = np.zeros((ncols, 12), dtype=np.uint64)
+        self.ctx.check(lib().zkc_commit_dev(self.ctx._h, self._h, C.c_int(basis), _dp(polys_dev), C.c_size_t(length), C.c_uint32(ncols), _hp(out)))
+        return out

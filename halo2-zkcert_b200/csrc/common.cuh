@@ -1,0 +1,116 @@
+// Shared host-side plumbing for libzkcert_cuda.so: context, error handling, scratch memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/zkcert_cuda.h"
+#include "ff.cuh"
+
+namespace zkc {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace zkc
+
+// The opaque context: one per GPU.  All public calls lock `mu` (thread-safe per ctx).
+struct zkc_ctx {
+  int dev = 0;
+  cudaStream_t stream = nullptr;      // stream all kernels are launched on
+  cudaStream_t own_stream = nullptr;  // created with the ctx
+  std::string err;
+  uint64_t launches = 0;
+  std::recursive_mutex mu;
+  int sm_count = 148;
+  // grow-only scratch arenas (index = purpose), freed with the ctx
+  zkc::DevBuf scratch[8];
+  // twiddle tables: log_n -> device table of omega_n^i, i < n/2 (canonical root of unity)
+  std::map<uint32_t, zkc::Fr*> twiddles;
+  void* pinned = nullptr;  // small pinned staging buffer for results
+  size_t pinned_bytes = 0;
+};
+
+namespace zkc {
+
+inline int set_err(zkc_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define ZKC_CUDA_TRY(ctx, expr)                                                                     \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      return zkc::set_err(ctx, _e == cudaErrorMemoryAllocation ? ZKC_ERR_OOM : ZKC_ERR_CUDA,       \
+                          std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+    }                                                                                               \
+  } while (0)
+
+#define ZKC_TRY(expr)                 \
+  do {                                \
+    int _s = (expr);                  \
+    if (_s != ZKC_OK) return _s;      \
+  } while (0)
+
+#define ZKC_LAUNCH_CHECK(ctx)                                  \
+  do {                                                         \
+    (ctx)->launches++;                                         \
+    ZKC_CUDA_TRY(ctx, cudaGetLastError());                     \
+  } while (0)
+
+// Ensure scratch arena `slot` holds at least `bytes`; contents are NOT preserved on growth.
+inline int scratch_reserve(zkc_ctx* ctx, int slot, size_t bytes, void** out) {
+  DevBuf& b = ctx->scratch[slot];
+  if (b.bytes < bytes) {
+    if (b.p) { ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); ZKC_CUDA_TRY(ctx, cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
+    size_t want = bytes + (bytes >> 3);
+    ZKC_CUDA_TRY(ctx, cudaMalloc(&b.p, want));
+    b.bytes = want;
+  }
+  *out = b.p;
+  return ZKC_OK;
+}
+
+inline int pinned_reserve(zkc_ctx* ctx, size_t bytes, void** out) {
+  if (ctx->pinned_bytes < bytes) {
+    if (ctx->pinned) { ZKC_CUDA_TRY(ctx, cudaFreeHost(ctx->pinned)); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+    ZKC_CUDA_TRY(ctx, cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_bytes = bytes;
+  }
+  *out = ctx->pinned;
+  return ZKC_OK;
+}
+
+struct CtxLock {
+  zkc_ctx* c;
+  explicit CtxLock(zkc_ctx* ctx) : c(ctx) { c->mu.lock(); cudaSetDevice(c->dev); }
+  ~CtxLock() { c->mu.unlock(); }
+};
+
+// scratch slots
+enum { SCR_NTT = 0, SCR_MSM = 1, SCR_MSM2 = 2, SCR_HOSTIO = 3, SCR_HOSTIO2 = 4, SCR_MISC = 5, SCR_MISC2 = 6, SCR_MISC3 = 7 };
+
+// Fr constants shared by host code (canonical integers, little-endian 32-bit words)
+static const uint32_t FR_ROOT_OF_UNITY_RAW[8] = {0x60c37c9cu, 0xd34f1ed9u, 0xd39329c8u, 0x3215cf6du, 0x3dd31f74u, 0x98865ea9u, 0x166d18b7u, 0x03ddb9f5u};
+static const uint32_t FR_ZETA_RAW[8] = {0x36636f23u, 0xb8ca0b2du, 0xec2bc5e9u, 0xcc37a73fu, 0x3fd84104u, 0x048b6e19u, 0xe131a029u, 0x30644e72u};
+static const uint32_t FR_ZETA_ALT_RAW[8] = {0xb99c90ddu, 0x8b17ea66u, 0x8d8daaa7u, 0x5bfc4108u, 0x41a91758u, 0xb3c4d79du, 0u, 0u};
+static const uint32_t FR_DELTA_RAW[8] = {0xe533e9a2u, 0x870e56bbu, 0x5e963f25u, 0x5b5f898eu, 0xd4c86e71u, 0x64ec26aau, 0x22c6f0cau, 0x09226b6eu};
+static const uint32_t FR_S = 28;
+
+inline Fr fr_from_raw_words(const uint32_t w[8]) { Fr t; for (int i = 0; i < 8; ++i) t.v[i] = w[i]; return fe_from_canonical(t); }
+inline Fr fr_from_u64(uint64_t x) { Fr t = fe_zero<FrP>(); t.v[0] = (uint32_t)x; t.v[1] = (uint32_t)(x >> 32); return fe_from_canonical(t); }
+inline Fr fr_root_of_unity(uint32_t log_n) {  // canonical 2^log_n-th root: ROOT^(2^(S - log_n))
+  Fr w = fr_from_raw_words(FR_ROOT_OF_UNITY_RAW);
+  for (uint32_t i = log_n; i < FR_S; ++i) w = fe_sqr(w);
+  return w;
+}
+inline Fr fr_pow(Fr x, uint64_t e) { return fe_pow_u64(x, e); }
+
+}  // namespace zkc

@@ -1,0 +1,154 @@
+// Context, device-memory helpers and element-wise Fr/Fq vector kernels of libzkcert_cuda.so.
+#include "common.cuh"
+
+using namespace zkc;
+
+extern "C" const char* zkc_version(void) { return "halo2-zkcert_b200 0.1 (sm_100a)"; }
+
+extern "C" int zkc_ctx_create(int device, zkc_ctx** out) {
+  if (!out) return ZKC_ERR_BAD_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  // No CPU fallback: without a device every entry point fails loudly.
+  if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return ZKC_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return ZKC_ERR_CUDA;
+  zkc_ctx* c = new zkc_ctx();
+  c->dev = device;
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ZKC_ERR_CUDA; }
+  c->stream = c->own_stream;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return ZKC_OK;
+}
+
+extern "C" void zkc_ctx_destroy(zkc_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->dev);
+  cudaStreamSynchronize(c->stream);
+  for (auto& b : c->scratch) if (b.p) cudaFree(b.p);
+  for (auto& kv : c->twiddles) cudaFree(kv.second);
+  if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+extern "C" const char* zkc_last_error(const zkc_ctx* c) { return c ? c->err.c_str() : "no context (no CUDA device?)"; }
+extern "C" uint64_t zkc_ctx_launch_count(const zkc_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int zkc_ctx_set_stream(zkc_ctx* c, void* s) {
+  if (!c) return ZKC_ERR_BAD_ARG;
+  CtxLock lock(c);
+  ZKC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return ZKC_OK;
+}
+extern "C" int zkc_ctx_sync(zkc_ctx* c) {
+  if (!c) return ZKC_ERR_BAD_ARG;
+  CtxLock lock(c);
+  ZKC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return ZKC_OK;
+}
+
+extern "C" int zkc_dev_alloc(zkc_ctx* c, size_t bytes, void** dptr) {
+  if (!c || !dptr) return ZKC_ERR_BAD_ARG;
+  CtxLock lock(c);
+  ZKC_CUDA_TRY(c, cudaMalloc(dptr, bytes ? bytes : 1));
+  return ZKC_OK;
+}
+extern "C" int zkc_dev_free(zkc_ctx* c, void* dptr) {
+  if (!c) return ZKC_ERR_BAD_ARG;
+  CtxLock lock(c);
+  ZKC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  ZKC_CUDA_TRY(c, cudaFree(dptr));
+  return ZKC_OK;
+}
+extern "C" int zkc_h2d(zkc_ctx* c, void* dptr, const void* hptr, size_t bytes) {
+  if (!c) return ZKC_ERR_BAD_ARG;
+  CtxLock lock(c);
+  ZKC_CUDA_TRY(c, cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, c->stream));
+  ZKC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return ZKC_OK;
+}
+extern "C" int zkc_d2h(zkc_ctx* c, void* hptr, const void* dptr, size_t bytes) {
+  if (!c) return ZKC_ERR_BAD_ARG;
+  CtxLock lock(c);
+  ZKC_CUDA_TRY(c, cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+  ZKC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return ZKC_OK;
+}
+
+// ---- element-wise vector ops -------------------------------------------------------------------
+namespace zkc {
+
+template <class P>
+__global__ void k_vec_op(int op, const Fe<P>* a, const Fe<P>* b, Fe<P>* out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<P> x = fe_load(a + i), r;
+  switch (op) {
+    case ZKC_OP_ADD: r = fe_add(x, fe_load(b + i)); break;
+    case ZKC_OP_SUB: r = fe_sub(x, fe_load(b + i)); break;
+    case ZKC_OP_MUL: r = fe_mul(x, fe_load(b + i)); break;
+    case ZKC_OP_FROM_CANONICAL: r = fe_from_canonical(x); break;
+    case ZKC_OP_TO_CANONICAL: r = fe_to_canonical(x); break;
+    case ZKC_OP_NEG: r = fe_neg(x); break;
+    default: r = x;
+  }
+  fe_store(out + i, r);
+}
+
+// Batch inversion (Montgomery's trick) with zeros passed through, as halo2's `batch_invert`.
+// Each thread owns BI_CHUNK elements strided by the grid so that global accesses stay coalesced.
+#define BI_CHUNK 8
+template <class P>
+__global__ void k_batch_inv(const Fe<P>* a, Fe<P>* out, size_t n, size_t stride) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= stride) return;
+  Fe<P> v[BI_CHUNK], pre[BI_CHUNK];
+  Fe<P> acc = fe_one<P>();
+#pragma unroll
+  for (int j = 0; j < BI_CHUNK; ++j) {
+    const size_t i = t + (size_t)j * stride;
+    v[j] = (i < n) ? fe_load(a + i) : fe_zero<P>();
+    pre[j] = acc;
+    if (!fe_is_zero(v[j])) acc = fe_mul(acc, v[j]);
+  }
+  acc = fe_inv(acc);
+#pragma unroll
+  for (int j = BI_CHUNK - 1; j >= 0; --j) {
+    const size_t i = t + (size_t)j * stride;
+    if (i < n) {
+      if (fe_is_zero(v[j])) { fe_store(out + i, v[j]); }
+      else { fe_store(out + i, fe_mul(acc, pre[j])); acc = fe_mul(acc, v[j]); }
+    }
+  }
+}
+
+template <class P>
+int vec_op_impl(zkc_ctx* ctx, int op, const Fe<P>* a, const Fe<P>* b, Fe<P>* out, size_t n) {
+  if (n == 0) return ZKC_OK;
+  if (op == ZKC_OP_INV) {
+    const size_t stride = (n + BI_CHUNK - 1) / BI_CHUNK;
+    k_batch_inv<P><<<(unsigned)((stride + 127) / 128), 128, 0, ctx->stream>>>(a, out, n, stride);
+  } else {
+    k_vec_op<P><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(op, a, b, out, n);
+  }
+  ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+
+int fr_batch_invert(zkc_ctx* ctx, const Fr* a, Fr* out, size_t n) { return vec_op_impl<FrP>(ctx, ZKC_OP_INV, a, nullptr, out, n); }
+
+}  // namespace zkc
+
+extern "C" int zkc_field_vec_op_dev(zkc_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n) {
+  if (!ctx || !a || !out) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_field_vec_op_dev: null argument");
+  if ((op == ZKC_OP_ADD || op == ZKC_OP_SUB || op == ZKC_OP_MUL) && !b) return set_err(ctx, ZKC_ERR_BAD_ARG, "binary op needs b");
+  if (op < 0 || op > ZKC_OP_NEG) return set_err(ctx, ZKC_ERR_BAD_ARG, "unknown op");
+  CtxLock lock(ctx);
+  if (field == 0) return vec_op_impl<FrP>(ctx, op, (const Fr*)a, (const Fr*)b, (Fr*)out, n);
+  if (field == 1) return vec_op_impl<FqP>(ctx, op, (const Fq*)a, (const Fq*)b, (Fq*)out, n);
+  return set_err(ctx, ZKC_ERR_BAD_ARG, "field must be 0 (Fr) or 1 (Fq)");
+}

@@ -1,0 +1,320 @@
+// BN254 Fr / Fq Montgomery arithmetic for sm_100a, 8 x 32-bit limbs in registers.
+//
+// Replaces halo2curves::bn256::{Fr,Fq} (halo2curves 0.4.0 @ e185711, pinned at
+// /root/reference/Cargo.lock:1359-1380).  Bytes are identical to the
+// reference's `[u64; 4]` little-endian Montgomery limbs (R = 2^256), so host buffers pass through
+// the C ABI with zero conversion.  All results are canonical (< modulus).
+//
+// Multiplication: row-interleaved Montgomery (CIOS) on *64-bit column accumulators*.  Products of
+// even limbs of `a` land on even 64-bit columns (E), odd limbs on odd columns (O), so each
+// 32x32->64 product + 64-bit accumulate + carry is ONE `IMAD.WIDE.U32(.X)` (PTX: mul.wide.u32 +
+// add.cc.u64 / addc.cc.u64, which ptxas fuses).  After each row the low limb is cancelled with
+// m = t0 * (-p^-1) and the state shifts one limb by swapping the roles of E and O; the limb that
+// falls between the two alignments is carried as a 32-bit `pend` word whose only effect is a
+// carry-in bit into the next odd chain.  16 IMAD.WIDE + ~5 other instructions per row.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define ZKC_HD __host__ __device__ __forceinline__
+#define ZKC_D __device__ __forceinline__
+#else
+#define ZKC_HD inline
+#define ZKC_D inline
+#endif
+
+namespace zkc {
+
+typedef unsigned long long u64;
+
+struct FrP {
+  static constexpr uint32_t INV = 0xefffffffu;
+  ZKC_HD static constexpr uint32_t M(int i) {
+    return i == 0 ? 0xf0000001u : i == 1 ? 0x43e1f593u : i == 2 ? 0x79b97091u : i == 3 ? 0x2833e848u
+         : i == 4 ? 0x8181585du : i == 5 ? 0xb85045b6u : i == 6 ? 0xe131a029u : 0x30644e72u;
+  }
+  ZKC_HD static constexpr uint32_t ONE(int i) {  // R mod r
+    return i == 0 ? 0x4ffffffbu : i == 1 ? 0xac96341cu : i == 2 ? 0x9f60cd29u : i == 3 ? 0x36fc7695u
+         : i == 4 ? 0x7879462eu : i == 5 ? 0x666ea36fu : i == 6 ? 0x9a07df2fu : 0x0e0a77c1u;
+  }
+  ZKC_HD static constexpr uint32_t R2(int i) {  // R^2 mod r
+    return i == 0 ? 0xae216da7u : i == 1 ? 0x1bb8e645u : i == 2 ? 0xe35c59e3u : i == 3 ? 0x53fe3ab1u
+         : i == 4 ? 0x53bb8085u : i == 5 ? 0x8c49833du : i == 6 ? 0x7f4e44a5u : 0x0216d0b1u;
+  }
+};
+struct FqP {
+  static constexpr uint32_t INV = 0xe4866389u;
+  ZKC_HD static constexpr uint32_t M(int i) {
+    return i == 0 ? 0xd87cfd47u : i == 1 ? 0x3c208c16u : i == 2 ? 0x6871ca8du : i == 3 ? 0x97816a91u
+         : i == 4 ? 0x8181585du : i == 5 ? 0xb85045b6u : i == 6 ? 0xe131a029u : 0x30644e72u;
+  }
+  ZKC_HD static constexpr uint32_t ONE(int i) {  // R mod p
+    return i == 0 ? 0xc58f0d9du : i == 1 ? 0xd35d438du : i == 2 ? 0xf5c70b3du : i == 3 ? 0x0a78eb28u
+         : i == 4 ? 0x7879462cu : i == 5 ? 0x666ea36fu : i == 6 ? 0x9a07df2fu : 0x0e0a77c1u;
+  }
+  ZKC_HD static constexpr uint32_t R2(int i) {  // R^2 mod p
+    return i == 0 ? 0x538afa89u : i == 1 ? 0xf32cfc5bu : i == 2 ? 0xd44501fbu : i == 3 ? 0xb5e71911u
+         : i == 4 ? 0x0a417ff6u : i == 5 ? 0x47ab1effu : i == 6 ? 0xcab8351fu : 0x06d89f71u;
+  }
+};
+
+template <class P>
+struct alignas(16) Fe {
+  uint32_t v[8];
+};
+typedef Fe<FrP> Fr;
+typedef Fe<FqP> Fq;
+
+template <class P> ZKC_HD Fe<P> fe_zero() { Fe<P> r; for (int i = 0; i < 8; ++i) r.v[i] = 0; return r; }
+template <class P> ZKC_HD Fe<P> fe_one() { Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = P::ONE(i); return r; }
+template <class P> ZKC_HD Fe<P> fe_r2() { Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = P::R2(i); return r; }
+template <class P> ZKC_HD bool fe_is_zero(const Fe<P>& a) {
+  return (a.v[0] | a.v[1] | a.v[2] | a.v[3] | a.v[4] | a.v[5] | a.v[6] | a.v[7]) == 0;
+}
+template <class P> ZKC_HD bool fe_eq(const Fe<P>& a, const Fe<P>& b) {
+  uint32_t d = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d |= a.v[i] ^ b.v[i];
+  return d == 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+
+// r = a - M with borrow-out; returns borrow (1 if a < M)
+template <class P> ZKC_D uint32_t sub_mod_raw(uint32_t* r, const uint32_t* a) {
+  uint32_t bw;
+  asm("sub.cc.u32 %0,%9,%17;\n\t"
+      "subc.cc.u32 %1,%10,%18;\n\t"
+      "subc.cc.u32 %2,%11,%19;\n\t"
+      "subc.cc.u32 %3,%12,%20;\n\t"
+      "subc.cc.u32 %4,%13,%21;\n\t"
+      "subc.cc.u32 %5,%14,%22;\n\t"
+      "subc.cc.u32 %6,%15,%23;\n\t"
+      "subc.cc.u32 %7,%16,%24;\n\t"
+      "subc.u32 %8,0,0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(bw)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(P::M(0)), "r"(P::M(1)), "r"(P::M(2)), "r"(P::M(3)), "r"(P::M(4)), "r"(P::M(5)), "r"(P::M(6)), "r"(P::M(7)));
+  return bw;  // 0 or 0xffffffff
+}
+
+// final reduction of a value in [0, 2M)
+template <class P> ZKC_D void reduce_once(uint32_t* t) {
+  uint32_t s[8];
+  uint32_t bw = sub_mod_raw<P>(s, t);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = bw ? t[i] : s[i];
+}
+
+template <class P> ZKC_D Fe<P> fe_add(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> r;
+  asm("add.cc.u32 %0,%8,%16;\n\t"
+      "addc.cc.u32 %1,%9,%17;\n\t"
+      "addc.cc.u32 %2,%10,%18;\n\t"
+      "addc.cc.u32 %3,%11,%19;\n\t"
+      "addc.cc.u32 %4,%12,%20;\n\t"
+      "addc.cc.u32 %5,%13,%21;\n\t"
+      "addc.cc.u32 %6,%14,%22;\n\t"
+      "addc.u32 %7,%15,%23;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  reduce_once<P>(r.v);  // a + b < 2M < 2^255: no carry out of limb 7
+  return r;
+}
+
+template <class P> ZKC_D Fe<P> fe_sub(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> r;
+  uint32_t bw;
+  asm("sub.cc.u32 %0,%9,%17;\n\t"
+      "subc.cc.u32 %1,%10,%18;\n\t"
+      "subc.cc.u32 %2,%11,%19;\n\t"
+      "subc.cc.u32 %3,%12,%20;\n\t"
+      "subc.cc.u32 %4,%13,%21;\n\t"
+      "subc.cc.u32 %5,%14,%22;\n\t"
+      "subc.cc.u32 %6,%15,%23;\n\t"
+      "subc.cc.u32 %7,%16,%24;\n\t"
+      "subc.u32 %8,0,0;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(bw)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  // add back M masked by the borrow
+  asm("add.cc.u32 %0,%0,%8;\n\t"
+      "addc.cc.u32 %1,%1,%9;\n\t"
+      "addc.cc.u32 %2,%2,%10;\n\t"
+      "addc.cc.u32 %3,%3,%11;\n\t"
+      "addc.cc.u32 %4,%4,%12;\n\t"
+      "addc.cc.u32 %5,%5,%13;\n\t"
+      "addc.cc.u32 %6,%6,%14;\n\t"
+      "addc.u32 %7,%7,%15;"
+      : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7])
+      : "r"(P::M(0) & bw), "r"(P::M(1) & bw), "r"(P::M(2) & bw), "r"(P::M(3) & bw), "r"(P::M(4) & bw), "r"(P::M(5) & bw),
+        "r"(P::M(6) & bw), "r"(P::M(7) & bw));
+  return r;
+}
+
+// acc(4 x u64) += x[0..3] * m, carry-out accumulated into the 32-bit `top`
+#define ZKC_CHAIN4_CO(e0, e1, e2, e3, top, x0, x1, x2, x3, m)                               \
+  asm("{\n\t.reg .u64 t;\n\t"                                                                \
+      "mul.wide.u32 t,%5,%9;\n\tadd.cc.u64 %0,%0,t;\n\t"                                     \
+      "mul.wide.u32 t,%6,%9;\n\taddc.cc.u64 %1,%1,t;\n\t"                                    \
+      "mul.wide.u32 t,%7,%9;\n\taddc.cc.u64 %2,%2,t;\n\t"                                    \
+      "mul.wide.u32 t,%8,%9;\n\taddc.cc.u64 %3,%3,t;\n\t"                                    \
+      "addc.u32 %4,%4,0;\n\t}"                                                               \
+      : "+l"(e0), "+l"(e1), "+l"(e2), "+l"(e3), "+r"(top)                                    \
+      : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(m))
+// acc(4 x u64) += x[0..3] * m   (provably no carry-out: see header comment / DESIGN.md)
+#define ZKC_CHAIN4(o0, o1, o2, o3, x0, x1, x2, x3, m)                                        \
+  asm("{\n\t.reg .u64 t;\n\t"                                                                \
+      "mul.wide.u32 t,%4,%8;\n\tadd.cc.u64 %0,%0,t;\n\t"                                     \
+      "mul.wide.u32 t,%5,%8;\n\taddc.cc.u64 %1,%1,t;\n\t"                                    \
+      "mul.wide.u32 t,%6,%8;\n\taddc.cc.u64 %2,%2,t;\n\t"                                    \
+      "mul.wide.u32 t,%7,%8;\n\taddc.u64 %3,%3,t;\n\t}"                                      \
+      : "+l"(o0), "+l"(o1), "+l"(o2), "+l"(o3)                                               \
+      : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(m))
+// same, with carry-in = (pend != 0)
+#define ZKC_CHAIN4_CI(o0, o1, o2, o3, x0, x1, x2, x3, m, pend)                               \
+  asm("{\n\t.reg .u64 t;\n\t.reg .u32 d;\n\t"                                                \
+      "add.cc.u32 d,%9,0xffffffff;\n\t"                                                      \
+      "mul.wide.u32 t,%4,%8;\n\taddc.cc.u64 %0,%0,t;\n\t"                                    \
+      "mul.wide.u32 t,%5,%8;\n\taddc.cc.u64 %1,%1,t;\n\t"                                    \
+      "mul.wide.u32 t,%6,%8;\n\taddc.cc.u64 %2,%2,t;\n\t"                                    \
+      "mul.wide.u32 t,%7,%8;\n\taddc.u64 %3,%3,t;\n\t}"                                      \
+      : "+l"(o0), "+l"(o1), "+l"(o2), "+l"(o3)                                               \
+      : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(m), "r"(pend))
+
+template <class P> ZKC_D Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
+  u64 e0 = 0, e1 = 0, e2 = 0, e3 = 0, o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+  uint32_t pend = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t bi = b.v[i];
+    uint32_t top = 0;
+    ZKC_CHAIN4_CO(e0, e1, e2, e3, top, a.v[0], a.v[2], a.v[4], a.v[6], bi);
+    ZKC_CHAIN4(o0, o1, o2, o3, a.v[1], a.v[3], a.v[5], a.v[7], bi);
+    const uint32_t m = ((uint32_t)e0 + pend) * P::INV;
+    ZKC_CHAIN4_CO(e0, e1, e2, e3, top, P::M(0), P::M(2), P::M(4), P::M(6), m);
+    ZKC_CHAIN4_CI(o0, o1, o2, o3, P::M(1), P::M(3), P::M(5), P::M(7), m, pend);
+    // shift one limb: E <- O, O <- E >> 64, pend <- hi32(E0)
+    const uint32_t np = (uint32_t)(e0 >> 32);
+    const u64 n0 = o0, n1 = o1, n2 = o2, n3 = o3;
+    o0 = e1; o1 = e2; o2 = e3; o3 = (u64)top;
+    e0 = n0; e1 = n1; e2 = n2; e3 = n3;
+    pend = np;
+  }
+  Fe<P> r;
+  asm("add.cc.u32 %0,%8,%16;\n\t"
+      "addc.cc.u32 %1,%9,%17;\n\t"
+      "addc.cc.u32 %2,%10,%18;\n\t"
+      "addc.cc.u32 %3,%11,%19;\n\t"
+      "addc.cc.u32 %4,%12,%20;\n\t"
+      "addc.cc.u32 %5,%13,%21;\n\t"
+      "addc.cc.u32 %6,%14,%22;\n\t"
+      "addc.u32 %7,%15,%23;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+      : "r"((uint32_t)e0), "r"((uint32_t)(e0 >> 32)), "r"((uint32_t)e1), "r"((uint32_t)(e1 >> 32)), "r"((uint32_t)e2),
+        "r"((uint32_t)(e2 >> 32)), "r"((uint32_t)e3), "r"((uint32_t)(e3 >> 32)),
+        "r"(pend), "r"((uint32_t)o0), "r"((uint32_t)(o0 >> 32)), "r"((uint32_t)o1), "r"((uint32_t)(o1 >> 32)),
+        "r"((uint32_t)o2), "r"((uint32_t)(o2 >> 32)), "r"((uint32_t)o3));
+  reduce_once<P>(r.v);
+  return r;
+}
+
+#else  // ---- host path (unit tests of logic layered above the field ops; never the product path) ----
+
+template <class P> inline bool geq_mod(const uint32_t* a) {
+  for (int i = 7; i >= 0; --i) { if (a[i] > P::M(i)) return true; if (a[i] < P::M(i)) return false; }
+  return true;
+}
+template <class P> inline void sub_mod_inplace(uint32_t* a) {
+  int64_t bw = 0;
+  for (int i = 0; i < 8; ++i) { int64_t d = (int64_t)a[i] - P::M(i) + bw; a[i] = (uint32_t)d; bw = d >> 32; }
+}
+template <class P> inline Fe<P> fe_add(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> r; u64 c = 0;
+  for (int i = 0; i < 8; ++i) { c += (u64)a.v[i] + b.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
+  if (geq_mod<P>(r.v)) sub_mod_inplace<P>(r.v);
+  return r;
+}
+template <class P> inline Fe<P> fe_sub(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> r; int64_t bw = 0;
+  for (int i = 0; i < 8; ++i) { int64_t d = (int64_t)a.v[i] - b.v[i] + bw; r.v[i] = (uint32_t)d; bw = d >> 32; }
+  if (bw) { u64 c = 0; for (int i = 0; i < 8; ++i) { c += (u64)r.v[i] + P::M(i); r.v[i] = (uint32_t)c; c >>= 32; } }
+  return r;
+}
+template <class P> inline Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
+  uint32_t t[10] = {0};
+  for (int i = 0; i < 8; ++i) {
+    u64 c = 0;
+    for (int j = 0; j < 8; ++j) { c += (u64)a.v[j] * b.v[i] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
+    c += t[8]; t[8] = (uint32_t)c; t[9] = (uint32_t)(c >> 32);
+    uint32_t m = t[0] * P::INV;
+    c = ((u64)m * P::M(0) + t[0]) >> 32;
+    for (int j = 1; j < 8; ++j) { c += (u64)m * P::M(j) + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
+    c += t[8]; t[7] = (uint32_t)c; t[8] = t[9] + (uint32_t)(c >> 32); t[9] = 0;
+  }
+  Fe<P> r; for (int i = 0; i < 8; ++i) r.v[i] = t[i];
+  if (geq_mod<P>(r.v)) sub_mod_inplace<P>(r.v);
+  return r;
+}
+#endif
+
+template <class P> ZKC_HD Fe<P> fe_sqr(const Fe<P>& a) { return fe_mul(a, a); }
+template <class P> ZKC_HD Fe<P> fe_neg(const Fe<P>& a) { return fe_sub(fe_zero<P>(), a); }
+template <class P> ZKC_HD Fe<P> fe_dbl(const Fe<P>& a) { return fe_add(a, a); }
+template <class P> ZKC_HD Fe<P> fe_from_canonical(const Fe<P>& a) { return fe_mul(a, fe_r2<P>()); }
+template <class P> ZKC_HD Fe<P> fe_to_canonical(const Fe<P>& a) {
+  Fe<P> o = fe_zero<P>(); o.v[0] = 1; return fe_mul(a, o);
+}
+// x^e for a small exponent
+template <class P> ZKC_HD Fe<P> fe_pow_u64(Fe<P> x, u64 e) {
+  Fe<P> acc = fe_one<P>();
+  while (e) { if (e & 1) acc = fe_mul(acc, x); x = fe_sqr(x); e >>= 1; }
+  return acc;
+}
+// Fermat inversion (0 -> 0).  ~380 multiplications; batch inversion is preferred on hot paths.
+template <class P> ZKC_HD Fe<P> fe_inv(const Fe<P>& a) {
+  Fe<P> acc = fe_one<P>();
+  for (int i = 7; i >= 0; --i) {
+    uint32_t w = P::M(i) - (i == 0 ? 2u : 0u);
+    for (int bit = 31; bit >= 0; --bit) {
+      acc = fe_sqr(acc);
+      if ((w >> bit) & 1) acc = fe_mul(acc, a);
+    }
+  }
+  return acc;
+}
+
+// ---- 16-byte vector load/store helpers -----------------------------------------------------------
+#if defined(__CUDACC__)
+template <class P> ZKC_D Fe<P> fe_load(const Fe<P>* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  Fe<P> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+template <class P> ZKC_D Fe<P> fe_load_nc(const Fe<P>* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  Fe<P> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+template <class P> ZKC_D void fe_store(Fe<P>* p, const Fe<P>& r) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+template <class P> ZKC_D Fe<P> fe_from_halves(const uint4& a, const uint4& b) {
+  Fe<P> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+template <class P> ZKC_D uint4 fe_lo(const Fe<P>& r) { return make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]); }
+template <class P> ZKC_D uint4 fe_hi(const Fe<P>& r) { return make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]); }
+#endif
+
+}  // namespace zkc

@@ -1,0 +1,459 @@
+// Radix-2^s Fr NTT for sm_100a: replaces halo2_proofs::arithmetic::best_fft and the
+// EvaluationDomain conversions built on it (halo2_proofs 0.2.0 @4b42325 src/arithmetic.rs,
+// src/poly/domain.rs — un-vendored, pinned at /root/reference/Cargo.lock:1320-1336; SURVEY.md §8a
+// rows a4/a5, Appendix A.4).  Same I/O convention as upstream: natural order in, natural order out.
+//
+// Decomposition (four-step, recursive): N = L1 * L2 [* L3].  Every pass stages a tile of
+// 2^s x C elements in shared memory as two 16-byte planes (limbs 0-3 / limbs 4-7) so that a warp
+// touching consecutive elements is bank-conflict free, runs s in-place DIF stages there, and writes
+// the tile back with the in-tile bit reversal undone for free:
+//   * strided pass  : tile = all L rows (stride B) x C contiguous columns; in place; the result is
+//                     multiplied by the inter-pass twiddle w_{L*B}^(b*k) on the way out.
+//   * last pass     : tile = C rows of L contiguous elements; output is written transposed
+//                     (digit-reversed), C contiguous elements per output row, which is what makes
+//                     the whole transform natural-order without a separate permutation pass.
+// Coset scaling (zeta^(i mod 3), EvaluationDomain::distribute_powers_zeta), zero padding to the
+// extended domain and the 1/n scaling of inverse transforms are fused into the first load / last
+// store.  One twiddle table w_N^i (i < N/2) per size serves forward and inverse transforms.
+#include "common.cuh"
+
+namespace zkc {
+
+struct NttPass {
+  const Fr* src;
+  Fr* dst;
+  uint64_t src_stride, dst_stride;  // per-column strides in elements
+  uint64_t n_in;                    // valid input elements per column (rest read as zero)
+  const Fr* tw;                     // w_N^i, i < N/2
+  uint32_t log_n, s, logC;
+  uint32_t logB;          // strided pass: inner stride
+  uint32_t logN1, logN2;  // last pass: rows A = N1*N2, output index = k1 + N1*k2 + A*kp
+  int inverse, pre, post;
+  Fr pre1, pre2;          // in[i] *= pre^(i mod 3)
+  Fr post0, post1, post2; // out[i] *= post[i mod 3]
+};
+
+__device__ __forceinline__ Fr tw_get(const Fr* tw, uint64_t e, uint32_t log_n, int inverse) {
+  const uint64_t N = 1ull << log_n;
+  if (inverse) e = (N - e) & (N - 1);
+  const uint64_t half = N >> 1;
+  const bool neg = e >= half;
+  Fr w = fe_load_nc(tw + (neg ? e - half : e));
+  return neg ? fe_neg(w) : w;
+}
+
+__device__ __forceinline__ void butterfly_dif(uint4* lo, uint4* hi, uint32_t i0, uint32_t i1, const Fr* tw, uint64_t e,
+                                              uint32_t log_n, int inverse) {
+  Fr a = fe_from_halves<FrP>(lo[i0], hi[i0]);
+  Fr b = fe_from_halves<FrP>(lo[i1], hi[i1]);
+  Fr sum = fe_add(a, b);
+  Fr diff = fe_sub(a, b);
+  if (e != 0) diff = fe_mul(diff, tw_get(tw, e, log_n, inverse));
+  lo[i0] = fe_lo(sum); hi[i0] = fe_hi(sum);
+  lo[i1] = fe_lo(diff); hi[i1] = fe_hi(diff);
+}
+
+#define NTT_THREADS 256
+#define NTT_PLANE_PAD 4  // uint4 units: offsets the high plane by 64 B so paired accesses hit distinct banks
+
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_strided(NttPass p) {
+  extern __shared__ uint4 sm[];
+  const uint32_t L = 1u << p.s, C = 1u << p.logC, T = L << p.logC;
+  uint4* lo = sm;
+  uint4* hi = sm + T + NTT_PLANE_PAD;
+  const Fr* src = p.src + (uint64_t)blockIdx.y * p.src_stride;
+  Fr* dst = p.dst + (uint64_t)blockIdx.y * p.dst_stride;
+  const uint32_t tiles_per_a = 1u << (p.logB - p.logC);
+  const uint64_t a = blockIdx.x >> (p.logB - p.logC);
+  const uint64_t b0 = (uint64_t)(blockIdx.x & (tiles_per_a - 1)) << p.logC;
+  const uint64_t base = ((a << p.s) << p.logB) + b0;
+
+  for (uint32_t e = threadIdx.x; e < T; e += NTT_THREADS) {
+    const uint32_t l = e >> p.logC, c = e & (C - 1);
+    const uint64_t g = base + ((uint64_t)l << p.logB) + c;
+    Fr x = fe_zero<FrP>();
+    if (g < p.n_in) {
+      x = fe_load(src + g);
+      if (p.pre) {
+        const uint32_t m = (uint32_t)(g % 3);
+        if (m == 1) x = fe_mul(x, p.pre1); else if (m == 2) x = fe_mul(x, p.pre2);
+      }
+    }
+    lo[e] = fe_lo(x); hi[e] = fe_hi(x);
+  }
+  __syncthreads();
+
+  for (uint32_t logh = p.s; logh-- > 0;) {
+    const uint32_t h = 1u << logh;
+    for (uint32_t bt = threadIdx.x; bt < (T >> 1); bt += NTT_THREADS) {
+      const uint32_t c = bt & (C - 1), pr = bt >> p.logC;
+      const uint32_t j = pr & (h - 1);
+      const uint32_t i = ((pr - j) << 1) | j;
+      const uint32_t i0 = (i << p.logC) + c;
+      butterfly_dif(lo, hi, i0, i0 + (h << p.logC), p.tw, (uint64_t)j << (p.log_n - 1 - logh), p.log_n, p.inverse);
+    }
+    __syncthreads();
+  }
+
+  const uint32_t tw_shift = p.log_n - p.s - p.logB;
+  for (uint32_t e = threadIdx.x; e < T; e += NTT_THREADS) {
+    const uint32_t k = e >> p.logC, c = e & (C - 1);
+    const uint32_t row = __brev(k) >> (32 - p.s);
+    Fr x = fe_from_halves<FrP>(lo[(row << p.logC) + c], hi[(row << p.logC) + c]);
+    const uint64_t ex = ((b0 + c) * (uint64_t)k) << tw_shift;
+    if (ex != 0) x = fe_mul(x, tw_get(p.tw, ex, p.log_n, p.inverse));
+    fe_store(dst + base + ((uint64_t)k << p.logB) + c, x);
+  }
+}
+
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_last(NttPass p) {
+  extern __shared__ uint4 sm[];
+  const uint32_t L = 1u << p.s, C = 1u << p.logC, T = L << p.logC;
+  const uint32_t pitch = L + (C > 1 ? 1u : 0u);
+  uint4* lo = sm;
+  uint4* hi = sm + pitch * C + NTT_PLANE_PAD;
+  const Fr* src = p.src + (uint64_t)blockIdx.y * p.src_stride;
+  Fr* dst = p.dst + (uint64_t)blockIdx.y * p.dst_stride;
+  const uint64_t N2 = 1ull << p.logN2;
+  const uint64_t kb = blockIdx.x >> p.logN2, k2 = blockIdx.x & (N2 - 1);
+
+  for (uint32_t e = threadIdx.x; e < T; e += NTT_THREADS) {
+    const uint32_t c = e >> p.s, i = e & (L - 1);
+    const uint64_t row = (((kb << p.logC) + c) << p.logN2) + k2;
+    const uint64_t g = (row << p.s) + i;
+    Fr x = fe_zero<FrP>();
+    if (g < p.n_in) {
+      x = fe_load(src + g);
+      if (p.pre) {
+        const uint32_t m = (uint32_t)(g % 3);
+        if (m == 1) x = fe_mul(x, p.pre1); else if (m == 2) x = fe_mul(x, p.pre2);
+      }
+    }
+    lo[c * pitch + i] = fe_lo(x); hi[c * pitch + i] = fe_hi(x);
+  }
+  __syncthreads();
+
+  for (uint32_t logh = p.s; logh-- > 0;) {
+    const uint32_t h = 1u << logh;
+    for (uint32_t bt = threadIdx.x; bt < (T >> 1); bt += NTT_THREADS) {
+      const uint32_t c = bt >> (p.s - 1), pr = bt & ((L >> 1) - 1);
+      const uint32_t j = pr & (h - 1);
+      const uint32_t i = ((pr - j) << 1) | j;
+      const uint32_t i0 = c * pitch + i;
+      butterfly_dif(lo, hi, i0, i0 + h, p.tw, (uint64_t)j << (p.log_n - 1 - logh), p.log_n, p.inverse);
+    }
+    __syncthreads();
+  }
+
+  const uint32_t logA = p.logN1 + p.logN2;
+  for (uint32_t e = threadIdx.x; e < T; e += NTT_THREADS) {
+    const uint32_t c = e & (C - 1), kp = e >> p.logC;
+    const uint32_t pos = __brev(kp) >> (32 - p.s);
+    Fr x = fe_from_halves<FrP>(lo[c * pitch + pos], hi[c * pitch + pos]);
+    const uint64_t o = ((kb << p.logC) + c) + (k2 << p.logN1) + ((uint64_t)kp << logA);
+    if (p.post) {
+      const uint32_t m = (uint32_t)(o % 3);
+      x = fe_mul(x, m == 0 ? p.post0 : (m == 1 ? p.post1 : p.post2));
+    }
+    fe_store(dst + o, x);
+  }
+}
+
+// tw[i] = omega^i, i < half_n; each thread fills a run of 64 entries.
+__global__ void k_gen_twiddles(Fr* tw, Fr omega, uint64_t half_n) {
+  const uint64_t start = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 64;
+  if (start >= half_n) return;
+  Fr w = fe_pow_u64(omega, start);
+  const uint64_t end = start + 64 < half_n ? start + 64 : half_n;
+  for (uint64_t i = start; i < end; ++i) { fe_store(tw + i, w); w = fe_mul(w, omega); }
+}
+
+__global__ void k_scale_periodic(Fr* a, const Fr* t, uint32_t mask, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fe_store(a + i, fe_mul(fe_load(a + i), fe_load_nc(t + (i & mask))));
+}
+
+static int get_twiddles(zkc_ctx* ctx, uint32_t log_n, const Fr** out) {
+  auto it = ctx->twiddles.find(log_n);
+  if (it != ctx->twiddles.end()) { *out = it->second; return ZKC_OK; }
+  const uint64_t half = log_n == 0 ? 1 : (1ull << (log_n - 1));
+  Fr* tw = nullptr;
+  ZKC_CUDA_TRY(ctx, cudaMalloc(&tw, half * sizeof(Fr)));
+  const Fr omega = fr_root_of_unity(log_n);
+  const uint64_t threads = (half + 63) / 64;
+  k_gen_twiddles<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(tw, omega, half);
+  ZKC_LAUNCH_CHECK(ctx);
+  ctx->twiddles[log_n] = tw;
+  *out = tw;
+  return ZKC_OK;
+}
+
+struct NttOpts {
+  int inverse = 0;
+  uint64_t n_in = 0;      // 0 = full
+  int pre = 0; Fr pre1, pre2;
+  int post = 0; Fr post0, post1, post2;
+};
+
+static const uint32_t LOG_TILE = 11;  // 2^11 elements = 64 KiB of shared memory per CTA
+
+static int launch_pass(zkc_ctx* ctx, bool last, const NttPass& p, uint32_t grid_x, uint32_t ncols) {
+
+  const uint32_t L = 1u << p.s, C = 1u << p.logC;
+  size_t smem = last ? (size_t)(2 * (L + (C > 1 ? 1 : 0)) * C + NTT_PLANE_PAD) * sizeof(uint4)
+                     : (size_t)(2 * L * C + NTT_PLANE_PAD) * sizeof(uint4);
+  {
+    ZKC_CUDA_TRY(ctx, cudaFuncSetAttribute(last ? (const void*)k_ntt_last : (const void*)k_ntt_strided,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+
+  }
+  dim3 grid(grid_x, ncols);
+  if (last) k_ntt_last<<<grid, NTT_THREADS, smem, ctx->stream>>>(p);
+  else k_ntt_strided<<<grid, NTT_THREADS, smem, ctx->stream>>>(p);
+  ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+
+// Transform `ncols` columns: src (column stride src_stride, n_in valid elements) -> dst (stride
+// dst_stride, N elements).  src == dst (with equal strides) is allowed.
+int ntt_run(zkc_ctx* ctx, const Fr* src, uint64_t src_stride, Fr* dst, uint64_t dst_stride, uint32_t log_n, uint32_t ncols,
+            const NttOpts& o) {
+  if (log_n == 0 || ncols == 0) {
+    if (log_n == 0 && src != dst && ncols) {
+      ZKC_CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, dst_stride * sizeof(Fr), src, src_stride * sizeof(Fr), sizeof(Fr), ncols,
+                                          cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return ZKC_OK;
+  }
+  if (log_n > 27) return set_err(ctx, ZKC_ERR_BAD_ARG, "ntt: log_n > 27 unsupported");
+  const uint64_t N = 1ull << log_n;
+  const Fr* tw;
+  ZKC_TRY(get_twiddles(ctx, log_n, &tw));
+  NttPass base{};
+  base.tw = tw; base.log_n = log_n; base.inverse = o.inverse;
+  base.n_in = N;
+  auto first = [&](NttPass& p) { p.src = src; p.src_stride = src_stride; p.n_in = o.n_in ? o.n_in : N; p.pre = o.pre; p.pre1 = o.pre1; p.pre2 = o.pre2; };
+  auto final_ = [&](NttPass& p) { p.dst = dst; p.dst_stride = dst_stride; p.post = o.post; p.post0 = o.post0; p.post1 = o.post1; p.post2 = o.post2; };
+
+  if (log_n <= LOG_TILE) {
+    NttPass p = base; first(p); final_(p);
+    p.s = log_n; p.logC = 0; p.logN1 = 0; p.logN2 = 0;
+    return launch_pass(ctx, true, p, 1, ncols);
+  }
+  // bound the scratch: process columns in chunks of <= 1 GiB
+  uint32_t chunk = (uint32_t)std::max<uint64_t>(1, (1ull << 30) / (N * sizeof(Fr)));
+  if (chunk > ncols) chunk = ncols;
+  Fr* tmp;
+  ZKC_TRY(scratch_reserve(ctx, SCR_NTT, (size_t)chunk * N * sizeof(Fr), (void**)&tmp));
+  for (uint32_t c0 = 0; c0 < ncols; c0 += chunk) {
+    const uint32_t nc = std::min(chunk, ncols - c0);
+    const Fr* csrc = src + (uint64_t)c0 * src_stride;
+    Fr* cdst = dst + (uint64_t)c0 * dst_stride;
+    if (log_n <= 2 * 9) {
+      const uint32_t s1 = (log_n + 1) / 2, s2 = log_n - s1;
+      NttPass p1 = base; first(p1); p1.src = csrc;
+      p1.dst = tmp; p1.dst_stride = N; p1.s = s1; p1.logB = s2; p1.logC = std::min(3u, std::min(LOG_TILE - s1, s2));
+      ZKC_TRY(launch_pass(ctx, false, p1, 1u << (s2 - p1.logC), nc));
+      NttPass p2 = base; final_(p2); p2.dst = cdst;
+      p2.src = tmp; p2.src_stride = N; p2.s = s2; p2.logN1 = s1; p2.logN2 = 0; p2.logC = std::min(3u, std::min(LOG_TILE - s2, s1));
+      ZKC_TRY(launch_pass(ctx, true, p2, 1u << (s1 - p2.logC), nc));
+    } else {
+      const uint32_t s1 = (log_n + 2) / 3, s2 = (log_n - s1 + 1) / 2, s3 = log_n - s1 - s2;
+      NttPass p1 = base; first(p1); p1.src = csrc;
+      p1.dst = tmp; p1.dst_stride = N; p1.s = s1; p1.logB = s2 + s3; p1.logC = std::min(3u, LOG_TILE - s1);
+      ZKC_TRY(launch_pass(ctx, false, p1, 1u << (s2 + s3 - p1.logC), nc));
+      NttPass p2 = base;
+      p2.src = tmp; p2.src_stride = N; p2.dst = tmp; p2.dst_stride = N; p2.s = s2; p2.logB = s3; p2.logC = std::min(3u, std::min(LOG_TILE - s2, s3));
+      ZKC_TRY(launch_pass(ctx, false, p2, 1u << (s1 + s3 - p2.logC), nc));
+      NttPass p3 = base; final_(p3); p3.dst = cdst;
+      p3.src = tmp; p3.src_stride = N; p3.s = s3; p3.logN1 = s1; p3.logN2 = s2; p3.logC = std::min(3u, std::min(LOG_TILE - s3, s1));
+      ZKC_TRY(launch_pass(ctx, true, p3, 1u << (s1 + s2 - p3.logC), nc));
+    }
+  }
+  return ZKC_OK;
+}
+
+}  // namespace zkc
+
+using namespace zkc;
+
+// ---- EvaluationDomain --------------------------------------------------------------------------
+struct zkc_domain {
+  zkc_ctx* ctx;
+  uint32_t k, extended_k, j;
+  int zeta_choice;
+  Fr omega, omega_inv, extended_omega, extended_omega_inv, g_coset, g_coset_inv, ifft_divisor, extended_ifft_divisor;
+  Fr* t_inv_dev = nullptr;  // 2^(extended_k - k) inverted vanishing evaluations
+};
+
+static inline void fr_to_abi(const Fr& f, zkc_fr* o) { memcpy(o, f.v, 32); }
+static inline Fr fr_from_abi(const zkc_fr* i) { Fr f; memcpy(f.v, i, 32); return f; }
+
+extern "C" int zkc_domain_create(zkc_ctx* ctx, uint32_t j, uint32_t k, int zeta_choice, zkc_domain** out) {
+  if (!ctx || !out || j < 2 || k > 26) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_domain_create: bad arguments");
+  CtxLock lock(ctx);
+  zkc_domain* d = new zkc_domain();
+  d->ctx = ctx; d->k = k; d->j = j; d->zeta_choice = zeta_choice;
+  const uint64_t n = 1ull << k;
+  d->extended_k = k;
+  while ((1ull << d->extended_k) < n * (j - 1)) d->extended_k++;
+  if (d->extended_k > 27) { delete d; return set_err(ctx, ZKC_ERR_BAD_ARG, "extended domain too large"); }
+  d->extended_omega = fr_root_of_unity(d->extended_k);
+  d->extended_omega_inv = fe_inv(d->extended_omega);
+  d->omega = fr_root_of_unity(k);
+  d->omega_inv = fe_inv(d->omega);
+  d->g_coset = fr_from_raw_words(zeta_choice == 0 ? FR_ZETA_RAW : FR_ZETA_ALT_RAW);
+  d->g_coset_inv = fe_sqr(d->g_coset);
+  d->ifft_divisor = fe_inv(fr_from_u64(n));
+  d->extended_ifft_divisor = fe_inv(fr_from_u64(1ull << d->extended_k));
+  const uint32_t tl = 1u << (d->extended_k - k);
+  std::vector<Fr> t(tl);
+  Fr cur = d->g_coset;
+  for (uint32_t i = 0; i < tl; ++i) {
+    t[i] = fe_inv(fe_sub(fe_pow_u64(cur, n), fe_one<FrP>()));
+    cur = fe_mul(cur, d->extended_omega);
+  }
+  cudaError_t e = cudaMalloc(&d->t_inv_dev, tl * sizeof(Fr));
+  if (e == cudaSuccess) e = cudaMemcpy(d->t_inv_dev, t.data(), tl * sizeof(Fr), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { delete d; return set_err(ctx, ZKC_ERR_CUDA, std::string("zkc_domain_create: ") + cudaGetErrorString(e)); }
+  *out = d;
+  return ZKC_OK;
+}
+
+extern "C" void zkc_domain_free(zkc_domain* d) {
+  if (!d) return;
+  if (d->t_inv_dev) cudaFree(d->t_inv_dev);
+  delete d;
+}
+
+extern "C" int zkc_domain_get_info(const zkc_domain* d, zkc_domain_info* o) {
+  if (!d || !o) return ZKC_ERR_BAD_ARG;
+  o->k = d->k; o->extended_k = d->extended_k; o->j = d->j;
+  fr_to_abi(d->omega, &o->omega); fr_to_abi(d->omega_inv, &o->omega_inv);
+  fr_to_abi(d->extended_omega, &o->extended_omega); fr_to_abi(d->extended_omega_inv, &o->extended_omega_inv);
+  fr_to_abi(d->g_coset, &o->g_coset); fr_to_abi(d->g_coset_inv, &o->g_coset_inv);
+  fr_to_abi(d->ifft_divisor, &o->ifft_divisor); fr_to_abi(d->extended_ifft_divisor, &o->extended_ifft_divisor);
+  return ZKC_OK;
+}
+
+namespace zkc {
+// internal entry points used by the prover pipeline as well
+int dom_lagrange_to_coeff(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint32_t ncols) {
+  NttOpts o; o.inverse = 1; o.post = 1; o.post0 = o.post1 = o.post2 = d->ifft_divisor;
+  return ntt_run(ctx, a, 1ull << d->k, a, 1ull << d->k, d->k, ncols, o);
+}
+int dom_coeff_to_lagrange(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint32_t ncols) {
+  NttOpts o;
+  return ntt_run(ctx, a, 1ull << d->k, a, 1ull << d->k, d->k, ncols, o);
+}
+int dom_coeff_to_extended(zkc_ctx* ctx, const zkc_domain* d, const Fr* in, uint64_t in_stride, Fr* out, uint32_t ncols) {
+  NttOpts o; o.n_in = 1ull << d->k; o.pre = 1; o.pre1 = d->g_coset; o.pre2 = fe_sqr(d->g_coset);
+  return ntt_run(ctx, in, in_stride, out, 1ull << d->extended_k, d->extended_k, ncols, o);
+}
+int dom_extended_to_coeff(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint32_t ncols) {
+  NttOpts o; o.inverse = 1; o.post = 1;
+  o.post0 = d->extended_ifft_divisor;
+  o.post1 = fe_mul(d->extended_ifft_divisor, d->g_coset_inv);
+  o.post2 = fe_mul(d->extended_ifft_divisor, fe_sqr(d->g_coset_inv));
+  const uint64_t en = 1ull << d->extended_k;
+  ZKC_TRY(ntt_run(ctx, a, en, a, en, d->extended_k, ncols, o));
+  // upstream truncates to n*(j-1) coefficients; the buffer keeps its size, so zero the tail
+  const uint64_t keep = (1ull << d->k) * (d->j - 1);
+  if (keep < en) {
+    ZKC_CUDA_TRY(ctx, cudaMemset2DAsync(a + keep, en * sizeof(Fr), 0, (en - keep) * sizeof(Fr), ncols, ctx->stream));
+  }
+  return ZKC_OK;
+}
+int dom_divide_by_vanishing(zkc_ctx* ctx, const zkc_domain* d, Fr* a) {
+  const uint64_t en = 1ull << d->extended_k;
+  k_scale_periodic<<<(unsigned)((en + 255) / 256), 256, 0, ctx->stream>>>(a, d->t_inv_dev, (1u << (d->extended_k - d->k)) - 1, en);
+  ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+
+// best_fft with an arbitrary root: only omega = canonical root or its inverse occur upstream
+int fft_any(zkc_ctx* ctx, Fr* a, const Fr& omega, uint32_t log_n, uint32_t ncols) {
+  if (log_n > 27) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_fft_fr: log_n > 27");
+  const Fr root = fr_root_of_unity(log_n);
+  NttOpts o;
+  if (fe_eq(omega, root)) o.inverse = 0;
+  else if (fe_eq(fe_mul(omega, root), fe_one<FrP>())) o.inverse = 1;
+  else return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_fft_fr: omega is not the domain generator or its inverse");
+  return ntt_run(ctx, a, 1ull << log_n, a, 1ull << log_n, log_n, ncols, o);
+}
+}  // namespace zkc
+
+// host-buffer wrapper: upload, run, download
+template <class F>
+static int with_host_buffer(zkc_ctx* ctx, const void* in, size_t in_bytes, void* out, size_t out_bytes, size_t dev_bytes, F body) {
+  void* d;
+  ZKC_TRY(scratch_reserve(ctx, SCR_HOSTIO, dev_bytes, &d));
+  if (in_bytes) ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(d, in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ZKC_TRY(body((Fr*)d));
+  if (out_bytes) ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(out, d, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKC_OK;
+}
+
+extern "C" int zkc_fft_fr_dev(zkc_ctx* ctx, zkc_fr* a, const zkc_fr* omega, uint32_t log_n, uint32_t ncols) {
+  if (!ctx || !a || !omega) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_fft_fr_dev: null argument");
+  CtxLock lock(ctx);
+  return fft_any(ctx, (Fr*)a, fr_from_abi(omega), log_n, ncols);
+}
+extern "C" int zkc_fft_fr(zkc_ctx* ctx, zkc_fr* a, const zkc_fr* omega, uint32_t log_n) {
+  if (!ctx || !a || !omega) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_fft_fr: null argument");
+  CtxLock lock(ctx);
+  const size_t bytes = sizeof(Fr) << log_n;
+  const Fr w = fr_from_abi(omega);
+  return with_host_buffer(ctx, a, bytes, a, bytes, bytes, [&](Fr* d) { return fft_any(ctx, d, w, log_n, 1); });
+}
+
+extern "C" int zkc_lagrange_to_coeff_dev(zkc_ctx* ctx, const zkc_domain* d, zkc_fr* a, uint32_t ncols) {
+  if (!ctx || !d || !a) return set_err(ctx, ZKC_ERR_BAD_ARG, "null argument");
+  CtxLock lock(ctx); return dom_lagrange_to_coeff(ctx, d, (Fr*)a, ncols);
+}
+extern "C" int zkc_coeff_to_lagrange_dev(zkc_ctx* ctx, const zkc_domain* d, zkc_fr* a, uint32_t ncols) {
+  if (!ctx || !d || !a) return set_err(ctx, ZKC_ERR_BAD_ARG, "null argument");
+  CtxLock lock(ctx); return dom_coeff_to_lagrange(ctx, d, (Fr*)a, ncols);
+}
+extern "C" int zkc_coeff_to_extended_dev(zkc_ctx* ctx, const zkc_domain* d, const zkc_fr* in, zkc_fr* out, uint32_t ncols) {
+  if (!ctx || !d || !in || !out) return set_err(ctx, ZKC_ERR_BAD_ARG, "null argument");
+  CtxLock lock(ctx); return dom_coeff_to_extended(ctx, d, (const Fr*)in, 1ull << d->k, (Fr*)out, ncols);
+}
+extern "C" int zkc_extended_to_coeff_dev(zkc_ctx* ctx, const zkc_domain* d, zkc_fr* a, uint32_t ncols) {
+  if (!ctx || !d || !a) return set_err(ctx, ZKC_ERR_BAD_ARG, "null argument");
+  CtxLock lock(ctx); return dom_extended_to_coeff(ctx, d, (Fr*)a, ncols);
+}
+extern "C" int zkc_divide_by_vanishing_dev(zkc_ctx* ctx, const zkc_domain* d, zkc_fr* a) {
+  if (!ctx || !d || !a) return set_err(ctx, ZKC_ERR_BAD_ARG, "null argument");
+  CtxLock lock(ctx); return dom_divide_by_vanishing(ctx, d, (Fr*)a);
+}
+
+extern "C" int zkc_lagrange_to_coeff(zkc_ctx* ctx, const zkc_domain* d, zkc_fr* a) {
+  if (!ctx || !d || !a) return set_err(ctx, ZKC_ERR_BAD_ARG, "null argument");
+  CtxLock lock(ctx);
+  const size_t bytes = sizeof(Fr) << d->k;
+  return with_host_buffer(ctx, a, bytes, a, bytes, bytes, [&](Fr* dv) { return dom_lagrange_to_coeff(ctx, d, dv, 1); });
+}
+extern "C" int zkc_coeff_to_lagrange(zkc_ctx* ctx, const zkc_domain* d, zkc_fr* a) {
+  if (!ctx || !d || !a) return set_err(ctx, ZKC_ERR_BAD_ARG, "null argument");
+  CtxLock lock(ctx);
+  const size_t bytes = sizeof(Fr) << d->k;
+  return with_host_buffer(ctx, a, bytes, a, bytes, bytes, [&](Fr* dv) { return dom_coeff_to_lagrange(ctx, d, dv, 1); });
+}
+extern "C" int zkc_coeff_to_extended(zkc_ctx* ctx, const zkc_domain* d, const zkc_fr* coeffs, zkc_fr* out) {
+  if (!ctx || !d || !coeffs || !out) return set_err(ctx, ZKC_ERR_BAD_ARG, "null argument");
+  CtxLock lock(ctx);
+  const size_t nb = sizeof(Fr) << d->k, eb = sizeof(Fr) << d->extended_k;
+  void* din;
+  ZKC_TRY(scratch_reserve(ctx, SCR_HOSTIO2, nb, &din));
+  ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(din, coeffs, nb, cudaMemcpyHostToDevice, ctx->stream));
+  return with_host_buffer(ctx, nullptr, 0, out, eb, eb, [&](Fr* dv) { return dom_coeff_to_extended(ctx, d, (const Fr*)din, 1ull << d->k, dv, 1); });
+}
+extern "C" int zkc_extended_to_coeff(zkc_ctx* ctx, const zkc_domain* d, zkc_fr* a) {
+  if (!ctx || !d || !a) return set_err(ctx, ZKC_ERR_BAD_ARG, "null argument");
+  CtxLock lock(ctx);
+  const size_t eb = sizeof(Fr) << d->extended_k;
+  return with_host_buffer(ctx, a, eb, a, eb, eb, [&](Fr* dv) { return dom_extended_to_coeff(ctx, d, dv, 1); });
+}

@@ -1,0 +1,136 @@
+/*
+ * zkcert_cuda.h — C ABI of libzkcert_cuda.so: the B200 (sm_100a) implementation of the halo2-axiom
+ * `create_proof` hot path that zkCert/halo2-zkcert drives.
+ *
+ * The reference has no FFI for this path: its boundary is Rust generics inside the un-vendored
+ * `halo2_proofs` 0.2.0 crate (axiom fork @4b42325, /root/reference/Cargo.lock:1320-1336) and
+ * `halo2curves` 0.4.0 (@e185711, Cargo.lock:1359-1380).  Each entry point below names the Rust
+ * operator it replaces and the reference call sites that reach it.  INTEGRATION.md
+ * shows the `extern "C"` block a maintainer adds to the patched halo2_proofs.
+ *
+ * Conventions
+ *   - zkc_fr / zkc_fq: 32 bytes, little-endian limbs of the Montgomery residue (R = 2^256): the
+ *     exact memory of halo2curves `Fr` / `Fq`, so `&[Fr]` passes as `const zkc_fr*` unconverted.
+ *   - zkc_g1_affine: (x, y), 64 bytes, identity = (0, 0) — halo2curves `G1Affine`.
+ *   - zkc_g1: Jacobian (x, y, z), 96 bytes — halo2curves `G1`.  Results are returned normalised
+ *     (z = 1, or (0, 1, 0) for the identity).
+ *   - Every function returns a zkc_status; 0 = OK.  No C++ exception crosses the ABI.  There is
+ *     NO CPU fallback: without a CUDA device every compute call returns ZKC_ERR_CUDA.
+ *   - `*_dev` variants take device pointers (data already resident in HBM); the plain variants
+ *     take host pointers and include the host<->device copies.
+ *   - Randomness and the Fiat-Shamir transcript never cross this boundary except through the
+ *     `zkc_prover_*` session, which mirrors `plonk::create_proof` and takes the RNG seed and the
+ *     transcript kind from the caller.
+ *   - One zkc_ctx per GPU; calls on one ctx are serialised internally (thread-safe per ctx).
+ */
+#ifndef ZKCERT_CUDA_H
+#define ZKCERT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[4]; } zkc_fr;
+typedef struct { uint64_t l[4]; } zkc_fq;
+typedef struct { zkc_fq x, y; } zkc_g1_affine;
+typedef struct { zkc_fq x, y, z; } zkc_g1;
+
+typedef struct zkc_ctx zkc_ctx;
+typedef struct zkc_domain zkc_domain;
+typedef struct zkc_srs zkc_srs;
+typedef struct zkc_pk zkc_pk;
+
+typedef enum {
+  ZKC_OK = 0,
+  ZKC_ERR_BAD_ARG = 1,
+  ZKC_ERR_CUDA = 2,
+  ZKC_ERR_OOM = 3,
+  /* mirrors of halo2_proofs::plonk::Error */
+  ZKC_ERR_INVALID_INSTANCES = 10,
+  ZKC_ERR_CONSTRAINT_SYSTEM_FAILURE = 11, /* e.g. lookup input not in table */
+  ZKC_ERR_BOUNDS_FAILURE = 12,
+  ZKC_ERR_OPENING = 13,
+  ZKC_ERR_SYNTHESIS = 14,
+  ZKC_ERR_NOT_ENOUGH_ROWS = 15,
+  ZKC_ERR_TRANSCRIPT = 16
+} zkc_status;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int zkc_ctx_create(int device, zkc_ctx** out);
+void zkc_ctx_destroy(zkc_ctx* ctx);
+const char* zkc_last_error(const zkc_ctx* ctx);
+/* Adopt an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the ctx's own. */
+int zkc_ctx_set_stream(zkc_ctx* ctx, void* cuda_stream);
+int zkc_ctx_sync(zkc_ctx* ctx);
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+uint64_t zkc_ctx_launch_count(const zkc_ctx* ctx);
+const char* zkc_version(void);
+
+/* ---- device memory helpers (so non-CUDA hosts can keep columns resident) ------------------- */
+int zkc_dev_alloc(zkc_ctx* ctx, size_t bytes, void** dptr);
+int zkc_dev_free(zkc_ctx* ctx, void* dptr);
+int zkc_h2d(zkc_ctx* ctx, void* dptr, const void* hptr, size_t bytes);
+int zkc_d2h(zkc_ctx* ctx, void* hptr, const void* dptr, size_t bytes);
+
+/* ---- field vectors: halo2curves Fr/Fq arithmetic ---------------------------- */
+typedef enum {
+  ZKC_OP_ADD = 0, ZKC_OP_SUB = 1, ZKC_OP_MUL = 2, ZKC_OP_INV = 3 /* batch_invert; 0 -> 0 */,
+  ZKC_OP_FROM_CANONICAL = 4, ZKC_OP_TO_CANONICAL = 5, ZKC_OP_NEG = 6
+} zkc_vec_op;
+/* field: 0 = Fr, 1 = Fq.  out[i] = a[i] (op) b[i]; b may be NULL for unary ops.  Device pointers. */
+int zkc_field_vec_op_dev(zkc_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
+
+/* ---- best_fft (halo2_proofs::arithmetic::best_fft) -------------------------- */
+/* In place, natural order in and out: a[j] <- sum_i a[i] * omega^(i*j).  `omega` must have order
+ * 2^log_n.  Host buffer variant (drop-in) and device-resident batched variant (ncols contiguous
+ * columns of 2^log_n elements). */
+int zkc_fft_fr(zkc_ctx* ctx, zkc_fr* a, const zkc_fr* omega, uint32_t log_n);
+int zkc_fft_fr_dev(zkc_ctx* ctx, zkc_fr* a_dev, const zkc_fr* omega, uint32_t log_n, uint32_t ncols);
+
+/* ---- EvaluationDomain (halo2_proofs::poly::EvaluationDomain) ----------------- */
+typedef struct {
+  uint32_t k, extended_k, j;
+  zkc_fr omega, omega_inv, extended_omega, extended_omega_inv, g_coset, g_coset_inv;
+  zkc_fr ifft_divisor, extended_ifft_divisor;
+} zkc_domain_info;
+/* EvaluationDomain::new(j, k); zeta_choice selects Fr::ZETA (0 = halo2curves' constant; SURVEY OPEN-4). */
+int zkc_domain_create(zkc_ctx* ctx, uint32_t j, uint32_t k, int zeta_choice, zkc_domain** out);
+void zkc_domain_free(zkc_domain* dom);
+int zkc_domain_get_info(const zkc_domain* dom, zkc_domain_info* out);
+/* host-buffer drop-ins */
+int zkc_lagrange_to_coeff(zkc_ctx* ctx, const zkc_domain* dom, zkc_fr* a /* n, in place */);
+int zkc_coeff_to_lagrange(zkc_ctx* ctx, const zkc_domain* dom, zkc_fr* a /* n, in place */);
+int zkc_coeff_to_extended(zkc_ctx* ctx, const zkc_domain* dom, const zkc_fr* coeffs /* n */, zkc_fr* out /* 2^extended_k */);
+int zkc_extended_to_coeff(zkc_ctx* ctx, const zkc_domain* dom, zkc_fr* a /* 2^extended_k in place; tail zeroed */);
+/* device-resident, batched over ncols contiguous columns */
+int zkc_lagrange_to_coeff_dev(zkc_ctx* ctx, const zkc_domain* dom, zkc_fr* a_dev, uint32_t ncols);
+int zkc_coeff_to_lagrange_dev(zkc_ctx* ctx, const zkc_domain* dom, zkc_fr* a_dev, uint32_t ncols);
+int zkc_coeff_to_extended_dev(zkc_ctx* ctx, const zkc_domain* dom, const zkc_fr* coeffs_dev, zkc_fr* out_dev, uint32_t ncols);
+int zkc_extended_to_coeff_dev(zkc_ctx* ctx, const zkc_domain* dom, zkc_fr* a_dev, uint32_t ncols);
+int zkc_divide_by_vanishing_dev(zkc_ctx* ctx, const zkc_domain* dom, zkc_fr* a_dev);
+
+/* ---- best_multiexp / ParamsKZG ------------------------------------------ */
+/* best_multiexp(coeffs, bases) -> G1 (normalised Jacobian).  Host pointers. */
+int zkc_msm_g1(zkc_ctx* ctx, const zkc_fr* scalars, const zkc_g1_affine* bases, size_t n, zkc_g1* out);
+/* device-resident variant: `ncols` scalar columns of n against the same n bases; out[ncols] on host. */
+int zkc_msm_g1_dev(zkc_ctx* ctx, const zkc_fr* scalars_dev, const zkc_g1_affine* bases_dev, size_t n, uint32_t ncols, zkc_g1* out);
+
+/* ParamsKZG: uploads g and g_lagrange once; g2 / s_g2 stay with the host verifier. */
+typedef enum { ZKC_BASIS_COEFF = 0, ZKC_BASIS_LAGRANGE = 1 } zkc_basis;
+int zkc_srs_load(zkc_ctx* ctx, uint32_t k, const zkc_g1_affine* g, const zkc_g1_affine* g_lagrange, zkc_srs** out);
+/* ParamsKZG::setup(k, rng) with the secret handed in (gen_srs draws it from ChaCha20 zero seed,
+ * /root/reference/src/helpers.rs:210): g[i] = [s^i]G, g_lagrange[i] = [l_i(s)]G, built on the device. */
+int zkc_srs_setup(zkc_ctx* ctx, uint32_t k, const zkc_fr* s, zkc_srs** out);
+void zkc_srs_free(zkc_srs* srs);
+int zkc_srs_get(zkc_ctx* ctx, const zkc_srs* srs, int basis, zkc_g1_affine* out /* n, host */);
+/* ParamsKZG::commit / commit_lagrange: poly has len <= n entries. */
+int zkc_commit(zkc_ctx* ctx, const zkc_srs* srs, int basis, const zkc_fr* poly, size_t len, zkc_g1* out);
+int zkc_commit_dev(zkc_ctx* ctx, const zkc_srs* srs, int basis, const zkc_fr* polys_dev, size_t len, uint32_t ncols, zkc_g1* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKCERT_CUDA_H */
