@@ -1,0 +1,497 @@
+// Signed-window Pippenger G1 MSM for sm_100a: replaces halo2_proofs::arithmetic::best_multiexp and
+// ParamsKZG::{commit, commit_lagrange} (halo2_proofs 0.2.0 @4b42325 src/arithmetic.rs,
+// src/poly/kzg/commitment.rs — un-vendored, pinned at /root/reference/Cargo.lock:1320-1336;
+// SURVEY.md §8a rows a3/a6, Appendix A.3).  The sum of [s_i]P_i is a unique group element, so the
+// bytes after normalisation equal the CPU prover's whatever the algorithm.
+//
+// Pipeline (all device-resident, one stream, no host round trip until the final 2 KB):
+//   1 k_msm_digits   scalar -> canonical -> signed c-bit digits; histogram of bucket sizes (atomics)
+//   2 k_msm_scan     exclusive scan of the histogram (bucket offsets)
+//   3 k_msm_scatter  counting sort: entries (point index | sign, bucket key) grouped by bucket
+//   4 k_msm_accum    SEGMENTED FLAT WALK: thread t owns entries [tT, (t+1)T) whatever buckets they
+//                    fall in, accumulates with XYZZ mixed adds and flushes one partial per bucket it
+//                    touches into slot (key + t).  Work per thread is constant, so bit-, byte- and
+//                    limb-valued witness columns (a few giant buckets) run as fast as uniform scalars.
+//   5 k_msm_gather   one thread per bucket sums its (usually 1-3) partials; buckets with many
+//                    partials are queued and reduced by a whole CTA (k_msm_gather_heavy).
+//   6 k_msm_reduce   sum_b b*S_b per window as c independent tree reductions U_t = sum of buckets
+//                    whose index has bit t set (no serial running sum), then 2^t weights by Horner.
+// With a resident SRS the bases are expanded once into W tables 2^(c*w) * P_i, so all windows of
+// all points share ONE bucket set per column and step 6 shrinks by a factor W.
+#include "common.cuh"
+#include "ec.cuh"
+#include <algorithm>
+
+namespace zkc {
+
+struct MsmGeom {
+  uint32_t c;          // window bits
+  uint32_t W;          // number of windows: W*c >= 255
+  uint32_t NB;         // buckets per window = 2^(c-1)
+  uint32_t sets;       // bucket sets per column: W (generic bases) or 1 (precomputed tables)
+  uint64_t n;          // points per column
+  uint32_t ncols;
+  uint32_t T;          // entries per accumulate thread
+  ZKC_HD uint64_t nbtot() const { return (uint64_t)ncols * sets * NB; }
+  ZKC_HD uint64_t emax() const { return (uint64_t)ncols * W * n; }
+};
+
+// signed digits of the canonical scalar; writes dig[(col*W + w)*n + i] = mag | sign << 31
+__global__ void k_msm_digits(const Fr* scalars, uint32_t* dig, uint32_t* counts, MsmGeom g) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.n * g.ncols) return;
+  const uint32_t col = (uint32_t)(idx / g.n);
+  const uint64_t i = idx - (uint64_t)col * g.n;
+  const Fr s = fe_to_canonical(fe_load(scalars + idx));
+  uint32_t carry = 0;
+  const uint32_t full = 1u << g.c;
+  for (uint32_t w = 0; w < g.W; ++w) {
+    const uint32_t bit = w * g.c;
+    const uint32_t word = bit >> 5, sh = bit & 31;
+    uint64_t v = word < 8 ? s.v[word] : 0;
+    if (word + 1 < 8) v |= (uint64_t)s.v[word + 1] << 32;
+    uint32_t raw = ((uint32_t)(v >> sh) & (full - 1)) + carry;
+    uint32_t sign = 0;
+    carry = 0;
+    if (raw > g.NB) { raw = full - raw; sign = 1; carry = 1; }
+    dig[((uint64_t)col * g.W + w) * g.n + i] = raw | (sign << 31);
+    if (raw) {
+      const uint64_t key = ((uint64_t)col * g.sets + (g.sets == 1 ? 0 : w)) * g.NB + (raw - 1);
+      atomicAdd(counts + key, 1u);
+    }
+  }
+}
+
+// single-CTA exclusive scan: offsets[i] = sum counts[0..i), offsets[n] = total; cursor = copy of offsets
+__global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t* counts, uint32_t* offsets, uint32_t* cursor, uint64_t n) {
+  __shared__ uint32_t part[1024];
+  const uint32_t t = threadIdx.x;
+  const uint64_t per = (n + 1023) / 1024;
+  const uint64_t lo = t * per, hi = lo + per < n ? lo + per : n;
+  uint32_t s = 0;
+  for (uint64_t i = lo; i < hi; ++i) s += counts[i];
+  part[t] = s;
+  __syncthreads();
+  for (uint32_t d = 1; d < 1024; d <<= 1) {
+    uint32_t v = t >= d ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  uint32_t run = t ? part[t - 1] : 0;
+  for (uint64_t i = lo; i < hi; ++i) { offsets[i] = run; cursor[i] = run; run += counts[i]; }
+  if (t == 1023) offsets[n] = part[1023];
+}
+
+__global__ void k_msm_scatter(const uint32_t* dig, uint32_t* cursor, uint32_t* ent_pt, uint32_t* ent_key, MsmGeom g) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.emax()) return;
+  const uint32_t d = dig[idx];
+  const uint32_t mag = d & 0x7fffffffu;
+  if (!mag) return;
+  const uint64_t cw = idx / g.n;            // col*W + w
+  const uint64_t i = idx - cw * g.n;
+  const uint32_t col = (uint32_t)(cw / g.W), w = (uint32_t)(cw - (uint64_t)col * g.W);
+  const uint64_t key = ((uint64_t)col * g.sets + (g.sets == 1 ? 0 : w)) * g.NB + (mag - 1);
+  const uint32_t pos = atomicAdd(cursor + key, 1u);
+  const uint64_t pt = g.sets == 1 ? (uint64_t)w * g.n + i : i;   // precomputed tables are laid out [w][i]
+  ent_pt[pos] = (uint32_t)pt | (d & 0x80000000u);
+  ent_key[pos] = (uint32_t)key;
+}
+
+__global__ void __launch_bounds__(128) k_msm_accum(const G1Affine* bases, const uint32_t* ent_pt, const uint32_t* ent_key,
+                                                   const uint32_t* offsets, G1Xyzz* partial, MsmGeom g) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t E = offsets[g.nbtot()];
+  const uint64_t p0 = t * g.T;
+  if (p0 >= E) return;
+  const uint64_t p1 = p0 + g.T < E ? p0 + g.T : E;
+  G1Xyzz acc = xyzz_identity();
+  uint32_t cur = ent_key[p0];
+  for (uint64_t p = p0; p < p1; ++p) {
+    const uint32_t k = ent_key[p];
+    if (k != cur) { xyzz_store(partial + cur + t, acc); acc = xyzz_identity(); cur = k; }
+    const uint32_t e = ent_pt[p];
+    const G1Affine q = affine_load_nc(bases + (e & 0x7fffffffu));
+    if (!affine_is_identity(q)) xyzz_madd(acc, q, (e >> 31) != 0);
+  }
+  xyzz_store(partial + cur + t, acc);
+}
+
+#define MSM_HEAVY 12
+__global__ void __launch_bounds__(128) k_msm_gather(const uint32_t* offsets, const G1Xyzz* partial, G1Xyzz* buckets,
+                                                    uint32_t* heavy_list, uint32_t* heavy_count, MsmGeom g) {
+  const uint64_t key = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (key >= g.nbtot()) return;
+  const uint32_t off = offsets[key], cnt = offsets[key + 1] - off;
+  if (cnt == 0) { xyzz_store(buckets + key, xyzz_identity()); return; }
+  const uint64_t first = key + off / g.T, last = key + (off + cnt - 1) / g.T;
+  if (last - first + 1 > MSM_HEAVY) { heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)key; return; }
+  G1Xyzz acc = xyzz_load(partial + first);
+  for (uint64_t s = first + 1; s <= last; ++s) xyzz_add(acc, xyzz_load(partial + s));
+  xyzz_store(buckets + key, acc);
+}
+
+// block-wide XYZZ tree reduction through shared memory; result valid in thread 0
+__device__ __forceinline__ G1Xyzz block_reduce_xyzz(G1Xyzz acc, G1Xyzz* sm) {
+  const uint32_t t = threadIdx.x;
+  xyzz_store(sm + t, acc);
+  __syncthreads();
+  for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
+    if (t < d) { G1Xyzz a = xyzz_load(sm + t); xyzz_add(a, xyzz_load(sm + t + d)); xyzz_store(sm + t, a); }
+    __syncthreads();
+  }
+  G1Xyzz r = xyzz_load(sm);
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(256) k_msm_gather_heavy(const uint32_t* offsets, const G1Xyzz* partial, G1Xyzz* buckets,
+                                                          const uint32_t* heavy_list, const uint32_t* heavy_count, MsmGeom g) {
+  extern __shared__ uint4 smraw[];
+  G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smraw);
+  const uint32_t nh = *heavy_count;
+  for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+    const uint64_t key = heavy_list[h];
+    const uint32_t off = offsets[key], cnt = offsets[key + 1] - off;
+    const uint64_t first = key + off / g.T, last = key + (off + cnt - 1) / g.T;
+    G1Xyzz acc = xyzz_identity();
+    for (uint64_t s = first + threadIdx.x; s <= last; s += blockDim.x) xyzz_add(acc, xyzz_load(partial + s));
+    G1Xyzz r = block_reduce_xyzz(acc, sm);
+    if (threadIdx.x == 0) xyzz_store(buckets + key, r);
+  }
+}
+
+// U[set][t] = sum of buckets b in [1, NB] of the set with bit t of b set.  grid = (c, nsets)
+__global__ void __launch_bounds__(256) k_msm_reduce(const G1Xyzz* buckets, G1Xyzz* U, MsmGeom g) {
+  extern __shared__ uint4 smraw[];
+  G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smraw);
+  const uint32_t t = blockIdx.x;
+  const uint64_t set = blockIdx.y;
+  const G1Xyzz* bk = buckets + set * g.NB;
+  G1Xyzz acc = xyzz_identity();
+  for (uint32_t b = threadIdx.x + 1; b <= g.NB; b += blockDim.x)
+    if ((b >> t) & 1) xyzz_add(acc, xyzz_load(bk + (b - 1)));
+  G1Xyzz r = block_reduce_xyzz(acc, sm);
+  if (threadIdx.x == 0) xyzz_store(U + set * g.c + t, r);
+}
+
+// ---- host-side epilogue: Horner over bit sums and windows (a few hundred point ops) -------------
+static G1Xyzz host_combine(const G1Xyzz* U, const MsmGeom& g) {
+  G1Xyzz total = xyzz_identity();
+  for (int set = (int)g.sets - 1; set >= 0; --set) {
+    G1Xyzz r = xyzz_identity();
+    for (int t = (int)g.c - 1; t >= 0; --t) { r = xyzz_dbl(r); xyzz_add(r, U[(size_t)set * g.c + t]); }
+    for (uint32_t d = 0; d < g.c; ++d) total = xyzz_dbl(total);
+    xyzz_add(total, r);
+  }
+  return total;
+}
+
+static void xyzz_to_abi(const G1Xyzz& p, zkc_g1* out) {
+  G1Affine a = xyzz_to_affine(p);
+  Fq one = fe_one<FqP>(), zero = fe_zero<FqP>();
+  if (affine_is_identity(a)) {  // halo2curves G1::identity() = (0, 1, 0)
+    memcpy(&out->x, zero.v, 32); memcpy(&out->y, one.v, 32); memcpy(&out->z, zero.v, 32);
+  } else {
+    memcpy(&out->x, a.x.v, 32); memcpy(&out->y, a.y.v, 32); memcpy(&out->z, one.v, 32);
+  }
+}
+
+uint32_t msm_pick_c(uint64_t n, bool precomputed) {
+  uint32_t lg = 0;
+  while ((1ull << (lg + 1)) <= n) ++lg;
+  int c = precomputed ? (int)lg - 2 : (int)lg - 4;
+  if (precomputed && lg >= 20) c = (int)lg - 3;
+  return (uint32_t)std::max(3, std::min(20, c));
+}
+
+MsmGeom msm_geom(uint64_t n, uint32_t ncols, uint32_t c, bool precomputed) {
+  MsmGeom g;
+  g.c = c; g.W = (255 + c - 1) / c; g.NB = 1u << (c - 1); g.sets = precomputed ? 1 : g.W; g.n = n; g.ncols = ncols;
+  const uint64_t e = g.emax();
+  uint32_t T = 32;
+  while (T > 4 && e / T < 148ull * 512) T >>= 1;
+  g.T = T;
+  return g;
+}
+
+// Core: `ncols` scalar columns (n each, contiguous) against `bases` (n points, or W tables of n when
+// precomputed).  Writes ncols results to `out` (host).
+int msm_run(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, uint32_t ncols, uint32_t c, bool precomputed, zkc_g1* out) {
+  if (ncols == 0) return ZKC_OK;
+  if (n == 0) {
+    for (uint32_t i = 0; i < ncols; ++i) xyzz_to_abi(xyzz_identity(), out + i);
+    return ZKC_OK;
+  }
+  if (n >= (1ull << 31) / 32) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: n too large");
+  // bound memory: process columns in chunks
+  MsmGeom g1 = msm_geom(n, 1, c, precomputed);
+  const uint64_t per_col = g1.emax() * 12 + g1.nbtot() * (128 + 12) + (g1.nbtot() + g1.emax() / g1.T + 1) * 128;
+  uint32_t chunk = (uint32_t)std::max<uint64_t>(1, (3ull << 30) / per_col);
+  chunk = std::min(chunk, ncols);
+  for (uint32_t c0 = 0; c0 < ncols; c0 += chunk) {
+    const uint32_t nc = std::min(chunk, ncols - c0);
+    MsmGeom g = msm_geom(n, nc, c, precomputed);
+    const uint64_t nbt = g.nbtot(), em = g.emax();
+    if (nbt + em / g.T + 1 >= (1ull << 32) || em >= (1ull << 32)) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: batch too large");
+    const uint64_t nslots = nbt + (em + g.T - 1) / g.T + 1;
+    // carve scratch
+    size_t o = 0;
+    auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    const size_t o_counts = carve(nbt * 4), o_offsets = carve((nbt + 1) * 4), o_cursor = carve(nbt * 4), o_heavyc = carve(4),
+                 o_heavy = carve(nbt * 4), o_dig = carve(em * 4), o_pt = carve(em * 4), o_key = carve(em * 4),
+                 o_part = carve(nslots * sizeof(G1Xyzz)), o_bk = carve(nbt * sizeof(G1Xyzz)),
+                 o_U = carve((size_t)nc * g.sets * g.c * sizeof(G1Xyzz));
+    char* base;
+    ZKC_TRY(scratch_reserve(ctx, SCR_MSM, o, (void**)&base));
+    uint32_t* counts = (uint32_t*)(base + o_counts); uint32_t* offsets = (uint32_t*)(base + o_offsets);
+    uint32_t* cursor = (uint32_t*)(base + o_cursor); uint32_t* heavyc = (uint32_t*)(base + o_heavyc);
+    uint32_t* heavy = (uint32_t*)(base + o_heavy); uint32_t* dig = (uint32_t*)(base + o_dig);
+    uint32_t* ent_pt = (uint32_t*)(base + o_pt); uint32_t* ent_key = (uint32_t*)(base + o_key);
+    G1Xyzz* partial = (G1Xyzz*)(base + o_part); G1Xyzz* buckets = (G1Xyzz*)(base + o_bk); G1Xyzz* U = (G1Xyzz*)(base + o_U);
+    cudaStream_t st = ctx->stream;
+    ZKC_CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, nbt * 4, st));
+    ZKC_CUDA_TRY(ctx, cudaMemsetAsync(heavyc, 0, 4, st));
+    const uint64_t npts = n * nc;
+    k_msm_digits<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(scalars + (uint64_t)c0 * n, dig, counts, g);
+    ZKC_LAUNCH_CHECK(ctx);
+    k_msm_scan<<<1, 1024, 0, st>>>(counts, offsets, cursor, nbt);
+    ZKC_LAUNCH_CHECK(ctx);
+    k_msm_scatter<<<(unsigned)((em + 255) / 256), 256, 0, st>>>(dig, cursor, ent_pt, ent_key, g);
+    ZKC_LAUNCH_CHECK(ctx);
+    const uint64_t nthreads = (em + g.T - 1) / g.T;
+    k_msm_accum<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(bases, ent_pt, ent_key, offsets, partial, g);
+    ZKC_LAUNCH_CHECK(ctx);
+    k_msm_gather<<<(unsigned)((nbt + 127) / 128), 128, 0, st>>>(offsets, partial, buckets, heavy, heavyc, g);
+    ZKC_LAUNCH_CHECK(ctx);
+    k_msm_gather_heavy<<<ctx->sm_count * 2, 256, 256 * sizeof(G1Xyzz), st>>>(offsets, partial, buckets, heavy, heavyc, g);
+    ZKC_LAUNCH_CHECK(ctx);
+    if ((uint64_t)nc * g.sets > 65535) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: too many bucket sets in one batch");
+    dim3 rg(g.c, nc * g.sets);
+    k_msm_reduce<<<rg, 256, 256 * sizeof(G1Xyzz), st>>>(buckets, U, g);
+    ZKC_LAUNCH_CHECK(ctx);
+    const size_t ubytes = (size_t)nc * g.sets * g.c * sizeof(G1Xyzz);
+    void* hU;
+    ZKC_TRY(pinned_reserve(ctx, ubytes, &hU));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(hU, U, ubytes, cudaMemcpyDeviceToHost, st));
+    ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    for (uint32_t col = 0; col < nc; ++col) {
+      G1Xyzz r = host_combine((const G1Xyzz*)hU + (size_t)col * g.sets * g.c, g);
+      xyzz_to_abi(r, out + c0 + col);
+    }
+  }
+  return ZKC_OK;
+}
+
+// ---- SRS: resident bases + window tables ----------------------------------------------------------
+// table[w][i] = 2^(c*w) * P_i in affine form; thread per point walks the windows.
+__global__ void k_srs_expand(G1Affine* table, uint64_t n, uint32_t c, uint32_t W) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p = affine_load_nc(table + i);
+  for (uint32_t w = 1; w < W; ++w) {
+    G1Xyzz q = xyzz_from_affine(p);
+    for (uint32_t d = 0; d < c; ++d) q = xyzz_dbl(q);
+    p = xyzz_to_affine(q);
+    fe_store(&table[(uint64_t)w * n + i].x, p.x);
+    fe_store(&table[(uint64_t)w * n + i].y, p.y);
+  }
+}
+
+// out[i] = [scalar_i] G via 8-bit fixed windows over a table tab[w][d] = [d * 256^w] G
+__global__ void k_fixed_base_table(G1Affine* tab) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;   // w*256 + d
+  if (idx >= 32 * 256) return;
+  const uint32_t w = idx >> 8, d = idx & 255;
+  G1Affine gen; gen.x = fe_zero<FqP>(); gen.x.v[0] = 1; gen.x = fe_from_canonical(gen.x);
+  gen.y = fe_zero<FqP>(); gen.y.v[0] = 2; gen.y = fe_from_canonical(gen.y);
+  G1Xyzz acc = xyzz_identity();
+  // [d]G by double-and-add, then 8*w doublings
+  for (int bit = 7; bit >= 0; --bit) { acc = xyzz_dbl(acc); if ((d >> bit) & 1) xyzz_madd(acc, gen, false); }
+  for (uint32_t k = 0; k < 8 * w; ++k) acc = xyzz_dbl(acc);
+  G1Affine a = xyzz_to_affine(acc);
+  fe_store(&tab[idx].x, a.x); fe_store(&tab[idx].y, a.y);
+}
+__global__ void k_fixed_base_mul(const Fr* scalars, const G1Affine* tab, G1Affine* out, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fr s = fe_to_canonical(fe_load(scalars + i));
+  G1Xyzz acc = xyzz_identity();
+  for (uint32_t w = 0; w < 32; ++w) {
+    const uint32_t d = (s.v[w >> 2] >> ((w & 3) * 8)) & 255;
+    if (d) xyzz_madd(acc, affine_load_nc(tab + w * 256 + d), false);
+  }
+  G1Affine a = xyzz_to_affine(acc);
+  fe_store(&out[i].x, a.x); fe_store(&out[i].y, a.y);
+}
+// pw[i] = s^i
+__global__ void k_powers(Fr* pw, Fr s, uint64_t n) {
+  const uint64_t start = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 64;
+  if (start >= n) return;
+  Fr w = fe_pow_u64(s, start);
+  const uint64_t end = start + 64 < n ? start + 64 : n;
+  for (uint64_t i = start; i < end; ++i) { fe_store(pw + i, w); w = fe_mul(w, s); }
+}
+// den[i] = s - omega^i (omega powers read from pw)
+__global__ void k_lagrange_den(const Fr* wpow, Fr s, Fr* den, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fe_store(den + i, fe_sub(s, fe_load(wpow + i)));
+}
+// sc[i] = zn * omega^i * deninv[i]
+__global__ void k_lagrange_scalars(const Fr* wpow, const Fr* deninv, Fr zn, Fr* sc, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fe_store(sc + i, fe_mul(fe_mul(zn, fe_load(wpow + i)), fe_load(deninv + i)));
+}
+
+int fr_batch_invert(zkc_ctx* ctx, const Fr* a, Fr* out, size_t n);
+
+}  // namespace zkc
+
+using namespace zkc;
+
+struct zkc_srs {
+  zkc_ctx* ctx;
+  uint32_t k, c, W;
+  uint64_t n;
+  G1Affine* tab[2] = {nullptr, nullptr};  // [basis] -> W tables of n affine points ([0] = the SRS itself)
+};
+
+static int srs_expand(zkc_ctx* ctx, zkc_srs* s) {
+  for (int b = 0; b < 2; ++b) {
+    if (s->W > 1) {
+      k_srs_expand<<<(unsigned)((s->n + 127) / 128), 128, 0, ctx->stream>>>(s->tab[b], s->n, s->c, s->W);
+      ZKC_LAUNCH_CHECK(ctx);
+    }
+  }
+  ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKC_OK;
+}
+
+static int srs_alloc(zkc_ctx* ctx, uint32_t k, zkc_srs** out) {
+  zkc_srs* s = new zkc_srs();
+  s->ctx = ctx; s->k = k; s->n = 1ull << k;
+  s->c = msm_pick_c(s->n, true);
+  s->W = (255 + s->c - 1) / s->c;
+  for (int b = 0; b < 2; ++b) {
+    cudaError_t e = cudaMalloc(&s->tab[b], (size_t)s->W * s->n * sizeof(G1Affine));
+    if (e != cudaSuccess) {
+      if (s->tab[0]) cudaFree(s->tab[0]);
+      delete s;
+      return set_err(ctx, ZKC_ERR_OOM, std::string("zkc_srs: ") + cudaGetErrorString(e));
+    }
+  }
+  *out = s;
+  return ZKC_OK;
+}
+
+extern "C" void zkc_srs_free(zkc_srs* s) {
+  if (!s) return;
+  for (int b = 0; b < 2; ++b) if (s->tab[b]) cudaFree(s->tab[b]);
+  delete s;
+}
+
+extern "C" int zkc_srs_load(zkc_ctx* ctx, uint32_t k, const zkc_g1_affine* g, const zkc_g1_affine* gl, zkc_srs** out) {
+  if (!ctx || !g || !gl || !out || k > 26) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_srs_load: bad arguments");
+  CtxLock lock(ctx);
+  zkc_srs* s;
+  ZKC_TRY(srs_alloc(ctx, k, &s));
+  const size_t bytes = s->n * sizeof(G1Affine);
+  cudaError_t e = cudaMemcpyAsync(s->tab[0], g, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->tab[1], gl, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) { zkc_srs_free(s); return set_err(ctx, ZKC_ERR_CUDA, cudaGetErrorString(e)); }
+  int st = srs_expand(ctx, s);
+  if (st != ZKC_OK) { zkc_srs_free(s); return st; }
+  *out = s;
+  return ZKC_OK;
+}
+
+extern "C" int zkc_srs_setup(zkc_ctx* ctx, uint32_t k, const zkc_fr* s_abi, zkc_srs** out) {
+  if (!ctx || !s_abi || !out || k > 26) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_srs_setup: bad arguments");
+  CtxLock lock(ctx);
+  zkc_srs* s;
+  ZKC_TRY(srs_alloc(ctx, k, &s));
+  const uint64_t n = s->n;
+  Fr sec; memcpy(sec.v, s_abi, 32);
+  Fr *pw, *den;
+  G1Affine* tab;
+  int st = scratch_reserve(ctx, SCR_MISC, n * sizeof(Fr), (void**)&pw);
+  if (st == ZKC_OK) st = scratch_reserve(ctx, SCR_MISC2, n * sizeof(Fr), (void**)&den);
+  if (st == ZKC_OK) st = scratch_reserve(ctx, SCR_MISC3, 32 * 256 * sizeof(G1Affine), (void**)&tab);
+  if (st != ZKC_OK) { zkc_srs_free(s); return st; }
+  cudaStream_t stream = ctx->stream;
+  const unsigned gb = (unsigned)((n + 127) / 128), gp = (unsigned)(((n + 63) / 64 + 127) / 128);
+  k_fixed_base_table<<<64, 128, 0, stream>>>(tab); ctx->launches++;
+  // g[i] = [s^i] G
+  k_powers<<<gp, 128, 0, stream>>>(pw, sec, n); ctx->launches++;
+  k_fixed_base_mul<<<gb, 128, 0, stream>>>(pw, tab, s->tab[0], n); ctx->launches++;
+  // g_lagrange[i] = [ (s^n - 1)/n * w^i / (s - w^i) ] G
+  const Fr omega = fr_root_of_unity(k);
+  const Fr zn = fe_mul(fe_sub(fe_pow_u64(sec, n), fe_one<FrP>()), fe_inv(fr_from_u64(n)));
+  k_powers<<<gp, 128, 0, stream>>>(pw, omega, n); ctx->launches++;
+  k_lagrange_den<<<gb, 128, 0, stream>>>(pw, sec, den, n); ctx->launches++;
+  st = fr_batch_invert(ctx, den, den, n);
+  if (st == ZKC_OK) {
+    k_lagrange_scalars<<<gb, 128, 0, stream>>>(pw, den, zn, den, n); ctx->launches++;
+    k_fixed_base_mul<<<gb, 128, 0, stream>>>(den, tab, s->tab[1], n); ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) st = set_err(ctx, ZKC_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (st == ZKC_OK) st = srs_expand(ctx, s);
+  if (st != ZKC_OK) { zkc_srs_free(s); return st; }
+  *out = s;
+  return ZKC_OK;
+}
+
+extern "C" int zkc_srs_get(zkc_ctx* ctx, const zkc_srs* s, int basis, zkc_g1_affine* out) {
+  if (!ctx || !s || !out || basis < 0 || basis > 1) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_srs_get: bad arguments");
+  CtxLock lock(ctx);
+  ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(out, s->tab[basis], s->n * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
+  ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKC_OK;
+}
+
+namespace zkc {
+// commit `ncols` device-resident polynomials of `len` <= n coefficients (column stride = len)
+int srs_commit_dev(zkc_ctx* ctx, const zkc_srs* s, int basis, const Fr* polys, uint64_t len, uint32_t ncols, zkc_g1* out) {
+  if (len > s->n) return set_err(ctx, ZKC_ERR_BAD_ARG, "commit: polynomial longer than the SRS");
+  if (len == s->n) return msm_run(ctx, polys, s->tab[basis], len, ncols, s->c, true, out);
+  // shorter polynomials: the window tables are laid out with stride n, so fall back to the generic
+  // (non-precomputed) walk over the first `len` bases.
+  return msm_run(ctx, polys, s->tab[basis], len, ncols, msm_pick_c(len, false), false, out);
+}
+}  // namespace zkc
+
+extern "C" int zkc_commit_dev(zkc_ctx* ctx, const zkc_srs* s, int basis, const zkc_fr* polys, size_t len, uint32_t ncols, zkc_g1* out) {
+  if (!ctx || !s || !polys || !out || basis < 0 || basis > 1) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_commit_dev: bad arguments");
+  CtxLock lock(ctx);
+  return srs_commit_dev(ctx, s, basis, (const Fr*)polys, len, ncols, out);
+}
+extern "C" int zkc_commit(zkc_ctx* ctx, const zkc_srs* s, int basis, const zkc_fr* poly, size_t len, zkc_g1* out) {
+  if (!ctx || !s || !poly || !out || basis < 0 || basis > 1) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_commit: bad arguments");
+  CtxLock lock(ctx);
+  void* d;
+  ZKC_TRY(scratch_reserve(ctx, SCR_HOSTIO, std::max<size_t>(len, 1) * sizeof(Fr), &d));
+  if (len) ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(d, poly, len * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  return srs_commit_dev(ctx, s, basis, (const Fr*)d, len, 1, out);
+}
+
+extern "C" int zkc_msm_g1_dev(zkc_ctx* ctx, const zkc_fr* scalars, const zkc_g1_affine* bases, size_t n, uint32_t ncols, zkc_g1* out) {
+  if (!ctx || !out || (n && (!scalars || !bases))) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_msm_g1_dev: bad arguments");
+  CtxLock lock(ctx);
+  return msm_run(ctx, (const Fr*)scalars, (const G1Affine*)bases, n, ncols, msm_pick_c(n ? n : 1, false), false, out);
+}
+extern "C" int zkc_msm_g1(zkc_ctx* ctx, const zkc_fr* scalars, const zkc_g1_affine* bases, size_t n, zkc_g1* out) {
+  if (!ctx || !out || (n && (!scalars || !bases))) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_msm_g1: bad arguments");
+  CtxLock lock(ctx);
+  void *ds, *db;
+  ZKC_TRY(scratch_reserve(ctx, SCR_HOSTIO, std::max<size_t>(n, 1) * sizeof(Fr), &ds));
+  ZKC_TRY(scratch_reserve(ctx, SCR_HOSTIO2, std::max<size_t>(n, 1) * sizeof(G1Affine), &db));
+  if (n) {
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(ds, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(db, bases, n * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return msm_run(ctx, (const Fr*)ds, (const G1Affine*)db, n, 1, msm_pick_c(n ? n : 1, false), false, out);
+}
