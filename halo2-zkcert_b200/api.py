@@ -87,7 +87,7 @@ class Context:
 
     def use_torch_stream(self):
         import torch
-        self.check(lib().zkc_ctx_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        self.check(lib().zkc_ctx_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream), C.c_int(1)))
 
     def sync(self):
         self.check(lib().zkc_ctx_sync(self._h))
@@ -95,6 +95,16 @@ class Context:
     @property
     def launches(self):
         return int(lib().zkc_ctx_launch_count(self._h))
+
+    def profile_enable(self, on=True):
+        self.check(lib().zkc_profile_enable(self._h, C.c_int(1 if on else 0)))
+
+    def profile_report(self):
+        """{phase: {"ms": total CUDA-event ms, "n": launches}} since the last report (synchronises)."""
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        self.check(lib().zkc_profile_report(self._h, buf, C.c_size_t(len(buf))))
+        return json.loads(buf.value.decode() or "{}")
 
     def close(self):
         if self._h:

@@ -35,6 +35,12 @@ struct zkc_ctx {
   std::map<uint32_t, zkc::Fr*> twiddles;
   void* pinned = nullptr;  // small pinned staging buffer for results
   size_t pinned_bytes = 0;
+  // optional per-phase CUDA-event timers (zkc_profile_*): name -> accumulated ms / count
+  bool profiling = false;
+  struct ProfRec { std::string name; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  std::map<std::string, std::pair<double, uint64_t>> prof_acc;
 };
 
 namespace zkc {
@@ -87,6 +93,23 @@ inline int pinned_reserve(zkc_ctx* ctx, size_t bytes, void** out) {
   *out = ctx->pinned;
   return ZKC_OK;
 }
+
+// RAII CUDA-event timer around a phase; active only while profiling is enabled on the ctx.
+struct ProfScope {
+  zkc_ctx* c; int idx = -1;
+  ProfScope(zkc_ctx* ctx, const char* name) : c(ctx) {
+    if (!c->profiling) return;
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; ++i) {
+      if (!c->prof_pool.empty()) { ev[i] = c->prof_pool.back(); c->prof_pool.pop_back(); }
+      else cudaEventCreate(&ev[i]);
+    }
+    cudaEventRecord(ev[0], c->stream);
+    c->prof_pending.push_back({name, ev[0], ev[1]});
+    idx = (int)c->prof_pending.size() - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(c->prof_pending[idx].e1, c->stream); }
+};
 
 struct CtxLock {
   zkc_ctx* c;

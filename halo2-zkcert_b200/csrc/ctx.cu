@@ -30,6 +30,8 @@ extern "C" void zkc_ctx_destroy(zkc_ctx* c) {
   for (auto& b : c->scratch) if (b.p) cudaFree(b.p);
   for (auto& kv : c->twiddles) cudaFree(kv.second);
   if (c->pinned) cudaFreeHost(c->pinned);
+  for (auto& r : c->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto e : c->prof_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -37,17 +39,47 @@ extern "C" void zkc_ctx_destroy(zkc_ctx* c) {
 extern "C" const char* zkc_last_error(const zkc_ctx* c) { return c ? c->err.c_str() : "no context (no CUDA device?)"; }
 extern "C" uint64_t zkc_ctx_launch_count(const zkc_ctx* c) { return c ? c->launches : 0; }
 
-extern "C" int zkc_ctx_set_stream(zkc_ctx* c, void* s) {
+extern "C" int zkc_ctx_set_stream(zkc_ctx* c, void* s, int external) {
   if (!c) return ZKC_ERR_BAD_ARG;
   CtxLock lock(c);
   ZKC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  c->stream = external ? (cudaStream_t)s : c->own_stream;
   return ZKC_OK;
 }
 extern "C" int zkc_ctx_sync(zkc_ctx* c) {
   if (!c) return ZKC_ERR_BAD_ARG;
   CtxLock lock(c);
   ZKC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return ZKC_OK;
+}
+
+extern "C" int zkc_profile_enable(zkc_ctx* c, int on) {
+  if (!c) return ZKC_ERR_BAD_ARG;
+  CtxLock lock(c);
+  c->profiling = on != 0;
+  return ZKC_OK;
+}
+extern "C" int zkc_profile_report(zkc_ctx* c, char* buf, size_t cap) {
+  if (!c || !buf || cap == 0) return ZKC_ERR_BAD_ARG;
+  CtxLock lock(c);
+  ZKC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (auto& r : c->prof_pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { auto& a = c->prof_acc[r.name]; a.first += ms; a.second++; }
+    c->prof_pool.push_back(r.e0); c->prof_pool.push_back(r.e1);
+  }
+  c->prof_pending.clear();
+  std::string js = "{";
+  bool first = true;
+  for (auto& kv : c->prof_acc) {
+    char tmp[256];
+    snprintf(tmp, sizeof tmp, "%s\"%s\": {\"ms\": %.6f, \"n\": %llu}", first ? "" : ", ", kv.first.c_str(), kv.second.first,
+             (unsigned long long)kv.second.second);
+    js += tmp; first = false;
+  }
+  js += "}";
+  c->prof_acc.clear();
+  snprintf(buf, cap, "%s", js.c_str());
   return ZKC_OK;
 }
 

@@ -254,23 +254,30 @@ int msm_run(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, 
     ZKC_CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, nbt * 4, st));
     ZKC_CUDA_TRY(ctx, cudaMemsetAsync(heavyc, 0, 4, st));
     const uint64_t npts = n * nc;
-    k_msm_digits<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(scalars + (uint64_t)c0 * n, dig, counts, g);
-    ZKC_LAUNCH_CHECK(ctx);
-    k_msm_scan<<<1, 1024, 0, st>>>(counts, offsets, cursor, nbt);
-    ZKC_LAUNCH_CHECK(ctx);
-    k_msm_scatter<<<(unsigned)((em + 255) / 256), 256, 0, st>>>(dig, cursor, ent_pt, ent_key, g);
-    ZKC_LAUNCH_CHECK(ctx);
+    { ProfScope _p(ctx, "msm.digits");
+      k_msm_digits<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(scalars + (uint64_t)c0 * n, dig, counts, g);
+      ZKC_LAUNCH_CHECK(ctx); }
+    { ProfScope _p(ctx, "msm.scan");
+      k_msm_scan<<<1, 1024, 0, st>>>(counts, offsets, cursor, nbt);
+      ZKC_LAUNCH_CHECK(ctx); }
+    { ProfScope _p(ctx, "msm.scatter");
+      k_msm_scatter<<<(unsigned)((em + 255) / 256), 256, 0, st>>>(dig, cursor, ent_pt, ent_key, g);
+      ZKC_LAUNCH_CHECK(ctx); }
     const uint64_t nthreads = (em + g.T - 1) / g.T;
-    k_msm_accum<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(bases, ent_pt, ent_key, offsets, partial, g);
-    ZKC_LAUNCH_CHECK(ctx);
-    k_msm_gather<<<(unsigned)((nbt + 127) / 128), 128, 0, st>>>(offsets, partial, buckets, heavy, heavyc, g);
-    ZKC_LAUNCH_CHECK(ctx);
-    k_msm_gather_heavy<<<ctx->sm_count * 2, 256, 256 * sizeof(G1Xyzz), st>>>(offsets, partial, buckets, heavy, heavyc, g);
-    ZKC_LAUNCH_CHECK(ctx);
+    { ProfScope _p(ctx, "msm.accum");
+      k_msm_accum<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(bases, ent_pt, ent_key, offsets, partial, g);
+      ZKC_LAUNCH_CHECK(ctx); }
+    { ProfScope _p(ctx, "msm.gather");
+      k_msm_gather<<<(unsigned)((nbt + 127) / 128), 128, 0, st>>>(offsets, partial, buckets, heavy, heavyc, g);
+      ZKC_LAUNCH_CHECK(ctx); }
+    { ProfScope _p(ctx, "msm.gather_heavy");
+      k_msm_gather_heavy<<<ctx->sm_count * 2, 256, 256 * sizeof(G1Xyzz), st>>>(offsets, partial, buckets, heavy, heavyc, g);
+      ZKC_LAUNCH_CHECK(ctx); }
     if ((uint64_t)nc * g.sets > 65535) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: too many bucket sets in one batch");
     dim3 rg(g.c, nc * g.sets);
-    k_msm_reduce<<<rg, 256, 256 * sizeof(G1Xyzz), st>>>(buckets, U, g);
-    ZKC_LAUNCH_CHECK(ctx);
+    { ProfScope _p(ctx, "msm.reduce");
+      k_msm_reduce<<<rg, 256, 256 * sizeof(G1Xyzz), st>>>(buckets, U, g);
+      ZKC_LAUNCH_CHECK(ctx); }
     const size_t ubytes = (size_t)nc * g.sets * g.c * sizeof(G1Xyzz);
     void* hU;
     ZKC_TRY(pinned_reserve(ctx, ubytes, &hU));

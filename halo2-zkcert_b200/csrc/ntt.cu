@@ -209,6 +209,7 @@ static int launch_pass(zkc_ctx* ctx, bool last, const NttPass& p, uint32_t grid_
 
   }
   dim3 grid(grid_x, ncols);
+  ProfScope _p(ctx, last ? "ntt.last" : "ntt.strided");
   if (last) k_ntt_last<<<grid, NTT_THREADS, smem, ctx->stream>>>(p);
   else k_ntt_strided<<<grid, NTT_THREADS, smem, ctx->stream>>>(p);
   ZKC_LAUNCH_CHECK(ctx);

@@ -62,12 +62,19 @@ typedef enum {
 int zkc_ctx_create(int device, zkc_ctx** out);
 void zkc_ctx_destroy(zkc_ctx* ctx);
 const char* zkc_last_error(const zkc_ctx* ctx);
-/* Adopt an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the ctx's own. */
-int zkc_ctx_set_stream(zkc_ctx* ctx, void* cuda_stream);
+/* external != 0: adopt an externally owned cudaStream_t (e.g. torch's current stream; the handle 0 is
+ * the legacy default stream).  external == 0: go back to the ctx's own non-blocking stream. */
+int zkc_ctx_set_stream(zkc_ctx* ctx, void* cuda_stream, int external);
 int zkc_ctx_sync(zkc_ctx* ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 uint64_t zkc_ctx_launch_count(const zkc_ctx* ctx);
 const char* zkc_version(void);
+/* Per-phase CUDA-event timers on the ctx stream (the NVTX-range equivalent).  While
+ * enabled every internal phase (msm.accum, ntt.pass, quotient, ...) is bracketed by events;
+ * zkc_profile_report synchronises, then writes a JSON object {"phase": {"ms": total, "n": count}, ...}
+ * into buf (truncated to cap) and clears the accumulators. */
+int zkc_profile_enable(zkc_ctx* ctx, int on);
+int zkc_profile_report(zkc_ctx* ctx, char* buf, size_t cap);
 
 /* ---- device memory helpers (so non-CUDA hosts can keep columns resident) ------------------- */
 int zkc_dev_alloc(zkc_ctx* ctx, size_t bytes, void** dptr);

@@ -211,3 +211,56 @@ def srs_setup(k, s_mont, want_lagrange=True):
     gl = np.empty((n, 8), dtype=np.uint64) if want_lagrange else None
     lib().orc_srs_setup(C.c_uint32(k), _p(np.ascontiguousarray(s_mont, dtype=np.uint64)), _p(g), None if gl is None else _p(gl))
     return g, gl
+
+
+# ---- polynomial helpers (orc_poly.cpp) ---------------------------------------------------------
+def vec_scalar(op, a, s):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.empty_like(a)
+    lib().orc_fr_vec_scalar(C.c_int({"add": 0, "sub": 1, "mul": 2, "rsub": 3}[op]), _p(a), _p(np.ascontiguousarray(s, dtype=np.uint64)), _p(out),
+                            C.c_size_t(a.shape[0]))
+    return out
+
+
+def vec_vec(op, a, b):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64)
+    assert a.shape == b.shape
+    out = np.empty_like(a)
+    lib().orc_fr_vec_vec(C.c_int({"add": 0, "sub": 1, "mul": 2}[op]), _p(a), _p(b), _p(out), C.c_size_t(a.shape[0]))
+    return out
+
+
+def batch_invert(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.empty_like(a)
+    lib().orc_fr_batch_invert(_p(a), _p(out), C.c_size_t(a.shape[0]))
+    return out
+
+
+def eval_poly(coeffs, x):
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64)
+    out = np.empty((1, 4), dtype=np.uint64)
+    lib().orc_eval_poly(_p(coeffs), C.c_size_t(coeffs.shape[0]), _p(np.ascontiguousarray(x, dtype=np.uint64)), _p(out))
+    return out
+
+
+def kate_division(a, z):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.zeros((max(a.shape[0] - 1, 0), 4), dtype=np.uint64)
+    lib().orc_kate_division(_p(a), C.c_size_t(a.shape[0]), _p(np.ascontiguousarray(z, dtype=np.uint64)), _p(out))
+    return out
+
+
+def prefix_product(r, start):
+    r = np.ascontiguousarray(r, dtype=np.uint64)
+    out = np.empty_like(r)
+    lib().orc_prefix_product(_p(r), C.c_size_t(r.shape[0]), _p(np.ascontiguousarray(start, dtype=np.uint64)), _p(out))
+    return out
+
+
+def powers(base, n, first=None):
+    out = np.empty((n, 4), dtype=np.uint64)
+    f = fr_from_ints([1]) if first is None else np.ascontiguousarray(first, dtype=np.uint64)
+    lib().orc_powers(_p(np.ascontiguousarray(base, dtype=np.uint64)), _p(f), C.c_size_t(n), _p(out))
+    return out
