@@ -306,3 +306,81 @@ class ParamsKZG:
         out = np.zeros((ncols, 12), dtype=np.uint64)
         self.ctx.check(lib().zkc_commit_dev(self.ctx._h, self._h, C.c_int(basis), _dp(polys_dev), C.c_size_t(length), C.c_uint32(ncols), _hp(out)))
         return out
+
+
+# ---- ProvingKey / create_proof --------------------------------------------------------------------
+class ProveOpts(C.Structure):
+    _fields_ = [("transcript", C.c_int), ("multiopen", C.c_int), ("advice_blinding", C.c_int), ("blind_draws", C.c_int),
+                ("point_format", C.c_int), ("rng_seed", C.c_uint8 * 32)]
+
+
+class ProvingKey:
+    """halo2_proofs::plonk::ProvingKey resident on the device (zkc_pk).
+
+    cs: circuit.ConstraintSystem; fixed / sigma: (num_columns * n, 4) Montgomery Lagrange columns
+    (pk.fixed_values, pk.permutation.permutations); transcript_repr: (1, 4) Montgomery."""
+
+    def __init__(self, params, cs, fixed, sigma, transcript_repr, zeta_choice=0):
+        self.params, self.cs, self.ctx = params, cs, params.ctx
+        n = cs.n
+        blob = cs.serialize()
+        fixed = _np(fixed, 4) if cs.num_fixed else np.zeros((0, 4), dtype=np.uint64)
+        sigma = _np(sigma, 4) if cs.permutation else np.zeros((0, 4), dtype=np.uint64)
+        assert fixed.shape[0] == cs.num_fixed * n and sigma.shape[0] == len(cs.permutation) * n
+        tr = _np(transcript_repr, 4)
+        self._h = C.c_void_p()
+        self.ctx.check(lib().zkc_pk_load(self.ctx._h, params._h, blob, C.c_size_t(len(blob)), _hp(fixed), _hp(sigma), _hp(tr),
+                                         C.c_int(zeta_choice), C.byref(self._h)))
+        info = (C.c_uint32 * 8)()
+        lib().zkc_pk_info(self._h, info)
+        self.k, self.extended_k, self.degree, self.blinding_factors, self.num_sets, self.num_lookups = list(info)[:6]
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().zkc_pk_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def commitments(self):
+        """(vk.fixed_commitments, vk.permutation.commitments) as affine (m, 8) arrays"""
+        f = np.zeros((self.cs.num_fixed, 8), dtype=np.uint64)
+        s = np.zeros((len(self.cs.permutation), 8), dtype=np.uint64)
+        self.ctx.check(lib().zkc_pk_get_commitments(self.ctx._h, self._h, _hp(f), _hp(s)))
+        return f, s
+
+
+def create_proof(pk, advice, instances, rng_seed, transcript="blake2b", multiopen="shplonk", advice_blinding="axiom", blind_draws=False,
+                 point_format=0):
+    """plonk::create_proof for one circuit.  advice: (num_advice * n, 4) Montgomery, numpy (host) or
+    torch CUDA tensor (already resident); instances: list of (len, 4) Montgomery arrays; rng_seed: 32
+    bytes for ChaCha20Rng::from_seed.  Returns the proof bytes."""
+    ctx = pk.ctx
+    o = ProveOpts()
+    o.transcript = {"blake2b": 0, "keccak": 1}[transcript]
+    o.multiopen = {"shplonk": 0, "gwc": 1}[multiopen]
+    o.advice_blinding = {"axiom": 0, "pse": 1}[advice_blinding]
+    o.blind_draws = 1 if blind_draws else 0
+    o.point_format = point_format
+    o.rng_seed[:] = list(rng_seed)
+    on_dev = hasattr(advice, "is_cuda")
+    if on_dev:
+        adv_ptr = _dp(advice)
+    else:
+        advice = _np(advice, 4)
+        adv_ptr = _hp(advice)
+    inst = [_np(i, 4) if len(i) else np.zeros((0, 4), dtype=np.uint64) for i in instances]
+    ptrs = (C.c_void_p * max(len(inst), 1))(*[i.ctypes.data for i in inst])
+    lens = (C.c_size_t * max(len(inst), 1))(*[i.shape[0] for i in inst])
+    cap = 1 << 20
+    buf = (C.c_uint8 * cap)()
+    plen = C.c_size_t(0)
+    ctx.check(lib().zkc_prove(ctx._h, pk._h, adv_ptr, C.c_int(1 if on_dev else 0), ptrs, lens, C.byref(o), buf, C.c_size_t(cap), C.byref(plen)))
+    return bytes(buf[:plen.value])
+
+
+def seed_from_u64(state):
+    out = (C.c_uint8 * 32)()
+    lib().zkc_seed_from_u64(C.c_uint64(state), out)
+    return bytes(out)

@@ -41,7 +41,8 @@ def build(force=False, verbose=False):
                         glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "host", "*.h*")) +
                         glob.glob(os.path.join(HERE, "..", "include", "*.h")))):
             continue
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", src, "-o", obj]
+        lang = "cu" if src.endswith(".cu") else "c++"   # host-only sources never see __CUDA_ARCH__
+        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose and lang == "cu" else []) + ["-x", lang, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()
@@ -49,7 +50,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
-    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    subprocess.check_call([NVCC, "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
     return LIB
 
 

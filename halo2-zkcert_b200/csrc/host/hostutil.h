@@ -1,0 +1,70 @@
+// Host-side pieces of the create_proof driver that stay on the CPU in the reference too:
+// Fiat-Shamir transcripts (halo2_proofs::transcript::{Blake2bWrite, Keccak256Write}, Challenge255),
+// the ChaCha20 RNG that feeds Fr::random (rand_chacha 0.3.1 / halo2curves `from_u512`), and small
+// scalar helpers.  SURVEY.md §8a rows a13/a14, Appendix A.2/A.12.  Upstream sources are not vendored
+// (/root/reference/Cargo.lock:313 blake2b_simd, :2635 sha3, :2195 rand_chacha, :1320 halo2_proofs).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../ff.cuh"
+#include "../ec.cuh"
+
+namespace zkc {
+namespace host {
+
+// ---- Blake2b-512 with personalisation (RFC 7693) ----------------------------------------------------
+struct Blake2b {
+  uint64_t h[8];
+  uint64_t t[2];
+  uint8_t buf[128];
+  size_t buflen;
+  void init(const char personal[16]);
+  void update(const uint8_t* in, size_t len);
+  void finalize(uint8_t out[64]) const;   // does not disturb the running state (clone + finalize)
+ private:
+  void compress(const uint8_t block[128], bool last);
+};
+
+// ---- Keccak-256 (original padding 0x01) ---------------------------------------------------------------
+void keccak256(const uint8_t* in, size_t len, uint8_t out[32]);
+
+// ---- ChaCha20 RNG as rand_chacha::ChaCha20Rng (64-bit block counter, stream 0) ----------------------
+struct ChaCha20Rng {
+  uint32_t key[8];
+  uint64_t counter;
+  uint32_t block[16];
+  int pos;  // next unread word in block; 16 = empty
+  explicit ChaCha20Rng(const uint8_t seed[32]);
+  uint32_t next_u32();
+  uint64_t next_u64();
+  Fr fr_random();   // halo2curves Fr::random: 8 x next_u64 as a 512-bit LE integer, reduced mod r
+};
+// rand_core SeedableRng::seed_from_u64 (PCG32 expansion)
+void seed_from_u64(uint64_t state, uint8_t seed[32]);
+
+// ---- scalar helpers ---------------------------------------------------------------------------------------
+Fr fr_from_u512_le(const uint8_t bytes[64]);      // from_uniform_bytes
+void fr_to_repr(const Fr& a, uint8_t out[32]);    // canonical little-endian
+void fq_to_repr(const Fq& a, uint8_t out[32]);
+int fr_cmp_canonical(const Fr& a, const Fr& b);   // Ord for Fr
+
+// ---- transcripts --------------------------------------------------------------------------------------------
+struct Transcript {
+  int kind;          // 0 = Blake2b, 1 = Keccak256
+  int point_format;  // SURVEY OPEN-5
+  Blake2b b2;
+  std::vector<uint8_t> kbuf;
+  std::vector<uint8_t> proof;
+  Transcript(int kind, int point_format);
+  void absorb(const uint8_t* p, size_t n);
+  Fr squeeze_challenge();
+  int common_point(const G1Affine& p);   // returns nonzero on identity
+  void common_scalar(const Fr& s);
+  int write_point(const G1Affine& p);
+  void write_scalar(const Fr& s);
+};
+
+}  // namespace host
+}  // namespace zkc

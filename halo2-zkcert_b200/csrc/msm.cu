@@ -394,6 +394,8 @@ static int srs_alloc(zkc_ctx* ctx, uint32_t k, zkc_srs** out) {
   return ZKC_OK;
 }
 
+extern "C" uint32_t zkc_srs_k(const zkc_srs* s) { return s ? s->k : 0; }
+
 extern "C" void zkc_srs_free(zkc_srs* s) {
   if (!s) return;
   for (int b = 0; b < 2; ++b) if (s->tab[b]) cudaFree(s->tab[b]);

@@ -189,6 +189,8 @@ static int get_twiddles(zkc_ctx* ctx, uint32_t log_n, const Fr** out) {
   return ZKC_OK;
 }
 
+int ntt_twiddles(zkc_ctx* ctx, uint32_t log_n, const Fr** out) { return get_twiddles(ctx, log_n, out); }
+
 struct NttOpts {
   int inverse = 0;
   uint64_t n_in = 0;      // 0 = full

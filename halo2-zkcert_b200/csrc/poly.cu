@@ -1,0 +1,451 @@
+// Device polynomial / column primitives of the create_proof pipeline.
+//
+// What each replaces in halo2_proofs 0.2.0 @4b42325 (un-vendored; /root/reference/Cargo.lock:1320-1336):
+//   fr_scan(MUL)        the serial running products of permutation::prover / lookup::prover (a8, a9)
+//   fr_kate_division    arithmetic::kate_division (serial synthetic division) as powers + suffix add-scan (a11)
+//   fr_eval_batch       arithmetic::eval_polynomial (serial Horner), one CTA tree per (poly, point) (a11)
+//   fr_lincomb          the `poly * scalar + poly` folds of ProverSHPLONK / ProverGWC (a12)
+//   eval_program        plonk::evaluation::GraphEvaluator over Lagrange rows / the extended coset (a7, a9)
+//   sort_u256           the `sort` inside lookup::prover::permute_expression_pair (a9) as a bitonic network
+#include "poly.cuh"
+
+namespace zkc {
+
+// ---- scans ---------------------------------------------------------------------------------------------
+#define SCAN_CH 16
+
+template <int OP> __device__ __forceinline__ Fr scan_op(const Fr& a, const Fr& b) { return OP == SCAN_MUL ? fe_mul(a, b) : fe_add(a, b); }
+template <int OP> __device__ __forceinline__ Fr scan_id() { return OP == SCAN_MUL ? fe_one<FrP>() : fe_zero<FrP>(); }
+
+template <int OP>
+__global__ void k_scan_chunk_totals(const Fr* in, Fr* tot, uint64_t n, int reverse) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t lo = t * SCAN_CH;
+  if (lo >= n) return;
+  const uint64_t hi = lo + SCAN_CH < n ? lo + SCAN_CH : n;
+  Fr acc = scan_id<OP>();
+  for (uint64_t i = lo; i < hi; ++i) acc = scan_op<OP>(acc, fe_load(in + (reverse ? n - 1 - i : i)));
+  fe_store(tot + t, acc);
+}
+
+// single CTA: tot[c] <- start (op) fold_{c' < c} tot[c']
+template <int OP>
+__global__ void __launch_bounds__(1024) k_scan_totals(Fr* tot, uint64_t nchunks, Fr start) {
+  extern __shared__ uint4 smraw[];
+  Fr* sm = reinterpret_cast<Fr*>(smraw);
+  const uint32_t t = threadIdx.x;
+  const uint64_t per = (nchunks + 1023) / 1024;
+  const uint64_t lo = (uint64_t)t * per, hi = lo + per < nchunks ? lo + per : nchunks;
+  Fr acc = scan_id<OP>();
+  for (uint64_t i = lo; i < hi; ++i) acc = scan_op<OP>(acc, fe_load(tot + i));
+  fe_store(sm + t, acc);
+  __syncthreads();
+  for (uint32_t d = 1; d < 1024; d <<= 1) {
+    Fr v = scan_id<OP>();
+    const bool act = t >= d;
+    if (act) v = fe_load(sm + t - d);
+    __syncthreads();
+    if (act) fe_store(sm + t, scan_op<OP>(v, fe_load(sm + t)));
+    __syncthreads();
+  }
+  Fr run = t ? scan_op<OP>(start, fe_load(sm + t - 1)) : start;
+  for (uint64_t i = lo; i < hi; ++i) { Fr v = fe_load(tot + i); fe_store(tot + i, run); run = scan_op<OP>(run, v); }
+}
+
+template <int OP>
+__global__ void k_scan_apply(const Fr* in, Fr* out, const Fr* tot, uint64_t n, int reverse) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t lo = t * SCAN_CH;
+  if (lo >= n) return;
+  const uint64_t hi = lo + SCAN_CH < n ? lo + SCAN_CH : n;
+  Fr run = fe_load(tot + t);
+  for (uint64_t i = lo; i < hi; ++i) {
+    const uint64_t idx = reverse ? n - 1 - i : i;
+    Fr v = fe_load(in + idx);
+    fe_store(out + idx, run);
+    run = scan_op<OP>(run, v);
+  }
+}
+
+int fr_scan(zkc_ctx* ctx, const Fr* in, Fr* out, uint64_t n, int op, int reverse, const Fr& start) {
+  if (n == 0) return ZKC_OK;
+  ProfScope _p(ctx, op == SCAN_MUL ? "scan.mul" : "scan.add");
+  const uint64_t nchunks = (n + SCAN_CH - 1) / SCAN_CH;
+  Fr* tot;
+  ZKC_TRY(scratch_reserve(ctx, SCR_MISC, nchunks * sizeof(Fr), (void**)&tot));
+  const unsigned grid = (unsigned)((nchunks + 127) / 128);
+  cudaStream_t st = ctx->stream;
+  if (op == SCAN_MUL) {
+    k_scan_chunk_totals<SCAN_MUL><<<grid, 128, 0, st>>>(in, tot, n, reverse); ZKC_LAUNCH_CHECK(ctx);
+    k_scan_totals<SCAN_MUL><<<1, 1024, 1024 * sizeof(Fr), st>>>(tot, nchunks, start); ZKC_LAUNCH_CHECK(ctx);
+    k_scan_apply<SCAN_MUL><<<grid, 128, 0, st>>>(in, out, tot, n, reverse); ZKC_LAUNCH_CHECK(ctx);
+  } else {
+    k_scan_chunk_totals<SCAN_ADD><<<grid, 128, 0, st>>>(in, tot, n, reverse); ZKC_LAUNCH_CHECK(ctx);
+    k_scan_totals<SCAN_ADD><<<1, 1024, 1024 * sizeof(Fr), st>>>(tot, nchunks, start); ZKC_LAUNCH_CHECK(ctx);
+    k_scan_apply<SCAN_ADD><<<grid, 128, 0, st>>>(in, out, tot, n, reverse); ZKC_LAUNCH_CHECK(ctx);
+  }
+  return ZKC_OK;
+}
+
+// u32 exclusive scan: three phases with 1024-element chunks per CTA
+__global__ void __launch_bounds__(256) k_u32_block_sums(const uint32_t* in, uint32_t* sums, uint64_t n) {
+  __shared__ uint32_t sm[256];
+  const uint64_t base = (uint64_t)blockIdx.x * 1024;
+  uint32_t s = 0;
+  for (uint32_t e = threadIdx.x; e < 1024; e += 256) { const uint64_t i = base + e; if (i < n) s += in[i]; }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (uint32_t d = 128; d > 0; d >>= 1) { if (threadIdx.x < d) sm[threadIdx.x] += sm[threadIdx.x + d]; __syncthreads(); }
+  if (threadIdx.x == 0) sums[blockIdx.x] = sm[0];
+}
+__global__ void __launch_bounds__(1024) k_u32_scan_sums(uint32_t* sums, uint64_t nb, uint32_t* total) {
+  __shared__ uint32_t part[1024];
+  const uint32_t t = threadIdx.x;
+  const uint64_t per = (nb + 1023) / 1024;
+  const uint64_t lo = (uint64_t)t * per, hi = lo + per < nb ? lo + per : nb;
+  uint32_t s = 0;
+  for (uint64_t i = lo; i < hi; ++i) s += sums[i];
+  part[t] = s;
+  __syncthreads();
+  for (uint32_t d = 1; d < 1024; d <<= 1) {
+    uint32_t v = t >= d ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  uint32_t run = t ? part[t - 1] : 0;
+  for (uint64_t i = lo; i < hi; ++i) { uint32_t v = sums[i]; sums[i] = run; run += v; }
+  if (t == 1023 && total) *total = part[1023];
+}
+__global__ void __launch_bounds__(256) k_u32_apply(const uint32_t* in, uint32_t* out, const uint32_t* sums, uint64_t n) {
+  __shared__ uint32_t sm[256];
+  const uint64_t base = (uint64_t)blockIdx.x * 1024 + (uint64_t)threadIdx.x * 4;
+  uint32_t v[4], s = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { v[e] = base + e < n ? in[base + e] : 0; s += v[e]; }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (uint32_t d = 1; d < 256; d <<= 1) {
+    uint32_t x = threadIdx.x >= d ? sm[threadIdx.x - d] : 0;
+    __syncthreads();
+    sm[threadIdx.x] += x;
+    __syncthreads();
+  }
+  uint32_t run = sums[blockIdx.x] + (threadIdx.x ? sm[threadIdx.x - 1] : 0);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { if (base + e < n) out[base + e] = run; run += v[e]; }
+}
+
+int u32_scan(zkc_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* total_dev) {
+  if (n == 0) { if (total_dev) ZKC_CUDA_TRY(ctx, cudaMemsetAsync(total_dev, 0, 4, ctx->stream)); return ZKC_OK; }
+  const uint64_t nb = (n + 1023) / 1024;
+  uint32_t* sums;
+  ZKC_TRY(scratch_reserve(ctx, SCR_MISC2, nb * 4, (void**)&sums));
+  cudaStream_t st = ctx->stream;
+  k_u32_block_sums<<<(unsigned)nb, 256, 0, st>>>(in, sums, n); ZKC_LAUNCH_CHECK(ctx);
+  k_u32_scan_sums<<<1, 1024, 0, st>>>(sums, nb, total_dev); ZKC_LAUNCH_CHECK(ctx);
+  k_u32_apply<<<(unsigned)nb, 256, 0, st>>>(in, out, sums, n); ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+
+// ---- element-wise helpers -------------------------------------------------------------------------------
+__global__ void k_powers64(Fr* out, Fr base, Fr first, uint64_t n) {
+  const uint64_t start = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 64;
+  if (start >= n) return;
+  Fr w = fe_mul(first, fe_pow_u64(base, start));
+  const uint64_t end = start + 64 < n ? start + 64 : n;
+  for (uint64_t i = start; i < end; ++i) { fe_store(out + i, w); w = fe_mul(w, base); }
+}
+int fr_powers(zkc_ctx* ctx, Fr* out, uint64_t n, const Fr& base, const Fr& first) {
+  if (n == 0) return ZKC_OK;
+  const uint64_t threads = (n + 63) / 64;
+  k_powers64<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(out, base, first, n);
+  ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+
+#define LINCOMB_MAX 32
+struct LincombArgs { const Fr* polys[LINCOMB_MAX]; Fr coefs[LINCOMB_MAX]; uint32_t count; int accumulate; };
+__global__ void k_lincomb(Fr* out, uint64_t n, LincombArgs a) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr acc = a.accumulate ? fe_load(out + i) : fe_zero<FrP>();
+  for (uint32_t j = 0; j < a.count; ++j) acc = fe_add(acc, fe_mul(fe_load(a.polys[j] + i), a.coefs[j]));
+  fe_store(out + i, acc);
+}
+int fr_lincomb(zkc_ctx* ctx, Fr* out, uint64_t n, const std::vector<const Fr*>& polys, const std::vector<Fr>& coefs) {
+  ProfScope _p(ctx, "lincomb");
+  if (polys.empty()) { ZKC_CUDA_TRY(ctx, cudaMemsetAsync(out, 0, n * sizeof(Fr), ctx->stream)); return ZKC_OK; }
+  for (size_t off = 0; off < polys.size(); off += LINCOMB_MAX) {
+    LincombArgs a;
+    a.count = (uint32_t)std::min<size_t>(LINCOMB_MAX, polys.size() - off);
+    a.accumulate = off != 0;
+    for (uint32_t j = 0; j < a.count; ++j) { a.polys[j] = polys[off + j]; a.coefs[j] = coefs[off + j]; }
+    k_lincomb<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(out, n, a);
+    ZKC_LAUNCH_CHECK(ctx);
+  }
+  return ZKC_OK;
+}
+
+#define SUBLOW_MAX 16
+struct SubLowArgs { Fr v[SUBLOW_MAX]; uint32_t m; };
+__global__ void k_sub_low(Fr* a, SubLowArgs s) {
+  const uint32_t i = threadIdx.x;
+  if (i < s.m) fe_store(a + i, fe_sub(fe_load(a + i), s.v[i]));
+}
+int fr_sub_low(zkc_ctx* ctx, Fr* a, const std::vector<Fr>& low) {
+  if (low.empty()) return ZKC_OK;
+  if (low.size() > SUBLOW_MAX) return set_err(ctx, ZKC_ERR_BAD_ARG, "fr_sub_low: too many coefficients");
+  SubLowArgs s; s.m = (uint32_t)low.size();
+  for (size_t i = 0; i < low.size(); ++i) s.v[i] = low[i];
+  k_sub_low<<<1, 32, 0, ctx->stream>>>(a, s);
+  ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+
+__global__ void k_scale(Fr* a, uint64_t n, Fr s) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) fe_store(a + i, fe_mul(fe_load(a + i), s));
+}
+int fr_scale(zkc_ctx* ctx, Fr* a, uint64_t n, const Fr& s) {
+  if (!n) return ZKC_OK;
+  k_scale<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a, n, s);
+  ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+__global__ void k_mul_add(Fr* a, const Fr* b, uint64_t n, Fr s) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) fe_store(a + i, fe_add(fe_mul(fe_load(a + i), s), fe_load(b + i)));
+}
+int fr_mul_add(zkc_ctx* ctx, Fr* a, const Fr* b, uint64_t n, const Fr& s) {
+  if (!n) return ZKC_OK;
+  k_mul_add<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a, b, n, s);
+  ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+
+// ---- kate division: q_j = z^-(j+1) * sum_{i>j} a_i z^i -----------------------------------------------------
+__global__ void k_mul_vec(const Fr* a, const Fr* b, Fr* out, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) fe_store(out + i, fe_mul(fe_load(a + i), fe_load(b + i)));
+}
+__global__ void k_shift_down(const Fr* a, Fr* q, uint64_t n) {  // z == 0: q_j = a_{j+1}
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) fe_store(q + i, i + 1 < n ? fe_load(a + i + 1) : fe_zero<FrP>());
+}
+int fr_kate_division(zkc_ctx* ctx, const Fr* a, Fr* q, uint64_t n, const Fr& z, Fr* tmp1, Fr* tmp2) {
+  if (n == 0) return ZKC_OK;
+  ProfScope _p(ctx, "kate_division");
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (fe_is_zero(z)) {
+    k_shift_down<<<grid, 256, 0, ctx->stream>>>(a, tmp1, n); ZKC_LAUNCH_CHECK(ctx);
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(q, tmp1, n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+    return ZKC_OK;
+  }
+  const Fr zinv = fe_inv(z);
+  ZKC_TRY(fr_powers(ctx, tmp1, n, z, fe_one<FrP>()));                       // z^i
+  k_mul_vec<<<grid, 256, 0, ctx->stream>>>(a, tmp1, tmp2, n); ZKC_LAUNCH_CHECK(ctx);   // a_i z^i
+  ZKC_TRY(fr_scan(ctx, tmp2, tmp2, n, SCAN_ADD, 1, fe_zero<FrP>()));        // suffix sums, exclusive
+  ZKC_TRY(fr_powers(ctx, tmp1, n, zinv, zinv));                             // z^-(j+1)
+  k_mul_vec<<<grid, 256, 0, ctx->stream>>>(tmp2, tmp1, q, n); ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+
+// ---- batched polynomial evaluation ---------------------------------------------------------------------------
+// grid = (blocks_per_poly, n_evals); each CTA of 256 threads evaluates a 4096-coefficient slice at
+// the point (16-coefficient Horner per thread, then a shared-memory tree with x^(16*2^l) factors).
+#define EV_PER_THREAD 16
+#define EV_THREADS 256
+struct EvalJob { const Fr* poly; Fr x; };
+__global__ void __launch_bounds__(EV_THREADS) k_eval_slices(const EvalJob* jobs, uint64_t n, Fr* partial, uint32_t blocks_per_poly) {
+  __shared__ uint4 smraw[EV_THREADS * 2];
+  Fr* sm = reinterpret_cast<Fr*>(smraw);
+  const EvalJob job = jobs[blockIdx.y];
+  const Fr x = job.x;
+  const uint64_t base = ((uint64_t)blockIdx.x * EV_THREADS + threadIdx.x) * EV_PER_THREAD;
+  Fr acc = fe_zero<FrP>();
+  for (int e = EV_PER_THREAD - 1; e >= 0; --e) {
+    const uint64_t i = base + e;
+    Fr c = i < n ? fe_load(job.poly + i) : fe_zero<FrP>();
+    acc = fe_add(fe_mul(acc, x), c);
+  }
+  fe_store(sm + threadIdx.x, acc);
+  __syncthreads();
+  Fr xp = fe_pow_u64(x, EV_PER_THREAD);   // x^16, squared each level
+  for (uint32_t d = 1; d < EV_THREADS; d <<= 1) {
+    if ((threadIdx.x & (2 * d - 1)) == 0) {
+      Fr lo = fe_load(sm + threadIdx.x), hi = fe_load(sm + threadIdx.x + d);
+      fe_store(sm + threadIdx.x, fe_add(lo, fe_mul(hi, xp)));
+    }
+    xp = fe_sqr(xp);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) fe_store(partial + (uint64_t)blockIdx.y * blocks_per_poly + blockIdx.x, fe_load(sm));
+}
+// one warp per evaluation: sum_b X^b * partial[b], X = x^4096, by strided Horner + shuffle-free tree in smem
+__global__ void __launch_bounds__(32) k_eval_combine(const EvalJob* jobs, const Fr* partial, uint32_t blocks_per_poly, Fr* out) {
+  __shared__ uint4 smraw[32 * 2];
+  Fr* sm = reinterpret_cast<Fr*>(smraw);
+  const Fr X = fe_pow_u64(jobs[blockIdx.x].x, (u64)EV_THREADS * EV_PER_THREAD);
+  const Fr* p = partial + (uint64_t)blockIdx.x * blocks_per_poly;
+  // lane l handles blocks b = l, l+32, ...: value_l = sum_m p[l + 32m] (X^32)^m
+  const Fr X32 = fe_pow_u64(X, 32);
+  Fr acc = fe_zero<FrP>();
+  int cnt = ((int)blocks_per_poly - (int)threadIdx.x + 31) / 32;
+  for (int m = cnt - 1; m >= 0; --m) acc = fe_add(fe_mul(acc, X32), fe_load(p + threadIdx.x + 32 * m));
+  fe_store(sm + threadIdx.x, fe_mul(acc, fe_pow_u64(X, threadIdx.x)));
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    Fr s = fe_zero<FrP>();
+    for (int l = 0; l < 32; ++l) s = fe_add(s, fe_load(sm + l));
+    fe_store(out + blockIdx.x, s);
+  }
+}
+int fr_eval_batch(zkc_ctx* ctx, const std::vector<const Fr*>& polys, uint64_t n, const std::vector<Fr>& points, std::vector<Fr>& out) {
+  const size_t m = polys.size();
+  out.resize(m);
+  if (m == 0) return ZKC_OK;
+  ProfScope _p(ctx, "eval_batch");
+  const uint32_t bpp = (uint32_t)((n + EV_THREADS * EV_PER_THREAD - 1) / (EV_THREADS * EV_PER_THREAD));
+  std::vector<EvalJob> jobs(m);
+  for (size_t i = 0; i < m; ++i) { jobs[i].poly = polys[i]; jobs[i].x = points[i]; }
+  char* base;
+  const size_t o_jobs = 0, o_part = (m * sizeof(EvalJob) + 255) & ~(size_t)255, o_out = o_part + ((m * bpp * sizeof(Fr) + 255) & ~(size_t)255);
+  ZKC_TRY(scratch_reserve(ctx, SCR_MISC3, o_out + m * sizeof(Fr), (void**)&base));
+  ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(base + o_jobs, jobs.data(), m * sizeof(EvalJob), cudaMemcpyHostToDevice, ctx->stream));
+  // the pageable source above is consumed synchronously by cudaMemcpyAsync (staged), safe to reuse
+  for (size_t off = 0; off < m; off += 65535) {
+    const uint32_t cnt = (uint32_t)std::min<size_t>(65535, m - off);
+    dim3 grid(bpp, cnt);
+    k_eval_slices<<<grid, EV_THREADS, 0, ctx->stream>>>((const EvalJob*)(base + o_jobs) + off, n, (Fr*)(base + o_part) + off * bpp, bpp);
+    ZKC_LAUNCH_CHECK(ctx);
+    k_eval_combine<<<cnt, 32, 0, ctx->stream>>>((const EvalJob*)(base + o_jobs) + off, (const Fr*)(base + o_part) + off * bpp, bpp,
+                                               (Fr*)(base + o_out) + off);
+    ZKC_LAUNCH_CHECK(ctx);
+  }
+  ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(out.data(), base + o_out, m * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKC_OK;
+}
+
+// ---- constraint-system program interpreter ---------------------------------------------------------------------
+#define PROG_STACK 12
+__global__ void __launch_bounds__(128) k_eval_program(const uint32_t* words, uint32_t npairs, const Fr* consts, DevQueries q, Fr* out,
+                                                      uint64_t rows, uint32_t rot_scale, Fr mult, int accumulate) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  Fr stack[PROG_STACK];
+  int sp = 0;
+  Fr acc = accumulate ? fe_load(out + i) : fe_zero<FrP>();
+  for (uint32_t pc = 0; pc < npairs; ++pc) {
+    const uint32_t op = words[2 * pc], arg = words[2 * pc + 1];
+    switch (op) {
+      case 0: stack[sp++] = fe_load_nc(consts + arg); break;
+      case 1: case 2: case 3: {
+        const uint32_t col = op == 1 ? q.aq_col[arg] : (op == 2 ? q.fq_col[arg] : q.iq_col[arg]);
+        const int32_t rot = op == 1 ? q.aq_rot[arg] : (op == 2 ? q.fq_rot[arg] : q.iq_rot[arg]);
+        const Fr* colp = op == 1 ? q.advice[col] : (op == 2 ? q.fixed[col] : q.instance[col]);
+        const uint64_t idx = (i + rows + (int64_t)rot * (int64_t)rot_scale) & (rows - 1);   // rows is a power of two
+        stack[sp++] = fe_load(colp + idx);
+        break;
+      }
+      case 4: stack[sp - 1] = fe_neg(stack[sp - 1]); break;
+      case 5: stack[sp - 2] = fe_add(stack[sp - 2], stack[sp - 1]); --sp; break;
+      case 6: stack[sp - 2] = fe_mul(stack[sp - 2], stack[sp - 1]); --sp; break;
+      case 7: stack[sp - 1] = fe_mul(stack[sp - 1], fe_load_nc(consts + arg)); break;
+      default: acc = fe_add(fe_mul(acc, mult), stack[--sp]); break;   // OP_END
+    }
+  }
+  fe_store(out + i, acc);
+}
+int eval_program(zkc_ctx* ctx, const DevProgram& prog, const DevQueries& q, Fr* out, uint64_t rows, uint32_t rot_scale, const Fr& mult,
+                 int accumulate) {
+  ProfScope _p(ctx, "eval_program");
+  if (prog.npairs == 0) {
+    if (!accumulate) ZKC_CUDA_TRY(ctx, cudaMemsetAsync(out, 0, rows * sizeof(Fr), ctx->stream));
+    return ZKC_OK;
+  }
+  k_eval_program<<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(prog.words, prog.npairs, prog.consts, q, out, rows, rot_scale, mult,
+                                                                           accumulate);
+  ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+
+// ---- bitonic sort of 256-bit canonical keys -------------------------------------------------------------------------
+__device__ __forceinline__ bool u256_gt(const Fr& a, const Fr& b) {
+#pragma unroll
+  for (int i = 7; i >= 0; --i) {
+    if (a.v[i] > b.v[i]) return true;
+    if (a.v[i] < b.v[i]) return false;
+  }
+  return false;
+}
+#define SORT_TILE 1024
+// all (k, j) steps with j < SORT_TILE for k in [k_lo, k_hi] done inside shared memory
+__global__ void __launch_bounds__(512) k_bitonic_local(Fr* keys, uint64_t k_lo, uint64_t k_hi, int only_tail) {
+  __shared__ uint4 smraw[SORT_TILE * 2];
+  Fr* sm = reinterpret_cast<Fr*>(smraw);
+  const uint64_t base = (uint64_t)blockIdx.x * SORT_TILE;
+  for (uint32_t e = threadIdx.x; e < SORT_TILE; e += 512) fe_store(sm + e, fe_load(keys + base + e));
+  __syncthreads();
+  for (uint64_t k = k_lo; k <= k_hi; k <<= 1) {
+    uint64_t j0 = only_tail ? (SORT_TILE >> 1) : (k >> 1);
+    if (j0 > (SORT_TILE >> 1)) j0 = SORT_TILE >> 1;
+    for (uint64_t j = j0; j > 0; j >>= 1) {
+      const uint32_t t = threadIdx.x;                 // 512 threads <-> 512 pairs
+      const uint32_t lo = (uint32_t)(((t & ~(uint32_t)(j - 1)) << 1) | (t & (uint32_t)(j - 1)));
+      const uint32_t hi = lo + (uint32_t)j;
+      const bool asc = (((base + lo) & k) == 0);
+      Fr a = fe_load(sm + lo), b = fe_load(sm + hi);
+      if (u256_gt(a, b) == asc) { fe_store(sm + lo, b); fe_store(sm + hi, a); }
+      __syncthreads();
+    }
+  }
+  for (uint32_t e = threadIdx.x; e < SORT_TILE; e += 512) fe_store(keys + base + e, fe_load(sm + e));
+}
+__global__ void k_bitonic_global(Fr* keys, uint64_t n, uint64_t j, uint64_t k) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (n >> 1)) return;
+  const uint64_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+  const uint64_t hi = lo + j;
+  const bool asc = ((lo & k) == 0);
+  Fr a = fe_load(keys + lo), b = fe_load(keys + hi);
+  if (u256_gt(a, b) == asc) { fe_store(keys + lo, b); fe_store(keys + hi, a); }
+}
+__global__ void k_sort_small(Fr* keys, uint32_t n) {   // n < SORT_TILE: single thread block, global memory
+  for (uint32_t k = 2; k <= n; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+        const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo + j;
+        const bool asc = ((lo & k) == 0);
+        Fr a = fe_load(keys + lo), b = fe_load(keys + hi);
+        if (u256_gt(a, b) == asc) { fe_store(keys + lo, b); fe_store(keys + hi, a); }
+      }
+      __syncthreads();
+    }
+}
+int sort_u256(zkc_ctx* ctx, Fr* keys, uint64_t n) {
+  if (n < 2) return ZKC_OK;
+  if (n & (n - 1)) return set_err(ctx, ZKC_ERR_BAD_ARG, "sort_u256: n must be a power of two");
+  ProfScope _p(ctx, "sort_u256");
+  cudaStream_t st = ctx->stream;
+  if (n < SORT_TILE) {
+    k_sort_small<<<1, 256, 0, st>>>(keys, (uint32_t)n);
+    ZKC_LAUNCH_CHECK(ctx);
+    return ZKC_OK;
+  }
+  const unsigned tiles = (unsigned)(n / SORT_TILE);
+  k_bitonic_local<<<tiles, 512, 0, st>>>(keys, 2, SORT_TILE, 0);
+  ZKC_LAUNCH_CHECK(ctx);
+  for (uint64_t k = SORT_TILE * 2; k <= n; k <<= 1) {
+    for (uint64_t j = k >> 1; j >= SORT_TILE; j >>= 1) {
+      k_bitonic_global<<<(unsigned)(((n >> 1) + 255) / 256), 256, 0, st>>>(keys, n, j, k);
+      ZKC_LAUNCH_CHECK(ctx);
+    }
+    k_bitonic_local<<<tiles, 512, 0, st>>>(keys, k, k, 1);
+    ZKC_LAUNCH_CHECK(ctx);
+  }
+  return ZKC_OK;
+}
+
+}  // namespace zkc

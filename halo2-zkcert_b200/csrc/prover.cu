@@ -1,0 +1,901 @@
+// create_proof on the B200: the host-side driver that mirrors halo2_proofs::plonk::create_proof
+// (halo2_proofs 0.2.0 "halo2-axiom" @4b42325 src/plonk/prover.rs, with ProverSHPLONK / ProverGWC and
+// the Blake2b / Keccak256 transcripts) — un-vendored, pinned at /root/reference/Cargo.lock:1320-1336;
+// reached from /root/reference/src/helpers.rs:233,299 and src/bin/cli.rs:320,369,462 through
+// snark-verifier-sdk's gen_snark_shplonk.  SURVEY.md §3.2 is the step list this file follows.
+//
+// The host keeps what the reference keeps on the CPU: transcript hashing, challenge derivation,
+// the RNG cursor, rotation-set bookkeeping and O(#queries) scalar work.  Every O(n) operation runs
+// on the device; columns stay resident in HBM from the advice upload to the last opening proof,
+// and only commitments (64 B), evaluations (32 B) and challenges cross PCIe.
+#include "prover_kernels.cuh"
+#include "ec.cuh"
+#include "host/hostutil.h"
+#include <algorithm>
+#include <functional>
+#include <memory>
+
+namespace zkc {
+// implemented in ntt.cu / msm.cu
+int ntt_twiddles(zkc_ctx* ctx, uint32_t log_n, const Fr** out);
+int dom_lagrange_to_coeff(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint32_t ncols);
+int dom_coeff_to_extended(zkc_ctx* ctx, const zkc_domain* d, const Fr* in, uint64_t in_stride, Fr* out, uint32_t ncols);
+int dom_extended_to_coeff(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint32_t ncols);
+int dom_divide_by_vanishing(zkc_ctx* ctx, const zkc_domain* d, Fr* a);
+int srs_commit_dev(zkc_ctx* ctx, const zkc_srs* s, int basis, const Fr* polys, uint64_t len, uint32_t ncols, zkc_g1* out);
+}  // namespace zkc
+
+using namespace zkc;
+using zkc::host::Transcript;
+
+#define PROG_STACK_HOST_MAX 12   // must not exceed PROG_STACK of the device interpreter (poly.cu)
+extern "C" uint32_t zkc_srs_k(const zkc_srs* srs);
+
+// ---- parsed constraint system --------------------------------------------------------------------------
+namespace {
+
+struct HostProgram {
+  std::vector<uint32_t> words;     // (op, arg) pairs
+  std::vector<Fr> consts;          // Montgomery
+  uint32_t nexprs = 0;
+  std::vector<uint32_t> degrees;   // per expression
+};
+
+struct Cs {
+  uint32_t k = 0, num_advice = 0, num_fixed = 0, num_instance = 0, min_degree = 0;
+  std::vector<std::pair<uint32_t, int32_t>> aq, fq, iq;
+  std::vector<std::pair<uint32_t, uint32_t>> perm;   // (kind, column)
+  HostProgram gates;
+  std::vector<std::pair<HostProgram, HostProgram>> lookups;
+  uint32_t blinding_factors = 0, degree = 0, chunk_len = 0;
+  uint64_t n() const { return 1ull << k; }
+  uint64_t usable() const { return n() - (blinding_factors + 1); }
+  uint32_t nsets() const { return perm.empty() ? 0 : (uint32_t)((perm.size() + chunk_len - 1) / chunk_len); }
+};
+
+struct Reader {
+  const uint8_t* p; size_t len, pos = 0; bool ok = true;
+  uint32_t u32() { if (pos + 4 > len) { ok = false; return 0; } uint32_t v; memcpy(&v, p + pos, 4); pos += 4; return v; }
+  void bytes(void* out, size_t n) { if (pos + n > len) { ok = false; memset(out, 0, n); return; } memcpy(out, p + pos, n); pos += n; }
+};
+
+bool parse_program(Reader& r, uint32_t nexprs, HostProgram& out) {
+  out.nexprs = nexprs;
+  const uint32_t npairs = r.u32();
+  if (!r.ok || (size_t)npairs * 8 > r.len) return false;
+  out.words.resize((size_t)npairs * 2);
+  for (auto& w : out.words) w = r.u32();
+  const uint32_t nconsts = r.u32();
+  if (!r.ok || (size_t)nconsts * 32 > r.len) return false;
+  out.consts.resize(nconsts);
+  for (auto& c : out.consts) { Fr raw; r.bytes(raw.v, 32); c = fe_from_canonical(raw); }
+  // degrees (and a structural check) by abstract interpretation of the postfix stream
+  std::vector<uint32_t> st;
+  uint32_t ends = 0;
+  for (uint32_t i = 0; i < npairs; ++i) {
+    const uint32_t op = out.words[2 * i], arg = out.words[2 * i + 1];
+    switch (op) {
+      case 0: if (arg >= nconsts) return false; st.push_back(0); break;
+      case 1: case 2: case 3: st.push_back(1); break;
+      case 4: if (st.empty()) return false; break;
+      case 5: if (st.size() < 2) return false; { uint32_t b = st.back(); st.pop_back(); st.back() = std::max(st.back(), b); } break;
+      case 6: if (st.size() < 2) return false; { uint32_t b = st.back(); st.pop_back(); st.back() += b; } break;
+      case 7: if (st.empty() || arg >= nconsts) return false; break;
+      case 8: if (st.size() != 1) return false; out.degrees.push_back(st.back()); st.clear(); ++ends; break;
+      default: return false;
+    }
+    if (st.size() > PROG_STACK_HOST_MAX) return false;
+  }
+  return r.ok && ends == nexprs && st.empty();
+}
+
+}  // namespace
+
+// ---- proving key -------------------------------------------------------------------------------------------
+struct zkc_pk {
+  zkc_ctx* ctx = nullptr;
+  const zkc_srs* srs = nullptr;
+  Cs cs;
+  zkc_domain* dom = nullptr;
+  uint32_t ext_k = 0;
+  Fr transcript_repr;
+  // device-resident columns
+  Fr *fixed_values = nullptr, *fixed_polys = nullptr, *fixed_cosets = nullptr;
+  Fr *sigma_values = nullptr, *sigma_polys = nullptr, *sigma_cosets = nullptr;
+  Fr *l0 = nullptr, *l_last = nullptr, *l_active = nullptr, *omega_pows = nullptr;
+  // programs + query tables
+  DevProgram gates;
+  std::vector<std::pair<DevProgram, DevProgram>> lookups;
+  uint32_t* qtab = nullptr;          // aq_col, aq_rot, fq_col, fq_rot, iq_col, iq_rot packed
+  const Fr** fixed_val_ptrs = nullptr;   // device arrays of column pointers
+  const Fr** fixed_coset_ptrs = nullptr;
+  std::vector<void*> owned;          // everything to cudaFree
+  std::vector<G1Affine> fixed_comm, sigma_comm;
+};
+
+namespace {
+
+int upload_program(zkc_ctx* ctx, zkc_pk* pk, const HostProgram& h, DevProgram& d) {
+  d.npairs = (uint32_t)(h.words.size() / 2); d.nconsts = (uint32_t)h.consts.size(); d.nexprs = h.nexprs;
+  if (d.npairs) {
+    ZKC_CUDA_TRY(ctx, cudaMalloc(&d.words, h.words.size() * 4)); pk->owned.push_back(d.words);
+    ZKC_CUDA_TRY(ctx, cudaMemcpy(d.words, h.words.data(), h.words.size() * 4, cudaMemcpyHostToDevice));
+  }
+  if (d.nconsts) {
+    ZKC_CUDA_TRY(ctx, cudaMalloc(&d.consts, h.consts.size() * sizeof(Fr))); pk->owned.push_back(d.consts);
+    ZKC_CUDA_TRY(ctx, cudaMemcpy(d.consts, h.consts.data(), h.consts.size() * sizeof(Fr), cudaMemcpyHostToDevice));
+  }
+  return ZKC_OK;
+}
+
+template <class T> int dev_alloc(zkc_ctx* ctx, zkc_pk* pk, T** p, size_t count) {
+  ZKC_CUDA_TRY(ctx, cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+  pk->owned.push_back((void*)*p);
+  return ZKC_OK;
+}
+
+void g1_from_abi(const zkc_g1& j, G1Affine& a) {
+  Fq z; memcpy(z.v, &j.z, 32);
+  if (fe_is_zero(z)) { a.x = fe_zero<FqP>(); a.y = fe_zero<FqP>(); return; }
+  memcpy(a.x.v, &j.x, 32); memcpy(a.y.v, &j.y, 32);
+}
+
+int commit_points(zkc_ctx* ctx, const zkc_srs* srs, int basis, const Fr* polys, uint64_t len, uint32_t ncols, std::vector<G1Affine>& out) {
+  std::vector<zkc_g1> tmp(ncols);
+  ZKC_TRY(srs_commit_dev(ctx, srs, basis, polys, len, ncols, tmp.data()));
+  out.resize(ncols);
+  for (uint32_t i = 0; i < ncols; ++i) g1_from_abi(tmp[i], out[i]);
+  return ZKC_OK;
+}
+
+}  // namespace
+
+extern "C" void zkc_pk_free(zkc_pk* pk) {
+  if (!pk) return;
+  cudaSetDevice(pk->ctx->dev);
+  cudaStreamSynchronize(pk->ctx->stream);
+  for (void* p : pk->owned) cudaFree(p);
+  if (pk->dom) zkc_domain_free(pk->dom);
+  delete pk;
+}
+
+extern "C" int zkc_pk_load(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs_len, const zkc_fr* fixed,
+                           const zkc_fr* sigma, const zkc_fr* transcript_repr, int zeta_choice, zkc_pk** out) {
+  if (!ctx || !srs || !cs_blob || !transcript_repr || !out) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: null argument");
+  CtxLock lock(ctx);
+  std::unique_ptr<zkc_pk, void (*)(zkc_pk*)> pk(new zkc_pk(), zkc_pk_free);
+  pk->ctx = ctx; pk->srs = srs;
+  Cs& cs = pk->cs;
+  Reader r{cs_blob, cs_len};
+  uint8_t magic[4]; r.bytes(magic, 4);
+  if (memcmp(magic, "ZKCS", 4) != 0 || r.u32() != 1) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: bad constraint-system blob");
+  cs.k = r.u32(); cs.num_advice = r.u32(); cs.num_fixed = r.u32(); cs.num_instance = r.u32(); cs.min_degree = r.u32();
+  if (!r.ok || cs.k > 26 || cs.k != zkc_srs_k(srs)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: k does not match the SRS");
+  auto read_queries = [&](std::vector<std::pair<uint32_t, int32_t>>& q, uint32_t ncols) {
+    const uint32_t m = r.u32();
+    if (!r.ok || m > (1u << 20)) { r.ok = false; return; }
+    q.resize(m);
+    for (auto& e : q) { e.first = r.u32(); e.second = (int32_t)r.u32(); if (e.first >= ncols) r.ok = false; }
+  };
+  read_queries(cs.aq, cs.num_advice); read_queries(cs.fq, cs.num_fixed); read_queries(cs.iq, cs.num_instance);
+  const uint32_t nperm = r.u32();
+  if (!r.ok || nperm > (1u << 16)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: truncated blob");
+  cs.perm.resize(nperm);
+  for (auto& e : cs.perm) {
+    e.first = r.u32(); e.second = r.u32();
+    const uint32_t lim = e.first == 0 ? cs.num_advice : (e.first == 1 ? cs.num_fixed : cs.num_instance);
+    if (e.first > 2 || e.second >= lim) r.ok = false;
+  }
+  const uint32_t npolys = r.u32();
+  if (!r.ok || !parse_program(r, npolys, cs.gates)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: bad gate program");
+  const uint32_t nlk = r.u32();
+  if (!r.ok || nlk > 4096) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: truncated blob");
+  cs.lookups.resize(nlk);
+  for (auto& lk : cs.lookups) {
+    const uint32_t ni = r.u32();
+    if (!r.ok || !parse_program(r, ni, lk.first)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: bad lookup input program");
+    const uint32_t nt = r.u32();
+    if (!r.ok || !parse_program(r, nt, lk.second)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: bad lookup table program");
+  }
+  // query indices inside programs must be in range
+  auto check_prog = [&](const HostProgram& h) {
+    for (size_t i = 0; i < h.words.size(); i += 2) {
+      const uint32_t op = h.words[i], arg = h.words[i + 1];
+      if ((op == 1 && arg >= cs.aq.size()) || (op == 2 && arg >= cs.fq.size()) || (op == 3 && arg >= cs.iq.size())) return false;
+    }
+    return true;
+  };
+  bool okp = check_prog(cs.gates);
+  for (auto& lk : cs.lookups) okp = okp && check_prog(lk.first) && check_prog(lk.second);
+  if (!okp) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: query index out of range");
+  // A.5 numbers
+  {
+    std::vector<uint32_t> per_col(cs.num_advice, 0);
+    for (auto& q : cs.aq) per_col[q.first]++;
+    uint32_t f = 3;
+    for (uint32_t c : per_col) f = std::max(f, c);
+    cs.blinding_factors = f + 2;
+    uint32_t d = 3;
+    for (auto& lk : cs.lookups) {
+      uint32_t di = 1, dt = 1;
+      for (uint32_t x : lk.first.degrees) di = std::max(di, x);
+      for (uint32_t x : lk.second.degrees) dt = std::max(dt, x);
+      d = std::max(d, std::max(4u, 2 + di + dt));
+    }
+    for (uint32_t x : cs.gates.degrees) d = std::max(d, x);
+    cs.degree = std::max(d, std::max(cs.min_degree, 1u));
+    cs.chunk_len = cs.degree - 2;
+  }
+  const uint64_t n = cs.n();
+  if (n < cs.blinding_factors + 3) return set_err(ctx, ZKC_ERR_NOT_ENOUGH_ROWS, "zkc_pk_load: not enough rows for the blinding factors");
+  if (cs.chunk_len > PERM_MAX_CHUNK) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: permutation chunk longer than PERM_MAX_CHUNK");
+  if (cs.nsets() > PERM_MAX_SETS) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: too many permutation sets");
+  if ((cs.num_fixed && !fixed) || (nperm && !sigma)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: missing fixed / sigma columns");
+  ZKC_TRY(zkc_domain_create(ctx, cs.degree, cs.k, zeta_choice, &pk->dom));
+  zkc_domain_info di;
+  zkc_domain_get_info(pk->dom, &di);
+  pk->ext_k = di.extended_k;
+  const uint64_t en = 1ull << pk->ext_k;
+  memcpy(pk->transcript_repr.v, transcript_repr, 32);
+  zkc_pk* P = pk.get();
+  const uint32_t F = cs.num_fixed, S = nperm;
+  // fixed + sigma: values -> polys -> cosets
+  ZKC_TRY(dev_alloc(ctx, P, &P->fixed_values, (size_t)F * n)); ZKC_TRY(dev_alloc(ctx, P, &P->fixed_polys, (size_t)F * n));
+  ZKC_TRY(dev_alloc(ctx, P, &P->fixed_cosets, (size_t)F * en));
+  ZKC_TRY(dev_alloc(ctx, P, &P->sigma_values, (size_t)S * n)); ZKC_TRY(dev_alloc(ctx, P, &P->sigma_polys, (size_t)S * n));
+  ZKC_TRY(dev_alloc(ctx, P, &P->sigma_cosets, (size_t)S * en));
+  cudaStream_t st = ctx->stream;
+  if (F) {
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(P->fixed_values, fixed, (size_t)F * n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(P->fixed_polys, P->fixed_values, (size_t)F * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    ZKC_TRY(dom_lagrange_to_coeff(ctx, P->dom, P->fixed_polys, F));
+    ZKC_TRY(dom_coeff_to_extended(ctx, P->dom, P->fixed_polys, n, P->fixed_cosets, F));
+  }
+  if (S) {
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(P->sigma_values, sigma, (size_t)S * n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(P->sigma_polys, P->sigma_values, (size_t)S * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    ZKC_TRY(dom_lagrange_to_coeff(ctx, P->dom, P->sigma_polys, S));
+    ZKC_TRY(dom_coeff_to_extended(ctx, P->dom, P->sigma_polys, n, P->sigma_cosets, S));
+  }
+  // l0, l_last, l_blind -> cosets; l_active = 1 - l_last - l_blind
+  {
+    ZKC_TRY(dev_alloc(ctx, P, &P->l0, en)); ZKC_TRY(dev_alloc(ctx, P, &P->l_last, en)); ZKC_TRY(dev_alloc(ctx, P, &P->l_active, en));
+    Fr* tmp;   // three Lagrange columns
+    ZKC_CUDA_TRY(ctx, cudaMalloc(&tmp, 3 * n * sizeof(Fr)));
+    ZKC_CUDA_TRY(ctx, cudaMemsetAsync(tmp, 0, 3 * n * sizeof(Fr), st));
+    const Fr one = fe_one<FrP>();
+    const uint32_t bf = cs.blinding_factors;
+    std::vector<Fr> ones(bf, one);
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(tmp, &one, sizeof(Fr), cudaMemcpyHostToDevice, st));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(tmp + n + (n - bf - 1), &one, sizeof(Fr), cudaMemcpyHostToDevice, st));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(tmp + 2 * n + (n - bf), ones.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    int s1 = dom_lagrange_to_coeff(ctx, P->dom, tmp, 3);
+    Fr* lb = nullptr;
+    if (s1 == ZKC_OK && cudaMalloc(&lb, en * sizeof(Fr)) != cudaSuccess) s1 = set_err(ctx, ZKC_ERR_OOM, "zkc_pk_load: out of memory");
+    if (s1 == ZKC_OK) s1 = dom_coeff_to_extended(ctx, P->dom, tmp, n, P->l0, 1);
+    if (s1 == ZKC_OK) s1 = dom_coeff_to_extended(ctx, P->dom, tmp + n, n, P->l_last, 1);
+    if (s1 == ZKC_OK) s1 = dom_coeff_to_extended(ctx, P->dom, tmp + 2 * n, n, lb, 1);
+    if (s1 == ZKC_OK) { k_l_active<<<(unsigned)((en + 255) / 256), 256, 0, st>>>(P->l_last, lb, P->l_active, en); ctx->launches++; }
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    if (lb) cudaFree(lb);
+    ZKC_TRY(s1);
+  }
+  // omega^i
+  ZKC_TRY(dev_alloc(ctx, P, &P->omega_pows, n));
+  {
+    Fr omega; memcpy(omega.v, &di.omega, 32);
+    ZKC_TRY(fr_powers(ctx, P->omega_pows, n, omega, fe_one<FrP>()));
+  }
+  // programs, query tables, pointer tables
+  ZKC_TRY(upload_program(ctx, P, cs.gates, P->gates));
+  P->lookups.resize(cs.lookups.size());
+  for (size_t i = 0; i < cs.lookups.size(); ++i) {
+    ZKC_TRY(upload_program(ctx, P, cs.lookups[i].first, P->lookups[i].first));
+    ZKC_TRY(upload_program(ctx, P, cs.lookups[i].second, P->lookups[i].second));
+  }
+  {
+    std::vector<uint32_t> q;
+    for (auto* v : {&cs.aq, &cs.fq, &cs.iq}) {
+      for (auto& e : *v) q.push_back(e.first);
+      for (auto& e : *v) q.push_back((uint32_t)e.second);
+    }
+    ZKC_TRY(dev_alloc(ctx, P, &P->qtab, q.size()));
+    if (!q.empty()) ZKC_CUDA_TRY(ctx, cudaMemcpy(P->qtab, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<const Fr*> pv(F), pc(F);
+    for (uint32_t c = 0; c < F; ++c) { pv[c] = P->fixed_values + (size_t)c * n; pc[c] = P->fixed_cosets + (size_t)c * en; }
+    ZKC_TRY(dev_alloc(ctx, P, &P->fixed_val_ptrs, F)); ZKC_TRY(dev_alloc(ctx, P, &P->fixed_coset_ptrs, F));
+    if (F) {
+      ZKC_CUDA_TRY(ctx, cudaMemcpy(P->fixed_val_ptrs, pv.data(), F * sizeof(void*), cudaMemcpyHostToDevice));
+      ZKC_CUDA_TRY(ctx, cudaMemcpy(P->fixed_coset_ptrs, pc.data(), F * sizeof(void*), cudaMemcpyHostToDevice));
+    }
+  }
+  // vk commitments (keygen_vk: fixed and permutation columns are committed in the Lagrange basis)
+  if (F) ZKC_TRY(commit_points(ctx, srs, 1, P->fixed_values, n, F, P->fixed_comm));
+  if (S) ZKC_TRY(commit_points(ctx, srs, 1, P->sigma_values, n, S, P->sigma_comm));
+  ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  *out = pk.release();
+  return ZKC_OK;
+}
+
+extern "C" int zkc_pk_get_commitments(zkc_ctx* ctx, const zkc_pk* pk, zkc_g1_affine* fixed_out, zkc_g1_affine* sigma_out) {
+  if (!ctx || !pk) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_get_commitments: null argument");
+  if (fixed_out && !pk->fixed_comm.empty()) memcpy(fixed_out, pk->fixed_comm.data(), pk->fixed_comm.size() * sizeof(G1Affine));
+  if (sigma_out && !pk->sigma_comm.empty()) memcpy(sigma_out, pk->sigma_comm.data(), pk->sigma_comm.size() * sizeof(G1Affine));
+  return ZKC_OK;
+}
+
+extern "C" int zkc_pk_info(const zkc_pk* pk, uint32_t* out /* k, extended_k, degree, blinding_factors, nsets, nlookups, nfixed, nperm */) {
+  if (!pk || !out) return ZKC_ERR_BAD_ARG;
+  out[0] = pk->cs.k; out[1] = pk->ext_k; out[2] = pk->cs.degree; out[3] = pk->cs.blinding_factors; out[4] = pk->cs.nsets();
+  out[5] = (uint32_t)pk->cs.lookups.size(); out[6] = pk->cs.num_fixed; out[7] = (uint32_t)pk->cs.perm.size();
+  return ZKC_OK;
+}
+
+// ---- create_proof ----------------------------------------------------------------------------------------------
+namespace {
+
+// stream-ordered temporary allocations for one proof
+struct Pool {
+  zkc_ctx* ctx;
+  std::vector<void*> ptrs;
+  explicit Pool(zkc_ctx* c) : ctx(c) {}
+  ~Pool() { for (void* p : ptrs) cudaFreeAsync(p, ctx->stream); }
+  template <class T> int get(T** out, size_t count) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), ctx->stream);
+    if (e != cudaSuccess) return set_err(ctx, ZKC_ERR_OOM, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+    ptrs.push_back(p);
+    *out = (T*)p;
+    return ZKC_OK;
+  }
+};
+
+// RNG cursor over the proof's ChaCha20 stream: Fr::random consumes exactly one 64-byte block
+struct Rng {
+  host::ChaCha20Rng cpu;
+  ChaChaKey key;
+  uint64_t drawn = 0;
+  explicit Rng(const uint8_t seed[32]) : cpu(seed) { memcpy(key.k, seed, 32); }
+  Fr draw() { ++drawn; return cpu.fr_random(); }
+  // n draws generated on the device; the host cursor skips the same blocks
+  int bulk(zkc_ctx* ctx, Fr* out, uint64_t n) {
+    if (!n) return ZKC_OK;
+    k_chacha_fr<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(out, key, drawn, n);
+    ZKC_LAUNCH_CHECK(ctx);
+    drawn += n;
+    cpu.counter = drawn; cpu.pos = 16;
+    return ZKC_OK;
+  }
+};
+
+struct Query { const Fr* poly; Fr point; Fr eval; };
+
+Fr rotate_omega(const Fr& x, const Fr& omega, const Fr& omega_inv, int32_t rot) {
+  return rot >= 0 ? fe_mul(x, fe_pow_u64(omega, (u64)rot)) : fe_mul(x, fe_pow_u64(omega_inv, (u64)(-(int64_t)rot)));
+}
+
+// coefficients of the interpolation polynomial through (points[i], evals[i])
+std::vector<Fr> lagrange_interpolate(const std::vector<Fr>& pts, const std::vector<Fr>& evals) {
+  const size_t m = pts.size();
+  std::vector<Fr> coeffs(m, fe_zero<FrP>());
+  if (m == 1) { coeffs[0] = evals[0]; return coeffs; }
+  for (size_t j = 0; j < m; ++j) {
+    std::vector<Fr> num(1, fe_one<FrP>());
+    Fr den = fe_one<FrP>();
+    for (size_t kx = 0; kx < m; ++kx) {
+      if (kx == j) continue;
+      std::vector<Fr> nxt(num.size() + 1, fe_zero<FrP>());
+      for (size_t i = 0; i < num.size(); ++i) {
+        nxt[i + 1] = fe_add(nxt[i + 1], num[i]);
+        nxt[i] = fe_sub(nxt[i], fe_mul(pts[kx], num[i]));
+      }
+      num.swap(nxt);
+      den = fe_mul(den, fe_sub(pts[j], pts[kx]));
+    }
+    const Fr scale = fe_mul(evals[j], fe_inv(den));
+    for (size_t i = 0; i < m; ++i) coeffs[i] = fe_add(coeffs[i], fe_mul(num[i], scale));
+  }
+  return coeffs;
+}
+Fr eval_small(const std::vector<Fr>& c, const Fr& x) {
+  Fr acc = fe_zero<FrP>();
+  for (size_t i = c.size(); i-- > 0;) acc = fe_add(fe_mul(acc, x), c[i]);
+  return acc;
+}
+Fr vanishing_eval(const std::vector<Fr>& roots, const Fr& z) {
+  Fr acc = fe_one<FrP>();
+  for (auto& r : roots) acc = fe_mul(acc, fe_sub(z, r));
+  return acc;
+}
+
+struct RotationSet {
+  std::vector<Fr> points;                       // ascending canonical order (BTreeSet<Fr>)
+  std::vector<const Fr*> polys;                 // first-appearance order
+  std::vector<std::vector<Fr>> evals;           // per poly, in point order
+};
+
+void build_rotation_sets(const std::vector<Query>& queries, std::vector<RotationSet>& sets, std::vector<Fr>& super_points) {
+  auto less = [](const Fr& a, const Fr& b) { return host::fr_cmp_canonical(a, b) < 0; };
+  auto same = [](const Fr& a, const Fr& b) { return fe_eq(a, b); };
+  auto insert_sorted = [&](std::vector<Fr>& v, const Fr& p) {
+    for (auto& e : v) if (same(e, p)) return;
+    v.insert(std::upper_bound(v.begin(), v.end(), p, less), p);
+  };
+  std::vector<std::pair<const Fr*, std::vector<Fr>>> poly_points;
+  for (auto& q : queries) {
+    insert_sorted(super_points, q.point);
+    bool found = false;
+    for (auto& e : poly_points) if (e.first == q.poly) { insert_sorted(e.second, q.point); found = true; break; }
+    if (!found) poly_points.push_back({q.poly, std::vector<Fr>{q.point}});
+  }
+  for (auto& pp : poly_points) {
+    RotationSet* tgt = nullptr;
+    for (auto& s : sets) {
+      if (s.points.size() != pp.second.size()) continue;
+      bool eq = true;
+      for (size_t i = 0; i < s.points.size() && eq; ++i) eq = same(s.points[i], pp.second[i]);
+      if (eq) { tgt = &s; break; }
+    }
+    if (!tgt) { sets.push_back(RotationSet()); tgt = &sets.back(); tgt->points = pp.second; }
+    tgt->polys.push_back(pp.first);
+    std::vector<Fr> ev;
+    for (auto& pt : tgt->points)
+      for (auto& q : queries) if (q.poly == pp.first && same(q.point, pt)) { ev.push_back(q.eval); break; }
+    tgt->evals.push_back(ev);
+  }
+}
+
+}  // namespace
+
+extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, int advice_on_device, const zkc_fr* const* instances,
+                         const size_t* instance_lens, const zkc_prove_opts* opts, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+  if (!ctx || !pk || !opts || !proof_len || (pk->cs.num_advice && !advice) || (pk->cs.num_instance && (!instances || !instance_lens)))
+    return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_prove: null argument");
+  CtxLock lock(ctx);
+  const Cs& cs = pk->cs;
+  const zkc_srs* srs = pk->srs;
+  const uint64_t n = cs.n(), en = 1ull << pk->ext_k, U = cs.usable();
+  const uint32_t bf = cs.blinding_factors, A = cs.num_advice, I = cs.num_instance, L = (uint32_t)cs.lookups.size(), Pn = cs.nsets();
+  const uint32_t rot_scale = 1u << (pk->ext_k - cs.k);
+  cudaStream_t st = ctx->stream;
+  Pool pool(ctx);
+  Rng rng(opts->rng_seed);
+  Transcript tr(opts->transcript, opts->point_format);
+  zkc_domain_info di;
+  zkc_domain_get_info(pk->dom, &di);
+  Fr omega, omega_inv, zeta;
+  memcpy(omega.v, &di.omega, 32); memcpy(omega_inv.v, &di.omega_inv, 32); memcpy(zeta.v, &di.g_coset, 32);
+  const Fr ONE = fe_one<FrP>(), ZERO = fe_zero<FrP>();
+  const Fr DELTA = fr_from_raw_words(FR_DELTA_RAW);
+  auto grid = [](uint64_t cnt, unsigned b) { return (unsigned)((cnt + b - 1) / b); };
+  auto write_points = [&](const std::vector<G1Affine>& pts) -> int {
+    for (auto& p : pts) if (tr.write_point(p)) return set_err(ctx, ZKC_ERR_TRANSCRIPT, "cannot write points at infinity to the transcript");
+    return ZKC_OK;
+  };
+
+  // 0. vk
+  tr.common_scalar(pk->transcript_repr);
+
+  // 1. instances: values are absorbed as scalars (KZG: QUERY_INSTANCE = false); Lagrange columns zero-padded
+  Fr *inst_values, *inst_polys;
+  ZKC_TRY(pool.get(&inst_values, (size_t)I * n)); ZKC_TRY(pool.get(&inst_polys, (size_t)I * n));
+  if (I) ZKC_CUDA_TRY(ctx, cudaMemsetAsync(inst_values, 0, (size_t)I * n * sizeof(Fr), st));
+  for (uint32_t c = 0; c < I; ++c) {
+    if (instance_lens[c] > U) return set_err(ctx, ZKC_ERR_INVALID_INSTANCES, "instance column longer than the usable rows");
+    for (size_t i = 0; i < instance_lens[c]; ++i) { Fr v; memcpy(v.v, &instances[c][i], 32); tr.common_scalar(v); }
+    if (instance_lens[c])
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(inst_values + (size_t)c * n, instances[c], instance_lens[c] * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  }
+  if (I) {
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(inst_polys, inst_values, (size_t)I * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, inst_polys, I));
+  }
+
+  // 2. advice: upload, blinding policy, commit (Lagrange basis), to coefficient form
+  Fr *adv_values, *adv_polys;
+  ZKC_TRY(pool.get(&adv_values, (size_t)A * n)); ZKC_TRY(pool.get(&adv_polys, (size_t)A * n));
+  if (A) {
+    ProfScope _p(ctx, "prove.advice_h2d");
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(adv_values, advice, (size_t)A * n * sizeof(Fr), advice_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  }
+  {
+    std::vector<Fr> tail;
+    for (uint32_t c = 0; c < A; ++c) {
+      if (opts->advice_blinding == 0) {   // axiom: last row := 1, nothing drawn (SURVEY OPEN-1)
+        ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(adv_values + (size_t)c * n + (n - 1), &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));
+      } else {                            // PSE: the unusable rows are random
+        tail.resize(bf + 1);
+        for (auto& v : tail) v = rng.draw();
+        ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(adv_values + (size_t)c * n + U, tail.data(), (bf + 1) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      }
+    }
+    if (opts->blind_draws) for (uint32_t c = 0; c < A; ++c) rng.draw();
+  }
+  std::vector<G1Affine> pts;
+  if (A) {
+    ZKC_TRY(commit_points(ctx, srs, 1, adv_values, n, A, pts));
+    ZKC_TRY(write_points(pts));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(adv_polys, adv_values, (size_t)A * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, adv_polys, A));
+  }
+  // column pointer tables for the two evaluation domains
+  const Fr** ptrs_dev;
+  ZKC_TRY(pool.get(&ptrs_dev, (size_t)2 * (A + I) + 1));
+  Fr *adv_cosets, *inst_cosets;
+  ZKC_TRY(pool.get(&adv_cosets, (size_t)A * en)); ZKC_TRY(pool.get(&inst_cosets, (size_t)I * en));
+  {
+    std::vector<const Fr*> h(2 * (A + I) + 1, nullptr);
+    for (uint32_t c = 0; c < A; ++c) { h[c] = adv_values + (size_t)c * n; h[A + I + c] = adv_cosets + (size_t)c * en; }
+    for (uint32_t c = 0; c < I; ++c) { h[A + c] = inst_values + (size_t)c * n; h[2 * A + I + c] = inst_cosets + (size_t)c * en; }
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(ptrs_dev, h.data(), h.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+    ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  }
+  DevQueries qlag, qext;
+  {
+    const uint32_t* q = pk->qtab;
+    const size_t na = cs.aq.size(), nf = cs.fq.size(), ni = cs.iq.size();
+    qlag.aq_col = q; qlag.aq_rot = (const int32_t*)(q + na);
+    qlag.fq_col = q + 2 * na; qlag.fq_rot = (const int32_t*)(q + 2 * na + nf);
+    qlag.iq_col = q + 2 * na + 2 * nf; qlag.iq_rot = (const int32_t*)(q + 2 * na + 2 * nf + ni);
+    qext = qlag;
+    qlag.advice = ptrs_dev; qlag.instance = ptrs_dev + A; qlag.fixed = pk->fixed_val_ptrs;
+    qext.advice = ptrs_dev + A + I; qext.instance = ptrs_dev + 2 * A + I; qext.fixed = pk->fixed_coset_ptrs;
+  }
+
+  // 3. theta
+  const Fr theta = tr.squeeze_challenge();
+
+  // 4. lookups: theta-compression, permute_expression_pair, commit A', S'
+  //    per lookup: comp (2 x n: input, table), perm values (2 x n: A', S'), perm polys (2 x n), z values / poly
+  Fr *lk_comp, *lk_perm, *lk_perm_polys, *lk_z, *lk_z_polys;
+  ZKC_TRY(pool.get(&lk_comp, (size_t)2 * L * n)); ZKC_TRY(pool.get(&lk_perm, (size_t)2 * L * n));
+  ZKC_TRY(pool.get(&lk_perm_polys, (size_t)2 * L * n)); ZKC_TRY(pool.get(&lk_z, (size_t)L * n)); ZKC_TRY(pool.get(&lk_z_polys, (size_t)L * n));
+  if (L) {
+    Fr *ca, *ct, *tails;
+    uint32_t *flags, *ranks, *replist, *counts;
+    ZKC_TRY(pool.get(&ca, n)); ZKC_TRY(pool.get(&ct, n)); ZKC_TRY(pool.get(&tails, (size_t)2 * (bf + 1)));
+    ZKC_TRY(pool.get(&flags, 2 * n)); ZKC_TRY(pool.get(&ranks, 2 * n)); ZKC_TRY(pool.get(&replist, n)); ZKC_TRY(pool.get(&counts, 4));
+    for (uint32_t l = 0; l < L; ++l) {
+      ProfScope _p(ctx, "prove.lookup_permute");
+      Fr* comp_in = lk_comp + (size_t)2 * l * n; Fr* comp_tab = comp_in + n;
+      Fr* ap = lk_perm + (size_t)2 * l * n; Fr* sp = ap + n;
+      ZKC_TRY(eval_program(ctx, pk->lookups[l].first, qlag, comp_in, n, 1, theta, 0));
+      ZKC_TRY(eval_program(ctx, pk->lookups[l].second, qlag, comp_tab, n, 1, theta, 0));
+      k_lookup_prepare<<<grid(n, 256), 256, 0, st>>>(comp_in, ca, U, n); ZKC_LAUNCH_CHECK(ctx);
+      k_lookup_prepare<<<grid(n, 256), 256, 0, st>>>(comp_tab, ct, U, n); ZKC_LAUNCH_CHECK(ctx);
+      ZKC_TRY(sort_u256(ctx, ca, n));
+      ZKC_TRY(sort_u256(ctx, ct, n));
+      ZKC_CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, 16, st));
+      k_lookup_flags<<<grid(U, 128), 128, 0, st>>>(ca, ct, flags, flags + n, counts, U); ZKC_LAUNCH_CHECK(ctx);
+      ZKC_TRY(u32_scan(ctx, flags, ranks, U, counts + 2));
+      ZKC_TRY(u32_scan(ctx, flags + n, ranks + n, U, counts + 3));
+      k_lookup_replist<<<grid(U, 256), 256, 0, st>>>(flags, ranks, replist, U); ZKC_LAUNCH_CHECK(ctx);
+      // S' is built in canonical form inside `ct`'s sibling buffer: reuse comp space? no - use sp as canonical scratch
+      k_lookup_assign<<<grid(U, 256), 256, 0, st>>>(ca, ct, flags, flags + n, ranks + n, replist, counts + 2, sp, U); ZKC_LAUNCH_CHECK(ctx);
+      uint32_t hc[4];
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(hc, counts, 16, cudaMemcpyDeviceToHost, st));
+      ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      if (hc[0] != hc[1] || hc[2] != hc[3])
+        return set_err(ctx, ZKC_ERR_CONSTRAINT_SYSTEM_FAILURE, "lookup: an input value is not in the table (permute_expression_pair)");
+      // blinding tails: A' first, then S' (A.6 step 5)
+      std::vector<Fr> t(2 * (bf + 1));
+      for (auto& v : t) v = rng.draw();
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(tails, t.data(), t.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+      k_lookup_finish<<<grid(n, 256), 256, 0, st>>>(ca, tails, ap, U, n); ZKC_LAUNCH_CHECK(ctx);
+      k_lookup_finish<<<grid(n, 256), 256, 0, st>>>(sp, tails + (bf + 1), sp, U, n); ZKC_LAUNCH_CHECK(ctx);
+      ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));   // `t` goes out of scope
+      if (opts->blind_draws) { rng.draw(); rng.draw(); }
+      ZKC_TRY(commit_points(ctx, srs, 1, ap, n, 2, pts));
+      ZKC_TRY(write_points(pts));
+    }
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(lk_perm_polys, lk_perm, (size_t)2 * L * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, lk_perm_polys, 2 * L));
+  }
+
+  // 5. beta, gamma
+  const Fr beta = tr.squeeze_challenge();
+  const Fr gamma = tr.squeeze_challenge();
+
+  // 6. permutation grand products: one scan across all sets chains z_j[0] = z_{j-1}[U]
+  Fr *pz, *pz_polys;
+  ZKC_TRY(pool.get(&pz, (size_t)Pn * n)); ZKC_TRY(pool.get(&pz_polys, (size_t)Pn * n));
+  auto column_ptr = [&](uint32_t kind, uint32_t idx, bool coset) -> const Fr* {
+    if (kind == 0) return coset ? adv_cosets + (size_t)idx * en : adv_values + (size_t)idx * n;
+    if (kind == 1) return coset ? pk->fixed_cosets + (size_t)idx * en : pk->fixed_values + (size_t)idx * n;
+    return coset ? inst_cosets + (size_t)idx * en : inst_values + (size_t)idx * n;
+  };
+  auto perm_args = [&](uint32_t set, bool coset) {
+    PermSetArgs a;
+    a.m = 0;
+    Fr db = coset ? fe_mul(beta, zeta) : beta;
+    for (uint32_t g = 0; g < set * cs.chunk_len; ++g) db = fe_mul(db, DELTA);
+    for (uint32_t t = 0; t < cs.chunk_len && set * cs.chunk_len + t < cs.perm.size(); ++t) {
+      const uint32_t g = set * cs.chunk_len + t;
+      a.cols[t] = column_ptr(cs.perm[g].first, cs.perm[g].second, coset);
+      a.sigmas[t] = coset ? pk->sigma_cosets + (size_t)g * en : pk->sigma_values + (size_t)g * n;
+      a.delta_beta[t] = db;
+      db = fe_mul(db, DELTA);
+      a.m++;
+    }
+    return a;
+  };
+  if (Pn) {
+    ProfScope _p(ctx, "prove.perm_product");
+    Fr *num, *den, *tails;
+    ZKC_TRY(pool.get(&num, (size_t)Pn * U + 1)); ZKC_TRY(pool.get(&den, (size_t)Pn * U + 1)); ZKC_TRY(pool.get(&tails, (size_t)Pn * bf));
+    for (uint32_t s = 0; s < Pn; ++s) {
+      k_perm_num_den<<<grid(U, 128), 128, 0, st>>>(perm_args(s, false), pk->omega_pows, beta, gamma, num + (size_t)s * U, den + (size_t)s * U, U);
+      ZKC_LAUNCH_CHECK(ctx);
+    }
+    ZKC_TRY(fr_batch_invert(ctx, den, den, (size_t)Pn * U));
+    k_pk_mul_vec<<<grid((size_t)Pn * U, 256), 256, 0, st>>>(num, den, num, (size_t)Pn * U); ZKC_LAUNCH_CHECK(ctx);
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(num + (size_t)Pn * U, &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));   // pad: scan length Pn*U + 1
+    ZKC_TRY(fr_scan(ctx, num, den, (size_t)Pn * U + 1, SCAN_MUL, 0, ONE));
+    std::vector<Fr> t((size_t)Pn * bf);
+    for (uint32_t s = 0; s < Pn; ++s) {
+      for (uint32_t i = 0; i < bf; ++i) t[(size_t)s * bf + i] = rng.draw();
+      if (opts->blind_draws) rng.draw();
+    }
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(tails, t.data(), t.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    k_assemble_z<<<grid((size_t)Pn * n, 256), 256, 0, st>>>(den, tails, pz, n, U, bf, Pn); ZKC_LAUNCH_CHECK(ctx);
+    ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    ZKC_TRY(commit_points(ctx, srs, 1, pz, n, Pn, pts));
+    ZKC_TRY(write_points(pts));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(pz_polys, pz, (size_t)Pn * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, pz_polys, Pn));
+  }
+
+  // 7. lookup grand products
+  if (L) {
+    ProfScope _p(ctx, "prove.lookup_product");
+    Fr *num, *den, *tails;
+    ZKC_TRY(pool.get(&num, U + 1)); ZKC_TRY(pool.get(&den, U + 1)); ZKC_TRY(pool.get(&tails, bf));
+    for (uint32_t l = 0; l < L; ++l) {
+      const Fr* comp_in = lk_comp + (size_t)2 * l * n; const Fr* comp_tab = comp_in + n;
+      const Fr* ap = lk_perm + (size_t)2 * l * n; const Fr* sp = ap + n;
+      k_lookup_num_den<<<grid(U, 128), 128, 0, st>>>(comp_in, comp_tab, ap, sp, beta, gamma, num, den, U); ZKC_LAUNCH_CHECK(ctx);
+      ZKC_TRY(fr_batch_invert(ctx, den, den, U));
+      k_pk_mul_vec<<<grid(U, 256), 256, 0, st>>>(num, den, num, U); ZKC_LAUNCH_CHECK(ctx);
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(num + U, &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));
+      ZKC_TRY(fr_scan(ctx, num, den, U + 1, SCAN_MUL, 0, ONE));
+      std::vector<Fr> t(bf);
+      for (auto& v : t) v = rng.draw();
+      if (opts->blind_draws) rng.draw();
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(tails, t.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, st));
+      k_assemble_z<<<grid(n, 256), 256, 0, st>>>(den, tails, lk_z + (size_t)l * n, n, U, bf, 1); ZKC_LAUNCH_CHECK(ctx);
+      ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    }
+    ZKC_TRY(commit_points(ctx, srs, 1, lk_z, n, L, pts));
+    ZKC_TRY(write_points(pts));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(lk_z_polys, lk_z, (size_t)L * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, lk_z_polys, L));
+  }
+
+  // 8. vanishing argument: random polynomial, n draws generated on the device from the same stream
+  Fr* random_poly;
+  ZKC_TRY(pool.get(&random_poly, n));
+  ZKC_TRY(rng.bulk(ctx, random_poly, n));
+  if (opts->blind_draws) rng.draw();
+  ZKC_TRY(commit_points(ctx, srs, 0, random_poly, n, 1, pts));
+  ZKC_TRY(write_points(pts));
+
+  // 9. y
+  const Fr y = tr.squeeze_challenge();
+
+  // 10. h(X) numerator on the extended coset
+  Fr *hval, *pz_cosets, *lk_cosets, *lk_comp_cosets;
+  ZKC_TRY(pool.get(&hval, en)); ZKC_TRY(pool.get(&pz_cosets, (size_t)Pn * en));
+  ZKC_TRY(pool.get(&lk_cosets, (size_t)3 * L * en)); ZKC_TRY(pool.get(&lk_comp_cosets, (size_t)2 * en));
+  {
+    ProfScope _p(ctx, "prove.quotient");
+    if (A) ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, adv_polys, n, adv_cosets, A));
+    if (I) ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, inst_polys, n, inst_cosets, I));
+    ZKC_TRY(eval_program(ctx, pk->gates, qext, hval, en, rot_scale, y, 0));
+    if (Pn) {
+      ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, pz_polys, n, pz_cosets, Pn));
+      PermFixedArgs fa; fa.nsets = Pn;
+      for (uint32_t s = 0; s < Pn; ++s) fa.z[s] = pz_cosets + (size_t)s * en;
+      const int64_t last_off = -(int64_t)(bf + 1) * rot_scale;
+      k_quot_perm_fixed<<<grid(en, 128), 128, 0, st>>>(hval, fa, pk->l0, pk->l_last, y, en, last_off); ZKC_LAUNCH_CHECK(ctx);
+      const Fr* tw_ext;
+      ZKC_TRY(ntt_twiddles(ctx, pk->ext_k, &tw_ext));
+      for (uint32_t s = 0; s < Pn; ++s) {
+        k_quot_perm_set<<<grid(en, 128), 128, 0, st>>>(hval, perm_args(s, true), pz_cosets + (size_t)s * en, pk->l_active, tw_ext, pk->ext_k, beta,
+                                                        gamma, y, en, rot_scale);
+        ZKC_LAUNCH_CHECK(ctx);
+      }
+    }
+    for (uint32_t l = 0; l < L; ++l) {
+      Fr* zc = lk_cosets + (size_t)3 * l * en; Fr* ac = zc + en; Fr* sc = ac + en;
+      ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, lk_z_polys + (size_t)l * n, n, zc, 1));
+      ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, lk_perm_polys + (size_t)2 * l * n, n, ac, 2));
+      ZKC_TRY(eval_program(ctx, pk->lookups[l].first, qext, lk_comp_cosets, en, rot_scale, theta, 0));
+      ZKC_TRY(eval_program(ctx, pk->lookups[l].second, qext, lk_comp_cosets + en, en, rot_scale, theta, 0));
+      k_quot_lookup<<<grid(en, 128), 128, 0, st>>>(hval, zc, ac, sc, lk_comp_cosets, lk_comp_cosets + en, pk->l0, pk->l_last, pk->l_active, beta,
+                                                    gamma, y, en, rot_scale);
+      ZKC_LAUNCH_CHECK(ctx);
+    }
+    // 11. divide by X^n - 1 on the coset, back to coefficients
+    ZKC_TRY(dom_divide_by_vanishing(ctx, pk->dom, hval));
+    ZKC_TRY(dom_extended_to_coeff(ctx, pk->dom, hval, 1));
+  }
+  const uint32_t q = cs.degree - 1;
+  if (opts->blind_draws) for (uint32_t i = 0; i < q; ++i) rng.draw();
+  ZKC_TRY(commit_points(ctx, srs, 0, hval, n, q, pts));
+  ZKC_TRY(write_points(pts));
+
+  // 12. x
+  const Fr x = tr.squeeze_challenge();
+  const Fr xn = fe_pow_u64(x, n);
+
+  // 13. evaluations — one batched launch for every (polynomial, point) pair of the proof
+  Fr* h_poly;   // sum_i xn^i * piece_i
+  ZKC_TRY(pool.get(&h_poly, n));
+  {
+    std::vector<const Fr*> ps; std::vector<Fr> cf;
+    Fr pw = ONE;
+    for (uint32_t i = 0; i < q; ++i) { ps.push_back(hval + (size_t)i * n); cf.push_back(pw); pw = fe_mul(pw, xn); }
+    ZKC_TRY(fr_lincomb(ctx, h_poly, n, ps, cf));
+  }
+  std::vector<Query> queries;        // upstream opening order (A.10)
+  std::vector<const Fr*> ev_polys; std::vector<Fr> ev_points;
+  auto want = [&](const Fr* poly, const Fr& pt) { ev_polys.push_back(poly); ev_points.push_back(pt); return ev_polys.size() - 1; };
+  const Fr x_next = rotate_omega(x, omega, omega_inv, 1), x_inv = rotate_omega(x, omega, omega_inv, -1);
+  const Fr x_last = rotate_omega(x, omega, omega_inv, -(int32_t)(bf + 1));
+  std::vector<size_t> i_adv, i_fix, i_sig, i_pz, i_lk;
+  for (auto& qq : cs.aq) i_adv.push_back(want(adv_polys + (size_t)qq.first * n, rotate_omega(x, omega, omega_inv, qq.second)));
+  for (auto& qq : cs.fq) i_fix.push_back(want(pk->fixed_polys + (size_t)qq.first * n, rotate_omega(x, omega, omega_inv, qq.second)));
+  const size_t i_rand = want(random_poly, x);
+  for (size_t g = 0; g < cs.perm.size(); ++g) i_sig.push_back(want(pk->sigma_polys + g * n, x));
+  for (uint32_t s = 0; s < Pn; ++s) {
+    i_pz.push_back(want(pz_polys + (size_t)s * n, x));
+    i_pz.push_back(want(pz_polys + (size_t)s * n, x_next));
+    if (s + 1 != Pn) i_pz.push_back(want(pz_polys + (size_t)s * n, x_last));
+  }
+  for (uint32_t l = 0; l < L; ++l) {
+    const Fr* zp = lk_z_polys + (size_t)l * n; const Fr* ap = lk_perm_polys + (size_t)2 * l * n; const Fr* sp = ap + n;
+    i_lk.push_back(want(zp, x)); i_lk.push_back(want(zp, x_next)); i_lk.push_back(want(ap, x)); i_lk.push_back(want(ap, x_inv));
+    i_lk.push_back(want(sp, x));
+  }
+  const size_t i_h = want(h_poly, x);
+  std::vector<Fr> ev;
+  ZKC_TRY(fr_eval_batch(ctx, ev_polys, n, ev_points, ev));
+  // transcript order (A.9): advice, fixed, random, sigma, permutation products, lookups
+  for (size_t i : i_adv) tr.write_scalar(ev[i]);
+  for (size_t i : i_fix) tr.write_scalar(ev[i]);
+  tr.write_scalar(ev[i_rand]);
+  for (size_t i : i_sig) tr.write_scalar(ev[i]);
+  for (size_t i : i_pz) tr.write_scalar(ev[i]);
+  for (size_t i : i_lk) tr.write_scalar(ev[i]);
+
+  // 14. opening queries in upstream order (A.10)
+  auto add_q = [&](size_t i) { queries.push_back(Query{ev_polys[i], ev_points[i], ev[i]}); };
+  for (size_t i : i_adv) add_q(i);
+  {
+    size_t pos = 0;
+    std::vector<size_t> lasts;
+    for (uint32_t s = 0; s < Pn; ++s) {
+      add_q(i_pz[pos]); add_q(i_pz[pos + 1]);
+      if (s + 1 != Pn) { lasts.push_back(i_pz[pos + 2]); pos += 3; } else pos += 2;
+    }
+    for (size_t r = lasts.size(); r-- > 0;) add_q(lasts[r]);
+  }
+  for (uint32_t l = 0; l < L; ++l) {
+    const size_t b = (size_t)5 * l;   // i_lk: z@x, z@x_next, a@x, a@x_inv, s@x
+    add_q(i_lk[b]); add_q(i_lk[b + 2]); add_q(i_lk[b + 4]); add_q(i_lk[b + 3]); add_q(i_lk[b + 1]);
+  }
+  for (size_t i : i_fix) add_q(i);
+  for (size_t i : i_sig) add_q(i);
+  add_q(i_h);
+  add_q(i_rand);
+
+  Fr *acc, *tmp1, *tmp2, *tmp3;
+  ZKC_TRY(pool.get(&acc, n)); ZKC_TRY(pool.get(&tmp1, n)); ZKC_TRY(pool.get(&tmp2, n)); ZKC_TRY(pool.get(&tmp3, n));
+  if (opts->multiopen == 0) {
+    // ---- SHPLONK (A.11) ----
+    ProfScope _p(ctx, "prove.shplonk");
+    const Fr yy = tr.squeeze_challenge();
+    std::vector<RotationSet> sets; std::vector<Fr> super_points;
+    build_rotation_sets(queries, sets, super_points);
+    const Fr v = tr.squeeze_challenge();
+    std::vector<std::vector<std::vector<Fr>>> rcoef(sets.size());   // [set][poly] -> r(X) coefficients
+    for (size_t s = 0; s < sets.size(); ++s)
+      for (size_t p = 0; p < sets[s].polys.size(); ++p) rcoef[s].push_back(lagrange_interpolate(sets[s].points, sets[s].evals[p]));
+    // h(X) = sum_i v^i * ( sum_j y^j (p_ij - r_ij) ) / Z_i
+    Fr pv = ONE;
+    for (size_t s = 0; s < sets.size(); ++s) {
+      std::vector<Fr> cf; std::vector<Fr> low(sets[s].points.size(), ZERO);
+      Fr py = ONE;
+      for (size_t p = 0; p < sets[s].polys.size(); ++p) {
+        cf.push_back(py);
+        for (size_t i = 0; i < low.size(); ++i) low[i] = fe_add(low[i], fe_mul(py, rcoef[s][p][i]));
+        py = fe_mul(py, yy);
+      }
+      ZKC_TRY(fr_lincomb(ctx, tmp1, n, sets[s].polys, cf));
+      ZKC_TRY(fr_sub_low(ctx, tmp1, low));
+      for (auto& root : sets[s].points) ZKC_TRY(fr_kate_division(ctx, tmp1, tmp1, n, root, tmp2, tmp3));
+      if (s == 0) { ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(acc, tmp1, n * sizeof(Fr), cudaMemcpyDeviceToDevice, st)); }
+      else ZKC_TRY(fr_lincomb(ctx, acc, n, {acc, tmp1}, {ONE, pv}));
+      pv = fe_mul(pv, v);
+    }
+    ZKC_TRY(commit_points(ctx, srs, 0, acc, n, 1, pts));
+    ZKC_TRY(write_points(pts));
+    const Fr u = tr.squeeze_challenge();
+    // L(X) = sum_i v^i z_i sum_j y^j (p_ij - r_ij(u)) - Z_T(u) h(X)
+    std::vector<const Fr*> ps; std::vector<Fr> cf;
+    Fr cst = ZERO, z0 = ZERO;
+    pv = ONE;
+    for (size_t s = 0; s < sets.size(); ++s) {
+      std::vector<Fr> diffs;
+      for (auto& sp : super_points) {
+        bool in = false;
+        for (auto& p : sets[s].points) if (fe_eq(p, sp)) { in = true; break; }
+        if (!in) diffs.push_back(sp);
+      }
+      const Fr zi = vanishing_eval(diffs, u);
+      if (s == 0) z0 = zi;
+      const Fr w = fe_mul(zi, pv);
+      Fr py = ONE;
+      for (size_t p = 0; p < sets[s].polys.size(); ++p) {
+        const Fr c = fe_mul(w, py);
+        // the same polynomial never sits in two sets, but may repeat across lincomb slots safely
+        ps.push_back(sets[s].polys[p]); cf.push_back(c);
+        cst = fe_add(cst, fe_mul(c, eval_small(rcoef[s][p], u)));
+        py = fe_mul(py, yy);
+      }
+      pv = fe_mul(pv, v);
+    }
+    const Fr zt = vanishing_eval(super_points, u);
+    ps.push_back(acc); cf.push_back(fe_neg(zt));
+    ZKC_TRY(fr_lincomb(ctx, tmp1, n, ps, cf));
+    ZKC_TRY(fr_sub_low(ctx, tmp1, {cst}));
+    ZKC_TRY(fr_kate_division(ctx, tmp1, tmp1, n, u, tmp2, tmp3));
+    if (fe_is_zero(z0)) return set_err(ctx, ZKC_ERR_OPENING, "shplonk: z_diff of the first rotation set is zero");
+    ZKC_TRY(fr_scale(ctx, tmp1, n, fe_inv(z0)));
+    ZKC_TRY(commit_points(ctx, srs, 0, tmp1, n, 1, pts));
+    ZKC_TRY(write_points(pts));
+  } else {
+    // ---- GWC (A.11): one witness per distinct point, first-appearance order, powers of v ----
+    ProfScope _p(ctx, "prove.gwc");
+    const Fr v = tr.squeeze_challenge();
+    std::vector<Fr> points;
+    for (auto& qq : queries) {
+      bool seen = false;
+      for (auto& p : points) if (fe_eq(p, qq.point)) { seen = true; break; }
+      if (!seen) points.push_back(qq.point);
+    }
+    for (auto& z : points) {
+      std::vector<const Fr*> ps; std::vector<Fr> cf;
+      Fr pvv = ONE, eacc = ZERO;
+      for (auto& qq : queries) {
+        if (!fe_eq(qq.point, z)) continue;
+        ps.push_back(qq.poly); cf.push_back(pvv);
+        eacc = fe_add(eacc, fe_mul(qq.eval, pvv));
+        pvv = fe_mul(pvv, v);
+      }
+      ZKC_TRY(fr_lincomb(ctx, tmp1, n, ps, cf));
+      ZKC_TRY(fr_sub_low(ctx, tmp1, {eacc}));
+      ZKC_TRY(fr_kate_division(ctx, tmp1, tmp1, n, z, tmp2, tmp3));
+      ZKC_TRY(commit_points(ctx, srs, 0, tmp1, n, 1, pts));
+      ZKC_TRY(write_points(pts));
+    }
+  }
+  ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  *proof_len = tr.proof.size();
+  if (!proof_out || proof_cap < tr.proof.size()) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_prove: proof buffer too small");
+  memcpy(proof_out, tr.proof.data(), tr.proof.size());
+  return ZKC_OK;
+}
+
+// Fr::random stream exposed for hosts that want to cross-check their RNG restatement
+extern "C" int zkc_rng_fr_random(const uint8_t seed[32], uint64_t skip, zkc_fr* out, size_t count) {
+  if (!seed || !out) return ZKC_ERR_BAD_ARG;
+  host::ChaCha20Rng r(seed);
+  r.counter = skip; r.pos = 16;
+  for (size_t i = 0; i < count; ++i) { Fr f = r.fr_random(); memcpy(&out[i], f.v, 32); }
+  return ZKC_OK;
+}
+extern "C" void zkc_seed_from_u64(uint64_t state, uint8_t seed[32]) { host::seed_from_u64(state, seed); }

@@ -137,6 +137,47 @@ int zkc_srs_get(zkc_ctx* ctx, const zkc_srs* srs, int basis, zkc_g1_affine* out 
 int zkc_commit(zkc_ctx* ctx, const zkc_srs* srs, int basis, const zkc_fr* poly, size_t len, zkc_g1* out);
 int zkc_commit_dev(zkc_ctx* ctx, const zkc_srs* srs, int basis, const zkc_fr* polys_dev, size_t len, uint32_t ncols, zkc_g1* out);
 
+uint32_t zkc_srs_k(const zkc_srs* srs);
+
+/* ---- ProvingKey + create_proof (halo2_proofs::plonk::{ProvingKey, create_proof}) ---
+ * The reference reaches this through snark-verifier-sdk gen_snark_shplonk
+ * (/root/reference/src/helpers.rs:233,299; src/bin/cli.rs:320,343,369,462,519).
+ *
+ * zkc_pk_load takes what `ProvingKey<G1Affine>` holds: the constraint system (`pk.vk.cs`, serialised as
+ * documented in halo2-zkcert_b200/circuit.py), the fixed columns and the permutation sigma columns
+ * in the Lagrange basis (`pk.fixed_values`, `pk.permutation.permutations`), and `vk.transcript_repr`.
+ * Coefficient forms, extended cosets, l0 / l_last / l_active_row and the vk commitments are rebuilt
+ * on the device. */
+int zkc_pk_load(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs_len, const zkc_fr* fixed /* num_fixed * n */,
+                const zkc_fr* sigma /* n_perm_columns * n */, const zkc_fr* transcript_repr, int zeta_choice, zkc_pk** out);
+void zkc_pk_free(zkc_pk* pk);
+/* vk.fixed_commitments / vk.permutation.commitments (host buffers sized num_fixed / n_perm_columns) */
+int zkc_pk_get_commitments(zkc_ctx* ctx, const zkc_pk* pk, zkc_g1_affine* fixed_out, zkc_g1_affine* sigma_out);
+/* out[8] = k, extended_k, cs.degree(), blinding_factors, #permutation sets, #lookups, #fixed, #permutation columns */
+int zkc_pk_info(const zkc_pk* pk, uint32_t* out);
+
+typedef struct {
+  int transcript;       /* 0 = Blake2bWrite<_, _, Challenge255>, 1 = Keccak256Write */
+  int multiopen;        /* 0 = ProverSHPLONK, 1 = ProverGWC */
+  int advice_blinding;  /* SURVEY OPEN-1: 0 = axiom (last row := 1, no draws), 1 = PSE (unusable rows random) */
+  int blind_draws;      /* SURVEY OPEN-2: 1 = one Fr::random per commitment for the (unused) KZG blind */
+  int point_format;     /* SURVEY OPEN-5: 0 = y-sign in bit 7; 1 = y-sign in bit 6, identity flag in bit 7 */
+  uint8_t rng_seed[32]; /* ChaCha20Rng::from_seed; every draw is Fr::random (one 64-byte keystream block) */
+} zkc_prove_opts;
+
+/* create_proof(params, pk, &[circuit], &[instances], rng, &mut transcript) for ONE circuit.
+ * `advice`: num_advice columns of n assigned cells (Montgomery; what WitnessCollection holds after
+ * batch_invert_assigned), host memory or, with advice_on_device != 0, device memory.  Rows past
+ * the usable range are overwritten by the blinding policy.  instances[c] has instance_lens[c] values.
+ * The proof bytes (commitments compressed to 32 B, evaluations 32 B) are written to proof_out. */
+int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, int advice_on_device, const zkc_fr* const* instances,
+              const size_t* instance_lens, const zkc_prove_opts* opts, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+
+/* host-side helpers mirrored for cross-checking a caller's RNG: Fr::random stream of ChaCha20Rng::from_seed(seed)
+ * starting at draw `skip`; rand_core's SeedableRng::seed_from_u64. */
+int zkc_rng_fr_random(const uint8_t seed[32], uint64_t skip, zkc_fr* out, size_t count);
+void zkc_seed_from_u64(uint64_t state, uint8_t seed[32]);
+
 #ifdef __cplusplus
 }
 #endif

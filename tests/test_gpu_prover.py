@@ -1,0 +1,102 @@
+"""GPU parity: zkc_prove through the C ABI vs the CPU oracle's create_proof — proof bytes identical for
+the same pk, witness, ChaCha20 seed and transcript; and the proofs verify under the independent verifier."""
+import numpy as np
+import pytest
+
+from oracle import orc, plonk, verifier
+from tests import pyref
+from tests.circuits import SRS_SECRET, cols_to_mont, oracle_setup, oracle_srs
+from tests.util import gpu_ctx, pkg
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_setup(circ, opk, zeta_choice=0):
+    p = pkg()
+    ctx = gpu_ctx()
+    cs = circ.cs
+    g, gl = oracle_srs(cs.k)
+    params = p.ParamsKZG(cs.k, g=g, g_lagrange=gl, ctx=ctx)
+    fixed = np.concatenate(opk.fixed_values) if opk.fixed_values else np.zeros((0, 4), dtype=np.uint64)
+    sigma = np.concatenate(opk.sigma_values) if opk.sigma_values else np.zeros((0, 4), dtype=np.uint64)
+    gpk = p.ProvingKey(params, cs, fixed, sigma, orc.fr_from_ints([opk.transcript_repr]), zeta_choice)
+    return params, gpk
+
+
+def vk_of(opk):
+    return verifier.VerifyingKey(opk.cs, opk.fixed_commitments, opk.sigma_commitments, opk.transcript_repr)
+
+
+@pytest.fixture(scope="module")
+def circuit_k6():
+    circ = pkg().synth.make_base_circuit(6, 2, seed=1)
+    opk, advice = oracle_setup(circ)
+    params, gpk = gpu_setup(circ, opk)
+    return circ, opk, advice, params, gpk
+
+
+def test_pk_matches_oracle_keygen(circuit_k6):
+    circ, opk, advice, params, gpk = circuit_k6
+    assert (gpk.k, gpk.extended_k, gpk.degree, gpk.blinding_factors, gpk.num_sets, gpk.num_lookups) == (6, 8, 4, 6, 3, 1)
+    f, s = gpk.commitments()
+    assert orc.g1_to_ints(f) == opk.fixed_commitments
+    assert orc.g1_to_ints(s) == opk.sigma_commitments
+
+
+@pytest.mark.parametrize("transcript,multiopen", [("blake2b", "shplonk"), ("keccak", "shplonk"), ("blake2b", "gwc"), ("keccak", "gwc")])
+def test_proof_bytes_match_oracle(circuit_k6, transcript, multiopen):
+    circ, opk, advice, params, gpk = circuit_k6
+    seed = pyref.seed_from_u64(42)
+    want = plonk.create_proof(opk, advice, circ.instances, pyref.ChaChaRng(seed, 20), transcript, multiopen)
+    inst = [orc.fr_from_ints(c) for c in circ.instances]
+    got = pkg().create_proof(gpk, np.concatenate(advice), inst, seed, transcript, multiopen)
+    assert got == want
+    assert verifier.verify_proof(vk_of(opk), pyref.G1_GEN, circ.instances, got, verifier.trapdoor_check(SRS_SECRET), transcript, multiopen)
+
+
+@pytest.mark.parametrize("opts", [dict(advice_blinding="pse"), dict(blind_draws=True), dict(point_format=1),
+                                  dict(advice_blinding="pse", blind_draws=True)])
+def test_open_switches_match_oracle(circuit_k6, opts):
+    circ, opk, advice, params, gpk = circuit_k6
+    seed = pyref.seed_from_u64(7)
+    want = plonk.create_proof(opk, advice, circ.instances, pyref.ChaChaRng(seed, 20), opts=plonk.ProverOptions(**opts))
+    inst = [orc.fr_from_ints(c) for c in circ.instances]
+    got = pkg().create_proof(gpk, np.concatenate(advice), inst, seed, **opts)
+    assert got == want
+
+
+def test_rng_and_seed_helpers():
+    assert pkg().seed_from_u64(0) == pyref.seed_from_u64(0)
+
+
+@pytest.mark.parametrize("k,a,seed", [(6, 1, 3), (8, 3, 4), (10, 2, 5), (12, 3, 6)])
+def test_proof_bytes_match_oracle_sizes(k, a, seed):
+    circ = pkg().synth.make_base_circuit(k, a, seed=seed)
+    opk, advice = oracle_setup(circ)
+    params, gpk = gpu_setup(circ, opk)
+    s = pyref.seed_from_u64(seed)
+    want = plonk.create_proof(opk, advice, circ.instances, pyref.ChaChaRng(s, 20))
+    inst = [orc.fr_from_ints(c) for c in circ.instances]
+    got = pkg().create_proof(gpk, np.concatenate(advice), inst, s)
+    assert got == want
+    assert verifier.verify_proof(vk_of(opk), pyref.G1_GEN, circ.instances, got, verifier.trapdoor_check(SRS_SECRET))
+
+
+def test_device_resident_advice_and_errors(circuit_k6):
+    import torch
+    circ, opk, advice, params, gpk = circuit_k6
+    seed = pyref.seed_from_u64(9)
+    inst = [orc.fr_from_ints(c) for c in circ.instances]
+    host = pkg().create_proof(gpk, np.concatenate(advice), inst, seed)
+    dev = torch.from_numpy(np.concatenate(advice).view(np.int64)).cuda()
+    assert pkg().create_proof(gpk, dev, inst, seed) == host
+    # lookup input outside the table -> plonk::Error::ConstraintSystemFailure
+    bad = [a.copy() for a in advice]
+    bad[-1][3] = orc.fr_from_ints([1 << 40])[0]
+    with pytest.raises(pkg().ZkcError) as e:
+        pkg().create_proof(gpk, np.concatenate(bad), inst, seed)
+    assert e.value.code == 11
+    # too many instances -> InvalidInstances
+    with pytest.raises(pkg().ZkcError) as e:
+        pkg().create_proof(gpk, np.concatenate(advice), [orc.fr_from_ints([1] * 64)], seed)
+    assert e.value.code == 10
