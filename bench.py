@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py — `create_proof` seconds on the RSA-2048 k=17 shape (BASELINE.json), one rank per GPU.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload rsa_k17|rsa_k15|...]
+
+A step = one create_proof (SHPLONK, Blake2b transcript, seeded ChaCha20) of a synthetic, satisfying
+BaseConfig circuit: k=17, 3 gate advice columns + 1 lookup advice column, 1 lookup, 6 permutation
+columns (README.md:48 shape; /root/reference/src/helpers.rs:97-172).  Independent proofs shard across
+GPUs with no collective (weak scaling; the cert chain's proofs are independent — BASELINE config 4).
+
+  value  = seconds per proof with the witness already resident in HBM (whole job: step time / N)
+  e2e    = the same through the host-buffer C ABI: witness copied from pinned host memory inside
+           the timed region, proof bytes returned to the host
+  roofline = the dominant kernel (MSM bucket accumulation) against the MEASURED integer-pipe peak
+           (IMAD.WIDE issue rate, profiles/r01_ffbench.json) — this path has no dense contraction
+           and is not HBM-bound; `roofline_hbm` gives the NTT kernels against the measured copy bandwidth.
+  cpu_baseline = the restated CPU oracle (not halo2-axiom itself: no Rust toolchain in this image)
+           on a bounded sample (k=15, same column shape), scaled by n*log2(n) to k=17.
+
+`--impl reference` times that CPU oracle alone (rank 0 only).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "rsa_k17": dict(k=17, gate_cols=3, desc="RSA-2048 PKCS#1 verify shape: k=17, 3 gate advice + 1 lookup advice, 1 lookup, 6 permutation columns"),
+    "rsa_k15": dict(k=15, gate_cols=12, desc="RSA-2048 wide-column shape: k=15, 12 gate advice + 1 lookup advice"),
+    "rsa_k13": dict(k=13, gate_cols=3, desc="reduced smoke shape k=13"),
+}
+SAMPLE_K = 15            # bounded CPU sample
+IMAD_WIDE_PEAK = None    # filled from profiles/r01_ffbench.json
+FQMUL_PER_MADD = 10      # XYZZ mixed add: 8M + 2S
+IMADW_PER_FQMUL = 128    # 64 (a*b) + 64 (m*p) IMAD.WIDE per Montgomery product
+
+
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)", "imadw": 8.63e12, "imadw_src": "profiles/r01_ffbench.json"}
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks["hbm_gbs"], peaks["hbm_src"] = float(mp["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    try:
+        fb = json.load(open(os.path.join(ROOT, "profiles", "r01_ffbench.json")))
+        peaks["imadw"] = float(fb["imad_wide_per_s"])
+    except Exception:
+        pass
+    return peaks
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, nm in enumerate(names):
+                if len(r) > 5 + i and r[5 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def cpu_oracle_seconds(sample_k, gate_cols, steps=1, warmup=0, seed=1):
+    """times the restated CPU oracle prover on the bounded sample; returns (seconds per proof, cores)"""
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    from oracle import orc, plonk
+    from tests import pyref
+    circ = pkg.synth.make_base_circuit(sample_k, gate_cols, seed=seed)
+    cs = circ.cs
+    g, gl = orc.srs_setup(sample_k, orc.fr_from_ints([pyref.ChaChaRng(bytes(32), 20).fr_random()]))
+    mapping = pkg.synth.build_permutation_mapping(cs, circ.copies)
+    sigma = pkg.synth.sigma_values(cs, mapping)
+    mont = lambda cols: [orc.fr_from_ints(c) for c in cols]
+    pk = plonk.keygen(cs, mont(circ.fixed), mont(sigma), g, gl, circ.transcript_repr())
+    advice = mont(circ.advice)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        plonk.create_proof(pk, advice, circ.instances, pyref.ChaChaRng(pyref.seed_from_u64(i), 20))
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), orc.lib().orc_default_threads()
+
+
+def scale_to(k_from, k_to):
+    return (2 ** k_to * k_to) / (2 ** k_from * k_from)
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    k = wl["k"]
+    sk = min(SAMPLE_K, k)
+    sec, cores = cpu_oracle_seconds(sk, wl["gate_cols"], steps=args.steps, warmup=min(args.warmup, 1))
+    value = sec * scale_to(sk, k)
+    sample = "restated CPU oracle (oracle/plonk.py + libzkc_oracle.so, not halo2-axiom) create_proof at k=%d, same column shape; " \
+             "%.3f s measured, scaled by n*log2(n) to k=%d" % (sk, sec, k)
+    line = {"metric": "create_proof_s", "value": value, "unit": "s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u256 (BN254 Fr/Fq, exact)", "data": "synthetic", "config": {"workload": args.workload, "desc": wl["desc"]},
+            "cpu_baseline": {"value": value, "unit": "s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rsa_k17", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import numpy as np
+    import torch
+    import __graft_entry__ as graft
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    pkg = graft.load_package()
+    ctx = pkg.Context(local)
+    ctx.use_torch_stream()
+    peaks = load_peaks()
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    # untimed setup: gen_srs + gen_pk + witness (each rank proves its own certificate: different seed)
+    w = pkg.workload.build(ctx, wl["k"], wl["gate_cols"], seed=100 + rank)
+    seeds = [pkg.seed_from_u64(1000 * rank + i) for i in range(W + K)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def run(advice, steps, warm):
+        total_ms, proofs = 0.0, []
+        for i in range(warm + steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            proof = pkg.create_proof(w.pk, advice, w.instances, seeds[i])
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warm:
+                total_ms += e0.elapsed_time(e1)
+                proofs.append(proof)
+        return total_ms, proofs
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    run(w.advice_dev, 0, W)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = ctx.launches
+    t_wall = time.perf_counter()
+    dev_ms, proofs_dev = run(w.advice_dev, K, 0)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = ctx.launches - l0
+    # per-kernel CUDA-event timers (zkc_profile_*) over the same K steps, on the launching stream;
+    # kept out of the headline loop because the extra event records perturb the host-side pacing
+    ctx.profile_enable(True)
+    ctx.profile_report()
+    prof_ms, proofs_prof = run(w.advice_dev, K, 0)
+    prof = ctx.profile_report()
+    ctx.profile_enable(False)
+    clocks = sampler.stop()
+    assert proofs_prof == proofs_dev
+    # ---- end-to-end timing: host (pinned) witness in, proof bytes out -------------------------------
+    run(w.advice_host, 0, 1)
+    barrier()
+    e2e_ms, proofs_e2e = run(w.advice_host, K, 0)
+    barrier()
+    assert proofs_dev == proofs_e2e, "device-resident and host-buffer paths must emit identical proofs"
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    dev_ms, e2e_ms = max_over_ranks(dev_ms), max_over_ranks(e2e_ms)
+    step_ms, e2e_step_ms = dev_ms / K, e2e_ms / K
+    if rank == 0:
+        accum = prof.get("msm.accum", {"ms": 0.0, "n": 0})
+        madds = prof.get("count:msm.madds", {"n": 0})["n"]
+        imadw = madds * FQMUL_PER_MADD * IMADW_PER_FQMUL
+        ach = imadw / (accum["ms"] * 1e-3) if accum["ms"] else 0.0
+        roofline = {"bound": "int", "kernel": "k_msm_accum (XYZZ bucket accumulation)", "achieved": ach / 1e12, "peak": peaks["imadw"] / 1e12,
+                    "unit": "T IMAD.WIDE/s", "frac": ach / peaks["imadw"], "traffic": None,
+                    "launches": accum["n"], "avg_launch_ms": accum["ms"] / max(accum["n"], 1),
+                    "algorithmic": "mixed adds per launch x 10 Fq-mul x 128 IMAD.WIDE (SURVEY 8d); peak = measured IMAD.WIDE issue rate (%s)" % peaks["imadw_src"],
+                    "share_of_step": accum["ms"] / prof_ms if prof_ms else None}
+        ntt_ms = sum(prof.get(kx, {"ms": 0.0})["ms"] for kx in ("ntt.strided", "ntt.last"))
+        n, en = 1 << wl["k"], 1 << w.pk.extended_k
+        line = {"metric": "create_proof_s", "value": step_ms / 1e3 / world, "unit": "s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": step_ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u256 (BN254 Fr/Fq Montgomery, exact integer)", "data": "synthetic",
+                "config": {"workload": args.workload, "desc": wl["desc"], "k": wl["k"], "extended_k": w.pk.extended_k,
+                           "proofs_per_step": world, "transcript": "blake2b", "multiopen": "shplonk",
+                           "l2": "flushed between steps (256 MiB memset, untimed)", "proof_bytes": len(proofs_dev[0])},
+                "e2e": {"value": e2e_step_ms / 1e3 / world, "unit": "s", "h2d_bytes_per_step": int(w.h2d_bytes),
+                        "d2h_bytes_per_step": len(proofs_dev[0])},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "roofline_hbm": {"bound": "hbm", "kernel": "k_ntt_strided + k_ntt_last", "achieved_gbs_note":
+                                 "NTT passes are integer-pipe bound on 254-bit fields; see DESIGN.md", "ntt_ms_per_step": ntt_ms / K,
+                                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_src": peaks["hbm_src"]},
+                "phases_ms_per_step": {kx: round(v["ms"] / K, 4) for kx, v in sorted(prof.items()) if not kx.startswith("count:")},
+                "msm_points_per_s": prof.get("count:msm.points", {"n": 0})["n"] / (sum(prof.get(kx, {"ms": 0.0})["ms"] for kx in prof if kx.startswith("msm.")) * 1e-3 or 1),
+                "wall_s_timed_region": t_wall}
+        if not args.no_cpu_baseline and world == 1:
+            sk = min(SAMPLE_K, wl["k"])
+            sec, cores = cpu_oracle_seconds(sk, wl["gate_cols"])
+            line["cpu_baseline"] = {"value": sec * scale_to(sk, wl["k"]), "unit": "s", "cores": cores, "kind": "port",
+                                    "sample": "restated CPU oracle create_proof at k=%d (same column shape), %.3f s measured, scaled by n*log2(n) to k=%d; "
+                                              "published halo2-axiom figures for this shape: 3.144 s (M1) / 1.813 s (c6a.48xlarge), README.md:48" % (sk, sec, wl["k"])}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -8,6 +8,6 @@ compute entry point raises `ZkcError` when no CUDA device is present.
 The directory name contains a hyphen, so import it through `__graft_entry__.load_package()` (or
 `importlib`), which registers it as the module `halo2_zkcert_b200`.
 """
-from . import api, circuit, synth  # noqa: F401
+from . import api, circuit, dist, synth, workload  # noqa: F401
 from .api import (ZkcError, Context, EvaluationDomain, ParamsKZG, ProvingKey, best_fft, best_multiexp, create_proof,  # noqa: F401
                   default_context, lib, lib_path, seed_from_u64)

@@ -125,6 +125,11 @@ class Context:
                                               None if b is None else _dp(b), _dp(out), C.c_size_t(n)))
         return out
 
+    def powers_dev(self, out, base, first):
+        """out[i] = first * base^i on the device (out: torch (n, 4) int64)"""
+        self.check(lib().zkc_fr_powers_dev(self._h, _dp(out), C.c_size_t(out.shape[0]), _hp(_np(base, 4)), _hp(_np(first, 4))))
+        return out
+
     # ---- best_fft ------------------------------------------------------------------------------
     def fft(self, a, omega, log_n):
         """best_fft(a, omega, log_n) on a host array; returns the transformed copy."""
@@ -384,3 +389,13 @@ def seed_from_u64(state):
     out = (C.c_uint8 * 32)()
     lib().zkc_seed_from_u64(C.c_uint64(state), out)
     return bytes(out)
+
+
+def fr_random_stream(seed, count, skip=0):
+    """Fr::random draws of ChaCha20Rng::from_seed(seed) as (count, 4) Montgomery limbs (host-side helper)"""
+    out = np.zeros((count, 4), dtype=np.uint64)
+    s = (C.c_uint8 * 32)(*list(seed))
+    st = lib().zkc_rng_fr_random(s, C.c_uint64(skip), _hp(out), C.c_size_t(count))
+    if st != 0:
+        raise ZkcError(st, "zkc_rng_fr_random")
+    return out

@@ -41,6 +41,7 @@ struct zkc_ctx {
   std::vector<ProfRec> prof_pending;
   std::vector<cudaEvent_t> prof_pool;
   std::map<std::string, std::pair<double, uint64_t>> prof_acc;
+  std::map<std::string, uint64_t> stats;   // work counters (e.g. msm.madds), reported with the profile
 };
 
 namespace zkc {

@@ -77,8 +77,14 @@ extern "C" int zkc_profile_report(zkc_ctx* c, char* buf, size_t cap) {
              (unsigned long long)kv.second.second);
     js += tmp; first = false;
   }
+  for (auto& kv : c->stats) {
+    char tmp[256];
+    snprintf(tmp, sizeof tmp, "%s\"count:%s\": {\"ms\": 0, \"n\": %llu}", first ? "" : ", ", kv.first.c_str(), (unsigned long long)kv.second);
+    js += tmp; first = false;
+  }
   js += "}";
   c->prof_acc.clear();
+  c->stats.clear();
   snprintf(buf, cap, "%s", js.c_str());
   return ZKC_OK;
 }
@@ -174,6 +180,14 @@ int vec_op_impl(zkc_ctx* ctx, int op, const Fe<P>* a, const Fe<P>* b, Fe<P>* out
 int fr_batch_invert(zkc_ctx* ctx, const Fr* a, Fr* out, size_t n) { return vec_op_impl<FrP>(ctx, ZKC_OP_INV, a, nullptr, out, n); }
 
 }  // namespace zkc
+
+namespace zkc { int fr_powers(zkc_ctx* ctx, Fr* out, uint64_t n, const Fr& base, const Fr& first); }
+extern "C" int zkc_fr_powers_dev(zkc_ctx* ctx, zkc_fr* out, size_t n, const zkc_fr* base, const zkc_fr* first) {
+  if (!ctx || !out || !base || !first) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_fr_powers_dev: null argument");
+  CtxLock lock(ctx);
+  Fr b, f; memcpy(b.v, base, 32); memcpy(f.v, first, 32);
+  return fr_powers(ctx, (Fr*)out, n, b, f);
+}
 
 extern "C" int zkc_field_vec_op_dev(zkc_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n) {
   if (!ctx || !a || !out) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_field_vec_op_dev: null argument");

@@ -280,9 +280,11 @@ int msm_run(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, 
       ZKC_LAUNCH_CHECK(ctx); }
     const size_t ubytes = (size_t)nc * g.sets * g.c * sizeof(G1Xyzz);
     void* hU;
-    ZKC_TRY(pinned_reserve(ctx, ubytes, &hU));
+    ZKC_TRY(pinned_reserve(ctx, ubytes + 16, &hU));
     ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(hU, U, ubytes, cudaMemcpyDeviceToHost, st));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync((char*)hU + ubytes, offsets + nbt, 4, cudaMemcpyDeviceToHost, st));
     ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    { uint32_t e; memcpy(&e, (char*)hU + ubytes, 4); ctx->stats["msm.madds"] += e; ctx->stats["msm.points"] += n * nc; }
     for (uint32_t col = 0; col < nc; ++col) {
       G1Xyzz r = host_combine((const G1Xyzz*)hU + (size_t)col * g.sets * g.c, g);
       xyzz_to_abi(r, out + c0 + col);

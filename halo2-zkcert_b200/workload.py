@@ -1,0 +1,64 @@
+"""Builds a complete proving workload (SRS, proving key, resident witness) for a synthetic circuit
+using only the product library — what bench.py, smoke() and the multi-GPU driver run.
+
+Off the timed path: this is the work `gen_srs` + `gen_pk` + witness synthesis do in the reference
+(/root/reference/src/helpers.rs:201-216, 236-266).  Montgomery conversion, the sigma table and the
+SRS are produced on the device; torch is only the allocator/indexer here.
+"""
+import numpy as np
+
+from . import api, synth
+from .circuit import R_MOD
+
+GEN_SRS_SEED = bytes(32)     # halo2-base gen_srs: ChaCha20Rng::from_seed([0; 32])
+
+
+def to_mont_dev(ctx, ints):
+    """canonical Python ints -> torch CUDA (len, 4) int64 Montgomery limbs"""
+    import torch
+    t = torch.from_numpy(synth.ints_to_limbs(ints).view(np.int64)).cuda(ctx.device)
+    out = torch.empty_like(t)
+    ctx.field_vec_op_dev("fr", "from_canonical", t, None, out)
+    return out
+
+
+def to_host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+class Workload:
+    pass
+
+
+def build(ctx, k, num_gate_cols, seed=0, circ=None, params=None):
+    import torch
+    w = Workload()
+    w.ctx = ctx
+    w.circ = circ or synth.make_base_circuit(k, num_gate_cols, seed=seed)
+    cs = w.circ.cs
+    n = cs.n
+    if params is None:
+        s = api.fr_random_stream(GEN_SRS_SEED, 1)
+        params = api.ParamsKZG.setup(k, s, ctx=ctx)
+    w.params = params
+    flat = lambda cols: [v for c in cols for v in c]
+    fixed = to_mont_dev(ctx, flat(w.circ.fixed))
+    w.advice_dev = to_mont_dev(ctx, flat(w.circ.advice))
+    w.instances = [to_host(to_mont_dev(ctx, c)) if len(c) else np.zeros((0, 4), dtype=np.uint64) for c in w.circ.instances]
+    # sigma_col[row] = DELTA^col' * omega^row' gathered through the permutation mapping
+    m = len(cs.permutation)
+    mapping = synth.build_permutation_mapping(cs, w.circ.copies)
+    dom = api.EvaluationDomain(cs.degree(), k, ctx=ctx)
+    table = torch.empty((m * n, 4), dtype=torch.int64, device="cuda:%d" % ctx.device)
+    dpow = to_host(to_mont_dev(ctx, [pow(synth.DELTA, c, R_MOD) for c in range(m)]))
+    for c in range(m):
+        ctx.powers_dev(table[c * n:(c + 1) * n], dom.omega, dpow[c:c + 1])
+    ctx.sync()
+    sigma = table[torch.from_numpy(mapping).cuda(ctx.device)]
+    tr = to_host(to_mont_dev(ctx, [w.circ.transcript_repr()]))
+    w.pk = api.ProvingKey(params, cs, to_host(fixed), to_host(sigma), tr)
+    # pinned host copy of the witness for the end-to-end (host-buffer) path
+    w.advice_pinned = w.advice_dev.cpu().pin_memory()
+    w.advice_host = w.advice_pinned.numpy().view(np.uint64)
+    w.h2d_bytes = w.advice_host.nbytes + sum(i.nbytes for i in w.instances)
+    return w

@@ -90,6 +90,9 @@ typedef enum {
 /* field: 0 = Fr, 1 = Fq.  out[i] = a[i] (op) b[i]; b may be NULL for unary ops.  Device pointers. */
 int zkc_field_vec_op_dev(zkc_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
 
+/* out[i] = first * base^i (arithmetic::powers; used for omega^i / DELTA^c tables at keygen).  Device pointer. */
+int zkc_fr_powers_dev(zkc_ctx* ctx, zkc_fr* out_dev, size_t n, const zkc_fr* base, const zkc_fr* first);
+
 /* ---- best_fft (halo2_proofs::arithmetic::best_fft) -------------------------- */
 /* In place, natural order in and out: a[j] <- sum_i a[i] * omega^(i*j).  `omega` must have order
  * 2^log_n.  Host buffer variant (drop-in) and device-resident batched variant (ncols contiguous

@@ -1,0 +1,122 @@
+"""CPU-side checks of the product's host logic: the C ABI library loads and exports every symbol
+include/zkcert_cuda.h declares, fails loudly without a GPU, the constraint-system wire format and
+A.5 numbers, the synthetic circuits (every gate / lookup / copy constraint satisfied), and the
+multi-GPU sharding helpers under gloo with world_size 2."""
+import ctypes
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from tests.util import ROOT, pkg
+from tests.pyref import R_MOD
+
+
+def test_library_exports_every_declared_symbol():
+    p = pkg()
+    lib = p.lib()
+    header = open(os.path.join(ROOT, "include", "zkcert_cuda.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = sorted(set(re.findall(r"\b(zkc_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert b"sm_100a" in lib.zkc_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    p = pkg()
+    with pytest.raises(p.ZkcError) as e:
+        p.Context(0)
+    assert e.value.code == 2
+    with pytest.raises(p.ZkcError):
+        p.best_fft(np.zeros((4, 4), dtype=np.uint64), np.zeros((1, 4), dtype=np.uint64), 2)
+
+
+def test_host_rng_helpers_match_known_answers():
+    p = pkg()
+    assert p.seed_from_u64(0).hex() == "ecf273f981b5cd4587f0467306ad6cadd0d0a3e33317e767f29bea72d78a7dfe"
+    s = p.api.fr_random_stream(bytes(32), 2)
+    rinv = pow(1 << 256, -1, R_MOD)
+    to_int = lambda row: sum(int(row[i]) << (64 * i) for i in range(4)) * rinv % R_MOD
+    assert to_int(s[0]) == 0x1c59a59b6cff4308740943526ade1d8c09f71b337a67269cc89586bcdd6dfcba   # gen_srs secret
+    assert np.array_equal(p.api.fr_random_stream(bytes(32), 1, skip=1), s[1:2])
+
+
+def test_constraint_system_numbers_and_wire_format():
+    p = pkg()
+    cs = p.synth.base_constraint_system(17, 3)
+    assert (cs.degree(), cs.blinding_factors(), cs.usable_rows(), cs.permutation_chunk_len(), cs.num_permutation_sets()) == \
+        (4, 6, (1 << 17) - 7, 2, 3)
+    assert (cs.num_advice, cs.num_fixed, cs.num_instance, len(cs.advice_queries), len(cs.fixed_queries)) == (4, 5, 1, 13, 5)
+    cs15 = p.synth.base_constraint_system(15, 12)
+    assert cs15.num_permutation_sets() == 8 and len(cs15.permutation) == 15
+    blob = cs.serialize()
+    assert blob[:4] == b"ZKCS" and struct.unpack_from("<6I", blob, 4) == (1, 17, 4, 5, 1, 0)
+    # postfix program of the FlexGate polynomial q*(a + b*c - d)
+    words, consts = cs.program(cs.gates[0])
+    ops = words[0::2]
+    from halo2_zkcert_b200.circuit import OP_ADVICE, OP_FIXED, OP_MUL, OP_ADD, OP_NEG, OP_END
+    assert ops == [OP_FIXED, OP_ADVICE, OP_ADVICE, OP_ADVICE, OP_MUL, OP_ADD, OP_ADVICE, OP_NEG, OP_ADD, OP_MUL, OP_END] and consts == []
+
+
+@pytest.mark.parametrize("k,a", [(6, 2), (9, 3)])
+def test_synthetic_circuit_is_satisfied(k, a):
+    p = pkg()
+    circ = p.synth.make_base_circuit(k, a, seed=5)
+    cs, n = circ.cs, 1 << k
+    U = cs.usable_rows()
+    for i in range(a):
+        col, sel = circ.advice[i], circ.fixed[i]
+        for r in range(U):
+            if sel[r]:
+                assert (col[r] + col[r + 1] * col[r + 2] - col[r + 3]) % R_MOD == 0
+    table = set(circ.fixed[a + 1][:U])
+    assert all(v in table for v in circ.advice[a][:U])
+    cols = {**{i: circ.advice[i] for i in range(a + 1)}, a + 1: circ.fixed[a], a + 2: circ.instances[0]}
+    assert len(circ.copies) > n // 16
+    for lc, lr, rc, rr in circ.copies:
+        assert cols[lc][lr] == cols[rc][rr]
+    # permutation mapping: a permutation whose cycles only join equal cells
+    mapping = p.synth.build_permutation_mapping(cs, circ.copies)
+    assert sorted(mapping.tolist()) == list(range(len(cs.permutation) * n))
+    val = lambda idx: (cols[idx // n][idx % n] if idx % n < len(cols[idx // n]) else 0)
+    moved = [i for i in range(len(mapping)) if mapping[i] != i]
+    assert moved and all(val(i) == val(int(mapping[i])) for i in moved)
+
+
+def _dist_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = pkg().dist
+    jobs = ["rsa_cert3", "sha_cert3", "rsa_cert2", "sha_cert2", "agg"]
+    proofs = d.prove_chain(jobs, lambda j: ("proof(%s)@%d" % (j, rank)).encode())
+    total = d.sum_partials(rank + 1, lambda a, b: a + b)
+    q.put((rank, proofs, total, d.shard_range(10, world, rank)))
+    dist.destroy_process_group()
+
+
+def test_sharding_helpers_gloo_world2():
+    import torch.multiprocessing as mp
+    d = pkg().dist
+    assert [d.shard_range(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert d.assign_round_robin(5, 2, 1) == [1, 3]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for pr in procs:
+        pr.join(timeout=60)
+    want = [b"proof(rsa_cert3)@0", b"proof(sha_cert3)@1", b"proof(rsa_cert2)@0", b"proof(sha_cert2)@1", b"proof(agg)@0"]
+    assert res[0][1] == want and res[1][1] == want          # every rank holds the chain's proofs in job order
+    assert res[0][2] == res[1][2] == 3
+    assert [r[3] for r in res] == [(0, 5), (5, 10)]
