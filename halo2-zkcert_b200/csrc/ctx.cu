@@ -19,6 +19,13 @@ extern "C" int zkc_ctx_create(int device, zkc_ctx** out) {
   c->stream = c->own_stream;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  // keep the stream-ordered pool's memory across synchronisations: per-proof temporaries are
+  // re-allocated from it without going back to the driver
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
   *out = c;
   return ZKC_OK;
 }

@@ -6,7 +6,7 @@
 //
 // Pipeline (all device-resident, one stream, no host round trip until the final 2 KB):
 //   1 k_msm_digits   scalar -> canonical -> signed c-bit digits; histogram of bucket sizes (atomics)
-//   2 k_msm_scan     exclusive scan of the histogram (bucket offsets)
+//   2 u32_scan       multi-CTA exclusive scan of the histogram (bucket offsets)
 //   3 k_msm_scatter  counting sort: entries (point index | sign, bucket key) grouped by bucket
 //   4 k_msm_accum    SEGMENTED FLAT WALK: thread t owns entries [tT, (t+1)T) whatever buckets they
 //                    fall in, accumulates with XYZZ mixed adds and flushes one partial per bucket it
@@ -14,8 +14,8 @@
 //                    limb-valued witness columns (a few giant buckets) run as fast as uniform scalars.
 //   5 k_msm_gather   one thread per bucket sums its (usually 1-3) partials; buckets with many
 //                    partials are queued and reduced by a whole CTA (k_msm_gather_heavy).
-//   6 k_msm_reduce   sum_b b*S_b per window as c independent tree reductions U_t = sum of buckets
-//                    whose index has bit t set (no serial running sum), then 2^t weights by Horner.
+//   6 k_msm_reduce1/2 sum_b b*S_b per window as c independent two-level tree reductions U_t = sum of
+//                    buckets whose index has bit t set (no serial running sum), then 2^t weights by Horner.
 // With a resident SRS the bases are expanded once into W tables 2^(c*w) * P_i, so all windows of
 // all points share ONE bucket set per column and step 6 shrinks by a factor W.
 #include "common.cuh"
@@ -60,27 +60,6 @@ __global__ void k_msm_digits(const Fr* scalars, uint32_t* dig, uint32_t* counts,
       atomicAdd(counts + key, 1u);
     }
   }
-}
-
-// single-CTA exclusive scan: offsets[i] = sum counts[0..i), offsets[n] = total; cursor = copy of offsets
-__global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t* counts, uint32_t* offsets, uint32_t* cursor, uint64_t n) {
-  __shared__ uint32_t part[1024];
-  const uint32_t t = threadIdx.x;
-  const uint64_t per = (n + 1023) / 1024;
-  const uint64_t lo = t * per, hi = lo + per < n ? lo + per : n;
-  uint32_t s = 0;
-  for (uint64_t i = lo; i < hi; ++i) s += counts[i];
-  part[t] = s;
-  __syncthreads();
-  for (uint32_t d = 1; d < 1024; d <<= 1) {
-    uint32_t v = t >= d ? part[t - d] : 0;
-    __syncthreads();
-    part[t] += v;
-    __syncthreads();
-  }
-  uint32_t run = t ? part[t - 1] : 0;
-  for (uint64_t i = lo; i < hi; ++i) { offsets[i] = run; cursor[i] = run; run += counts[i]; }
-  if (t == 1023) offsets[n] = part[1023];
 }
 
 __global__ void k_msm_scatter(const uint32_t* dig, uint32_t* cursor, uint32_t* ent_pt, uint32_t* ent_key, MsmGeom g) {
@@ -162,18 +141,31 @@ __global__ void __launch_bounds__(256) k_msm_gather_heavy(const uint32_t* offset
   }
 }
 
-// U[set][t] = sum of buckets b in [1, NB] of the set with bit t of b set.  grid = (c, nsets)
-__global__ void __launch_bounds__(256) k_msm_reduce(const G1Xyzz* buckets, G1Xyzz* U, MsmGeom g) {
+// Level 1: P[set][t][chunk] = sum of buckets b of the chunk whose index has bit t set.  grid = (c, nchunks, nsets)
+#define RED_CHUNK 1024
+__global__ void __launch_bounds__(256, 2) k_msm_reduce1(const G1Xyzz* buckets, G1Xyzz* P, MsmGeom g, uint32_t nchunks) {
   extern __shared__ uint4 smraw[];
   G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smraw);
-  const uint32_t t = blockIdx.x;
-  const uint64_t set = blockIdx.y;
+  const uint32_t t = blockIdx.x, ch = blockIdx.y;
+  const uint64_t set = blockIdx.z;
   const G1Xyzz* bk = buckets + set * g.NB;
   G1Xyzz acc = xyzz_identity();
-  for (uint32_t b = threadIdx.x + 1; b <= g.NB; b += blockDim.x)
+  const uint32_t lo = ch * RED_CHUNK, hi = min(g.NB, lo + RED_CHUNK);
+  for (uint32_t b = lo + threadIdx.x + 1; b <= hi; b += blockDim.x)
     if ((b >> t) & 1) xyzz_add(acc, xyzz_load(bk + (b - 1)));
   G1Xyzz r = block_reduce_xyzz(acc, sm);
-  if (threadIdx.x == 0) xyzz_store(U + set * g.c + t, r);
+  if (threadIdx.x == 0) xyzz_store(P + (set * g.c + t) * nchunks + ch, r);
+}
+// Level 2: U[set][t] = sum over chunks.  grid = (c, nsets), one warp
+__global__ void __launch_bounds__(32) k_msm_reduce2(const G1Xyzz* P, G1Xyzz* U, MsmGeom g, uint32_t nchunks) {
+  extern __shared__ uint4 smraw[];
+  G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smraw);
+  const uint64_t idx = (uint64_t)blockIdx.y * g.c + blockIdx.x;
+  const G1Xyzz* p = P + idx * nchunks;
+  G1Xyzz acc = xyzz_identity();
+  for (uint32_t c = threadIdx.x; c < nchunks; c += 32) xyzz_add(acc, xyzz_load(p + c));
+  G1Xyzz r = block_reduce_xyzz(acc, sm);
+  if (threadIdx.x == 0) xyzz_store(U + idx, r);
 }
 
 // ---- host-side epilogue: Horner over bit sums and windows (a few hundred point ops) -------------
@@ -197,6 +189,8 @@ static void xyzz_to_abi(const G1Xyzz& p, zkc_g1* out) {
     memcpy(&out->x, a.x.v, 32); memcpy(&out->y, a.y.v, 32); memcpy(&out->z, one.v, 32);
   }
 }
+
+int u32_scan(zkc_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* total_dev);   // poly.cu
 
 uint32_t msm_pick_c(uint64_t n, bool precomputed) {
   uint32_t lg = 0;
@@ -242,14 +236,15 @@ int msm_run(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, 
     const size_t o_counts = carve(nbt * 4), o_offsets = carve((nbt + 1) * 4), o_cursor = carve(nbt * 4), o_heavyc = carve(4),
                  o_heavy = carve(nbt * 4), o_dig = carve(em * 4), o_pt = carve(em * 4), o_key = carve(em * 4),
                  o_part = carve(nslots * sizeof(G1Xyzz)), o_bk = carve(nbt * sizeof(G1Xyzz)),
-                 o_U = carve((size_t)nc * g.sets * g.c * sizeof(G1Xyzz));
+                 o_U = carve((size_t)nc * g.sets * g.c * sizeof(G1Xyzz)),
+                 o_redp = carve((size_t)nc * g.sets * g.c * ((g.NB + 1023) / 1024) * sizeof(G1Xyzz));
     char* base;
     ZKC_TRY(scratch_reserve(ctx, SCR_MSM, o, (void**)&base));
     uint32_t* counts = (uint32_t*)(base + o_counts); uint32_t* offsets = (uint32_t*)(base + o_offsets);
     uint32_t* cursor = (uint32_t*)(base + o_cursor); uint32_t* heavyc = (uint32_t*)(base + o_heavyc);
     uint32_t* heavy = (uint32_t*)(base + o_heavy); uint32_t* dig = (uint32_t*)(base + o_dig);
     uint32_t* ent_pt = (uint32_t*)(base + o_pt); uint32_t* ent_key = (uint32_t*)(base + o_key);
-    G1Xyzz* partial = (G1Xyzz*)(base + o_part); G1Xyzz* buckets = (G1Xyzz*)(base + o_bk); G1Xyzz* U = (G1Xyzz*)(base + o_U);
+    G1Xyzz* partial = (G1Xyzz*)(base + o_part); G1Xyzz* buckets = (G1Xyzz*)(base + o_bk); G1Xyzz* U = (G1Xyzz*)(base + o_U); G1Xyzz* redp = (G1Xyzz*)(base + o_redp);
     cudaStream_t st = ctx->stream;
     ZKC_CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, nbt * 4, st));
     ZKC_CUDA_TRY(ctx, cudaMemsetAsync(heavyc, 0, 4, st));
@@ -258,8 +253,8 @@ int msm_run(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, 
       k_msm_digits<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(scalars + (uint64_t)c0 * n, dig, counts, g);
       ZKC_LAUNCH_CHECK(ctx); }
     { ProfScope _p(ctx, "msm.scan");
-      k_msm_scan<<<1, 1024, 0, st>>>(counts, offsets, cursor, nbt);
-      ZKC_LAUNCH_CHECK(ctx); }
+      ZKC_TRY(u32_scan(ctx, counts, offsets, nbt, offsets + nbt));
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(cursor, offsets, nbt * 4, cudaMemcpyDeviceToDevice, st)); }
     { ProfScope _p(ctx, "msm.scatter");
       k_msm_scatter<<<(unsigned)((em + 255) / 256), 256, 0, st>>>(dig, cursor, ent_pt, ent_key, g);
       ZKC_LAUNCH_CHECK(ctx); }
@@ -274,10 +269,15 @@ int msm_run(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, 
       k_msm_gather_heavy<<<ctx->sm_count * 2, 256, 256 * sizeof(G1Xyzz), st>>>(offsets, partial, buckets, heavy, heavyc, g);
       ZKC_LAUNCH_CHECK(ctx); }
     if ((uint64_t)nc * g.sets > 65535) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: too many bucket sets in one batch");
-    dim3 rg(g.c, nc * g.sets);
-    { ProfScope _p(ctx, "msm.reduce");
-      k_msm_reduce<<<rg, 256, 256 * sizeof(G1Xyzz), st>>>(buckets, U, g);
-      ZKC_LAUNCH_CHECK(ctx); }
+    {
+      ProfScope _p(ctx, "msm.reduce");
+      const uint32_t nchunks = (g.NB + RED_CHUNK - 1) / RED_CHUNK;
+      dim3 g1(g.c, nchunks, nc * g.sets), g2(g.c, nc * g.sets);
+      k_msm_reduce1<<<g1, 256, 256 * sizeof(G1Xyzz), st>>>(buckets, redp, g, nchunks);
+      ZKC_LAUNCH_CHECK(ctx);
+      k_msm_reduce2<<<g2, 32, 32 * sizeof(G1Xyzz), st>>>(redp, U, g, nchunks);
+      ZKC_LAUNCH_CHECK(ctx);
+    }
     const size_t ubytes = (size_t)nc * g.sets * g.c * sizeof(G1Xyzz);
     void* hU;
     ZKC_TRY(pinned_reserve(ctx, ubytes + 16, &hU));

@@ -2,7 +2,7 @@
 //
 // What each replaces in halo2_proofs 0.2.0 @4b42325 (un-vendored; /root/reference/Cargo.lock:1320-1336):
 //   fr_scan(MUL)        the serial running products of permutation::prover / lookup::prover (a8, a9)
-//   fr_kate_division    arithmetic::kate_division (serial synthetic division) as powers + suffix add-scan (a11)
+//   fr_kate_division    arithmetic::kate_division (serial synthetic division) as a blocked linear-recurrence scan (a11)
 //   fr_eval_batch       arithmetic::eval_polynomial (serial Horner), one CTA tree per (poly, point) (a11)
 //   fr_lincomb          the `poly * scalar + poly` folds of ProverSHPLONK / ProverGWC (a12)
 //   eval_program        plonk::evaluation::GraphEvaluator over Lagrange rows / the extended coset (a7, a9)
@@ -224,30 +224,68 @@ int fr_mul_add(zkc_ctx* ctx, Fr* a, const Fr* b, uint64_t n, const Fr& s) {
   return ZKC_OK;
 }
 
-// ---- kate division: q_j = z^-(j+1) * sum_{i>j} a_i z^i -----------------------------------------------------
-__global__ void k_mul_vec(const Fr* a, const Fr* b, Fr* out, uint64_t n) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) fe_store(out + i, fe_mul(fe_load(a + i), fe_load(b + i)));
+// ---- kate division: q_j = sum_{i>j} a_i z^(i-j-1), blocked synthetic division -----------------------------
+// phase 1: per 16-coefficient chunk P_c = sum_e a[c0+e] z^e; phase 2 (one CTA): carry_c = value of all
+// higher chunks at z (a linear recurrence with constant multiplier Z = z^16, solved by a Hillis-Steele
+// scan over Z^(per*2^s)); phase 3: q_{i-1} = a_i + z q_i inside each chunk starting from its carry.
+#define KD_CH 16
+__global__ void k_kd_chunk(const Fr* a, Fr* P, uint64_t n, Fr z) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t lo = t * KD_CH;
+  if (lo >= n) return;
+  const uint64_t hi = lo + KD_CH < n ? lo + KD_CH : n;
+  Fr acc = fe_zero<FrP>();
+  for (uint64_t i = hi; i-- > lo;) acc = fe_add(fe_mul(acc, z), fe_load(a + i));
+  fe_store(P + t, acc);
 }
-__global__ void k_shift_down(const Fr* a, Fr* q, uint64_t n) {  // z == 0: q_j = a_{j+1}
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) fe_store(q + i, i + 1 < n ? fe_load(a + i + 1) : fe_zero<FrP>());
+__global__ void __launch_bounds__(1024) k_kd_carry(Fr* P, uint64_t nchunks, Fr Z) {
+  extern __shared__ uint4 smraw[];
+  Fr* sm = reinterpret_cast<Fr*>(smraw);
+  const uint32_t t = threadIdx.x;
+  const uint64_t per = (nchunks + 1023) / 1024;
+  const uint64_t lo = (uint64_t)t * per, hi = lo + per < nchunks ? lo + per : nchunks;
+  Fr L = fe_zero<FrP>();                      // sum_{c in [lo,hi)} Z^(c-lo) P_c
+  for (uint64_t c = hi; c-- > lo && hi > lo;) L = fe_add(fe_mul(L, Z), fe_load(P + c));
+  fe_store(sm + t, L);
+  __syncthreads();
+  Fr M = fe_pow_u64(Z, per);                  // multiplier between neighbouring threads
+  for (uint32_t d = 1; d < 1024; d <<= 1) {
+    Fr v = fe_zero<FrP>();
+    const bool act = t + d < 1024;
+    if (act) v = fe_load(sm + t + d);
+    __syncthreads();
+    if (act) fe_store(sm + t, fe_add(fe_load(sm + t), fe_mul(M, v)));
+    M = fe_sqr(M);
+    __syncthreads();
+  }
+  Fr carry = t + 1 < 1024 ? fe_load(sm + t + 1) : fe_zero<FrP>();   // value of everything above this thread's range
+  for (uint64_t c = hi; c-- > lo && hi > lo;) {
+    const Fr pc = fe_load(P + c);
+    fe_store(P + c, carry);
+    carry = fe_add(pc, fe_mul(Z, carry));
+  }
+}
+__global__ void k_kd_apply(const Fr* a, Fr* q, const Fr* carry, uint64_t n, Fr z) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t lo = t * KD_CH;
+  if (lo >= n) return;
+  const uint64_t hi = lo + KD_CH < n ? lo + KD_CH : n;
+  Fr r = fe_load(carry + t);
+  for (uint64_t i = hi; i-- > lo;) {
+    const Fr ai = fe_load(a + i);
+    fe_store(q + i, r);
+    r = fe_add(ai, fe_mul(z, r));
+  }
 }
 int fr_kate_division(zkc_ctx* ctx, const Fr* a, Fr* q, uint64_t n, const Fr& z, Fr* tmp1, Fr* tmp2) {
+  (void)tmp2;
   if (n == 0) return ZKC_OK;
   ProfScope _p(ctx, "kate_division");
-  const unsigned grid = (unsigned)((n + 255) / 256);
-  if (fe_is_zero(z)) {
-    k_shift_down<<<grid, 256, 0, ctx->stream>>>(a, tmp1, n); ZKC_LAUNCH_CHECK(ctx);
-    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(q, tmp1, n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
-    return ZKC_OK;
-  }
-  const Fr zinv = fe_inv(z);
-  ZKC_TRY(fr_powers(ctx, tmp1, n, z, fe_one<FrP>()));                       // z^i
-  k_mul_vec<<<grid, 256, 0, ctx->stream>>>(a, tmp1, tmp2, n); ZKC_LAUNCH_CHECK(ctx);   // a_i z^i
-  ZKC_TRY(fr_scan(ctx, tmp2, tmp2, n, SCAN_ADD, 1, fe_zero<FrP>()));        // suffix sums, exclusive
-  ZKC_TRY(fr_powers(ctx, tmp1, n, zinv, zinv));                             // z^-(j+1)
-  k_mul_vec<<<grid, 256, 0, ctx->stream>>>(tmp2, tmp1, q, n); ZKC_LAUNCH_CHECK(ctx);
+  const uint64_t nchunks = (n + KD_CH - 1) / KD_CH;   // tmp1 (n elements) holds the nchunks partials
+  const unsigned grid = (unsigned)((nchunks + 127) / 128);
+  k_kd_chunk<<<grid, 128, 0, ctx->stream>>>(a, tmp1, n, z); ZKC_LAUNCH_CHECK(ctx);
+  k_kd_carry<<<1, 1024, 1024 * sizeof(Fr), ctx->stream>>>(tmp1, nchunks, fe_pow_u64(z, KD_CH)); ZKC_LAUNCH_CHECK(ctx);
+  k_kd_apply<<<grid, 128, 0, ctx->stream>>>(a, q, tmp1, n, z); ZKC_LAUNCH_CHECK(ctx);
   return ZKC_OK;
 }
 
