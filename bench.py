@@ -35,6 +35,8 @@ WORKLOADS = {
     "rsa_k17": dict(k=17, gate_cols=3, desc="RSA-2048 PKCS#1 verify shape: k=17, 3 gate advice + 1 lookup advice, 1 lookup, 6 permutation columns"),
     "rsa_k15": dict(k=15, gate_cols=12, desc="RSA-2048 wide-column shape: k=15, 12 gate advice + 1 lookup advice"),
     "rsa_k13": dict(k=13, gate_cols=3, desc="reduced smoke shape k=13"),
+    "sha_k19": dict(k=19, gate_cols=112, shape="sha_bit", desc="zkEVM SHA256-bit shape: k=19, 112 bit advice + 3 word advice columns, 187 gates, no lookup"),
+    "sha_k15": dict(k=15, gate_cols=112, shape="sha_bit", desc="SHA256-bit shape reduced to k=15"),
 }
 SAMPLE_K = 15            # bounded CPU sample
 IMAD_WIDE_PEAK = None    # filled from profiles/r01_ffbench.json
@@ -99,13 +101,13 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def cpu_oracle_seconds(sample_k, gate_cols, steps=1, warmup=0, seed=1):
+def cpu_oracle_seconds(sample_k, gate_cols, steps=1, warmup=0, seed=1, shape="base"):
     """times the restated CPU oracle prover on the bounded sample; returns (seconds per proof, cores)"""
     import __graft_entry__ as graft
     pkg = graft.load_package()
     from oracle import orc, plonk
     from tests import pyref
-    circ = pkg.synth.make_base_circuit(sample_k, gate_cols, seed=seed)
+    circ = pkg.synth.make_sha_bit_circuit(sample_k, gate_cols, seed=seed) if shape == "sha_bit" else pkg.synth.make_base_circuit(sample_k, gate_cols, seed=seed)
     cs = circ.cs
     g, gl = orc.srs_setup(sample_k, orc.fr_from_ints([pyref.ChaChaRng(bytes(32), 20).fr_random()]))
     mapping = pkg.synth.build_permutation_mapping(cs, circ.copies)
@@ -132,7 +134,9 @@ def run_reference(args, wl):
         return 0
     k = wl["k"]
     sk = min(SAMPLE_K, k)
-    sec, cores = cpu_oracle_seconds(sk, wl["gate_cols"], steps=args.steps, warmup=min(args.warmup, 1))
+    if wl.get("shape") == "sha_bit":
+        sk = min(12, k)
+    sec, cores = cpu_oracle_seconds(sk, wl["gate_cols"], steps=args.steps, warmup=min(args.warmup, 1), shape=wl.get("shape", "base"))
     value = sec * scale_to(sk, k)
     sample = "restated CPU oracle (oracle/plonk.py + libzkc_oracle.so, not halo2-axiom) create_proof at k=%d, same column shape; " \
              "%.3f s measured, scaled by n*log2(n) to k=%d" % (sk, sec, k)
@@ -177,7 +181,7 @@ def main():
     K = args.steps
 
     # untimed setup: gen_srs + gen_pk + witness (each rank proves its own certificate: different seed)
-    w = pkg.workload.build(ctx, wl["k"], wl["gate_cols"], seed=100 + rank)
+    w = pkg.workload.build(ctx, wl["k"], wl["gate_cols"], seed=100 + rank, shape=wl.get("shape", "base"))
     seeds = [pkg.seed_from_u64(1000 * rank + i) for i in range(W + K)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -264,8 +268,8 @@ def main():
                 "msm_points_per_s": prof.get("count:msm.points", {"n": 0})["n"] / (sum(prof.get(kx, {"ms": 0.0})["ms"] for kx in prof if kx.startswith("msm.")) * 1e-3 or 1),
                 "wall_s_timed_region": t_wall}
         if not args.no_cpu_baseline and world == 1:
-            sk = min(SAMPLE_K, wl["k"])
-            sec, cores = cpu_oracle_seconds(sk, wl["gate_cols"])
+            sk = min(12 if wl.get("shape") == "sha_bit" else SAMPLE_K, wl["k"])
+            sec, cores = cpu_oracle_seconds(sk, wl["gate_cols"], shape=wl.get("shape", "base"))
             line["cpu_baseline"] = {"value": sec * scale_to(sk, wl["k"]), "unit": "s", "cores": cores, "kind": "port",
                                     "sample": "restated CPU oracle create_proof at k=%d (same column shape), %.3f s measured, scaled by n*log2(n) to k=%d; "
                                               "published halo2-axiom figures for this shape: 3.144 s (M1) / 1.813 s (c6a.48xlarge), README.md:48" % (sk, sec, wl["k"])}

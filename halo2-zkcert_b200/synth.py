@@ -180,3 +180,123 @@ def ints_to_limbs(vals):
     """canonical ints -> (len, 4) uint64 little-endian limbs"""
     b = b"".join(int(v).to_bytes(32, "little") for v in vals)
     return np.frombuffer(b, dtype=np.uint64).reshape(-1, 4).copy()
+
+
+# ---- zkEVM-SHA256 "bit" circuit shape (BASELINE config 3) ---------------------------------------------
+def sha_bit_constraint_system(k, num_bit_cols=112, num_word_cols=3, n_xor=None, n_maj=8):
+    """~110 bit-valued advice columns constrained by many small gates, no lookups
+    (/root/reference/src/sha256_bit_circuit.rs:52-54: Sha256CircuitConfig + one instance column;
+    SURVEY §8 config 3).  Gates (all gated by one fixed selector q):
+      booleanity  q * b * (1 - b)                       for every bit column
+      xor         q * (a + b - 2ab - c(next row))       source columns -> derived column, rotation 1
+      maj         q * (d - (ab + ac + bc - 2abc))       degree 4
+      word        q * (w - sum_i 2^i b_i)               16 bits -> one word column
+    """
+    NB, NW = num_bit_cols, num_word_cols
+    nS = NB // 2
+    nD = NB - nS
+    n_xor = nD - n_maj if n_xor is None else n_xor
+    assert NB >= 16 * NW and n_xor + n_maj <= nD
+    advice_queries = [(c, 0) for c in range(NB + NW)]
+    rot1 = {}
+    for j in range(n_xor):
+        rot1[nS + j] = len(advice_queries)
+        advice_queries.append((nS + j, 1))
+    fixed_queries = [(0, 0), (1, 0)]         # q, constants
+    instance_queries = [(0, 0)]
+    q = ("fixed", 0)
+    one = ("const", 1)
+    A = lambda c: ("advice", c)
+    mul = lambda x, y: ("product", x, y)
+    add = lambda x, y: ("sum", x, y)
+    neg = lambda x: ("neg", x)
+    polys = []
+    for c in range(NB):
+        polys.append(mul(q, mul(A(c), add(one, neg(A(c))))))
+    for j in range(n_xor):
+        a, b = A((3 * j) % nS), A((3 * j + 1) % nS)
+        cn = ("advice", rot1[nS + j])
+        polys.append(mul(q, add(add(add(a, b), neg(("scaled", mul(a, b), 2))), neg(cn))))
+    for j in range(n_maj):
+        a, b, c = A((5 * j) % nS), A((5 * j + 2) % nS), A((5 * j + 4) % nS)
+        d = A(nS + n_xor + j)
+        ab, ac, bc = mul(a, b), mul(a, c), mul(b, c)
+        polys.append(mul(q, add(d, neg(add(add(add(ab, ac), bc), neg(("scaled", mul(ab, c), 2)))))))
+    for m in range(NW):
+        acc = None
+        for i in range(16):
+            term = ("scaled", A(16 * m + i), 1 << i)
+            acc = term if acc is None else add(acc, term)
+        polys.append(mul(q, add(A(NB + m), neg(acc))))
+    gates = [[p] for p in polys]
+    permutation = [(ANY_INSTANCE, 0)] + [(ANY_ADVICE, NB + m) for m in range(min(NW, 2))] + [(ANY_FIXED, 1)]
+    cs = ConstraintSystem(k, NB + NW, 2, 1, advice_queries, fixed_queries, instance_queries, gates, [], permutation)
+    cs.sha_layout = dict(NB=NB, NW=NW, nS=nS, n_xor=n_xor, n_maj=n_maj)
+    return cs
+
+
+class LimbCircuit(SynthCircuit):
+    """SynthCircuit whose columns are numpy canonical-limb arrays (n, 4) uint64 — for wide / tall shapes
+    where Python-int lists would be too slow.  `.advice` / `.fixed` materialise int lists on demand."""
+
+    def __init__(self, cs, fixed_limbs, copies, advice_limbs, instances, name):
+        self.cs, self.fixed_limbs, self.copies, self.advice_limbs, self.instances, self.name = cs, fixed_limbs, copies, advice_limbs, instances, name
+
+    @staticmethod
+    def _ints(limbs):
+        return [int(r[0]) | (int(r[1]) << 64) | (int(r[2]) << 128) | (int(r[3]) << 192) for r in limbs]
+
+    @property
+    def advice(self):
+        return [self._ints(c) for c in self.advice_limbs]
+
+    @property
+    def fixed(self):
+        return [self._ints(c) for c in self.fixed_limbs]
+
+
+def make_sha_bit_circuit(k, num_bit_cols=112, num_word_cols=3, blocks=16, seed=0, name=None):
+    """Witness for the SHA256-bit shape: `blocks` SHA blocks x 72 rows active (a 970-byte TBS like
+    certs/example_cert_3.pem hashes in 16 blocks), zeros elsewhere."""
+    cs = sha_bit_constraint_system(k, num_bit_cols, num_word_cols)
+    lay = cs.sha_layout
+    NB, NW, nS, n_xor, n_maj = lay["NB"], lay["NW"], lay["nS"], lay["n_xor"], lay["n_maj"]
+    n = 1 << k
+    U = cs.usable_rows()
+    R = min(72 * blocks, U - 2)                 # active rows 0..R-1 (the xor gate reads row r+1)
+    rng = np.random.default_rng(seed)
+    bits = np.zeros((NB, n), dtype=np.uint64)
+    bits[:nS, :R] = rng.integers(0, 2, size=(nS, R), dtype=np.uint64)
+    bits[nS + n_xor + n_maj:, :R] = rng.integers(0, 2, size=(NB - nS - n_xor - n_maj, R), dtype=np.uint64)
+    for j in range(n_xor):
+        a, b = bits[(3 * j) % nS], bits[(3 * j + 1) % nS]
+        bits[nS + j, 1:R + 1] = (a ^ b)[:R]
+    for j in range(n_maj):
+        a, b, c = bits[(5 * j) % nS], bits[(5 * j + 2) % nS], bits[(5 * j + 4) % nS]
+        bits[nS + n_xor + j, :R] = ((a & b) | (a & c) | (b & c))[:R]
+    words = np.zeros((NW, n), dtype=np.uint64)
+    for m in range(NW):
+        for i in range(16):
+            words[m] += bits[16 * m + i] << np.uint64(i)
+    def limbs(col):
+        out = np.zeros((n, 4), dtype=np.uint64)
+        out[:, 0] = col
+        return out
+    advice_limbs = [limbs(bits[c]) for c in range(NB)] + [limbs(words[m]) for m in range(NW)]
+    q = np.zeros(n, dtype=np.uint64)
+    q[:R] = 1
+    consts = np.zeros(n, dtype=np.uint64)
+    consts[:16] = np.arange(16, dtype=np.uint64)
+    fixed_limbs = [limbs(q), limbs(consts)]
+    # instances = two word cells (helpers.rs:255-258 exposes the digest as two field elements)
+    rows = [5 % R, 7 % R]
+    instances = [[int(words[0][rows[0]]), int(words[min(1, NW - 1)][rows[1]])]]
+    copies = [(0, 0, 1, rows[0])]
+    if NW >= 2:
+        copies.append((0, 1, 2, rows[1]))
+    else:
+        instances = [[instances[0][0]]]
+    # constants column cell 3 == a word cell forced to 3? keep it simple: tie constants[0] (=0) to an inactive word cell
+    pconst = len(cs.permutation) - 1
+    copies.append((pconst, 0, 1, U - 1))        # word column row U-1 is 0 (inactive)
+    return LimbCircuit(cs, fixed_limbs, copies, advice_limbs, instances, name or "sha_bit_k%d_b%d" % (k, NB))

@@ -22,6 +22,15 @@ def to_mont_dev(ctx, ints):
     return out
 
 
+def limbs_to_mont_dev(ctx, limbs):
+    """canonical (len, 4) uint64 limbs -> torch CUDA Montgomery limbs"""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(limbs).view(np.int64)).cuda(ctx.device)
+    out = torch.empty_like(t)
+    ctx.field_vec_op_dev("fr", "from_canonical", t, None, out)
+    return out
+
+
 def to_host(t):
     return t.cpu().numpy().view(np.uint64)
 
@@ -30,11 +39,13 @@ class Workload:
     pass
 
 
-def build(ctx, k, num_gate_cols, seed=0, circ=None, params=None):
+def build(ctx, k, num_gate_cols, seed=0, circ=None, params=None, shape="base"):
     import torch
     w = Workload()
     w.ctx = ctx
-    w.circ = circ or synth.make_base_circuit(k, num_gate_cols, seed=seed)
+    if circ is None:
+        circ = synth.make_sha_bit_circuit(k, num_gate_cols, seed=seed) if shape == "sha_bit" else synth.make_base_circuit(k, num_gate_cols, seed=seed)
+    w.circ = circ
     cs = w.circ.cs
     n = cs.n
     if params is None:
@@ -42,8 +53,12 @@ def build(ctx, k, num_gate_cols, seed=0, circ=None, params=None):
         params = api.ParamsKZG.setup(k, s, ctx=ctx)
     w.params = params
     flat = lambda cols: [v for c in cols for v in c]
-    fixed = to_mont_dev(ctx, flat(w.circ.fixed))
-    w.advice_dev = to_mont_dev(ctx, flat(w.circ.advice))
+    if hasattr(w.circ, "advice_limbs"):
+        fixed = limbs_to_mont_dev(ctx, np.concatenate(w.circ.fixed_limbs))
+        w.advice_dev = limbs_to_mont_dev(ctx, np.concatenate(w.circ.advice_limbs))
+    else:
+        fixed = to_mont_dev(ctx, flat(w.circ.fixed))
+        w.advice_dev = to_mont_dev(ctx, flat(w.circ.advice))
     w.instances = [to_host(to_mont_dev(ctx, c)) if len(c) else np.zeros((0, 4), dtype=np.uint64) for c in w.circ.instances]
     # sigma_col[row] = DELTA^col' * omega^row' gathered through the permutation mapping
     m = len(cs.permutation)

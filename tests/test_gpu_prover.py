@@ -100,3 +100,44 @@ def test_device_resident_advice_and_errors(circuit_k6):
     with pytest.raises(pkg().ZkcError) as e:
         pkg().create_proof(gpk, np.concatenate(advice), [orc.fr_from_ints([1] * 64)], seed)
     assert e.value.code == 10
+
+
+def test_sha_bit_shape_matches_oracle():
+    """BASELINE config-3 shape (many bit columns, ~75 small gates up to degree 4, rotation-1 queries, no
+    lookup) at a size the oracle finishes in seconds."""
+    circ = pkg().synth.make_sha_bit_circuit(9, 48, 3, blocks=4, seed=2)
+    opk, advice = oracle_setup(circ)
+    params, gpk = gpu_setup(circ, opk)
+    assert (gpk.degree, gpk.blinding_factors, gpk.num_sets, gpk.num_lookups) == (4, 5, 2, 0)
+    s = pyref.seed_from_u64(21)
+    for multiopen in ("shplonk", "gwc"):
+        want = plonk.create_proof(opk, advice, circ.instances, pyref.ChaChaRng(s, 20), multiopen=multiopen)
+        inst = [orc.fr_from_ints(c) for c in circ.instances]
+        got = pkg().create_proof(gpk, np.concatenate(advice), inst, s, multiopen=multiopen)
+        assert got == want
+        assert verifier.verify_proof(vk_of(opk), pyref.G1_GEN, circ.instances, got, verifier.trapdoor_check(SRS_SECRET), multiopen=multiopen)
+
+
+def test_wide_column_shape_matches_oracle():
+    """BASELINE config-2 shape (12 gate columns + lookup: 15 permutation columns, 8 sets) at k=9."""
+    circ = pkg().synth.make_base_circuit(9, 12, seed=8)
+    opk, advice = oracle_setup(circ)
+    params, gpk = gpu_setup(circ, opk)
+    assert gpk.num_sets == 8
+    s = pyref.seed_from_u64(22)
+    want = plonk.create_proof(opk, advice, circ.instances, pyref.ChaChaRng(s, 20))
+    got = pkg().create_proof(gpk, np.concatenate(advice), [orc.fr_from_ints(c) for c in circ.instances], s)
+    assert got == want
+
+
+def test_workload_builder_device_keygen_matches_oracle():
+    """workload.build derives Montgomery columns, the sigma table and the SRS on the device; its proof must
+    equal the oracle's built from the same synthetic circuit with host arithmetic."""
+    ctx = gpu_ctx()
+    w = pkg().workload.build(ctx, 8, 2, seed=3)
+    opk, advice = oracle_setup(w.circ)
+    f, sg = w.pk.commitments()
+    assert orc.g1_to_ints(f) == opk.fixed_commitments and orc.g1_to_ints(sg) == opk.sigma_commitments
+    s = pyref.seed_from_u64(5)
+    assert pkg().create_proof(w.pk, w.advice_dev, w.instances, s) == plonk.create_proof(opk, advice, w.circ.instances, pyref.ChaChaRng(s, 20))
+    assert pkg().create_proof(w.pk, w.advice_host, w.instances, s) == pkg().create_proof(w.pk, w.advice_dev, w.instances, s)
