@@ -36,6 +36,8 @@ WORKLOADS = {
     "rsa_k15": dict(k=15, gate_cols=12, desc="RSA-2048 wide-column shape: k=15, 12 gate advice + 1 lookup advice"),
     "rsa_k13": dict(k=13, gate_cols=3, desc="reduced smoke shape k=13"),
     "sha_k19": dict(k=19, gate_cols=112, shape="sha_bit", desc="zkEVM SHA256-bit shape: k=19, 112 bit advice + 3 word advice columns, 187 gates, no lookup"),
+    "agg_k22": dict(k=22, gate_cols=17, shape="base_fast", desc="X509 aggregation shape: BaseConfig k=22, 17 gate advice + 1 lookup advice (lookup_bits 21), 20 permutation columns"),
+    "agg_k20": dict(k=20, gate_cols=17, shape="base_fast", desc="aggregation shape reduced to k=20"),
     "sha_k15": dict(k=15, gate_cols=112, shape="sha_bit", desc="SHA256-bit shape reduced to k=15"),
 }
 SAMPLE_K = 15            # bounded CPU sample
@@ -107,10 +109,11 @@ def cpu_oracle_seconds(sample_k, gate_cols, steps=1, warmup=0, seed=1, shape="ba
     pkg = graft.load_package()
     from oracle import orc, plonk
     from tests import pyref
-    circ = pkg.synth.make_sha_bit_circuit(sample_k, gate_cols, seed=seed) if shape == "sha_bit" else pkg.synth.make_base_circuit(sample_k, gate_cols, seed=seed)
+    gen = {"sha_bit": pkg.synth.make_sha_bit_circuit, "base_fast": pkg.synth.make_base_circuit_fast, "base": pkg.synth.make_base_circuit}[shape]
+    circ = gen(sample_k, gate_cols, seed=seed)
     cs = circ.cs
     g, gl = orc.srs_setup(sample_k, orc.fr_from_ints([pyref.ChaChaRng(bytes(32), 20).fr_random()]))
-    mapping = pkg.synth.build_permutation_mapping(cs, circ.copies)
+    mapping = pkg.synth.build_permutation_mapping(cs, [tuple(int(v) for v in c) for c in circ.copies])
     sigma = pkg.synth.sigma_values(cs, mapping)
     mont = lambda cols: [orc.fr_from_ints(c) for c in cols]
     pk = plonk.keygen(cs, mont(circ.fixed), mont(sigma), g, gl, circ.transcript_repr())
@@ -134,7 +137,7 @@ def run_reference(args, wl):
         return 0
     k = wl["k"]
     sk = min(SAMPLE_K, k)
-    if wl.get("shape") == "sha_bit":
+    if wl.get("shape") in ("sha_bit", "base_fast"):
         sk = min(12, k)
     sec, cores = cpu_oracle_seconds(sk, wl["gate_cols"], steps=args.steps, warmup=min(args.warmup, 1), shape=wl.get("shape", "base"))
     value = sec * scale_to(sk, k)
@@ -268,7 +271,7 @@ def main():
                 "msm_points_per_s": prof.get("count:msm.points", {"n": 0})["n"] / (sum(prof.get(kx, {"ms": 0.0})["ms"] for kx in prof if kx.startswith("msm.")) * 1e-3 or 1),
                 "wall_s_timed_region": t_wall}
         if not args.no_cpu_baseline and world == 1:
-            sk = min(12 if wl.get("shape") == "sha_bit" else SAMPLE_K, wl["k"])
+            sk = min(12 if wl.get("shape") in ("sha_bit", "base_fast") else SAMPLE_K, wl["k"])
             sec, cores = cpu_oracle_seconds(sk, wl["gate_cols"], shape=wl.get("shape", "base"))
             line["cpu_baseline"] = {"value": sec * scale_to(sk, wl["k"]), "unit": "s", "cores": cores, "kind": "port",
                                     "sample": "restated CPU oracle create_proof at k=%d (same column shape), %.3f s measured, scaled by n*log2(n) to k=%d; "

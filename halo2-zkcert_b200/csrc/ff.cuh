@@ -247,19 +247,32 @@ template <class P> inline Fe<P> fe_sub(const Fe<P>& a, const Fe<P>& b) {
   if (bw) { u64 c = 0; for (int i = 0; i < 8; ++i) { c += (u64)r.v[i] + P::M(i); r.v[i] = (uint32_t)c; c >>= 32; } }
   return r;
 }
+// host product: 4 x 64-bit CIOS with 128-bit accumulators (the 8 x u32 limbs are the same bytes)
 template <class P> inline Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
-  uint32_t t[10] = {0};
-  for (int i = 0; i < 8; ++i) {
-    u64 c = 0;
-    for (int j = 0; j < 8; ++j) { c += (u64)a.v[j] * b.v[i] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
-    c += t[8]; t[8] = (uint32_t)c; t[9] = (uint32_t)(c >> 32);
-    uint32_t m = t[0] * P::INV;
-    c = ((u64)m * P::M(0) + t[0]) >> 32;
-    for (int j = 1; j < 8; ++j) { c += (u64)m * P::M(j) + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
-    c += t[8]; t[7] = (uint32_t)c; t[8] = t[9] + (uint32_t)(c >> 32); t[9] = 0;
+  typedef unsigned __int128 u128;
+  uint64_t A[4], B[4], M[4], t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) {
+    A[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+    B[i] = (uint64_t)b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32);
+    M[i] = (uint64_t)P::M(2 * i) | ((uint64_t)P::M(2 * i + 1) << 32);
   }
-  Fe<P> r; for (int i = 0; i < 8; ++i) r.v[i] = t[i];
-  if (geq_mod<P>(r.v)) sub_mod_inplace<P>(r.v);
+  // -M^-1 mod 2^64 from the 32-bit constant by one Newton step
+  const uint64_t inv32 = P::INV;
+  uint64_t ninv = (uint64_t)0 - inv32;                 // M^-1 mod 2^32 (as 64-bit)
+  ninv = ninv * (2 - M[0] * ninv);                     // now M^-1 mod 2^64
+  const uint64_t inv64 = (uint64_t)0 - ninv;
+  for (int i = 0; i < 4; ++i) {
+    u128 c = 0;
+    for (int j = 0; j < 4; ++j) { c += (u128)A[j] * B[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+    const uint64_t m = t[0] * inv64;
+    c = ((u128)m * M[0] + t[0]) >> 64;
+    for (int j = 1; j < 4; ++j) { c += (u128)m * M[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64); t[5] = 0;
+  }
+  Fe<P> r;
+  for (int i = 0; i < 4; ++i) { r.v[2 * i] = (uint32_t)t[i]; r.v[2 * i + 1] = (uint32_t)(t[i] >> 32); }
+  if (t[4] || geq_mod<P>(r.v)) sub_mod_inplace<P>(r.v);
   return r;
 }
 #endif

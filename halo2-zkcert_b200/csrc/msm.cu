@@ -195,8 +195,11 @@ int u32_scan(zkc_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, uint32
 uint32_t msm_pick_c(uint64_t n, bool precomputed) {
   uint32_t lg = 0;
   while ((1ull << (lg + 1)) <= n) ++lg;
-  int c = precomputed ? (int)lg - 2 : (int)lg - 4;
-  if (precomputed && lg >= 20) c = (int)lg - 3;
+  // measured on B200: shared-bucket (precomputed) layout wants ~4-8 partials per bucket for the
+  // gather phase: c = lg-2 up to 2^18, lg-3 at 2^19, lg-4 from 2^20; the per-window layout uses lg-4 throughout
+  int c = (int)lg - 4;
+  if (precomputed && lg <= 18) c = (int)lg - 2;
+  else if (precomputed && lg == 19) c = (int)lg - 3;
   return (uint32_t)std::max(3, std::min(20, c));
 }
 
@@ -204,8 +207,8 @@ MsmGeom msm_geom(uint64_t n, uint32_t ncols, uint32_t c, bool precomputed) {
   MsmGeom g;
   g.c = c; g.W = (255 + c - 1) / c; g.NB = 1u << (c - 1); g.sets = precomputed ? 1 : g.W; g.n = n; g.ncols = ncols;
   const uint64_t e = g.emax();
-  uint32_t T = 32;
-  while (T > 4 && e / T < 148ull * 512) T >>= 1;
+  uint32_t T = 64;   // entries per accumulate thread: as long as the grid still fills 3 CTAs x 128 threads per SM
+  while (T > 4 && e / T < 148ull * 384) T >>= 1;
   g.T = T;
   return g;
 }

@@ -300,3 +300,117 @@ def make_sha_bit_circuit(k, num_bit_cols=112, num_word_cols=3, blocks=16, seed=0
     pconst = len(cs.permutation) - 1
     copies.append((pconst, 0, 1, U - 1))        # word column row U-1 is 0 (inactive)
     return LimbCircuit(cs, fixed_limbs, copies, advice_limbs, instances, name or "sha_bit_k%d_b%d" % (k, NB))
+
+
+# ---- vectorised BaseConfig generator for tall circuits (aggregation k=22, BASELINE config 5) -----------
+def _mul_add_u64(a, b, c):
+    """(a + b*c) for uint64 arrays as three uint64 limbs (value < 2^129)"""
+    m32 = np.uint64(0xFFFFFFFF)
+    s32 = np.uint64(32)
+    b0, b1, c0, c1 = b & m32, b >> s32, c & m32, c >> s32
+    p00, p01, p10, p11 = b0 * c0, b0 * c1, b1 * c0, b1 * c1
+    mid = p01 + p10
+    carry_mid = (mid < p01).astype(np.uint64)
+    lo = p00 + (mid << s32)
+    carry_lo = (lo < p00).astype(np.uint64)
+    hi = p11 + (mid >> s32) + (carry_mid << s32) + carry_lo
+    lo2 = lo + a
+    c2 = (lo2 < lo).astype(np.uint64)
+    hi2 = hi + c2
+    top = (hi2 < hi).astype(np.uint64)
+    return lo2, hi2, top
+
+
+def _cells_u64(rng, shape):
+    """50 % bits, 25 % bytes, 25 % 64-bit limbs (halo2-ecc style non-native limbs are range-checked words)"""
+    kind = rng.integers(0, 4, size=shape, dtype=np.uint8)
+    v = rng.integers(0, 1 << 63, size=shape, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=shape, dtype=np.uint64)
+    v = np.where(kind < 2, v & np.uint64(1), np.where(kind == 2, v & np.uint64(0xFF), v))
+    return v
+
+
+def make_base_circuit_fast(k, num_gate_cols, seed=0, fill=0.9, copy_frac=0.25, n_instances=32, name=None):
+    """Same shape and constraint semantics as make_base_circuit, generated with numpy (no uniform-Fr cells)."""
+    cs = base_constraint_system(k, num_gate_cols)
+    A, n = num_gate_cols, 1 << k
+    U = cs.usable_rows()
+    lookup_bits = k - 1
+    rng = np.random.default_rng(seed)
+    ngates = U // 4
+    advice_limbs = [np.zeros((n, 4), dtype=np.uint64) for _ in range(A + 1)]
+    fixed_limbs = [np.zeros((n, 4), dtype=np.uint64) for _ in range(A + 2)]
+    active = rng.random((A, ngates)) < fill
+    for i in range(A):
+        cells = _cells_u64(rng, (ngates, 4))
+        lo, hi, top = _mul_add_u64(cells[:, 0], cells[:, 1], cells[:, 2])
+        act = active[i]
+        col = advice_limbs[i]
+        rows = np.arange(ngates) * 4
+        for r in range(3):
+            col[rows + r, 0] = cells[:, r]
+        col[rows + 3, 0] = np.where(act, lo, cells[:, 3])
+        col[rows + 3, 1] = np.where(act, hi, 0)
+        col[rows + 3, 2] = np.where(act, top, 0)
+        fixed_limbs[i][rows, 0] = act.astype(np.uint64)
+    look = advice_limbs[A]
+    look[:U, 0] = rng.integers(0, 1 << lookup_bits, size=U, dtype=np.uint64)
+    tl = min(U, 1 << lookup_bits)
+    fixed_limbs[A + 1][:tl, 0] = np.arange(tl, dtype=np.uint64)
+    n_const = min(64, U)
+    fixed_limbs[A][:n_const, 0] = np.where(np.arange(n_const) < 32, np.arange(n_const), rng.integers(0, 1 << 62, size=n_const)).astype(np.uint64)
+    inst = rng.integers(0, 256, size=n_instances, dtype=np.uint64)
+    instances = [[int(v) for v in inst]]
+    # destinations: cells of inactive gates; sources: constants / instances / lookup cells / cells of ACTIVE gates
+    fcol, fgate = np.nonzero(~active)
+    order = rng.permutation(len(fcol) * 4)
+    want = min(len(order), int(copy_frac * n))
+    sel = order[:want]
+    dcol, drow = fcol[sel // 4], fgate[sel // 4] * 4 + (sel % 4)
+    kind = np.arange(want) % 8
+    P_LOOK, P_CONST, P_INST = A, A + 1, A + 2
+    scol = np.empty(want, dtype=np.int64)
+    srow = np.empty(want, dtype=np.int64)
+    acol, agate = np.nonzero(active)
+    pick = rng.integers(0, len(acol), size=want)
+    scol[:], srow[:] = acol[pick], agate[pick] * 4 + rng.integers(0, 4, size=want)
+    m = kind == 0
+    scol[m], srow[m] = P_CONST, rng.integers(0, n_const, size=int(m.sum()))
+    m = (kind == 1) & (np.arange(want) // 8 < n_instances)
+    scol[m], srow[m] = P_INST, (np.arange(want) // 8)[m]
+    m = (kind == 2) | (kind == 3)
+    scol[m], srow[m] = P_LOOK, rng.integers(0, U, size=int(m.sum()))
+    inst_limbs = np.zeros((n_instances, 4), dtype=np.uint64)
+    inst_limbs[:, 0] = inst
+    sources = {**{i: advice_limbs[i] for i in range(A + 1)}, P_CONST: fixed_limbs[A], P_INST: inst_limbs}
+    for sc in np.unique(scol):
+        m = scol == sc
+        vals = sources[int(sc)][srow[m]]
+        for dc in np.unique(dcol[m]):
+            mm = m & (dcol == dc)
+            advice_limbs[int(dc)][drow[mm]] = sources[int(sc)][srow[mm]]
+        del vals
+    copies = np.stack([scol, srow, dcol.astype(np.int64), drow.astype(np.int64)], axis=1)
+    return LimbCircuit(cs, fixed_limbs, copies.tolist() if want < (1 << 16) else copies, advice_limbs, instances,
+                       name or "base_fast_k%d_a%d" % (k, A))
+
+
+def build_permutation_mapping_fast(cs, copies):
+    """Mapping for copy lists where every destination (columns 2,3) is a fresh singleton cell merged into its
+    source's cycle — the structure make_base_circuit_fast emits.  Equivalent to build_permutation_mapping:
+    merging a singleton `right` into the cycle of `left` swaps mapping[left] and mapping[right]."""
+    n, m = cs.n, len(cs.permutation)
+    mp = np.arange(m * n, dtype=np.int64)
+    copies = np.asarray(copies, dtype=np.int64)
+    left = copies[:, 0] * n + copies[:, 1]
+    right = copies[:, 2] * n + copies[:, 3]
+    # sequential semantics: process in order; group by `left` so repeated sources chain correctly
+    order = np.argsort(left, kind="stable")
+    left, right = left[order], right[order]
+    # for a run of copies sharing the same left cell L with rights r1..rt (in order), the swaps give:
+    #   mp[L] = rt, mp[rt] = r(t-1), ..., mp[r1] = old mp[L] = L
+    start = np.r_[True, left[1:] != left[:-1]]
+    end = np.r_[start[1:], True]
+    prev = np.r_[0, right[:-1]]
+    mp[right] = np.where(start, left, prev)
+    mp[left[end]] = right[end]
+    return mp

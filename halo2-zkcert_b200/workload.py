@@ -44,7 +44,8 @@ def build(ctx, k, num_gate_cols, seed=0, circ=None, params=None, shape="base"):
     w = Workload()
     w.ctx = ctx
     if circ is None:
-        circ = synth.make_sha_bit_circuit(k, num_gate_cols, seed=seed) if shape == "sha_bit" else synth.make_base_circuit(k, num_gate_cols, seed=seed)
+        gen = {"sha_bit": synth.make_sha_bit_circuit, "base_fast": synth.make_base_circuit_fast, "base": synth.make_base_circuit}[shape]
+        circ = gen(k, num_gate_cols, seed=seed)
     w.circ = circ
     cs = w.circ.cs
     n = cs.n
@@ -62,7 +63,10 @@ def build(ctx, k, num_gate_cols, seed=0, circ=None, params=None, shape="base"):
     w.instances = [to_host(to_mont_dev(ctx, c)) if len(c) else np.zeros((0, 4), dtype=np.uint64) for c in w.circ.instances]
     # sigma_col[row] = DELTA^col' * omega^row' gathered through the permutation mapping
     m = len(cs.permutation)
-    mapping = synth.build_permutation_mapping(cs, w.circ.copies)
+    if isinstance(w.circ.copies, np.ndarray):
+        mapping = synth.build_permutation_mapping_fast(cs, w.circ.copies)
+    else:
+        mapping = synth.build_permutation_mapping(cs, w.circ.copies)
     dom = api.EvaluationDomain(cs.degree(), k, ctx=ctx)
     table = torch.empty((m * n, 4), dtype=torch.int64, device="cuda:%d" % ctx.device)
     dpow = to_host(to_mont_dev(ctx, [pow(synth.DELTA, c, R_MOD) for c in range(m)]))
