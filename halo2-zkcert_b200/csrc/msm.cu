@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "ec.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace zkc {
 
@@ -87,28 +88,51 @@ __global__ void __launch_bounds__(128) k_msm_accum(const G1Affine* bases, const 
   const uint64_t p1 = p0 + g.T < E ? p0 + g.T : E;
   G1Xyzz acc = xyzz_identity();
   uint32_t cur = ent_key[p0];
+  // software pipeline: the next entry's base point is requested before the current mixed add is issued
+  uint32_t e = ent_pt[p0];
+  G1Affine q = affine_load_nc(bases + (e & 0x7fffffffu));
   for (uint64_t p = p0; p < p1; ++p) {
     const uint32_t k = ent_key[p];
+    const uint32_t e_cur = e;
+    const G1Affine q_cur = q;
+    if (p + 1 < p1) { e = ent_pt[p + 1]; q = affine_load_nc(bases + (e & 0x7fffffffu)); }
     if (k != cur) { xyzz_store(partial + cur + t, acc); acc = xyzz_identity(); cur = k; }
-    const uint32_t e = ent_pt[p];
-    const G1Affine q = affine_load_nc(bases + (e & 0x7fffffffu));
-    if (!affine_is_identity(q)) xyzz_madd(acc, q, (e >> 31) != 0);
+    if (!affine_is_identity(q_cur)) xyzz_madd(acc, q_cur, (e_cur >> 31) != 0);
   }
   xyzz_store(partial + cur + t, acc);
 }
 
-#define MSM_HEAVY 12
+#define MSM_HEAVY_PER_LANE 12
+__device__ __forceinline__ G1Xyzz xyzz_shfl_xor(const G1Xyzz& p, int mask) {
+  G1Xyzz r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    r.x.v[i] = __shfl_xor_sync(0xffffffffu, p.x.v[i], mask);
+    r.y.v[i] = __shfl_xor_sync(0xffffffffu, p.y.v[i], mask);
+    r.zz.v[i] = __shfl_xor_sync(0xffffffffu, p.zz.v[i], mask);
+    r.zzz.v[i] = __shfl_xor_sync(0xffffffffu, p.zzz.v[i], mask);
+  }
+  return r;
+}
 __global__ void __launch_bounds__(128) k_msm_gather(const uint32_t* offsets, const G1Xyzz* partial, G1Xyzz* buckets,
-                                                    uint32_t* heavy_list, uint32_t* heavy_count, MsmGeom g) {
-  const uint64_t key = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (key >= g.nbtot()) return;
-  const uint32_t off = offsets[key], cnt = offsets[key + 1] - off;
-  if (cnt == 0) { xyzz_store(buckets + key, xyzz_identity()); return; }
-  const uint64_t first = key + off / g.T, last = key + (off + cnt - 1) / g.T;
-  if (last - first + 1 > MSM_HEAVY) { heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)key; return; }
-  G1Xyzz acc = xyzz_load(partial + first);
-  for (uint64_t s = first + 1; s <= last; ++s) xyzz_add(acc, xyzz_load(partial + s));
-  xyzz_store(buckets + key, acc);
+                                                    uint32_t* heavy_list, uint32_t* heavy_count, MsmGeom g, uint32_t logG) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t key = tid >> logG;
+  const uint32_t G = 1u << logG, lane = (uint32_t)tid & (G - 1);
+  const bool valid = key < g.nbtot();     // whole groups are valid or not (nbtot * G is a multiple of the warp's group span)
+  uint32_t off = 0, cnt = 0;
+  if (valid) { off = offsets[key]; cnt = offsets[key + 1] - off; }
+  uint64_t first = 0, np = 0;
+  if (cnt) { first = key + off / g.T; np = key + (off + cnt - 1) / g.T - first + 1; }
+  const bool heavy = np > (uint64_t)MSM_HEAVY_PER_LANE * G;
+  G1Xyzz acc = xyzz_identity();
+  if (cnt && !heavy)
+    for (uint64_t s = lane; s < np; s += G) xyzz_add(acc, xyzz_load(partial + first + s));
+  for (uint32_t d = G >> 1; d > 0; d >>= 1) { G1Xyzz o = xyzz_shfl_xor(acc, (int)d); xyzz_add(acc, o); }
+  if (valid && lane == 0) {
+    if (heavy) heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)key;
+    else xyzz_store(buckets + key, acc);
+  }
 }
 
 // block-wide XYZZ tree reduction through shared memory; result valid in thread 0
@@ -125,7 +149,7 @@ __device__ __forceinline__ G1Xyzz block_reduce_xyzz(G1Xyzz acc, G1Xyzz* sm) {
   return r;
 }
 
-__global__ void __launch_bounds__(256) k_msm_gather_heavy(const uint32_t* offsets, const G1Xyzz* partial, G1Xyzz* buckets,
+__global__ void __launch_bounds__(128) k_msm_gather_heavy(const uint32_t* offsets, const G1Xyzz* partial, G1Xyzz* buckets,
                                                           const uint32_t* heavy_list, const uint32_t* heavy_count, MsmGeom g) {
   extern __shared__ uint4 smraw[];
   G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smraw);
@@ -143,7 +167,7 @@ __global__ void __launch_bounds__(256) k_msm_gather_heavy(const uint32_t* offset
 
 // Level 1: P[set][t][chunk] = sum of buckets b of the chunk whose index has bit t set.  grid = (c, nchunks, nsets)
 #define RED_CHUNK 1024
-__global__ void __launch_bounds__(256, 2) k_msm_reduce1(const G1Xyzz* buckets, G1Xyzz* P, MsmGeom g, uint32_t nchunks) {
+__global__ void __launch_bounds__(64) k_msm_reduce1(const G1Xyzz* buckets, G1Xyzz* P, MsmGeom g, uint32_t nchunks) {
   extern __shared__ uint4 smraw[];
   G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smraw);
   const uint32_t t = blockIdx.x, ch = blockIdx.y;
@@ -193,6 +217,7 @@ static void xyzz_to_abi(const G1Xyzz& p, zkc_g1* out) {
 int u32_scan(zkc_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* total_dev);   // poly.cu
 
 uint32_t msm_pick_c(uint64_t n, bool precomputed) {
+  if (const char* e = getenv(precomputed ? "ZKC_MSM_C_PRE" : "ZKC_MSM_C")) { int v = atoi(e); if (v >= 3 && v <= 20) return (uint32_t)v; }
   uint32_t lg = 0;
   while ((1ull << (lg + 1)) <= n) ++lg;
   // measured on B200: shared-bucket (precomputed) layout wants ~4-8 partials per bucket for the
@@ -207,8 +232,11 @@ MsmGeom msm_geom(uint64_t n, uint32_t ncols, uint32_t c, bool precomputed) {
   MsmGeom g;
   g.c = c; g.W = (255 + c - 1) / c; g.NB = 1u << (c - 1); g.sets = precomputed ? 1 : g.W; g.n = n; g.ncols = ncols;
   const uint64_t e = g.emax();
-  uint32_t T = 64;   // entries per accumulate thread: as long as the grid still fills 3 CTAs x 128 threads per SM
-  while (T > 4 && e / T < 148ull * 384) T >>= 1;
+  // entries per accumulate thread (B200 sweep): short chunks keep more warps in flight (T=8 reaches
+  // 0.99 of the IMAD.WIDE peak) but multiply the partials the gather phase must fold; 32 / 64 minimise the sum
+  uint32_t T = e >= (1ull << 26) ? 64 : 32;
+  if (const char* ev = getenv("ZKC_MSM_T")) { int v = atoi(ev); if (v >= 4 && v <= 128) T = (uint32_t)v; }
+  while (T > 4 && e / T < 148ull * 512) T >>= 1;
   g.T = T;
   return g;
 }
@@ -265,18 +293,25 @@ int msm_run(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, 
     { ProfScope _p(ctx, "msm.accum");
       k_msm_accum<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(bases, ent_pt, ent_key, offsets, partial, g);
       ZKC_LAUNCH_CHECK(ctx); }
-    { ProfScope _p(ctx, "msm.gather");
-      k_msm_gather<<<(unsigned)((nbt + 127) / 128), 128, 0, st>>>(offsets, partial, buckets, heavy, heavyc, g);
-      ZKC_LAUNCH_CHECK(ctx); }
-    { ProfScope _p(ctx, "msm.gather_heavy");
-      k_msm_gather_heavy<<<ctx->sm_count * 2, 256, 256 * sizeof(G1Xyzz), st>>>(offsets, partial, buckets, heavy, heavyc, g);
-      ZKC_LAUNCH_CHECK(ctx); }
+    {
+      // group width from the expected number of partials per bucket (entries per bucket / T)
+      const double avg_partials = (double)g.W * (double)n / (double)g.NB / (double)g.sets / (double)g.T + 1.0;
+      uint32_t logG = 0;
+      while (logG < 5 && (double)(1u << logG) * 3.0 < avg_partials) ++logG;
+      { ProfScope _p(ctx, "msm.gather");
+        const uint64_t nthr = nbt << logG;
+        k_msm_gather<<<(unsigned)((nthr + 127) / 128), 128, 0, st>>>(offsets, partial, buckets, heavy, heavyc, g, logG);
+        ZKC_LAUNCH_CHECK(ctx); }
+      { ProfScope _p(ctx, "msm.gather_heavy");
+        k_msm_gather_heavy<<<ctx->sm_count * 4, 128, 128 * sizeof(G1Xyzz), st>>>(offsets, partial, buckets, heavy, heavyc, g);
+        ZKC_LAUNCH_CHECK(ctx); }
+    }
     if ((uint64_t)nc * g.sets > 65535) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: too many bucket sets in one batch");
     {
       ProfScope _p(ctx, "msm.reduce");
       const uint32_t nchunks = (g.NB + RED_CHUNK - 1) / RED_CHUNK;
       dim3 g1(g.c, nchunks, nc * g.sets), g2(g.c, nc * g.sets);
-      k_msm_reduce1<<<g1, 256, 256 * sizeof(G1Xyzz), st>>>(buckets, redp, g, nchunks);
+      k_msm_reduce1<<<g1, 64, 64 * sizeof(G1Xyzz), st>>>(buckets, redp, g, nchunks);
       ZKC_LAUNCH_CHECK(ctx);
       k_msm_reduce2<<<g2, 32, 32 * sizeof(G1Xyzz), st>>>(redp, U, g, nchunks);
       ZKC_LAUNCH_CHECK(ctx);
