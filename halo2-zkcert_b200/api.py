@@ -399,3 +399,13 @@ def fr_random_stream(seed, count, skip=0):
     if st != 0:
         raise ZkcError(st, "zkc_rng_fr_random")
     return out
+
+
+def g1_sum(points):
+    """host-side sum of normalised Jacobian points (n, 12) -> (1, 12): point-sharded MSM epilogue"""
+    pts = _np(np.asarray(points, dtype=np.uint64).reshape(-1, 12), 12)
+    out = np.zeros((1, 12), dtype=np.uint64)
+    st = lib().zkc_g1_sum(_hp(pts), C.c_size_t(pts.shape[0]), _hp(out))
+    if st != 0:
+        raise ZkcError(st, "zkc_g1_sum")
+    return out

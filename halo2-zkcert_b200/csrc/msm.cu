@@ -544,3 +544,19 @@ extern "C" int zkc_msm_g1(zkc_ctx* ctx, const zkc_fr* scalars, const zkc_g1_affi
   }
   return msm_run(ctx, (const Fr*)ds, (const G1Affine*)db, n, 1, msm_pick_c(n ? n : 1, false), false, out);
 }
+
+// Host-side epilogue of a point-sharded MSM: sum of `n` normalised Jacobian partial results,
+// one per rank.  No device work; exact group arithmetic on the host.
+extern "C" int zkc_g1_sum(const zkc_g1* pts, size_t n, zkc_g1* out) {
+  if (!out || (n && !pts)) return ZKC_ERR_BAD_ARG;
+  G1Xyzz acc = xyzz_identity();
+  for (size_t i = 0; i < n; ++i) {
+    Fq z; memcpy(z.v, &pts[i].z, 32);
+    if (fe_is_zero(z)) continue;
+    if (!fe_eq(z, fe_one<FqP>())) return ZKC_ERR_BAD_ARG;   // only normalised points are accepted
+    G1Affine a; memcpy(a.x.v, &pts[i].x, 32); memcpy(a.y.v, &pts[i].y, 32);
+    xyzz_madd(acc, a, false);
+  }
+  xyzz_to_abi(acc, out);
+  return ZKC_OK;
+}

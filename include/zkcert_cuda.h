@@ -141,6 +141,9 @@ int zkc_commit(zkc_ctx* ctx, const zkc_srs* srs, int basis, const zkc_fr* poly, 
 int zkc_commit_dev(zkc_ctx* ctx, const zkc_srs* srs, int basis, const zkc_fr* polys_dev, size_t len, uint32_t ncols, zkc_g1* out);
 
 uint32_t zkc_srs_k(const zkc_srs* srs);
+/* Sum of n normalised Jacobian points on the host: the epilogue of a point-range-sharded MSM across GPUs
+ * (each rank runs zkc_msm_g1_dev on its slice of bases/scalars, the 96-byte partials are all-gathered). */
+int zkc_g1_sum(const zkc_g1* pts, size_t n, zkc_g1* out);
 
 /* ---- ProvingKey + create_proof (halo2_proofs::plonk::{ProvingKey, create_proof}) ---
  * The reference reaches this through snark-verifier-sdk gen_snark_shplonk
