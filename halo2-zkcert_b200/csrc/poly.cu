@@ -289,6 +289,82 @@ int fr_kate_division(zkc_ctx* ctx, const Fr* a, Fr* q, uint64_t n, const Fr& z, 
   return ZKC_OK;
 }
 
+// Several independent in-place divisions (different polynomials, different roots) in one set of launches:
+// blockIdx.y selects the job.  Used per "round" of SHPLONK (one root of every rotation set) and for all GWC points.
+struct KdBatch { Fr* a[KD_MAX_JOBS]; Fr z[KD_MAX_JOBS]; Fr Z[KD_MAX_JOBS]; uint32_t njobs; };
+__global__ void k_kd_chunk_b(KdBatch b, Fr* P, uint64_t n, uint64_t nchunks) {
+  const uint32_t j = blockIdx.y;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t lo = t * KD_CH;
+  if (lo >= n) return;
+  const uint64_t hi = lo + KD_CH < n ? lo + KD_CH : n;
+  const Fr z = b.z[j];
+  const Fr* a = b.a[j];
+  Fr acc = fe_zero<FrP>();
+  for (uint64_t i = hi; i-- > lo;) acc = fe_add(fe_mul(acc, z), fe_load(a + i));
+  fe_store(P + (uint64_t)j * nchunks + t, acc);
+}
+__global__ void __launch_bounds__(1024) k_kd_carry_b(KdBatch b, Fr* Pall, uint64_t nchunks) {
+  extern __shared__ uint4 smraw[];
+  Fr* sm = reinterpret_cast<Fr*>(smraw);
+  Fr* P = Pall + (uint64_t)blockIdx.x * nchunks;
+  const Fr Z = b.Z[blockIdx.x];
+  const uint32_t t = threadIdx.x;
+  const uint64_t per = (nchunks + 1023) / 1024;
+  const uint64_t lo = (uint64_t)t * per, hi = lo + per < nchunks ? lo + per : nchunks;
+  Fr L = fe_zero<FrP>();
+  for (uint64_t c = hi; c-- > lo && hi > lo;) L = fe_add(fe_mul(L, Z), fe_load(P + c));
+  fe_store(sm + t, L);
+  __syncthreads();
+  Fr M = fe_pow_u64(Z, per);
+  for (uint32_t d = 1; d < 1024; d <<= 1) {
+    Fr v = fe_zero<FrP>();
+    const bool act = t + d < 1024;
+    if (act) v = fe_load(sm + t + d);
+    __syncthreads();
+    if (act) fe_store(sm + t, fe_add(fe_load(sm + t), fe_mul(M, v)));
+    M = fe_sqr(M);
+    __syncthreads();
+  }
+  Fr carry = t + 1 < 1024 ? fe_load(sm + t + 1) : fe_zero<FrP>();
+  for (uint64_t c = hi; c-- > lo && hi > lo;) {
+    const Fr pc = fe_load(P + c);
+    fe_store(P + c, carry);
+    carry = fe_add(pc, fe_mul(Z, carry));
+  }
+}
+__global__ void k_kd_apply_b(KdBatch b, const Fr* carry, uint64_t n, uint64_t nchunks) {
+  const uint32_t j = blockIdx.y;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t lo = t * KD_CH;
+  if (lo >= n) return;
+  const uint64_t hi = lo + KD_CH < n ? lo + KD_CH : n;
+  const Fr z = b.z[j];
+  Fr* a = b.a[j];
+  Fr r = fe_load(carry + (uint64_t)j * nchunks + t);
+  for (uint64_t i = hi; i-- > lo;) {
+    const Fr ai = fe_load(a + i);
+    fe_store(a + i, r);
+    r = fe_add(ai, fe_mul(z, r));
+  }
+}
+int fr_kate_division_batch(zkc_ctx* ctx, const std::vector<Fr*>& polys, const std::vector<Fr>& roots, uint64_t n, Fr* tmp /* n elements */) {
+  if (n == 0 || polys.empty()) return ZKC_OK;
+  ProfScope _p(ctx, "kate_division");
+  const uint64_t nchunks = (n + KD_CH - 1) / KD_CH;
+  const unsigned gx = (unsigned)((nchunks + 127) / 128);
+  for (size_t off = 0; off < polys.size(); off += KD_MAX_JOBS) {
+    KdBatch b;
+    b.njobs = (uint32_t)std::min<size_t>(KD_MAX_JOBS, polys.size() - off);   // KD_MAX_JOBS * nchunks <= n
+    for (uint32_t j = 0; j < b.njobs; ++j) { b.a[j] = polys[off + j]; b.z[j] = roots[off + j]; b.Z[j] = fe_pow_u64(roots[off + j], KD_CH); }
+    dim3 grid(gx, b.njobs);
+    k_kd_chunk_b<<<grid, 128, 0, ctx->stream>>>(b, tmp, n, nchunks); ZKC_LAUNCH_CHECK(ctx);
+    k_kd_carry_b<<<b.njobs, 1024, 1024 * sizeof(Fr), ctx->stream>>>(b, tmp, nchunks); ZKC_LAUNCH_CHECK(ctx);
+    k_kd_apply_b<<<grid, 128, 0, ctx->stream>>>(b, tmp, n, nchunks); ZKC_LAUNCH_CHECK(ctx);
+  }
+  return ZKC_OK;
+}
+
 // ---- batched polynomial evaluation ---------------------------------------------------------------------------
 // grid = (blocks_per_poly, n_evals); each CTA of 256 threads evaluates a 4096-coefficient slice at
 // the point (16-coefficient Horner per thread, then a shared-memory tree with x^(16*2^l) factors).

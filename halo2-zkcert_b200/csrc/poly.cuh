@@ -41,6 +41,9 @@ int fr_scale(zkc_ctx* ctx, Fr* a, uint64_t n, const Fr& s);
 int fr_mul_add(zkc_ctx* ctx, Fr* a, const Fr* b, uint64_t n, const Fr& s);
 // kate_division: q(X) = (a(X) - a(z)) / (X - z); writes n coefficients (q[n-1] = 0).  Uses two scratch columns.
 int fr_kate_division(zkc_ctx* ctx, const Fr* a, Fr* q, uint64_t n, const Fr& z, Fr* tmp1, Fr* tmp2);
+// in-place batch: polys[j] <- polys[j] / (X - roots[j]) for independent jobs, one set of launches (tmp: n elements)
+#define KD_MAX_JOBS 16
+int fr_kate_division_batch(zkc_ctx* ctx, const std::vector<Fr*>& polys, const std::vector<Fr>& roots, uint64_t n, Fr* tmp);
 // evaluate polys[j] (n coefficients each) at points[j]; results to host `out`
 int fr_eval_batch(zkc_ctx* ctx, const std::vector<const Fr*>& polys, uint64_t n, const std::vector<Fr>& points, std::vector<Fr>& out);
 // batch inversion (zeros pass through)

@@ -550,9 +550,9 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
 
   // 4. lookups: theta-compression, permute_expression_pair, commit A', S'
   //    per lookup: comp (2 x n: input, table), perm values (2 x n: A', S'), perm polys (2 x n), z values / poly
-  Fr *lk_comp, *lk_perm, *lk_perm_polys, *lk_z, *lk_z_polys;
+  Fr *lk_comp, *lk_perm, *lk_perm_polys;
   ZKC_TRY(pool.get(&lk_comp, (size_t)2 * L * n)); ZKC_TRY(pool.get(&lk_perm, (size_t)2 * L * n));
-  ZKC_TRY(pool.get(&lk_perm_polys, (size_t)2 * L * n)); ZKC_TRY(pool.get(&lk_z, (size_t)L * n)); ZKC_TRY(pool.get(&lk_z_polys, (size_t)L * n));
+  ZKC_TRY(pool.get(&lk_perm_polys, (size_t)2 * L * n));
   if (L) {
     Fr *ca, *ct, *tails;
     uint32_t *flags, *ranks, *replist, *counts;
@@ -599,9 +599,13 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   const Fr beta = tr.squeeze_challenge();
   const Fr gamma = tr.squeeze_challenge();
 
-  // 6. permutation grand products: one scan across all sets chains z_j[0] = z_{j-1}[U]
-  Fr *pz, *pz_polys;
-  ZKC_TRY(pool.get(&pz, (size_t)Pn * n)); ZKC_TRY(pool.get(&pz_polys, (size_t)Pn * n));
+  // 6 + 7. permutation and lookup grand products.  Both depend only on (beta, gamma), so their denominators share
+  //        one batch inversion and their z columns one commitment launch; transcript and RNG order are upstream's:
+  //        permutation tails / points first, then the lookups'.  One scan across all permutation sets chains
+  //        z_j[0] = z_{j-1}[U].
+  Fr *z_all, *z_all_polys;
+  ZKC_TRY(pool.get(&z_all, (size_t)(Pn + L) * n)); ZKC_TRY(pool.get(&z_all_polys, (size_t)(Pn + L) * n));
+  Fr *pz = z_all, *pz_polys = z_all_polys, *lk_z = z_all + (size_t)Pn * n, *lk_z_polys = z_all_polys + (size_t)Pn * n;
   auto column_ptr = [&](uint32_t kind, uint32_t idx, bool coset) -> const Fr* {
     if (kind == 0) return coset ? adv_cosets + (size_t)idx * en : adv_values + (size_t)idx * n;
     if (kind == 1) return coset ? pk->fixed_cosets + (size_t)idx * en : pk->fixed_values + (size_t)idx * n;
@@ -622,56 +626,50 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
     }
     return a;
   };
-  if (Pn) {
-    ProfScope _p(ctx, "prove.perm_product");
+  if (Pn + L) {
+    ProfScope _p(ctx, "prove.grand_products");
+    // layout of num / den: [perm: Pn*U + 1] [lookup 0: U + 1] ... (the +1 pads make each scan emit z[U])
+    const size_t perm_len = Pn ? (size_t)Pn * U + 1 : 0, lk_len = U + 1, total = perm_len + (size_t)L * lk_len;
     Fr *num, *den, *tails;
-    ZKC_TRY(pool.get(&num, (size_t)Pn * U + 1)); ZKC_TRY(pool.get(&den, (size_t)Pn * U + 1)); ZKC_TRY(pool.get(&tails, (size_t)Pn * bf));
+    ZKC_TRY(pool.get(&num, total)); ZKC_TRY(pool.get(&den, total)); ZKC_TRY(pool.get(&tails, (size_t)(Pn + L) * bf));
     for (uint32_t s = 0; s < Pn; ++s) {
       k_perm_num_den<<<grid(U, 128), 128, 0, st>>>(perm_args(s, false), pk->omega_pows, beta, gamma, num + (size_t)s * U, den + (size_t)s * U, U);
       ZKC_LAUNCH_CHECK(ctx);
     }
-    ZKC_TRY(fr_batch_invert(ctx, den, den, (size_t)Pn * U));
-    k_pk_mul_vec<<<grid((size_t)Pn * U, 256), 256, 0, st>>>(num, den, num, (size_t)Pn * U); ZKC_LAUNCH_CHECK(ctx);
-    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(num + (size_t)Pn * U, &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));   // pad: scan length Pn*U + 1
-    ZKC_TRY(fr_scan(ctx, num, den, (size_t)Pn * U + 1, SCAN_MUL, 0, ONE));
-    std::vector<Fr> t((size_t)Pn * bf);
-    for (uint32_t s = 0; s < Pn; ++s) {
+    if (Pn) {
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(num + perm_len - 1, &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(den + perm_len - 1, &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));
+    }
+    for (uint32_t l = 0; l < L; ++l) {
+      const Fr* comp_in = lk_comp + (size_t)2 * l * n; const Fr* comp_tab = comp_in + n;
+      const Fr* ap = lk_perm + (size_t)2 * l * n; const Fr* sp = ap + n;
+      Fr* nl = num + perm_len + (size_t)l * lk_len; Fr* dl = den + perm_len + (size_t)l * lk_len;
+      k_lookup_num_den<<<grid(U, 128), 128, 0, st>>>(comp_in, comp_tab, ap, sp, beta, gamma, nl, dl, U); ZKC_LAUNCH_CHECK(ctx);
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(nl + U, &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(dl + U, &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));
+    }
+    ZKC_TRY(fr_batch_invert(ctx, den, den, total));
+    k_pk_mul_vec<<<grid(total, 256), 256, 0, st>>>(num, den, num, total); ZKC_LAUNCH_CHECK(ctx);
+    if (Pn) ZKC_TRY(fr_scan(ctx, num, den, perm_len, SCAN_MUL, 0, ONE));
+    for (uint32_t l = 0; l < L; ++l)
+      ZKC_TRY(fr_scan(ctx, num + perm_len + (size_t)l * lk_len, den + perm_len + (size_t)l * lk_len, lk_len, SCAN_MUL, 0, ONE));
+    // blinding tails in upstream draw order: every permutation set, then every lookup product
+    std::vector<Fr> t((size_t)(Pn + L) * bf);
+    for (uint32_t s = 0; s < Pn + L; ++s) {
       for (uint32_t i = 0; i < bf; ++i) t[(size_t)s * bf + i] = rng.draw();
       if (opts->blind_draws) rng.draw();
     }
     ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(tails, t.data(), t.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
-    k_assemble_z<<<grid((size_t)Pn * n, 256), 256, 0, st>>>(den, tails, pz, n, U, bf, Pn); ZKC_LAUNCH_CHECK(ctx);
-    ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    ZKC_TRY(commit_points(ctx, srs, 1, pz, n, Pn, pts));
-    ZKC_TRY(write_points(pts));
-    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(pz_polys, pz, (size_t)Pn * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-    ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, pz_polys, Pn));
-  }
-
-  // 7. lookup grand products
-  if (L) {
-    ProfScope _p(ctx, "prove.lookup_product");
-    Fr *num, *den, *tails;
-    ZKC_TRY(pool.get(&num, U + 1)); ZKC_TRY(pool.get(&den, U + 1)); ZKC_TRY(pool.get(&tails, bf));
+    if (Pn) { k_assemble_z<<<grid((size_t)Pn * n, 256), 256, 0, st>>>(den, tails, pz, n, U, bf, Pn); ZKC_LAUNCH_CHECK(ctx); }
     for (uint32_t l = 0; l < L; ++l) {
-      const Fr* comp_in = lk_comp + (size_t)2 * l * n; const Fr* comp_tab = comp_in + n;
-      const Fr* ap = lk_perm + (size_t)2 * l * n; const Fr* sp = ap + n;
-      k_lookup_num_den<<<grid(U, 128), 128, 0, st>>>(comp_in, comp_tab, ap, sp, beta, gamma, num, den, U); ZKC_LAUNCH_CHECK(ctx);
-      ZKC_TRY(fr_batch_invert(ctx, den, den, U));
-      k_pk_mul_vec<<<grid(U, 256), 256, 0, st>>>(num, den, num, U); ZKC_LAUNCH_CHECK(ctx);
-      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(num + U, &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));
-      ZKC_TRY(fr_scan(ctx, num, den, U + 1, SCAN_MUL, 0, ONE));
-      std::vector<Fr> t(bf);
-      for (auto& v : t) v = rng.draw();
-      if (opts->blind_draws) rng.draw();
-      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(tails, t.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, st));
-      k_assemble_z<<<grid(n, 256), 256, 0, st>>>(den, tails, lk_z + (size_t)l * n, n, U, bf, 1); ZKC_LAUNCH_CHECK(ctx);
-      ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      k_assemble_z<<<grid(n, 256), 256, 0, st>>>(den + perm_len + (size_t)l * lk_len, tails + (size_t)(Pn + l) * bf, lk_z + (size_t)l * n, n, U, bf, 1);
+      ZKC_LAUNCH_CHECK(ctx);
     }
-    ZKC_TRY(commit_points(ctx, srs, 1, lk_z, n, L, pts));
+    ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    ZKC_TRY(commit_points(ctx, srs, 1, z_all, n, Pn + L, pts));
     ZKC_TRY(write_points(pts));
-    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(lk_z_polys, lk_z, (size_t)L * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-    ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, lk_z_polys, L));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(z_all_polys, z_all, (size_t)(Pn + L) * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, z_all_polys, Pn + L));
   }
 
   // 8. vanishing argument: random polynomial, n draws generated on the device from the same stream
@@ -804,8 +802,11 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
     std::vector<std::vector<std::vector<Fr>>> rcoef(sets.size());   // [set][poly] -> r(X) coefficients
     for (size_t s = 0; s < sets.size(); ++s)
       for (size_t p = 0; p < sets[s].polys.size(); ++p) rcoef[s].push_back(lagrange_interpolate(sets[s].points, sets[s].evals[p]));
-    // h(X) = sum_i v^i * ( sum_j y^j (p_ij - r_ij) ) / Z_i
-    Fr pv = ONE;
+    // h(X) = sum_i v^i * ( sum_j y^j (p_ij - r_ij) ) / Z_i: numerators per set, then one batched division
+    // launch per "round" (the r-th root of every set that still has one), then one linear combination
+    Fr* setbuf;
+    ZKC_TRY(pool.get(&setbuf, sets.size() * n));
+    size_t max_roots = 0;
     for (size_t s = 0; s < sets.size(); ++s) {
       std::vector<Fr> cf; std::vector<Fr> low(sets[s].points.size(), ZERO);
       Fr py = ONE;
@@ -814,12 +815,20 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
         for (size_t i = 0; i < low.size(); ++i) low[i] = fe_add(low[i], fe_mul(py, rcoef[s][p][i]));
         py = fe_mul(py, yy);
       }
-      ZKC_TRY(fr_lincomb(ctx, tmp1, n, sets[s].polys, cf));
-      ZKC_TRY(fr_sub_low(ctx, tmp1, low));
-      for (auto& root : sets[s].points) ZKC_TRY(fr_kate_division(ctx, tmp1, tmp1, n, root, tmp2, tmp3));
-      if (s == 0) { ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(acc, tmp1, n * sizeof(Fr), cudaMemcpyDeviceToDevice, st)); }
-      else ZKC_TRY(fr_lincomb(ctx, acc, n, {acc, tmp1}, {ONE, pv}));
-      pv = fe_mul(pv, v);
+      ZKC_TRY(fr_lincomb(ctx, setbuf + s * n, n, sets[s].polys, cf));
+      ZKC_TRY(fr_sub_low(ctx, setbuf + s * n, low));
+      max_roots = std::max(max_roots, sets[s].points.size());
+    }
+    for (size_t r = 0; r < max_roots; ++r) {
+      std::vector<Fr*> jp; std::vector<Fr> jr;
+      for (size_t s = 0; s < sets.size(); ++s) if (sets[s].points.size() > r) { jp.push_back(setbuf + s * n); jr.push_back(sets[s].points[r]); }
+      ZKC_TRY(fr_kate_division_batch(ctx, jp, jr, n, tmp2));
+    }
+    {
+      std::vector<const Fr*> ps; std::vector<Fr> cf;
+      Fr pv = ONE;
+      for (size_t s = 0; s < sets.size(); ++s) { ps.push_back(setbuf + s * n); cf.push_back(pv); pv = fe_mul(pv, v); }
+      ZKC_TRY(fr_lincomb(ctx, acc, n, ps, cf));
     }
     ZKC_TRY(commit_points(ctx, srs, 0, acc, n, 1, pts));
     ZKC_TRY(write_points(pts));
@@ -827,7 +836,7 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
     // L(X) = sum_i v^i z_i sum_j y^j (p_ij - r_ij(u)) - Z_T(u) h(X)
     std::vector<const Fr*> ps; std::vector<Fr> cf;
     Fr cst = ZERO, z0 = ZERO;
-    pv = ONE;
+    Fr pv = ONE;
     for (size_t s = 0; s < sets.size(); ++s) {
       std::vector<Fr> diffs;
       for (auto& sp : super_points) {
@@ -867,7 +876,11 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
       for (auto& p : points) if (fe_eq(p, qq.point)) { seen = true; break; }
       if (!seen) points.push_back(qq.point);
     }
-    for (auto& z : points) {
+    Fr* wbuf;
+    ZKC_TRY(pool.get(&wbuf, points.size() * n));
+    std::vector<Fr*> jp;
+    for (size_t pi = 0; pi < points.size(); ++pi) {
+      const Fr& z = points[pi];
       std::vector<const Fr*> ps; std::vector<Fr> cf;
       Fr pvv = ONE, eacc = ZERO;
       for (auto& qq : queries) {
@@ -876,12 +889,13 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
         eacc = fe_add(eacc, fe_mul(qq.eval, pvv));
         pvv = fe_mul(pvv, v);
       }
-      ZKC_TRY(fr_lincomb(ctx, tmp1, n, ps, cf));
-      ZKC_TRY(fr_sub_low(ctx, tmp1, {eacc}));
-      ZKC_TRY(fr_kate_division(ctx, tmp1, tmp1, n, z, tmp2, tmp3));
-      ZKC_TRY(commit_points(ctx, srs, 0, tmp1, n, 1, pts));
-      ZKC_TRY(write_points(pts));
+      ZKC_TRY(fr_lincomb(ctx, wbuf + pi * n, n, ps, cf));
+      ZKC_TRY(fr_sub_low(ctx, wbuf + pi * n, {eacc}));
+      jp.push_back(wbuf + pi * n);
     }
+    ZKC_TRY(fr_kate_division_batch(ctx, jp, points, n, tmp2));
+    ZKC_TRY(commit_points(ctx, srs, 0, wbuf, n, (uint32_t)points.size(), pts));   // one launch for every witness commitment
+    ZKC_TRY(write_points(pts));
   }
   ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
   *proof_len = tr.proof.size();
