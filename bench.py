@@ -54,6 +54,10 @@ def load_peaks():
     except Exception:
         pass
     try:
+        peaks["accum_traffic"] = json.load(open(os.path.join(ROOT, "profiles", "r01_msm_accum_traffic.json")))["avg_traffic_bytes"]
+    except Exception:
+        peaks["accum_traffic"] = None
+    try:
         fb = json.load(open(os.path.join(ROOT, "profiles", "r01_ffbench.json")))
         peaks["imadw"] = float(fb["imad_wide_per_s"])
     except Exception:
@@ -221,11 +225,13 @@ def main():
     launches = ctx.launches - l0
     # per-kernel CUDA-event timers (zkc_profile_*) over the same K steps, on the launching stream;
     # kept out of the headline loop because the extra event records perturb the host-side pacing
+    ctx.set_overlap(False)     # one stream: each kernel's event time is its own, not shared with side-stream work
     ctx.profile_enable(True)
     ctx.profile_report()
     prof_ms, proofs_prof = run(w.advice_dev, K, 0)
     prof = ctx.profile_report()
     ctx.profile_enable(False)
+    ctx.set_overlap(True)
     clocks = sampler.stop()
     assert proofs_prof == proofs_dev
     # ---- end-to-end timing: host (pinned) witness in, proof bytes out -------------------------------
@@ -249,7 +255,9 @@ def main():
         imadw = madds * FQMUL_PER_MADD * IMADW_PER_FQMUL
         ach = imadw / (accum["ms"] * 1e-3) if accum["ms"] else 0.0
         roofline = {"bound": "int", "kernel": "k_msm_accum (XYZZ bucket accumulation)", "achieved": ach / 1e12, "peak": peaks["imadw"] / 1e12,
-                    "unit": "T IMAD.WIDE/s", "frac": ach / peaks["imadw"], "traffic": None,
+                    "unit": "T IMAD.WIDE/s", "frac": ach / peaks["imadw"], "traffic": peaks.get("accum_traffic"),
+                    "traffic_note": "avg dram__bytes_read+write per k_msm_accum launch, ncu capture of this workload (profiles/r01_msm_accum_traffic.json)",
+                    "timing_note": "per-kernel CUDA-event times from a separate pass of K steps with stream overlap disabled",
                     "launches": accum["n"], "avg_launch_ms": accum["ms"] / max(accum["n"], 1),
                     "algorithmic": "mixed adds per launch x 10 Fq-mul x 128 IMAD.WIDE (SURVEY 8d); peak = measured IMAD.WIDE issue rate (%s)" % peaks["imadw_src"],
                     "share_of_step": accum["ms"] / prof_ms if prof_ms else None}
@@ -267,6 +275,7 @@ def main():
                 "roofline_hbm": {"bound": "hbm", "kernel": "k_ntt_strided + k_ntt_last", "achieved_gbs_note":
                                  "NTT passes are integer-pipe bound on 254-bit fields; see DESIGN.md", "ntt_ms_per_step": ntt_ms / K,
                                  "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_src": peaks["hbm_src"]},
+                "phases_note": "CUDA-event ms per step with stream overlap disabled (sum exceeds ms_per_step when overlap hides work)",
                 "phases_ms_per_step": {kx: round(v["ms"] / K, 4) for kx, v in sorted(prof.items()) if not kx.startswith("count:")},
                 "msm_points_per_s": prof.get("count:msm.points", {"n": 0})["n"] / (sum(prof.get(kx, {"ms": 0.0})["ms"] for kx in prof if kx.startswith("msm.")) * 1e-3 or 1),
                 "wall_s_timed_region": t_wall}

@@ -89,6 +89,9 @@ class Context:
         import torch
         self.check(lib().zkc_ctx_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream), C.c_int(1)))
 
+    def set_overlap(self, on=True):
+        self.check(lib().zkc_ctx_set_overlap(self._h, C.c_int(1 if on else 0)))
+
     def sync(self):
         self.check(lib().zkc_ctx_sync(self._h))
 

@@ -25,12 +25,16 @@ struct zkc_ctx {
   int dev = 0;
   cudaStream_t stream = nullptr;      // stream all kernels are launched on
   cudaStream_t own_stream = nullptr;  // created with the ctx
+  cudaStream_t side_stream = nullptr; // second stream: work that is not on the Fiat-Shamir critical path (SideScope)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_pending = false;
+  bool overlap = true;                // zkc_ctx_set_overlap: 0 serialises side work on the main stream (clean per-kernel timing)
   std::string err;
   uint64_t launches = 0;
   std::recursive_mutex mu;
   int sm_count = 148;
   // grow-only scratch arenas (index = purpose), freed with the ctx
-  zkc::DevBuf scratch[8];
+  zkc::DevBuf scratch[16];   // [0..8) main stream, [8..16) side stream
   // twiddle tables: log_n -> device table of omega_n^i, i < n/2 (canonical root of unity)
   std::map<uint32_t, zkc::Fr*> twiddles;
   void* pinned = nullptr;  // small pinned staging buffer for results
@@ -74,7 +78,7 @@ inline int set_err(zkc_ctx* ctx, int code, const std::string& msg) {
 
 // Ensure scratch arena `slot` holds at least `bytes`; contents are NOT preserved on growth.
 inline int scratch_reserve(zkc_ctx* ctx, int slot, size_t bytes, void** out) {
-  DevBuf& b = ctx->scratch[slot];
+  DevBuf& b = ctx->scratch[slot + (ctx->stream == ctx->side_stream && ctx->side_stream ? 8 : 0)];
   if (b.bytes < bytes) {
     if (b.p) { ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); ZKC_CUDA_TRY(ctx, cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
     size_t want = bytes + (bytes >> 3);
@@ -111,6 +115,25 @@ struct ProfScope {
   }
   ~ProfScope() { if (idx >= 0) cudaEventRecord(c->prof_pending[idx].e1, c->stream); }
 };
+
+// Enqueue the enclosed work on the side stream, ordered after everything issued so far on the main stream.
+// side_join() makes the main stream wait for all side work issued so far.
+struct SideScope {
+  zkc_ctx* c; cudaStream_t saved;
+  explicit SideScope(zkc_ctx* ctx) : c(ctx), saved(ctx->stream) {
+    if (!c->overlap) return;
+    cudaEventRecord(c->ev_fork, saved);
+    cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0);
+    c->stream = c->side_stream;
+  }
+  ~SideScope() {
+    if (!c->overlap) return;
+    cudaEventRecord(c->ev_join, c->side_stream); c->side_pending = true; c->stream = saved;
+  }
+};
+inline void side_join(zkc_ctx* c) {
+  if (c->side_pending) { cudaStreamWaitEvent(c->stream, c->ev_join, 0); c->side_pending = false; }
+}
 
 struct CtxLock {
   zkc_ctx* c;

@@ -17,6 +17,9 @@ extern "C" int zkc_ctx_create(int device, zkc_ctx** out) {
   c->dev = device;
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ZKC_ERR_CUDA; }
   c->stream = c->own_stream;
+  if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete c; return ZKC_ERR_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
   // keep the stream-ordered pool's memory across synchronisations: per-proof temporaries are
@@ -39,6 +42,9 @@ extern "C" void zkc_ctx_destroy(zkc_ctx* c) {
   if (c->pinned) cudaFreeHost(c->pinned);
   for (auto& r : c->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto e : c->prof_pool) cudaEventDestroy(e);
+  if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -51,6 +57,14 @@ extern "C" int zkc_ctx_set_stream(zkc_ctx* c, void* s, int external) {
   CtxLock lock(c);
   ZKC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   c->stream = external ? (cudaStream_t)s : c->own_stream;
+  return ZKC_OK;
+}
+extern "C" int zkc_ctx_set_overlap(zkc_ctx* c, int on) {
+  if (!c) return ZKC_ERR_BAD_ARG;
+  CtxLock lock(c);
+  ZKC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  ZKC_CUDA_TRY(c, cudaStreamSynchronize(c->side_stream));
+  c->overlap = on != 0;
   return ZKC_OK;
 }
 extern "C" int zkc_ctx_sync(zkc_ctx* c) {

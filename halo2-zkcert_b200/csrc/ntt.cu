@@ -184,6 +184,8 @@ static int get_twiddles(zkc_ctx* ctx, uint32_t log_n, const Fr** out) {
   const uint64_t threads = (half + 63) / 64;
   k_gen_twiddles<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(tw, omega, half);
   ZKC_LAUNCH_CHECK(ctx);
+  // tables are shared by both streams of the ctx: make the one-time generation visible to either
+  ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->twiddles[log_n] = tw;
   *out = tw;
   return ZKC_OK;

@@ -341,7 +341,11 @@ struct Pool {
   zkc_ctx* ctx;
   std::vector<void*> ptrs;
   explicit Pool(zkc_ctx* c) : ctx(c) {}
-  ~Pool() { for (void* p : ptrs) cudaFreeAsync(p, ctx->stream); }
+  ~Pool() {
+    // error paths may leave side-stream work in flight: drain it before the buffers go back to the pool
+    if (ctx->side_pending) { cudaStreamSynchronize(ctx->side_stream); ctx->side_pending = false; }
+    for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
+  }
   template <class T> int get(T** out, size_t count) {
     void* p = nullptr;
     cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), ctx->stream);
@@ -515,17 +519,32 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
     if (opts->blind_draws) for (uint32_t c = 0; c < A; ++c) rng.draw();
   }
   std::vector<G1Affine> pts;
+  // every per-proof buffer is allocated up front on the main stream, so side-stream work never sees an
+  // allocation made after its fork point
+  const Fr** ptrs_dev;
+  ZKC_TRY(pool.get(&ptrs_dev, (size_t)2 * (A + I) + 1));
+  Fr *adv_cosets, *inst_cosets, *pz_cosets, *lk_cosets;
+  ZKC_TRY(pool.get(&adv_cosets, (size_t)A * en)); ZKC_TRY(pool.get(&inst_cosets, (size_t)I * en));
+  ZKC_TRY(pool.get(&pz_cosets, (size_t)Pn * en)); ZKC_TRY(pool.get(&lk_cosets, (size_t)3 * L * en));
+  Fr *lk_comp, *lk_perm, *lk_perm_polys, *z_all, *z_all_polys;
+  ZKC_TRY(pool.get(&lk_comp, (size_t)2 * L * n)); ZKC_TRY(pool.get(&lk_perm, (size_t)2 * L * n));
+  ZKC_TRY(pool.get(&lk_perm_polys, (size_t)2 * L * n));
+  ZKC_TRY(pool.get(&z_all, (size_t)(Pn + L) * n)); ZKC_TRY(pool.get(&z_all_polys, (size_t)(Pn + L) * n));
+  if (A + I) {
+    // off the Fiat-Shamir critical path: coefficient forms and extended cosets of advice / instance columns are
+    // not needed before step 10, so they run on the side stream underneath the latency-bound MSM phases
+    SideScope side(ctx);
+    if (A) {
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(adv_polys, adv_values, (size_t)A * n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+      ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, adv_polys, A));
+      ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, adv_polys, n, adv_cosets, A));
+    }
+    if (I) ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, inst_polys, n, inst_cosets, I));
+  }
   if (A) {
     ZKC_TRY(commit_points(ctx, srs, 1, adv_values, n, A, pts));
     ZKC_TRY(write_points(pts));
-    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(adv_polys, adv_values, (size_t)A * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-    ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, adv_polys, A));
   }
-  // column pointer tables for the two evaluation domains
-  const Fr** ptrs_dev;
-  ZKC_TRY(pool.get(&ptrs_dev, (size_t)2 * (A + I) + 1));
-  Fr *adv_cosets, *inst_cosets;
-  ZKC_TRY(pool.get(&adv_cosets, (size_t)A * en)); ZKC_TRY(pool.get(&inst_cosets, (size_t)I * en));
   {
     std::vector<const Fr*> h(2 * (A + I) + 1, nullptr);
     for (uint32_t c = 0; c < A; ++c) { h[c] = adv_values + (size_t)c * n; h[A + I + c] = adv_cosets + (size_t)c * en; }
@@ -550,9 +569,6 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
 
   // 4. lookups: theta-compression, permute_expression_pair, commit A', S'
   //    per lookup: comp (2 x n: input, table), perm values (2 x n: A', S'), perm polys (2 x n), z values / poly
-  Fr *lk_comp, *lk_perm, *lk_perm_polys;
-  ZKC_TRY(pool.get(&lk_comp, (size_t)2 * L * n)); ZKC_TRY(pool.get(&lk_perm, (size_t)2 * L * n));
-  ZKC_TRY(pool.get(&lk_perm_polys, (size_t)2 * L * n));
   if (L) {
     Fr *ca, *ct, *tails;
     uint32_t *flags, *ranks, *replist, *counts;
@@ -588,11 +604,16 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
       k_lookup_finish<<<grid(n, 256), 256, 0, st>>>(sp, tails + (bf + 1), sp, U, n); ZKC_LAUNCH_CHECK(ctx);
       ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));   // `t` goes out of scope
       if (opts->blind_draws) { rng.draw(); rng.draw(); }
+      {
+        SideScope side(ctx);   // A', S' coefficient forms and cosets (needed at steps 10 / 13)
+        Fr* pp = lk_perm_polys + (size_t)2 * l * n;
+        ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(pp, ap, (size_t)2 * n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+        ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, pp, 2));
+        ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, pp, n, lk_cosets + (size_t)3 * l * en + en, 2));
+      }
       ZKC_TRY(commit_points(ctx, srs, 1, ap, n, 2, pts));
       ZKC_TRY(write_points(pts));
     }
-    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(lk_perm_polys, lk_perm, (size_t)2 * L * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-    ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, lk_perm_polys, 2 * L));
   }
 
   // 5. beta, gamma
@@ -603,8 +624,6 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   //        one batch inversion and their z columns one commitment launch; transcript and RNG order are upstream's:
   //        permutation tails / points first, then the lookups'.  One scan across all permutation sets chains
   //        z_j[0] = z_{j-1}[U].
-  Fr *z_all, *z_all_polys;
-  ZKC_TRY(pool.get(&z_all, (size_t)(Pn + L) * n)); ZKC_TRY(pool.get(&z_all_polys, (size_t)(Pn + L) * n));
   Fr *pz = z_all, *pz_polys = z_all_polys, *lk_z = z_all + (size_t)Pn * n, *lk_z_polys = z_all_polys + (size_t)Pn * n;
   auto column_ptr = [&](uint32_t kind, uint32_t idx, bool coset) -> const Fr* {
     if (kind == 0) return coset ? adv_cosets + (size_t)idx * en : adv_values + (size_t)idx * n;
@@ -666,10 +685,15 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
       ZKC_LAUNCH_CHECK(ctx);
     }
     ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    {
+      SideScope side(ctx);   // z coefficient forms and cosets
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(z_all_polys, z_all, (size_t)(Pn + L) * n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+      ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, z_all_polys, Pn + L));
+      if (Pn) ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, pz_polys, n, pz_cosets, Pn));
+      for (uint32_t l = 0; l < L; ++l) ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, lk_z_polys + (size_t)l * n, n, lk_cosets + (size_t)3 * l * en, 1));
+    }
     ZKC_TRY(commit_points(ctx, srs, 1, z_all, n, Pn + L, pts));
     ZKC_TRY(write_points(pts));
-    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(z_all_polys, z_all, (size_t)(Pn + L) * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-    ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, z_all_polys, Pn + L));
   }
 
   // 8. vanishing argument: random polynomial, n draws generated on the device from the same stream
@@ -684,16 +708,13 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   const Fr y = tr.squeeze_challenge();
 
   // 10. h(X) numerator on the extended coset
-  Fr *hval, *pz_cosets, *lk_cosets, *lk_comp_cosets;
-  ZKC_TRY(pool.get(&hval, en)); ZKC_TRY(pool.get(&pz_cosets, (size_t)Pn * en));
-  ZKC_TRY(pool.get(&lk_cosets, (size_t)3 * L * en)); ZKC_TRY(pool.get(&lk_comp_cosets, (size_t)2 * en));
+  Fr *hval, *lk_comp_cosets;
+  ZKC_TRY(pool.get(&hval, en)); ZKC_TRY(pool.get(&lk_comp_cosets, (size_t)2 * en));
+  side_join(ctx);   // every coset produced on the side stream is complete from here on
   {
     ProfScope _p(ctx, "prove.quotient");
-    if (A) ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, adv_polys, n, adv_cosets, A));
-    if (I) ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, inst_polys, n, inst_cosets, I));
     ZKC_TRY(eval_program(ctx, pk->gates, qext, hval, en, rot_scale, y, 0));
     if (Pn) {
-      ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, pz_polys, n, pz_cosets, Pn));
       PermFixedArgs fa; fa.nsets = Pn;
       for (uint32_t s = 0; s < Pn; ++s) fa.z[s] = pz_cosets + (size_t)s * en;
       const int64_t last_off = -(int64_t)(bf + 1) * rot_scale;
@@ -708,8 +729,6 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
     }
     for (uint32_t l = 0; l < L; ++l) {
       Fr* zc = lk_cosets + (size_t)3 * l * en; Fr* ac = zc + en; Fr* sc = ac + en;
-      ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, lk_z_polys + (size_t)l * n, n, zc, 1));
-      ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, lk_perm_polys + (size_t)2 * l * n, n, ac, 2));
       ZKC_TRY(eval_program(ctx, pk->lookups[l].first, qext, lk_comp_cosets, en, rot_scale, theta, 0));
       ZKC_TRY(eval_program(ctx, pk->lookups[l].second, qext, lk_comp_cosets + en, en, rot_scale, theta, 0));
       k_quot_lookup<<<grid(en, 128), 128, 0, st>>>(hval, zc, ac, sc, lk_comp_cosets, lk_comp_cosets + en, pk->l0, pk->l_last, pk->l_active, beta,
@@ -897,6 +916,7 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
     ZKC_TRY(commit_points(ctx, srs, 0, wbuf, n, (uint32_t)points.size(), pts));   // one launch for every witness commitment
     ZKC_TRY(write_points(pts));
   }
+  side_join(ctx);
   ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
   *proof_len = tr.proof.size();
   if (!proof_out || proof_cap < tr.proof.size()) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_prove: proof buffer too small");

@@ -66,6 +66,10 @@ const char* zkc_last_error(const zkc_ctx* ctx);
  * the legacy default stream).  external == 0: go back to the ctx's own non-blocking stream. */
 int zkc_ctx_set_stream(zkc_ctx* ctx, void* cuda_stream, int external);
 int zkc_ctx_sync(zkc_ctx* ctx);
+/* zkc_prove runs work that is off the Fiat-Shamir critical path (coefficient forms, extended cosets) on a second
+ * stream underneath the latency-bound MSM phases.  on = 0 serialises everything on one stream (used when timing
+ * individual kernels); results are identical either way. */
+int zkc_ctx_set_overlap(zkc_ctx* ctx, int on);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 uint64_t zkc_ctx_launch_count(const zkc_ctx* ctx);
 const char* zkc_version(void);
