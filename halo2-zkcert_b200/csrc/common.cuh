@@ -26,7 +26,7 @@ struct zkc_ctx {
   cudaStream_t stream = nullptr;      // stream all kernels are launched on
   cudaStream_t own_stream = nullptr;  // created with the ctx
   cudaStream_t side_stream = nullptr; // second stream: work that is not on the Fiat-Shamir critical path (SideScope)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_msm_main = nullptr, ev_msm_side = nullptr;
   bool side_pending = false;
   bool overlap = true;                // zkc_ctx_set_overlap: 0 serialises side work on the main stream (clean per-kernel timing)
   std::string err;
@@ -37,8 +37,8 @@ struct zkc_ctx {
   zkc::DevBuf scratch[16];   // [0..8) main stream, [8..16) side stream
   // twiddle tables: log_n -> device table of omega_n^i, i < n/2 (canonical root of unity)
   std::map<uint32_t, zkc::Fr*> twiddles;
-  void* pinned = nullptr;  // small pinned staging buffer for results
-  size_t pinned_bytes = 0;
+  void* pinned[2] = {nullptr, nullptr};  // small pinned staging buffers for results ([1]: side stream)
+  size_t pinned_bytes[2] = {0, 0};
   // optional per-phase CUDA-event timers (zkc_profile_*): name -> accumulated ms / count
   bool profiling = false;
   struct ProfRec { std::string name; cudaEvent_t e0, e1; };
@@ -89,13 +89,13 @@ inline int scratch_reserve(zkc_ctx* ctx, int slot, size_t bytes, void** out) {
   return ZKC_OK;
 }
 
-inline int pinned_reserve(zkc_ctx* ctx, size_t bytes, void** out) {
-  if (ctx->pinned_bytes < bytes) {
-    if (ctx->pinned) { ZKC_CUDA_TRY(ctx, cudaFreeHost(ctx->pinned)); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
-    ZKC_CUDA_TRY(ctx, cudaMallocHost(&ctx->pinned, bytes));
-    ctx->pinned_bytes = bytes;
+inline int pinned_reserve(zkc_ctx* ctx, size_t bytes, void** out, int i = 0) {
+  if (ctx->pinned_bytes[i] < bytes) {
+    if (ctx->pinned[i]) { ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); ZKC_CUDA_TRY(ctx, cudaFreeHost(ctx->pinned[i])); ctx->pinned[i] = nullptr; ctx->pinned_bytes[i] = 0; }
+    ZKC_CUDA_TRY(ctx, cudaMallocHost(&ctx->pinned[i], bytes + 4096));
+    ctx->pinned_bytes[i] = bytes + 4096;
   }
-  *out = ctx->pinned;
+  *out = ctx->pinned[i];
   return ZKC_OK;
 }
 

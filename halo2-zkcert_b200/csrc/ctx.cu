@@ -19,7 +19,9 @@ extern "C" int zkc_ctx_create(int device, zkc_ctx** out) {
   c->stream = c->own_stream;
   if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete c; return ZKC_ERR_CUDA; }
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_msm_main, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_msm_side, cudaEventDisableTiming) != cudaSuccess) { delete c; return ZKC_ERR_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
   // keep the stream-ordered pool's memory across synchronisations: per-proof temporaries are
@@ -39,7 +41,9 @@ extern "C" void zkc_ctx_destroy(zkc_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& b : c->scratch) if (b.p) cudaFree(b.p);
   for (auto& kv : c->twiddles) cudaFree(kv.second);
-  if (c->pinned) cudaFreeHost(c->pinned);
+  for (int i = 0; i < 2; ++i) if (c->pinned[i]) cudaFreeHost(c->pinned[i]);
+  if (c->ev_msm_main) cudaEventDestroy(c->ev_msm_main);
+  if (c->ev_msm_side) cudaEventDestroy(c->ev_msm_side);
   for (auto& r : c->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto e : c->prof_pool) cudaEventDestroy(e);
   if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }

@@ -18,24 +18,11 @@
 //                    buckets whose index has bit t set (no serial running sum), then 2^t weights by Horner.
 // With a resident SRS the bases are expanded once into W tables 2^(c*w) * P_i, so all windows of
 // all points share ONE bucket set per column and step 6 shrinks by a factor W.
-#include "common.cuh"
-#include "ec.cuh"
+#include "msm.cuh"
 #include <algorithm>
 #include <cstdlib>
 
 namespace zkc {
-
-struct MsmGeom {
-  uint32_t c;          // window bits
-  uint32_t W;          // number of windows: W*c >= 255
-  uint32_t NB;         // buckets per window = 2^(c-1)
-  uint32_t sets;       // bucket sets per column: W (generic bases) or 1 (precomputed tables)
-  uint64_t n;          // points per column
-  uint32_t ncols;
-  uint32_t T;          // entries per accumulate thread
-  ZKC_HD uint64_t nbtot() const { return (uint64_t)ncols * sets * NB; }
-  ZKC_HD uint64_t emax() const { return (uint64_t)ncols * W * n; }
-};
 
 // signed digits of the canonical scalar; writes dig[(col*W + w)*n + i] = mag | sign << 31
 __global__ void k_msm_digits(const Fr* scalars, uint32_t* dig, uint32_t* counts, MsmGeom g) {
@@ -241,6 +228,91 @@ MsmGeom msm_geom(uint64_t n, uint32_t ncols, uint32_t c, bool precomputed) {
   return g;
 }
 
+// Enqueue one batch (all kernels + the async D2H of the c bit-plane sums per column) on ctx->stream.
+int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, uint32_t nc, uint32_t c, bool precomputed, MsmPending* pend,
+                int result_slot) {
+  MsmGeom g = msm_geom(n, nc, c, precomputed);
+  const uint64_t nbt = g.nbtot(), em = g.emax();
+  if (nbt + em / g.T + 1 >= (1ull << 32) || em >= (1ull << 32)) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: batch too large");
+  if ((uint64_t)nc * g.sets > 65535) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: too many bucket sets in one batch");
+  const uint64_t nslots = nbt + (em + g.T - 1) / g.T + 1;
+  size_t o = 0;
+  auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+  const size_t o_counts = carve(nbt * 4), o_offsets = carve((nbt + 1) * 4), o_cursor = carve(nbt * 4), o_heavyc = carve(4),
+               o_heavy = carve(nbt * 4), o_dig = carve(em * 4), o_pt = carve(em * 4), o_key = carve(em * 4),
+               o_part = carve(nslots * sizeof(G1Xyzz)), o_bk = carve(nbt * sizeof(G1Xyzz)),
+               o_U = carve((size_t)nc * g.sets * g.c * sizeof(G1Xyzz)),
+               o_redp = carve((size_t)nc * g.sets * g.c * ((g.NB + 1023) / 1024) * sizeof(G1Xyzz));
+  char* base;
+  ZKC_TRY(scratch_reserve(ctx, SCR_MSM, o, (void**)&base));
+  uint32_t* counts = (uint32_t*)(base + o_counts); uint32_t* offsets = (uint32_t*)(base + o_offsets);
+  uint32_t* cursor = (uint32_t*)(base + o_cursor); uint32_t* heavyc = (uint32_t*)(base + o_heavyc);
+  uint32_t* heavy = (uint32_t*)(base + o_heavy); uint32_t* dig = (uint32_t*)(base + o_dig);
+  uint32_t* ent_pt = (uint32_t*)(base + o_pt); uint32_t* ent_key = (uint32_t*)(base + o_key);
+  G1Xyzz* partial = (G1Xyzz*)(base + o_part); G1Xyzz* buckets = (G1Xyzz*)(base + o_bk); G1Xyzz* U = (G1Xyzz*)(base + o_U); G1Xyzz* redp = (G1Xyzz*)(base + o_redp);
+  cudaStream_t st = ctx->stream;
+  ZKC_CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, nbt * 4, st));
+  ZKC_CUDA_TRY(ctx, cudaMemsetAsync(heavyc, 0, 4, st));
+  const uint64_t npts = n * nc;
+  { ProfScope _p(ctx, "msm.digits");
+    k_msm_digits<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(scalars, dig, counts, g);
+    ZKC_LAUNCH_CHECK(ctx); }
+  { ProfScope _p(ctx, "msm.scan");
+    ZKC_TRY(u32_scan(ctx, counts, offsets, nbt, offsets + nbt));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(cursor, offsets, nbt * 4, cudaMemcpyDeviceToDevice, st)); }
+  { ProfScope _p(ctx, "msm.scatter");
+    k_msm_scatter<<<(unsigned)((em + 255) / 256), 256, 0, st>>>(dig, cursor, ent_pt, ent_key, g);
+    ZKC_LAUNCH_CHECK(ctx); }
+  const uint64_t nthreads = (em + g.T - 1) / g.T;
+  { ProfScope _p(ctx, "msm.accum");
+    k_msm_accum<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(bases, ent_pt, ent_key, offsets, partial, g);
+    ZKC_LAUNCH_CHECK(ctx); }
+  {
+    // group width from the expected number of partials per bucket (entries per bucket / T)
+    const double avg_partials = (double)g.W * (double)n / (double)g.NB / (double)g.sets / (double)g.T + 1.0;
+    uint32_t logG = 0;
+    while (logG < 5 && (double)(1u << logG) * 3.0 < avg_partials) ++logG;
+    { ProfScope _p(ctx, "msm.gather");
+      const uint64_t nthr = nbt << logG;
+      k_msm_gather<<<(unsigned)((nthr + 127) / 128), 128, 0, st>>>(offsets, partial, buckets, heavy, heavyc, g, logG);
+      ZKC_LAUNCH_CHECK(ctx); }
+    { ProfScope _p(ctx, "msm.gather_heavy");
+      k_msm_gather_heavy<<<ctx->sm_count * 4, 128, 128 * sizeof(G1Xyzz), st>>>(offsets, partial, buckets, heavy, heavyc, g);
+      ZKC_LAUNCH_CHECK(ctx); }
+  }
+  {
+    ProfScope _p(ctx, "msm.reduce");
+    const uint32_t nchunks = (g.NB + RED_CHUNK - 1) / RED_CHUNK;
+    dim3 g1(g.c, nchunks, nc * g.sets), g2(g.c, nc * g.sets);
+    k_msm_reduce1<<<g1, 64, 64 * sizeof(G1Xyzz), st>>>(buckets, redp, g, nchunks);
+    ZKC_LAUNCH_CHECK(ctx);
+    k_msm_reduce2<<<g2, 32, 32 * sizeof(G1Xyzz), st>>>(redp, U, g, nchunks);
+    ZKC_LAUNCH_CHECK(ctx);
+  }
+  const size_t ubytes = (size_t)nc * g.sets * g.c * sizeof(G1Xyzz);
+  void* hU;
+  ZKC_TRY(pinned_reserve(ctx, ubytes + 16, &hU, result_slot));   // slot 1: a batch whose result is consumed later
+  ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(hU, U, ubytes, cudaMemcpyDeviceToHost, st));
+  ZKC_CUDA_TRY(ctx, cudaMemcpyAsync((char*)hU + ubytes, offsets + nbt, 4, cudaMemcpyDeviceToHost, st));
+  cudaEvent_t ev = result_slot ? ctx->ev_msm_side : ctx->ev_msm_main;
+  ZKC_CUDA_TRY(ctx, cudaEventRecord(ev, st));
+  pend->g = g; pend->nc = nc; pend->n = n; pend->hU = hU; pend->ubytes = ubytes; pend->done = ev; pend->active = true;
+  return ZKC_OK;
+}
+
+// Wait for the batch, then the host-side epilogue (Horner over bit planes / windows, normalisation).
+int msm_finish(zkc_ctx* ctx, MsmPending* pend, zkc_g1* out) {
+  if (!pend->active) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm_finish: nothing pending");
+  ZKC_CUDA_TRY(ctx, cudaEventSynchronize(pend->done));
+  pend->active = false;
+  { uint32_t e; memcpy(&e, (char*)pend->hU + pend->ubytes, 4); ctx->stats["msm.madds"] += e; ctx->stats["msm.points"] += pend->n * pend->nc; }
+  for (uint32_t col = 0; col < pend->nc; ++col) {
+    G1Xyzz r = host_combine((const G1Xyzz*)pend->hU + (size_t)col * pend->g.sets * pend->g.c, pend->g);
+    xyzz_to_abi(r, out + col);
+  }
+  return ZKC_OK;
+}
+
 // Core: `ncols` scalar columns (n each, contiguous) against `bases` (n points, or W tables of n when
 // precomputed).  Writes ncols results to `out` (host).
 int msm_run(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, uint32_t ncols, uint32_t c, bool precomputed, zkc_g1* out) {
@@ -257,76 +329,9 @@ int msm_run(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, 
   chunk = std::min(chunk, ncols);
   for (uint32_t c0 = 0; c0 < ncols; c0 += chunk) {
     const uint32_t nc = std::min(chunk, ncols - c0);
-    MsmGeom g = msm_geom(n, nc, c, precomputed);
-    const uint64_t nbt = g.nbtot(), em = g.emax();
-    if (nbt + em / g.T + 1 >= (1ull << 32) || em >= (1ull << 32)) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: batch too large");
-    const uint64_t nslots = nbt + (em + g.T - 1) / g.T + 1;
-    // carve scratch
-    size_t o = 0;
-    auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
-    const size_t o_counts = carve(nbt * 4), o_offsets = carve((nbt + 1) * 4), o_cursor = carve(nbt * 4), o_heavyc = carve(4),
-                 o_heavy = carve(nbt * 4), o_dig = carve(em * 4), o_pt = carve(em * 4), o_key = carve(em * 4),
-                 o_part = carve(nslots * sizeof(G1Xyzz)), o_bk = carve(nbt * sizeof(G1Xyzz)),
-                 o_U = carve((size_t)nc * g.sets * g.c * sizeof(G1Xyzz)),
-                 o_redp = carve((size_t)nc * g.sets * g.c * ((g.NB + 1023) / 1024) * sizeof(G1Xyzz));
-    char* base;
-    ZKC_TRY(scratch_reserve(ctx, SCR_MSM, o, (void**)&base));
-    uint32_t* counts = (uint32_t*)(base + o_counts); uint32_t* offsets = (uint32_t*)(base + o_offsets);
-    uint32_t* cursor = (uint32_t*)(base + o_cursor); uint32_t* heavyc = (uint32_t*)(base + o_heavyc);
-    uint32_t* heavy = (uint32_t*)(base + o_heavy); uint32_t* dig = (uint32_t*)(base + o_dig);
-    uint32_t* ent_pt = (uint32_t*)(base + o_pt); uint32_t* ent_key = (uint32_t*)(base + o_key);
-    G1Xyzz* partial = (G1Xyzz*)(base + o_part); G1Xyzz* buckets = (G1Xyzz*)(base + o_bk); G1Xyzz* U = (G1Xyzz*)(base + o_U); G1Xyzz* redp = (G1Xyzz*)(base + o_redp);
-    cudaStream_t st = ctx->stream;
-    ZKC_CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, nbt * 4, st));
-    ZKC_CUDA_TRY(ctx, cudaMemsetAsync(heavyc, 0, 4, st));
-    const uint64_t npts = n * nc;
-    { ProfScope _p(ctx, "msm.digits");
-      k_msm_digits<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(scalars + (uint64_t)c0 * n, dig, counts, g);
-      ZKC_LAUNCH_CHECK(ctx); }
-    { ProfScope _p(ctx, "msm.scan");
-      ZKC_TRY(u32_scan(ctx, counts, offsets, nbt, offsets + nbt));
-      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(cursor, offsets, nbt * 4, cudaMemcpyDeviceToDevice, st)); }
-    { ProfScope _p(ctx, "msm.scatter");
-      k_msm_scatter<<<(unsigned)((em + 255) / 256), 256, 0, st>>>(dig, cursor, ent_pt, ent_key, g);
-      ZKC_LAUNCH_CHECK(ctx); }
-    const uint64_t nthreads = (em + g.T - 1) / g.T;
-    { ProfScope _p(ctx, "msm.accum");
-      k_msm_accum<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(bases, ent_pt, ent_key, offsets, partial, g);
-      ZKC_LAUNCH_CHECK(ctx); }
-    {
-      // group width from the expected number of partials per bucket (entries per bucket / T)
-      const double avg_partials = (double)g.W * (double)n / (double)g.NB / (double)g.sets / (double)g.T + 1.0;
-      uint32_t logG = 0;
-      while (logG < 5 && (double)(1u << logG) * 3.0 < avg_partials) ++logG;
-      { ProfScope _p(ctx, "msm.gather");
-        const uint64_t nthr = nbt << logG;
-        k_msm_gather<<<(unsigned)((nthr + 127) / 128), 128, 0, st>>>(offsets, partial, buckets, heavy, heavyc, g, logG);
-        ZKC_LAUNCH_CHECK(ctx); }
-      { ProfScope _p(ctx, "msm.gather_heavy");
-        k_msm_gather_heavy<<<ctx->sm_count * 4, 128, 128 * sizeof(G1Xyzz), st>>>(offsets, partial, buckets, heavy, heavyc, g);
-        ZKC_LAUNCH_CHECK(ctx); }
-    }
-    if ((uint64_t)nc * g.sets > 65535) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: too many bucket sets in one batch");
-    {
-      ProfScope _p(ctx, "msm.reduce");
-      const uint32_t nchunks = (g.NB + RED_CHUNK - 1) / RED_CHUNK;
-      dim3 g1(g.c, nchunks, nc * g.sets), g2(g.c, nc * g.sets);
-      k_msm_reduce1<<<g1, 64, 64 * sizeof(G1Xyzz), st>>>(buckets, redp, g, nchunks);
-      ZKC_LAUNCH_CHECK(ctx);
-      k_msm_reduce2<<<g2, 32, 32 * sizeof(G1Xyzz), st>>>(redp, U, g, nchunks);
-      ZKC_LAUNCH_CHECK(ctx);
-    }
-    const size_t ubytes = (size_t)nc * g.sets * g.c * sizeof(G1Xyzz);
-    void* hU;
-    ZKC_TRY(pinned_reserve(ctx, ubytes + 16, &hU));
-    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(hU, U, ubytes, cudaMemcpyDeviceToHost, st));
-    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync((char*)hU + ubytes, offsets + nbt, 4, cudaMemcpyDeviceToHost, st));
-    ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    { uint32_t e; memcpy(&e, (char*)hU + ubytes, 4); ctx->stats["msm.madds"] += e; ctx->stats["msm.points"] += n * nc; }
-    for (uint32_t col = 0; col < nc; ++col) {
-      G1Xyzz r = host_combine((const G1Xyzz*)hU + (size_t)col * g.sets * g.c, g);
-      xyzz_to_abi(r, out + c0 + col);
-    }
+    MsmPending pend;
+    ZKC_TRY(msm_enqueue(ctx, scalars + (uint64_t)c0 * n, bases, n, nc, c, precomputed, &pend, 0));
+    ZKC_TRY(msm_finish(ctx, &pend, out + c0));
   }
   return ZKC_OK;
 }
@@ -503,6 +508,11 @@ extern "C" int zkc_srs_get(zkc_ctx* ctx, const zkc_srs* s, int basis, zkc_g1_aff
 }
 
 namespace zkc {
+// asynchronous single-column commitment of a full-length polynomial (finish with msm_finish)
+int srs_commit_enqueue(zkc_ctx* ctx, const zkc_srs* s, int basis, const Fr* poly, uint64_t len, MsmPending* pend) {
+  if (len != s->n) return set_err(ctx, ZKC_ERR_BAD_ARG, "srs_commit_enqueue: full-length polynomials only");
+  return msm_enqueue(ctx, poly, s->tab[basis], len, 1, s->c, true, pend, 1);
+}
 // commit `ncols` device-resident polynomials of `len` <= n coefficients (column stride = len)
 int srs_commit_dev(zkc_ctx* ctx, const zkc_srs* s, int basis, const Fr* polys, uint64_t len, uint32_t ncols, zkc_g1* out) {
   if (len > s->n) return set_err(ctx, ZKC_ERR_BAD_ARG, "commit: polynomial longer than the SRS");

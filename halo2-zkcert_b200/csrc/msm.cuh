@@ -1,0 +1,37 @@
+// MSM geometry and the asynchronous enqueue / finish split shared by msm.cu and prover.cu.
+#pragma once
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace zkc {
+
+struct MsmGeom {
+  uint32_t c;          // window bits
+  uint32_t W;          // number of windows: W*c >= 255
+  uint32_t NB;         // buckets per window = 2^(c-1)
+  uint32_t sets;       // bucket sets per column: W (generic bases) or 1 (precomputed tables)
+  uint64_t n;          // points per column
+  uint32_t ncols;
+  uint32_t T;          // entries per accumulate thread
+  ZKC_HD uint64_t nbtot() const { return (uint64_t)ncols * sets * NB; }
+  ZKC_HD uint64_t emax() const { return (uint64_t)ncols * W * n; }
+};
+
+
+// one enqueued batch: results land in pinned host memory; `done` fires after the D2H copy
+struct MsmPending {
+  MsmGeom g;
+  uint32_t nc = 0;
+  uint64_t n = 0;
+  void* hU = nullptr;
+  size_t ubytes = 0;
+  cudaEvent_t done = nullptr;
+  bool active = false;
+};
+
+int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, uint32_t nc, uint32_t c, bool precomputed, MsmPending* pend,
+                int result_slot);
+int msm_finish(zkc_ctx* ctx, MsmPending* pend, zkc_g1* out);
+int srs_commit_enqueue(zkc_ctx* ctx, const zkc_srs* s, int basis, const Fr* poly, uint64_t len, MsmPending* pend);
+
+}  // namespace zkc

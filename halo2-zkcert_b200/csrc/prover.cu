@@ -9,7 +9,7 @@
 // on the device; columns stay resident in HBM from the advice upload to the last opening proof,
 // and only commitments (64 B), evaluations (32 B) and challenges cross PCIe.
 #include "prover_kernels.cuh"
-#include "ec.cuh"
+#include "msm.cuh"
 #include "host/hostutil.h"
 #include <algorithm>
 #include <functional>
@@ -363,15 +363,14 @@ struct Rng {
   uint64_t drawn = 0;
   explicit Rng(const uint8_t seed[32]) : cpu(seed) { memcpy(key.k, seed, 32); }
   Fr draw() { ++drawn; return cpu.fr_random(); }
-  // n draws generated on the device; the host cursor skips the same blocks
-  int bulk(zkc_ctx* ctx, Fr* out, uint64_t n) {
+  // draws [first, first + n) of the stream generated on the device (the host cursor is not moved)
+  int bulk_at(zkc_ctx* ctx, Fr* out, uint64_t first, uint64_t n) {
     if (!n) return ZKC_OK;
-    k_chacha_fr<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(out, key, drawn, n);
+    k_chacha_fr<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(out, key, first, n);
     ZKC_LAUNCH_CHECK(ctx);
-    drawn += n;
-    cpu.counter = drawn; cpu.pos = 16;
     return ZKC_OK;
   }
+  void skip(uint64_t n) { drawn += n; cpu.counter = drawn; cpu.pos = 16; }
 };
 
 struct Query { const Fr* poly; Fr point; Fr eval; };
@@ -530,6 +529,20 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   ZKC_TRY(pool.get(&lk_comp, (size_t)2 * L * n)); ZKC_TRY(pool.get(&lk_perm, (size_t)2 * L * n));
   ZKC_TRY(pool.get(&lk_perm_polys, (size_t)2 * L * n));
   ZKC_TRY(pool.get(&z_all, (size_t)(Pn + L) * n)); ZKC_TRY(pool.get(&z_all_polys, (size_t)(Pn + L) * n));
+  // The vanishing argument's random polynomial depends on nothing but the RNG: its n draws sit at a stream
+  // offset fixed by the constraint system and the blinding policy, so the polynomial and its commitment are
+  // produced first, on the side stream; the point is written to the transcript at step 8.
+  Fr* random_poly;
+  ZKC_TRY(pool.get(&random_poly, n));
+  const uint64_t draws_before_random = (opts->advice_blinding ? (uint64_t)A * (bf + 1) : 0) + (opts->blind_draws ? A : 0) +
+                                       (uint64_t)L * 2 * (bf + 1) + (opts->blind_draws ? 2 * L : 0) +
+                                       (uint64_t)(Pn + L) * bf + (opts->blind_draws ? (Pn + L) : 0);
+  MsmPending random_commit;
+  {
+    SideScope side(ctx);
+    ZKC_TRY(rng.bulk_at(ctx, random_poly, draws_before_random, n));
+    ZKC_TRY(srs_commit_enqueue(ctx, srs, 0, random_poly, n, &random_commit));
+  }
   if (A + I) {
     // off the Fiat-Shamir critical path: coefficient forms and extended cosets of advice / instance columns are
     // not needed before step 10, so they run on the side stream underneath the latency-bound MSM phases
@@ -697,12 +710,16 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   }
 
   // 8. vanishing argument: random polynomial, n draws generated on the device from the same stream
-  Fr* random_poly;
-  ZKC_TRY(pool.get(&random_poly, n));
-  ZKC_TRY(rng.bulk(ctx, random_poly, n));
+  if (rng.drawn != draws_before_random) return set_err(ctx, ZKC_ERR_SYNTHESIS, "internal: RNG draw schedule mismatch before the vanishing argument");
+  rng.skip(n);
   if (opts->blind_draws) rng.draw();
-  ZKC_TRY(commit_points(ctx, srs, 0, random_poly, n, 1, pts));
-  ZKC_TRY(write_points(pts));
+  {
+    zkc_g1 rp;
+    ZKC_TRY(msm_finish(ctx, &random_commit, &rp));
+    pts.resize(1);
+    g1_from_abi(rp, pts[0]);
+    ZKC_TRY(write_points(pts));
+  }
 
   // 9. y
   const Fr y = tr.squeeze_challenge();
