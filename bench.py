@@ -125,7 +125,7 @@ def cpu_oracle_seconds(sample_k, gate_cols, steps=1, warmup=0, seed=1, shape="ba
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        plonk.create_proof(pk, advice, circ.instances, pyref.ChaChaRng(pyref.seed_from_u64(i), 20))
+        plonk.create_proof(pk, advice, circ.instances, orc.ChaCha20Rng(pyref.seed_from_u64(i)))
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     return sum(times) / len(times), orc.lib().orc_default_threads()

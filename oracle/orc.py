@@ -264,3 +264,22 @@ def powers(base, n, first=None):
     f = fr_from_ints([1]) if first is None else np.ascontiguousarray(first, dtype=np.uint64)
     lib().orc_powers(_p(np.ascontiguousarray(base, dtype=np.uint64)), _p(f), C.c_size_t(n), _p(out))
     return out
+
+
+class ChaCha20Rng:
+    """rand_chacha::ChaCha20Rng restricted to Fr::random draws (each consumes one 64-byte keystream block)."""
+
+    def __init__(self, seed32: bytes):
+        self.seed = bytes(seed32)
+        self.drawn = 0
+
+    def fr_random_bulk(self, n):
+        """n draws as an (n, 4) Montgomery array"""
+        out = np.empty((n, 4), dtype=np.uint64)
+        lib().orc_chacha_fr_random(C.c_char_p(self.seed), C.c_uint64(self.drawn), C.c_size_t(n), _p(out))
+        self.drawn += n
+        return out
+
+    def fr_random(self):
+        """one draw as a canonical int"""
+        return fr_to_ints(self.fr_random_bulk(1))[0]

@@ -107,3 +107,32 @@ void orc_powers(const uint64_t* base, const uint64_t* first, size_t n, uint64_t*
 }
 
 }  // extern "C"
+
+// ---- ChaCha20Rng / Fr::random stream (rand_chacha 0.3.1 + halo2curves from_u512) -------------
+// draw #i = keystream block (skip + i) of ChaCha20(key = seed, 64-bit block counter, stream 0), read as a
+// 512-bit little-endian integer and reduced mod r.  Pinned against tests/pyref.py's pure-Python restatement
+// and the known answers of SURVEY §8c-4.
+static inline uint32_t rotl32(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+extern "C" void orc_chacha_fr_random(const uint8_t* seed, uint64_t skip, size_t count, uint64_t* out) {
+  uint32_t key[8]; memcpy(key, seed, 32);
+  parallel_chunks(count, default_threads(), [&](size_t lo, size_t hi, int) {
+    for (size_t i = lo; i < hi; ++i) {
+      const uint64_t ctr = skip + i;
+      uint32_t s[16] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                        (uint32_t)ctr, (uint32_t)(ctr >> 32), 0, 0};
+      uint32_t x[16]; memcpy(x, s, sizeof x);
+#define ORC_QR(a, b, c, d) \
+  x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 12); \
+  x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 7);
+      for (int r = 0; r < 10; ++r) {
+        ORC_QR(0, 4, 8, 12) ORC_QR(1, 5, 9, 13) ORC_QR(2, 6, 10, 14) ORC_QR(3, 7, 11, 15)
+        ORC_QR(0, 5, 10, 15) ORC_QR(1, 6, 11, 12) ORC_QR(2, 7, 8, 13) ORC_QR(3, 4, 9, 14)
+      }
+#undef ORC_QR
+      uint64_t wide[8];
+      for (int j = 0; j < 8; ++j) wide[j] = (uint64_t)(x[2 * j] + s[2 * j]) | ((uint64_t)(x[2 * j + 1] + s[2 * j + 1]) << 32);
+      Fr f = Fr::from_u512(wide);
+      memcpy(out + 4 * i, f.l, 32);
+    }
+  });
+}

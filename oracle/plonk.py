@@ -528,7 +528,7 @@ def create_proof(pk, advice_mont, instances, rng, transcript_kind="blake2b", mul
         lk["z_poly"] = orc.lagrange_to_coeff(j, k, z)
 
     # 8. vanishing: random polynomial
-    random_poly = orc.fr_from_ints([draw() for _ in range(n)])
+    random_poly = rng.fr_random_bulk(n) if hasattr(rng, "fr_random_bulk") else orc.fr_from_ints([draw() for _ in range(n)])
     if opts.blind_draws:
         draw()
     tr.write_point(commit(random_poly, pk.g))

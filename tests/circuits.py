@@ -32,3 +32,8 @@ def oracle_setup(circ, zeta_choice=0):
 
 def rng_for(seed):
     return pyref.ChaChaRng(pyref.seed_from_u64(seed), 20)
+
+
+def fast_rng_for(seed):
+    """the oracle's C++ ChaCha20 stream (same draws as rng_for, pinned in test_oracle_ops.py)"""
+    return orc.ChaCha20Rng(pyref.seed_from_u64(seed))

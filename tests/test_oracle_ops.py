@@ -182,3 +182,13 @@ def test_srs_setup_small():
     c2 = orc.best_multiexp(lag, gl, 2)
     assert np.array_equal(c1, c2)
     assert orc.g1_to_ints(c1)[0] == pyref.ec_mul(pyref.G1_GEN, pyref.poly_eval(coeffs, s))
+
+
+def test_oracle_chacha_stream_matches_python_restatement():
+    seed = pyref.seed_from_u64(77)
+    slow = pyref.ChaChaRng(seed, 20)
+    want = [slow.fr_random() for _ in range(40)]
+    fast = orc.ChaCha20Rng(seed)
+    assert [fast.fr_random() for _ in range(3)] == want[:3]
+    assert orc.fr_to_ints(fast.fr_random_bulk(37)) == want[3:]
+    assert orc.ChaCha20Rng(bytes(32)).fr_random() == 0x1c59a59b6cff4308740943526ade1d8c09f71b337a67269cc89586bcdd6dfcba

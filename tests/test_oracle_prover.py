@@ -6,7 +6,7 @@ import pytest
 
 from oracle import plonk, verifier, pairing
 from tests import pyref
-from tests.circuits import SRS_SECRET, oracle_setup, rng_for
+from tests.circuits import SRS_SECRET, fast_rng_for, oracle_setup, rng_for
 from tests.util import pkg
 
 
@@ -85,3 +85,8 @@ def test_lookup_value_outside_table_is_an_error(small):
     bad[-1][3] = plonk.M(1 << 40)[0]
     with pytest.raises(ValueError, match="ConstraintSystemFailure"):
         plonk.create_proof(pk, bad, circ.instances, rng_for(1))
+
+
+def test_fast_rng_gives_identical_proof(small):
+    circ, pk, advice = small
+    assert plonk.create_proof(pk, advice, circ.instances, rng_for(4)) == plonk.create_proof(pk, advice, circ.instances, fast_rng_for(4))
