@@ -128,6 +128,11 @@ class Context:
                                               None if b is None else _dp(b), _dp(out), C.c_size_t(n)))
         return out
 
+    def batch_invert_assigned_dev(self, num, den, out):
+        """poly::batch_invert_assigned on device columns: out = num / den (den = 0 -> 0)"""
+        self.check(lib().zkc_batch_invert_assigned_dev(self._h, _dp(num), _dp(den), _dp(out), C.c_size_t(num.shape[0])))
+        return out
+
     def powers_dev(self, out, base, first):
         """out[i] = first * base^i on the device (out: torch (n, 4) int64)"""
         self.check(lib().zkc_fr_powers_dev(self._h, _dp(out), C.c_size_t(out.shape[0]), _hp(_np(base, 4)), _hp(_np(first, 4))))

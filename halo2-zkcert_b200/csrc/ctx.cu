@@ -204,6 +204,11 @@ int vec_op_impl(zkc_ctx* ctx, int op, const Fe<P>* a, const Fe<P>* b, Fe<P>* out
 
 int fr_batch_invert(zkc_ctx* ctx, const Fr* a, Fr* out, size_t n) { return vec_op_impl<FrP>(ctx, ZKC_OP_INV, a, nullptr, out, n); }
 
+__global__ void k_mul_inplace(Fr* a, const Fr* b, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) fe_store(a + i, fe_mul(fe_load(a + i), fe_load(b + i)));
+}
+
 }  // namespace zkc
 
 namespace zkc { int fr_powers(zkc_ctx* ctx, Fr* out, uint64_t n, const Fr& base, const Fr& first); }
@@ -212,6 +217,18 @@ extern "C" int zkc_fr_powers_dev(zkc_ctx* ctx, zkc_fr* out, size_t n, const zkc_
   CtxLock lock(ctx);
   Fr b, f; memcpy(b.v, base, 32); memcpy(f.v, first, 32);
   return fr_powers(ctx, (Fr*)out, n, b, f);
+}
+
+// poly::batch_invert_assigned: Assigned::Rational(num, den) cells -> num * den^-1 (den = 0 -> 0, as upstream's
+// `Assigned::evaluate`); Trivial cells pass den = 1.
+extern "C" int zkc_batch_invert_assigned_dev(zkc_ctx* ctx, const zkc_fr* num, const zkc_fr* den, zkc_fr* out, size_t n) {
+  if (!ctx || !num || !den || !out) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_batch_invert_assigned_dev: null argument");
+  if (n == 0) return ZKC_OK;
+  CtxLock lock(ctx);
+  ZKC_TRY(fr_batch_invert(ctx, (const Fr*)den, (Fr*)out, n));
+  k_mul_inplace<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((Fr*)out, (const Fr*)num, n);
+  ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
 }
 
 extern "C" int zkc_field_vec_op_dev(zkc_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n) {

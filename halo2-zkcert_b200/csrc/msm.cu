@@ -44,8 +44,11 @@ __global__ void k_msm_digits(const Fr* scalars, uint32_t* dig, uint32_t* counts,
     if (raw > g.NB) { raw = full - raw; sign = 1; carry = 1; }
     dig[((uint64_t)col * g.W + w) * g.n + i] = raw | (sign << 31);
     if (raw) {
-      const uint64_t key = ((uint64_t)col * g.sets + (g.sets == 1 ? 0 : w)) * g.NB + (raw - 1);
-      atomicAdd(counts + key, 1u);
+      // warp-aggregated histogram update: lanes that hit the same bucket (bit / byte valued witness columns put
+      // most of a warp on one counter) elect a leader that adds their count once
+      const uint32_t key = (uint32_t)(((uint64_t)col * g.sets + (g.sets == 1 ? 0 : w)) * g.NB + (raw - 1));
+      const uint32_t peers = __match_any_sync(__activemask(), key);
+      if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(counts + key, (uint32_t)__popc(peers));
     }
   }
 }
@@ -59,8 +62,14 @@ __global__ void k_msm_scatter(const uint32_t* dig, uint32_t* cursor, uint32_t* e
   const uint64_t cw = idx / g.n;            // col*W + w
   const uint64_t i = idx - cw * g.n;
   const uint32_t col = (uint32_t)(cw / g.W), w = (uint32_t)(cw - (uint64_t)col * g.W);
-  const uint64_t key = ((uint64_t)col * g.sets + (g.sets == 1 ? 0 : w)) * g.NB + (mag - 1);
-  const uint32_t pos = atomicAdd(cursor + key, 1u);
+  const uint32_t key = (uint32_t)(((uint64_t)col * g.sets + (g.sets == 1 ? 0 : w)) * g.NB + (mag - 1));
+  // warp-aggregated slot allocation (same reason as in k_msm_digits)
+  const uint32_t peers = __match_any_sync(__activemask(), key);
+  const uint32_t lane = threadIdx.x & 31, leader = (uint32_t)(__ffs(peers) - 1);
+  uint32_t basepos = 0;
+  if (lane == leader) basepos = atomicAdd(cursor + key, (uint32_t)__popc(peers));
+  basepos = __shfl_sync(peers, basepos, leader);
+  const uint32_t pos = basepos + (uint32_t)__popc(peers & ((1u << lane) - 1));
   const uint64_t pt = g.sets == 1 ? (uint64_t)w * g.n + i : i;   // precomputed tables are laid out [w][i]
   ent_pt[pos] = (uint32_t)pt | (d & 0x80000000u);
   ent_key[pos] = (uint32_t)key;
@@ -90,6 +99,9 @@ __global__ void __launch_bounds__(128) k_msm_accum(const G1Affine* bases, const 
 }
 
 #define MSM_HEAVY_PER_LANE 12
+#define MSM_GIANT 4096        // partials: above this a bucket is sliced over MSM_GIANT_SLICES CTAs
+#define MSM_GIANT_SLICES 64
+#define MSM_GIANT_CAP 512
 __device__ __forceinline__ G1Xyzz xyzz_shfl_xor(const G1Xyzz& p, int mask) {
   G1Xyzz r;
 #pragma unroll
@@ -117,8 +129,18 @@ __global__ void __launch_bounds__(128) k_msm_gather(const uint32_t* offsets, con
     for (uint64_t s = lane; s < np; s += G) xyzz_add(acc, xyzz_load(partial + first + s));
   for (uint32_t d = G >> 1; d > 0; d >>= 1) { G1Xyzz o = xyzz_shfl_xor(acc, (int)d); xyzz_add(acc, o); }
   if (valid && lane == 0) {
-    if (heavy) heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)key;
-    else xyzz_store(buckets + key, acc);
+    if (heavy) {
+      // heavy_count[0] / heavy_list[0..nbt): one CTA per bucket; heavy_count[1] / giant list (after nbt): sliced over many CTAs
+      if (np > MSM_GIANT && heavy_count[1] < MSM_GIANT_CAP) {
+        const uint32_t gi = atomicAdd(heavy_count + 1, 1u);
+        if (gi < MSM_GIANT_CAP) heavy_list[g.nbtot() + gi] = (uint32_t)key;
+        else heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)key;
+      } else {
+        heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)key;
+      }
+    } else {
+      xyzz_store(buckets + key, acc);
+    }
   }
 }
 
@@ -149,6 +171,36 @@ __global__ void __launch_bounds__(128) k_msm_gather_heavy(const uint32_t* offset
     for (uint64_t s = first + threadIdx.x; s <= last; s += blockDim.x) xyzz_add(acc, xyzz_load(partial + s));
     G1Xyzz r = block_reduce_xyzz(acc, sm);
     if (threadIdx.x == 0) xyzz_store(buckets + key, r);
+  }
+}
+
+// giant buckets, pass 1: slice j of giant bucket gi -> hpart[gi * SLICES + j];  grid = (SLICES, lanes)
+__global__ void __launch_bounds__(128) k_msm_gather_giant1(const uint32_t* offsets, const G1Xyzz* partial, G1Xyzz* hpart,
+                                                           const uint32_t* heavy_list, const uint32_t* heavy_count, MsmGeom g) {
+  extern __shared__ uint4 smraw[];
+  G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smraw);
+  const uint32_t ng = min(heavy_count[1], (uint32_t)MSM_GIANT_CAP);
+  for (uint32_t gi = blockIdx.y; gi < ng; gi += gridDim.y) {
+    const uint64_t key = heavy_list[g.nbtot() + gi];
+    const uint32_t off = offsets[key], cnt = offsets[key + 1] - off;
+    const uint64_t first = key + off / g.T, np = key + (off + cnt - 1) / g.T - first + 1;
+    const uint64_t per = (np + MSM_GIANT_SLICES - 1) / MSM_GIANT_SLICES;
+    const uint64_t lo = (uint64_t)blockIdx.x * per, hi = lo + per < np ? lo + per : np;
+    G1Xyzz acc = xyzz_identity();
+    for (uint64_t s = lo + threadIdx.x; s < hi; s += blockDim.x) xyzz_add(acc, xyzz_load(partial + first + s));
+    G1Xyzz r = block_reduce_xyzz(acc, sm);
+    if (threadIdx.x == 0) xyzz_store(hpart + (uint64_t)gi * MSM_GIANT_SLICES + blockIdx.x, r);
+  }
+}
+// pass 2: fold the slices
+__global__ void __launch_bounds__(MSM_GIANT_SLICES) k_msm_gather_giant2(const G1Xyzz* hpart, G1Xyzz* buckets, const uint32_t* heavy_list,
+                                                                        const uint32_t* heavy_count, MsmGeom g) {
+  extern __shared__ uint4 smraw[];
+  G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smraw);
+  const uint32_t ng = min(heavy_count[1], (uint32_t)MSM_GIANT_CAP);
+  for (uint32_t gi = blockIdx.x; gi < ng; gi += gridDim.x) {
+    G1Xyzz r = block_reduce_xyzz(xyzz_load(hpart + (uint64_t)gi * MSM_GIANT_SLICES + threadIdx.x), sm);
+    if (threadIdx.x == 0) xyzz_store(buckets + heavy_list[g.nbtot() + gi], r);
   }
 }
 
@@ -204,7 +256,10 @@ static void xyzz_to_abi(const G1Xyzz& p, zkc_g1* out) {
 int u32_scan(zkc_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* total_dev);   // poly.cu
 
 uint32_t msm_pick_c(uint64_t n, bool precomputed) {
-  if (const char* e = getenv(precomputed ? "ZKC_MSM_C_PRE" : "ZKC_MSM_C")) { int v = atoi(e); if (v >= 3 && v <= 20) return (uint32_t)v; }
+  if (const char* e = getenv(precomputed ? "ZKC_MSM_C_PRE" : "ZKC_MSM_C")) {
+    int v = atoi(e);
+    if (v >= 3 && v <= 20) { const int W = (255 + v - 1) / v; return (uint32_t)((255 + W - 1) / W); }
+  }
   uint32_t lg = 0;
   while ((1ull << (lg + 1)) <= n) ++lg;
   // measured on B200: shared-bucket (precomputed) layout wants ~4-8 partials per bucket for the
@@ -212,12 +267,16 @@ uint32_t msm_pick_c(uint64_t n, bool precomputed) {
   int c = (int)lg - 4;
   if (precomputed && lg <= 18) c = (int)lg - 2;
   else if (precomputed && lg == 19) c = (int)lg - 3;
-  return (uint32_t)std::max(3, std::min(20, c));
+  c = std::max(3, std::min(20, c));
+  const int W = (255 + c - 1) / c;
+  return (uint32_t)((255 + W - 1) / W);   // same number of windows, evenly filled (see msm_geom)
 }
 
 MsmGeom msm_geom(uint64_t n, uint32_t ncols, uint32_t c, bool precomputed) {
   MsmGeom g;
-  g.c = c; g.W = (255 + c - 1) / c; g.NB = 1u << (c - 1); g.sets = precomputed ? 1 : g.W; g.n = n; g.ncols = ncols;
+  g.W = (255 + c - 1) / c;
+  c = (255 + g.W - 1) / g.W;   // same window count, evenly filled: a nearly empty top window would pile n/2^few entries on a handful of buckets
+  g.c = c; g.NB = 1u << (c - 1); g.sets = precomputed ? 1 : g.W; g.n = n; g.ncols = ncols;
   const uint64_t e = g.emax();
   // entries per accumulate thread (B200 sweep): short chunks keep more warps in flight (T=8 reaches
   // 0.99 of the IMAD.WIDE peak) but multiply the partials the gather phase must fold; 32 / 64 minimise the sum
@@ -238,8 +297,8 @@ int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t
   const uint64_t nslots = nbt + (em + g.T - 1) / g.T + 1;
   size_t o = 0;
   auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
-  const size_t o_counts = carve(nbt * 4), o_offsets = carve((nbt + 1) * 4), o_cursor = carve(nbt * 4), o_heavyc = carve(4),
-               o_heavy = carve(nbt * 4), o_dig = carve(em * 4), o_pt = carve(em * 4), o_key = carve(em * 4),
+  const size_t o_counts = carve(nbt * 4), o_offsets = carve((nbt + 1) * 4), o_cursor = carve(nbt * 4), o_heavyc = carve(8),
+               o_heavy = carve((nbt + MSM_GIANT_CAP) * 4), o_hpart = carve((size_t)MSM_GIANT_CAP * MSM_GIANT_SLICES * sizeof(G1Xyzz)), o_dig = carve(em * 4), o_pt = carve(em * 4), o_key = carve(em * 4),
                o_part = carve(nslots * sizeof(G1Xyzz)), o_bk = carve(nbt * sizeof(G1Xyzz)),
                o_U = carve((size_t)nc * g.sets * g.c * sizeof(G1Xyzz)),
                o_redp = carve((size_t)nc * g.sets * g.c * ((g.NB + 1023) / 1024) * sizeof(G1Xyzz));
@@ -249,10 +308,10 @@ int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t
   uint32_t* cursor = (uint32_t*)(base + o_cursor); uint32_t* heavyc = (uint32_t*)(base + o_heavyc);
   uint32_t* heavy = (uint32_t*)(base + o_heavy); uint32_t* dig = (uint32_t*)(base + o_dig);
   uint32_t* ent_pt = (uint32_t*)(base + o_pt); uint32_t* ent_key = (uint32_t*)(base + o_key);
-  G1Xyzz* partial = (G1Xyzz*)(base + o_part); G1Xyzz* buckets = (G1Xyzz*)(base + o_bk); G1Xyzz* U = (G1Xyzz*)(base + o_U); G1Xyzz* redp = (G1Xyzz*)(base + o_redp);
+  G1Xyzz* partial = (G1Xyzz*)(base + o_part); G1Xyzz* buckets = (G1Xyzz*)(base + o_bk); G1Xyzz* U = (G1Xyzz*)(base + o_U); G1Xyzz* redp = (G1Xyzz*)(base + o_redp); G1Xyzz* hpart = (G1Xyzz*)(base + o_hpart);
   cudaStream_t st = ctx->stream;
   ZKC_CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, nbt * 4, st));
-  ZKC_CUDA_TRY(ctx, cudaMemsetAsync(heavyc, 0, 4, st));
+  ZKC_CUDA_TRY(ctx, cudaMemsetAsync(heavyc, 0, 8, st));
   const uint64_t npts = n * nc;
   { ProfScope _p(ctx, "msm.digits");
     k_msm_digits<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(scalars, dig, counts, g);
@@ -278,6 +337,10 @@ int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t
       ZKC_LAUNCH_CHECK(ctx); }
     { ProfScope _p(ctx, "msm.gather_heavy");
       k_msm_gather_heavy<<<ctx->sm_count * 4, 128, 128 * sizeof(G1Xyzz), st>>>(offsets, partial, buckets, heavy, heavyc, g);
+      ZKC_LAUNCH_CHECK(ctx);
+      k_msm_gather_giant1<<<dim3(MSM_GIANT_SLICES, 16), 128, 128 * sizeof(G1Xyzz), st>>>(offsets, partial, hpart, heavy, heavyc, g);
+      ZKC_LAUNCH_CHECK(ctx);
+      k_msm_gather_giant2<<<64, MSM_GIANT_SLICES, MSM_GIANT_SLICES * sizeof(G1Xyzz), st>>>(hpart, buckets, heavy, heavyc, g);
       ZKC_LAUNCH_CHECK(ctx); }
   }
   {

@@ -94,6 +94,9 @@ typedef enum {
 /* field: 0 = Fr, 1 = Fq.  out[i] = a[i] (op) b[i]; b may be NULL for unary ops.  Device pointers. */
 int zkc_field_vec_op_dev(zkc_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
 
+/* poly::batch_invert_assigned: out[i] = num[i] / den[i] with den = 0 -> 0; device pointers. */
+int zkc_batch_invert_assigned_dev(zkc_ctx* ctx, const zkc_fr* num, const zkc_fr* den, zkc_fr* out, size_t n);
+
 /* out[i] = first * base^i (arithmetic::powers; used for omega^i / DELTA^c tables at keygen).  Device pointer. */
 int zkc_fr_powers_dev(zkc_ctx* ctx, zkc_fr* out_dev, size_t n, const zkc_fr* base, const zkc_fr* first);
 

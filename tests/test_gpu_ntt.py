@@ -123,3 +123,18 @@ def test_field_vec_ops():
             ctx.field_vec_op_dev(field, op, ta, None, out)
             ctx.sync()
             assert np.array_equal(to_host(out), orc.field_op(field, op, a)), (field, op)
+
+
+def test_batch_invert_assigned():
+    import torch
+    ctx = gpu_ctx()
+    n = 3000
+    num, den = random_fr_mont(n, 5), random_fr_mont(n, 6)
+    den[3] = 0
+    den[10] = orc.fr_from_ints([1])[0]
+    out = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    ctx.batch_invert_assigned_dev(to_dev(num), to_dev(den), out)
+    ctx.sync()
+    want = orc.field_op("fr", "mul", num, orc.field_op("fr", "inv", den))
+    assert np.array_equal(to_host(out), want)
+    assert not to_host(out)[3].any() and np.array_equal(to_host(out)[10], num[10])
