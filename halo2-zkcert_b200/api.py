@@ -393,6 +393,62 @@ def create_proof(pk, advice, instances, rng_seed, transcript="blake2b", multiope
     return bytes(buf[:plen.value])
 
 
+class AdviceColumn(C.Structure):
+    _fields_ = [("kind", C.c_int), ("data", C.c_void_p)]
+
+
+COMPACT_KINDS = {"fr": 0, "bits": 1, "u8": 2, "u16": 3, "u64": 4}
+
+
+class CompactAdvice:
+    """Witness columns in compact host form for zkc_prove_compact: list of (kind, numpy array)."""
+
+    def __init__(self, columns):
+        self.columns = [(COMPACT_KINDS[k], np.ascontiguousarray(a)) for k, a in columns]
+        self.nbytes = sum(a.nbytes for _, a in self.columns)
+
+    @staticmethod
+    def pack_canonical(col_limbs):
+        """choose the tightest encoding for one column of canonical (n, 4) uint64 limbs"""
+        hi = col_limbs[:, 1:].any()
+        lo = col_limbs[:, 0]
+        if hi:
+            raise ValueError("column does not fit 64 bits; pass it as ('fr', montgomery limbs)")
+        m = int(lo.max()) if lo.size else 0
+        if m <= 1:
+            return ("bits", np.packbits(lo.astype(np.uint8), bitorder="little"))
+        if m < 256:
+            return ("u8", lo.astype(np.uint8))
+        if m < 65536:
+            return ("u16", lo.astype(np.uint16))
+        return ("u64", lo.astype(np.uint64))
+
+
+def create_proof_compact(pk, compact, instances, rng_seed, transcript="blake2b", multiopen="shplonk", advice_blinding="axiom",
+                         blind_draws=False, point_format=0):
+    """create_proof with the witness handed over in compact host form (CompactAdvice)"""
+    ctx = pk.ctx
+    o = ProveOpts()
+    o.transcript = {"blake2b": 0, "keccak": 1}[transcript]
+    o.multiopen = {"shplonk": 0, "gwc": 1}[multiopen]
+    o.advice_blinding = {"axiom": 0, "pse": 1}[advice_blinding]
+    o.blind_draws = 1 if blind_draws else 0
+    o.point_format = point_format
+    o.rng_seed[:] = list(rng_seed)
+    cols = (AdviceColumn * max(len(compact.columns), 1))()
+    for i, (kind, arr) in enumerate(compact.columns):
+        cols[i].kind = kind
+        cols[i].data = arr.ctypes.data
+    inst = [_np(i, 4) if len(i) else np.zeros((0, 4), dtype=np.uint64) for i in instances]
+    ptrs = (C.c_void_p * max(len(inst), 1))(*[i.ctypes.data for i in inst])
+    lens = (C.c_size_t * max(len(inst), 1))(*[i.shape[0] for i in inst])
+    cap = 1 << 20
+    buf = (C.c_uint8 * cap)()
+    plen = C.c_size_t(0)
+    ctx.check(lib().zkc_prove_compact(ctx._h, pk._h, cols, ptrs, lens, C.byref(o), buf, C.c_size_t(cap), C.byref(plen)))
+    return bytes(buf[:plen.value])
+
+
 def seed_from_u64(state):
     out = (C.c_uint8 * 32)()
     lib().zkc_seed_from_u64(C.c_uint64(state), out)

@@ -950,3 +950,49 @@ extern "C" int zkc_rng_fr_random(const uint8_t seed[32], uint64_t skip, zkc_fr* 
   return ZKC_OK;
 }
 extern "C" void zkc_seed_from_u64(uint64_t state, uint8_t seed[32]) { host::seed_from_u64(state, seed); }
+
+// Compact witness upload: SHA256-bit style circuits assign almost only {0,1} cells, so the
+// host may hand columns over as bit / byte / u16 / u64 arrays; they are expanded to Montgomery form on the
+// device and the proof is identical to the one zkc_prove emits for the expanded columns.
+extern "C" int zkc_prove_compact(zkc_ctx* ctx, const zkc_pk* pk, const zkc_advice_column* cols, const zkc_fr* const* instances,
+                                 const size_t* instance_lens, const zkc_prove_opts* opts, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+  if (!ctx || !pk || !cols) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_prove_compact: null argument");
+  CtxLock lock(ctx);
+  const uint64_t n = pk->cs.n();
+  const uint32_t A = pk->cs.num_advice;
+  Fr* adv = nullptr;
+  uint8_t* stage = nullptr;
+  cudaStream_t st = ctx->stream;
+  ZKC_CUDA_TRY(ctx, cudaMallocAsync((void**)&adv, std::max<size_t>((size_t)A * n, 1) * sizeof(Fr), st));
+  size_t stage_bytes = 0, off = 0;
+  auto col_bytes = [&](int kind) -> size_t { return kind == 0 ? n * 32 : kind == 1 ? (n + 7) / 8 : kind == 2 ? n : kind == 3 ? n * 2 : n * 8; };
+  for (uint32_t c = 0; c < A; ++c) {
+    if (cols[c].kind < 0 || cols[c].kind > 4 || !cols[c].data) { cudaFreeAsync(adv, st); return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_prove_compact: bad column"); }
+    if (cols[c].kind) stage_bytes += (col_bytes(cols[c].kind) + 15) & ~(size_t)15;
+  }
+  int status = ZKC_OK;
+  if (stage_bytes && cudaMallocAsync((void**)&stage, stage_bytes, st) != cudaSuccess) status = set_err(ctx, ZKC_ERR_OOM, "zkc_prove_compact: out of memory");
+  {
+    ProfScope _p(ctx, "prove.advice_h2d");
+    for (uint32_t c = 0; c < A && status == ZKC_OK; ++c) {
+      const size_t b = col_bytes(cols[c].kind);
+      cudaError_t e;
+      if (cols[c].kind == 0) {
+        e = cudaMemcpyAsync(adv + (size_t)c * n, cols[c].data, b, cudaMemcpyHostToDevice, st);
+      } else {
+        e = cudaMemcpyAsync(stage + off, cols[c].data, b, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+          k_expand_compact<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stage + off, adv + (size_t)c * n, n, cols[c].kind);
+          ctx->launches++;
+          e = cudaGetLastError();
+        }
+        off += (b + 15) & ~(size_t)15;
+      }
+      if (e != cudaSuccess) status = set_err(ctx, ZKC_ERR_CUDA, cudaGetErrorString(e));
+    }
+  }
+  if (status == ZKC_OK) status = zkc_prove(ctx, pk, (const zkc_fr*)adv, 1, instances, instance_lens, opts, proof_out, proof_cap, proof_len);
+  if (stage) cudaFreeAsync(stage, st);
+  cudaFreeAsync(adv, st);
+  return status;
+}

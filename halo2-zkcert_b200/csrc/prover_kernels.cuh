@@ -209,6 +209,22 @@ __global__ void k_pk_mul_vec(const Fr* a, const Fr* b, Fr* out, uint64_t n) {
   if (i < n) fe_store(out + i, fe_mul(fe_load(a + i), fe_load(b + i)));
 }
 
+// compact witness columns (bit / byte / u16 / u64 cells) -> Montgomery Fr; kind: 1 bits (LSB first), 2 u8, 3 u16, 4 u64
+__global__ void k_expand_compact(const uint8_t* src, Fr* out, uint64_t n, int kind) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t v;
+  if (kind == 1) v = (src[i >> 3] >> (i & 7)) & 1;
+  else if (kind == 2) v = src[i];
+  else if (kind == 3) v = reinterpret_cast<const uint16_t*>(src)[i];
+  else v = reinterpret_cast<const uint64_t*>(src)[i];
+  Fr r;
+  if (v == 0) r = fe_zero<FrP>();
+  else if (v == 1) r = fe_one<FrP>();
+  else { Fr c = fe_zero<FrP>(); c.v[0] = (uint32_t)v; c.v[1] = (uint32_t)(v >> 32); r = fe_from_canonical(c); }
+  fe_store(out + i, r);
+}
+
 // l_active = 1 - l_last - l_blind (extended coset)
 __global__ void k_l_active(const Fr* l_last, const Fr* l_blind, Fr* out, uint64_t rows) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -80,4 +80,11 @@ def build(ctx, k, num_gate_cols, seed=0, circ=None, params=None, shape="base"):
     w.advice_pinned = w.advice_dev.cpu().pin_memory()
     w.advice_host = w.advice_pinned.numpy().view(np.uint64)
     w.h2d_bytes = w.advice_host.nbytes + sum(i.nbytes for i in w.instances)
+    # compact host form (bit / byte / u64 columns) when every cell of the witness fits 64 bits
+    w.compact = None
+    if hasattr(w.circ, "advice_limbs"):
+        try:
+            w.compact = api.CompactAdvice([api.CompactAdvice.pack_canonical(c) for c in w.circ.advice_limbs])
+        except ValueError:
+            w.compact = None
     return w

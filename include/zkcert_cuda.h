@@ -186,6 +186,13 @@ typedef struct {
 int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, int advice_on_device, const zkc_fr* const* instances,
               const size_t* instance_lens, const zkc_prove_opts* opts, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
 
+/* Compact witness columns: kind 0 = zkc_fr[n] (Montgomery), 1 = bit-packed (1 bit per cell, LSB first,
+ * ceil(n/8) bytes), 2 = uint8[n], 3 = uint16[n], 4 = uint64[n] (canonical small integers).  Host pointers.  The proof is
+ * byte-identical to zkc_prove on the expanded columns; the H2D volume of a SHA256-bit witness drops ~250x. */
+typedef struct { int kind; const void* data; } zkc_advice_column;
+int zkc_prove_compact(zkc_ctx* ctx, const zkc_pk* pk, const zkc_advice_column* cols /* num_advice */, const zkc_fr* const* instances,
+                      const size_t* instance_lens, const zkc_prove_opts* opts, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+
 /* host-side helpers mirrored for cross-checking a caller's RNG: Fr::random stream of ChaCha20Rng::from_seed(seed)
  * starting at draw `skip`; rand_core's SeedableRng::seed_from_u64. */
 int zkc_rng_fr_random(const uint8_t seed[32], uint64_t skip, zkc_fr* out, size_t count);

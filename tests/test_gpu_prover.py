@@ -177,3 +177,21 @@ def test_full_size_proofs_verify(k, cols, shape):
     if shape == "base" and k == 17:
         gwc = pkg().create_proof(w.pk, w.advice_dev, w.instances, seed, transcript="keccak", multiopen="gwc")
         assert _verify_workload(w, gwc, transcript_kind="keccak", multiopen="gwc")
+
+
+def test_compact_witness_upload_matches_full():
+    """zkc_prove_compact (bit-packed / u16 columns expanded on the device) emits the same bytes as zkc_prove."""
+    ctx = gpu_ctx()
+    w = pkg().workload.build(ctx, 10, 48, seed=4, shape="sha_bit")
+    assert w.compact is not None and w.compact.nbytes * 50 < w.advice_host.nbytes
+    kinds = {k for k, _ in w.compact.columns}
+    assert 1 in kinds            # bit-packed columns present
+    seed = pyref.seed_from_u64(31)
+    full = pkg().create_proof(w.pk, w.advice_host, w.instances, seed)
+    assert pkg().create_proof_compact(w.pk, w.compact, w.instances, seed) == full
+    assert _verify_workload(w, full)
+    # mixed: one column passed as full Montgomery limbs
+    n = 1 << 10
+    cols = list(w.compact.columns)
+    mixed = pkg().CompactAdvice([("fr", w.advice_host[:n])] + [({0: "fr", 1: "bits", 2: "u8", 3: "u16", 4: "u64"}[k], a) for k, a in cols[1:]])
+    assert pkg().create_proof_compact(w.pk, mixed, w.instances, seed) == full
