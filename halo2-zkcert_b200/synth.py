@@ -414,3 +414,46 @@ def build_permutation_mapping_fast(cs, copies):
     mp[right] = np.where(start, left, prev)
     mp[left[end]] = right[end]
     return mp
+
+
+# ---- small shapes that exercise the generic paths (tests) --------------------------------------------------
+def make_multi_lookup_circuit(k, seed=0, with_permutation=True):
+    """Two lookups — one with two theta-compressed expressions per side (compressed values are arbitrary field
+    elements, so the 256-bit sort and the permutation run on full-width keys), one single-column — plus a gate with
+    negative rotations, a Scaled / Constant expression, two instance columns and (optionally) no permutation at all."""
+    n = 1 << k
+    rng = random.Random(seed)
+    # advice: 0 = a, 1 = b (pair lookup), 2 = c (single lookup), 3 = d (gate: d = 3*a(prev) + c + 5)
+    advice_queries = [(0, 0), (1, 0), (2, 0), (3, 0), (0, -1)]
+    fixed_queries = [(0, 0), (1, 0), (2, 0)]        # t1, t2, q
+    instance_queries = [(0, 0), (1, 0)] if with_permutation else []
+    a, b, c, d, a_prev = (("advice", i) for i in range(5))
+    t1, t2, q = (("fixed", i) for i in range(3))
+    gate = ("product", q, ("sum", d, ("neg", ("sum", ("sum", ("scaled", a_prev, 3), c), ("const", 5)))))
+    lookups = [([a, b], [t1, t2]), ([("product", q, c)], [t1])]
+    permutation = [(ANY_ADVICE, 3), (ANY_INSTANCE, 0), (ANY_INSTANCE, 1)] if with_permutation else []
+    cs = ConstraintSystem(k, 4, 3, 2 if with_permutation else 0, advice_queries, fixed_queries, instance_queries, [[gate]], lookups, permutation)
+    U = cs.usable_rows()
+    tsize = max(4, U // 2)
+    fixed = [[0] * n for _ in range(3)]
+    for i in range(tsize):
+        fixed[0][i] = i
+        fixed[1][i] = (i * i * 0x1234567 + 7 * pow(3, i, R_MOD)) % R_MOD
+    # rows beyond the table repeat entry 0 so every usable table row is a valid pair
+    for i in range(tsize, U):
+        fixed[0][i], fixed[1][i] = fixed[0][0], fixed[1][0]
+    advice = [[0] * n for _ in range(4)]
+    for r in range(U):
+        j = rng.randrange(tsize)
+        advice[0][r], advice[1][r] = fixed[0][j], fixed[1][j]
+        advice[2][r] = rng.randrange(tsize)
+    for r in range(1, U):
+        fixed[2][r] = rng.getrandbits(1)
+        advice[3][r] = (3 * advice[0][r - 1] + advice[2][r] + 5) % R_MOD if fixed[2][r] else rng.randrange(R_MOD)
+    # where q = 0 the second lookup's input is 0, which is in t1 (entry 0)
+    copies, instances = [], []
+    if with_permutation:
+        rows = [r for r in range(1, U) if fixed[2][r]][:6]
+        instances = [[advice[3][r] for r in rows[:4]], [advice[3][r] for r in rows[4:6]]]
+        copies = [(1, i, 0, r) for i, r in enumerate(rows[:4])] + [(2, i, 0, r) for i, r in enumerate(rows[4:6])]
+    return SynthCircuit(cs, fixed, copies, advice, instances, "multi_lookup_k%d" % k)

@@ -195,3 +195,26 @@ def test_compact_witness_upload_matches_full():
     cols = list(w.compact.columns)
     mixed = pkg().CompactAdvice([("fr", w.advice_host[:n])] + [({0: "fr", 1: "bits", 2: "u8", 3: "u16", 4: "u64"}[k], a) for k, a in cols[1:]])
     assert pkg().create_proof_compact(w.pk, mixed, w.instances, seed) == full
+
+
+@pytest.mark.parametrize("k,with_perm", [(7, True), (9, True), (8, False)])
+def test_generic_paths_multi_lookup(k, with_perm):
+    """Two lookups (one theta-compressed over two expressions: full-width sort keys), degree-5 constraint system
+    (chunk_len 3), negative rotation, Scaled / Constant nodes, two instance columns, and the no-permutation case."""
+    circ = pkg().synth.make_multi_lookup_circuit(k, seed=k, with_permutation=with_perm)
+    opk, advice = oracle_setup(circ)
+    params, gpk = gpu_setup(circ, opk)
+    assert (gpk.degree, gpk.num_lookups, gpk.num_sets) == (5, 2, 1 if with_perm else 0)
+    s = pyref.seed_from_u64(100 + k)
+    inst = [orc.fr_from_ints(c) for c in circ.instances]
+    for transcript, multiopen in (("blake2b", "shplonk"), ("keccak", "gwc")):
+        want = plonk.create_proof(opk, advice, circ.instances, pyref.ChaChaRng(s, 20), transcript, multiopen)
+        got = pkg().create_proof(gpk, np.concatenate(advice), inst, s, transcript, multiopen)
+        assert got == want
+        assert verifier.verify_proof(vk_of(opk), pyref.G1_GEN, circ.instances, got, verifier.trapdoor_check(SRS_SECRET), transcript, multiopen)
+    # a pair that is not a table row -> ConstraintSystemFailure
+    bad = [a.copy() for a in advice]
+    bad[1][2] = orc.fr_from_ints([123456789])[0]
+    with pytest.raises(pkg().ZkcError) as e:
+        pkg().create_proof(gpk, np.concatenate(bad), inst, s)
+    assert e.value.code == 11
