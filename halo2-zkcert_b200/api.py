@@ -371,7 +371,7 @@ def create_proof(pk, advice, instances, rng_seed, transcript="blake2b", multiope
     bytes for ChaCha20Rng::from_seed.  Returns the proof bytes."""
     ctx = pk.ctx
     o = ProveOpts()
-    o.transcript = {"blake2b": 0, "keccak": 1}[transcript]
+    o.transcript = {"blake2b": 0, "keccak": 1, "evm": 2, "poseidon": 3}[transcript]
     o.multiopen = {"shplonk": 0, "gwc": 1}[multiopen]
     o.advice_blinding = {"axiom": 0, "pse": 1}[advice_blinding]
     o.blind_draws = 1 if blind_draws else 0
@@ -429,7 +429,7 @@ def create_proof_compact(pk, compact, instances, rng_seed, transcript="blake2b",
     """create_proof with the witness handed over in compact host form (CompactAdvice)"""
     ctx = pk.ctx
     o = ProveOpts()
-    o.transcript = {"blake2b": 0, "keccak": 1}[transcript]
+    o.transcript = {"blake2b": 0, "keccak": 1, "evm": 2, "poseidon": 3}[transcript]
     o.multiopen = {"shplonk": 0, "gwc": 1}[multiopen]
     o.advice_blinding = {"axiom": 0, "pse": 1}[advice_blinding]
     o.blind_draws = 1 if blind_draws else 0
@@ -473,3 +473,16 @@ def g1_sum(points):
     if st != 0:
         raise ZkcError(st, "zkc_g1_sum")
     return out
+
+
+def poseidon_spec():
+    """(round constants [65][3], MDS [3][3]) of the Poseidon transcript as Python ints"""
+    c = np.zeros((195, 4), dtype=np.uint64)
+    m = np.zeros((9, 4), dtype=np.uint64)
+    st = lib().zkc_poseidon_spec(_hp(c), _hp(m))
+    if st != 0:
+        raise ZkcError(st, "zkc_poseidon_spec")
+    toint = lambda row: sum(int(row[i]) << (64 * i) for i in range(4))
+    cs = [toint(r) for r in c]
+    ms = [toint(r) for r in m]
+    return [cs[3 * i:3 * i + 3] for i in range(65)], [ms[3 * i:3 * i + 3] for i in range(3)]

@@ -170,6 +170,93 @@ int fr_cmp_canonical(const Fr& a, const Fr& b) {
   return 0;
 }
 
+// ---- Poseidon ---------------------------------------------------------------------------------------------------
+namespace {
+struct Grain {
+  bool s[80];
+  int head = 0;   // ring buffer start
+  Grain() {
+    int n = 0;
+    auto append = [&](int bits, uint64_t v) { for (int i = bits - 1; i >= 0; --i) s[n++] = (v >> i) & 1; };
+    append(2, 1); append(4, 0); append(12, 254); append(12, 3); append(10, 8); append(10, 57); append(30, (1ull << 30) - 1);
+    for (int i = 0; i < 160; ++i) new_bit();
+  }
+  bool at(int i) const { return s[(head + i) % 80]; }
+  bool new_bit() {
+    const bool b = at(62) ^ at(51) ^ at(38) ^ at(23) ^ at(13) ^ at(0);
+    s[head] = b;              // drop the oldest bit, append the new one
+    head = (head + 1) % 80;
+    return b;
+  }
+  bool next_bit() {
+    bool b = new_bit();
+    while (!b) { new_bit(); b = new_bit(); }
+    return new_bit();
+  }
+  void take(uint8_t repr[32]) {   // 254 bits, MSB first, into a little-endian byte string
+    memset(repr, 0, 32);
+    for (int i = 0; i < 254; ++i) { const int p = 253 - i; if (next_bit()) repr[p / 8] |= (uint8_t)(1u << (p % 8)); }
+  }
+  Fr next_field_element() {
+    for (;;) {
+      uint8_t repr[32]; take(repr);
+      Fr v; memcpy(v.v, repr, 32);
+      if (!geq_mod<FrP>(v.v)) return fe_from_canonical(v);
+    }
+  }
+  Fr next_field_element_without_rejection() {
+    uint8_t repr[32]; take(repr);
+    Fr v; memcpy(v.v, repr, 32);
+    while (geq_mod<FrP>(v.v)) sub_mod_inplace<FrP>(v.v);
+    return fe_from_canonical(v);
+  }
+};
+struct PoseidonSpec {
+  Fr constants[65][3];
+  Fr mds[3][3];
+  PoseidonSpec() {
+    Grain g;
+    for (int r = 0; r < 65; ++r) for (int i = 0; i < 3; ++i) constants[r][i] = g.next_field_element();
+    Fr xs[3], ys[3];
+    for (int i = 0; i < 3; ++i) xs[i] = g.next_field_element_without_rejection();
+    for (int i = 0; i < 3; ++i) ys[i] = g.next_field_element_without_rejection();
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) mds[i][j] = fe_inv(fe_add(xs[i], ys[j]));
+  }
+};
+const PoseidonSpec& the_spec() { static const PoseidonSpec sp; return sp; }
+Fr pow5(const Fr& a) { Fr a2 = fe_sqr(a); return fe_mul(fe_sqr(a2), a); }
+void poseidon_permute(Fr st[3]) {
+  const PoseidonSpec& sp = the_spec();
+  for (int r = 0; r < 65; ++r) {
+    for (int i = 0; i < 3; ++i) st[i] = fe_add(st[i], sp.constants[r][i]);
+    if (r < 4 || r >= 61) { for (int i = 0; i < 3; ++i) st[i] = pow5(st[i]); }
+    else st[0] = pow5(st[0]);
+    Fr o[3];
+    for (int i = 0; i < 3; ++i) o[i] = fe_add(fe_add(fe_mul(sp.mds[i][0], st[0]), fe_mul(sp.mds[i][1], st[1])), fe_mul(sp.mds[i][2], st[2]));
+    st[0] = o[0]; st[1] = o[1]; st[2] = o[2];
+  }
+}
+}  // namespace
+
+void poseidon_spec(const Fr** constants, const Fr** mds) { *constants = &the_spec().constants[0][0]; *mds = &the_spec().mds[0][0]; }
+
+PoseidonSponge::PoseidonSponge() {
+  Fr c = fe_zero<FrP>(); c.v[2] = 1;    // 2^64
+  state[0] = fe_from_canonical(c); state[1] = fe_zero<FrP>(); state[2] = fe_zero<FrP>();
+}
+void PoseidonSponge::absorb(const Fr* chunk, size_t len) {
+  for (size_t i = 0; i < len; ++i) state[1 + i] = fe_add(state[1 + i], chunk[i]);
+  if (len < 2) state[1 + len] = fe_add(state[1 + len], fe_one<FrP>());
+  poseidon_permute(state);
+}
+Fr PoseidonSponge::squeeze() {
+  std::vector<Fr> b; b.swap(buf);
+  const bool exact = b.size() % 2 == 0;
+  for (size_t i = 0; i < b.size(); i += 2) absorb(b.data() + i, std::min<size_t>(2, b.size() - i));
+  if (exact) absorb(nullptr, 0);
+  return state[1];
+}
+
 // ---- transcripts --------------------------------------------------------------------------------------------
 Transcript::Transcript(int kind_, int pf) : kind(kind_), point_format(pf) {
   if (kind == 0) b2.init("Halo2-Transcript");
@@ -178,7 +265,22 @@ void Transcript::absorb(const uint8_t* p, size_t n) {
   if (kind == 0) b2.update(p, n);
   else kbuf.insert(kbuf.end(), p, p + n);
 }
+static void reverse32(uint8_t b[32]) { for (int i = 0; i < 16; ++i) { uint8_t t = b[i]; b[i] = b[31 - i]; b[31 - i] = t; } }
+
 Fr Transcript::squeeze_challenge() {
+  if (kind == 3) return pos.squeeze();
+  if (kind == 2) {
+    // EvmTranscript: keccak256(buf ++ [1 if len == 32]); the digest replaces the buffer; challenge = digest (BE) mod r
+    std::vector<uint8_t> t = kbuf;
+    if (t.size() == 32) t.push_back(1);
+    uint8_t h[32];
+    keccak256(t.data(), t.size(), h);
+    kbuf.assign(h, h + 32);
+    uint8_t wide[64];
+    memset(wide, 0, sizeof wide);
+    for (int i = 0; i < 32; ++i) wide[i] = h[31 - i];
+    return fr_from_u512_le(wide);
+  }
   const uint8_t prefix = 0;
   absorb(&prefix, 1);
   uint8_t d[64];
@@ -195,6 +297,20 @@ Fr Transcript::squeeze_challenge() {
 }
 int Transcript::common_point(const G1Affine& p) {
   if (affine_is_identity(p)) return 1;
+  if (kind == 3) {   // coordinates reduced from Fq into Fr (fe_to_fe)
+    uint8_t xb[32], yb[32];
+    fq_to_repr(p.x, xb); fq_to_repr(p.y, yb);
+    Fr e[2] = {fe_from_canonical(reduce_256(xb)), fe_from_canonical(reduce_256(yb))};
+    pos.update(e, 2);
+    return 0;
+  }
+  if (kind == 2) {
+    uint8_t b[64];
+    fq_to_repr(p.x, b); fq_to_repr(p.y, b + 32);
+    reverse32(b); reverse32(b + 32);
+    absorb(b, 64);
+    return 0;
+  }
   uint8_t b[65];
   b[0] = 1;
   fq_to_repr(p.x, b + 1);
@@ -203,6 +319,14 @@ int Transcript::common_point(const G1Affine& p) {
   return 0;
 }
 void Transcript::common_scalar(const Fr& s) {
+  if (kind == 3) { pos.update(&s, 1); return; }
+  if (kind == 2) {
+    uint8_t b[32];
+    fr_to_repr(s, b);
+    reverse32(b);
+    absorb(b, 32);
+    return;
+  }
   uint8_t b[33];
   b[0] = 2;
   fr_to_repr(s, b + 1);
@@ -213,6 +337,12 @@ int Transcript::write_point(const G1Affine& p) {
   uint8_t xb[32], yb[32];
   fq_to_repr(p.x, xb);
   fq_to_repr(p.y, yb);
+  if (kind == 2) {
+    reverse32(xb); reverse32(yb);
+    proof.insert(proof.end(), xb, xb + 32);
+    proof.insert(proof.end(), yb, yb + 32);
+    return 0;
+  }
   const uint8_t sign = yb[0] & 1;
   xb[31] |= point_format == 0 ? (uint8_t)(sign << 7) : (uint8_t)(sign << 6);
   proof.insert(proof.end(), xb, xb + 32);
@@ -222,6 +352,7 @@ void Transcript::write_scalar(const Fr& s) {
   common_scalar(s);
   uint8_t b[32];
   fr_to_repr(s, b);
+  if (kind == 2) reverse32(b);
   proof.insert(proof.end(), b, b + 32);
 }
 

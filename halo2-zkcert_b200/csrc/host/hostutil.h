@@ -50,9 +50,24 @@ void fr_to_repr(const Fr& a, uint8_t out[32]);    // canonical little-endian
 void fq_to_repr(const Fq& a, uint8_t out[32]);
 int fr_cmp_canonical(const Fr& a, const Fr& b);   // Ord for Fr
 
+// ---- Poseidon sponge of snark-verifier's PoseidonTranscript (T = 3, RATE = 2, R_F = 8, R_P = 57; SURVEY OPEN-7) ----
+struct PoseidonSponge {
+  Fr state[3];
+  std::vector<Fr> buf;
+  PoseidonSponge();
+  void update(const Fr* e, size_t n) { buf.insert(buf.end(), e, e + n); }
+  Fr squeeze();
+ private:
+  void absorb(const Fr* chunk, size_t len);
+};
+// round constants [65][3] and MDS [3][3] from the Grain LFSR (Montgomery form); exposed for tests
+void poseidon_spec(const Fr** constants, const Fr** mds);
+
 // ---- transcripts --------------------------------------------------------------------------------------------
 struct Transcript {
-  int kind;          // 0 = Blake2b, 1 = Keccak256
+  int kind;          // 0 = Blake2bWrite, 1 = Keccak256Write (halo2), 2 = snark-verifier EvmTranscript (Keccak, big-endian,
+                     // uncompressed points), 3 = snark-verifier PoseidonTranscript (what gen_snark_shplonk instantiates)
+  PoseidonSponge pos;
   int point_format;  // SURVEY OPEN-5
   Blake2b b2;
   std::vector<uint8_t> kbuf;

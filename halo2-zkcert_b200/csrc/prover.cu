@@ -465,6 +465,8 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   cudaStream_t st = ctx->stream;
   Pool pool(ctx);
   Rng rng(opts->rng_seed);
+  if (opts->transcript < 0 || opts->transcript > 3 || opts->multiopen < 0 || opts->multiopen > 1)
+    return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_prove: unknown transcript / multiopen");
   Transcript tr(opts->transcript, opts->point_format);
   zkc_domain_info di;
   zkc_domain_get_info(pk->dom, &di);
@@ -995,4 +997,14 @@ extern "C" int zkc_prove_compact(zkc_ctx* ctx, const zkc_pk* pk, const zkc_advic
   if (stage) cudaFreeAsync(stage, st);
   cudaFreeAsync(adv, st);
   return status;
+}
+
+// Poseidon spec (Grain-generated round constants and MDS) of the SDK transcript, canonical little-endian; for cross-checks
+extern "C" int zkc_poseidon_spec(zkc_fr* constants /* 65*3 */, zkc_fr* mds /* 3*3 */) {
+  if (!constants || !mds) return ZKC_ERR_BAD_ARG;
+  const Fr *c, *m;
+  host::poseidon_spec(&c, &m);
+  for (int i = 0; i < 195; ++i) { Fr v = fe_to_canonical(c[i]); memcpy(&constants[i], v.v, 32); }
+  for (int i = 0; i < 9; ++i) { Fr v = fe_to_canonical(m[i]); memcpy(&mds[i], v.v, 32); }
+  return ZKC_OK;
 }

@@ -170,7 +170,11 @@ int zkc_pk_get_commitments(zkc_ctx* ctx, const zkc_pk* pk, zkc_g1_affine* fixed_
 int zkc_pk_info(const zkc_pk* pk, uint32_t* out);
 
 typedef struct {
-  int transcript;       /* 0 = Blake2bWrite<_, _, Challenge255>, 1 = Keccak256Write */
+  int transcript;       /* 0 = Blake2bWrite<_, _, Challenge255>, 1 = Keccak256Write (halo2_proofs::transcript);
+                           2 = snark-verifier EvmTranscript (gen_evm_proof_shplonk, cli.rs:519): Keccak-256 sponge over
+                               big-endian words, 64-byte uncompressed points in the proof;
+                           3 = snark-verifier PoseidonTranscript<_, NativeLoader, _> with POSEIDON_SPEC (T=3, RATE=2, R_F=8,
+                               R_P=57) — what gen_snark_shplonk instantiates (helpers.rs:233,299; SURVEY OPEN-7) */
   int multiopen;        /* 0 = ProverSHPLONK, 1 = ProverGWC */
   int advice_blinding;  /* SURVEY OPEN-1: 0 = axiom (last row := 1, no draws), 1 = PSE (unusable rows random) */
   int blind_draws;      /* SURVEY OPEN-2: 1 = one Fr::random per commitment for the (unused) KZG blind */
@@ -197,6 +201,8 @@ int zkc_prove_compact(zkc_ctx* ctx, const zkc_pk* pk, const zkc_advice_column* c
  * starting at draw `skip`; rand_core's SeedableRng::seed_from_u64. */
 int zkc_rng_fr_random(const uint8_t seed[32], uint64_t skip, zkc_fr* out, size_t count);
 void zkc_seed_from_u64(uint64_t state, uint8_t seed[32]);
+/* Grain-generated Poseidon parameters of transcript kind 3 (canonical little-endian): 65 x 3 round constants, 3 x 3 MDS. */
+int zkc_poseidon_spec(zkc_fr* constants, zkc_fr* mds);
 
 #ifdef __cplusplus
 }

@@ -92,6 +92,41 @@ def keccak256(data: bytes) -> bytes:
     return out
 
 
+class EvmTranscriptWrite:
+    """snark-verifier `EvmTranscript<G1Affine, NativeLoader, _, Vec<u8>>` (snark-verifier 0.1.6 @7011e8c
+    src/system/halo2/transcript/evm.rs — un-vendored, /root/reference/Cargo.lock:2676-2693; instantiated by
+    gen_evm_proof_shplonk, /root/reference/src/bin/cli.rs:519).  Recalled behaviour (SURVEY OPEN-7):
+    the sponge buffer is a byte vector; points are absorbed / written as x || y, 32-byte big-endian each
+    (uncompressed); scalars as 32-byte big-endian; squeeze = keccak256(buf ++ [0x01 if len(buf) == 32]),
+    the digest replaces the buffer and is reduced mod r as a big-endian integer."""
+
+    def __init__(self):
+        self.buf = bytearray()
+        self.proof = bytearray()
+
+    def squeeze_challenge(self):
+        data = bytes(self.buf) + (b"\x01" if len(self.buf) == 32 else b"")
+        h = keccak256(data)
+        self.buf = bytearray(h)
+        return int.from_bytes(h, "big") % R_MOD
+
+    def common_point(self, pt):
+        if pt is None:
+            raise ValueError("cannot write points at infinity to the transcript")
+        self.buf += pt[0].to_bytes(32, "big") + pt[1].to_bytes(32, "big")
+
+    def common_scalar(self, s):
+        self.buf += int(s).to_bytes(32, "big")
+
+    def write_point(self, pt):
+        self.common_point(pt)
+        self.proof += pt[0].to_bytes(32, "big") + pt[1].to_bytes(32, "big")
+
+    def write_scalar(self, s):
+        self.common_scalar(s)
+        self.proof += int(s).to_bytes(32, "big")
+
+
 class TranscriptWrite:
     """Blake2bWrite / Keccak256Write with Challenge255."""
 
@@ -420,7 +455,13 @@ def create_proof(pk, advice_mont, instances, rng, transcript_kind="blake2b", mul
     n, k, j, bf = pk.n, pk.k, pk.j, cs.blinding_factors()
     U = n - (bf + 1)
     zc = pk.zeta_choice
-    tr = TranscriptWrite(transcript_kind, opts.point_format)
+    if transcript_kind == "evm":
+        tr = EvmTranscriptWrite()
+    elif transcript_kind == "poseidon":
+        from .poseidon import PoseidonTranscriptWrite
+        tr = PoseidonTranscriptWrite(opts.point_format)
+    else:
+        tr = TranscriptWrite(transcript_kind, opts.point_format)
     tr.common_scalar(pk.transcript_repr)
     draw = rng.fr_random
     rot_scale = 1 << (pk.ext_k - k)

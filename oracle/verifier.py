@@ -117,6 +117,41 @@ class TranscriptRead:
         return s
 
 
+class EvmTranscriptRead:
+    """reader side of oracle.plonk.EvmTranscriptWrite (64-byte big-endian uncompressed points)"""
+
+    def __init__(self, proof):
+        self.proof, self.pos, self.buf = bytes(proof), 0, bytearray()
+
+    def squeeze_challenge(self):
+        h = keccak256(bytes(self.buf) + (b"\x01" if len(self.buf) == 32 else b""))
+        self.buf = bytearray(h)
+        return int.from_bytes(h, "big") % R_MOD
+
+    def common_scalar(self, s):
+        self.buf += int(s).to_bytes(32, "big")
+
+    def common_point(self, pt):
+        self.buf += pt[0].to_bytes(32, "big") + pt[1].to_bytes(32, "big")
+
+    def read_point(self):
+        x = int.from_bytes(self.proof[self.pos:self.pos + 32], "big")
+        y = int.from_bytes(self.proof[self.pos + 32:self.pos + 64], "big")
+        self.pos += 64
+        if x >= P_MOD or y >= P_MOD or (y * y - x * x * x - 3) % P_MOD:
+            raise ValueError("point not on curve")
+        self.common_point((x, y))
+        return (x, y)
+
+    def read_scalar(self):
+        s = int.from_bytes(self.proof[self.pos:self.pos + 32], "big")
+        self.pos += 32
+        if s >= R_MOD:
+            raise ValueError("non-canonical scalar")
+        self.common_scalar(s)
+        return s
+
+
 def l_i(x, n, omega, i):
     """Lagrange basis polynomial of row i (mod n) evaluated at x"""
     wi = pow(omega, i % n, R_MOD)
@@ -133,7 +168,13 @@ def verify_proof(vk, g1_gen, instances, proof, check, transcript_kind="blake2b",
     cs = vk.cs
     n, k, bf = cs.n, cs.k, cs.blinding_factors()
     omega = pow(ROOT_OF_UNITY, 1 << (28 - k), R_MOD)
-    tr = TranscriptRead(proof, transcript_kind, point_format)
+    if transcript_kind == "evm":
+        tr = EvmTranscriptRead(proof)
+    elif transcript_kind == "poseidon":
+        from .poseidon import PoseidonTranscriptRead
+        tr = PoseidonTranscriptRead(proof, point_format)
+    else:
+        tr = TranscriptRead(proof, transcript_kind, point_format)
     tr.common_scalar(vk.transcript_repr)
     for col in instances:
         for v in col:

@@ -43,7 +43,8 @@ def test_pk_matches_oracle_keygen(circuit_k6):
     assert orc.g1_to_ints(s) == opk.sigma_commitments
 
 
-@pytest.mark.parametrize("transcript,multiopen", [("blake2b", "shplonk"), ("keccak", "shplonk"), ("blake2b", "gwc"), ("keccak", "gwc")])
+@pytest.mark.parametrize("transcript,multiopen", [("blake2b", "shplonk"), ("keccak", "shplonk"), ("blake2b", "gwc"), ("keccak", "gwc"),
+                                                  ("evm", "shplonk"), ("evm", "gwc"), ("poseidon", "shplonk"), ("poseidon", "gwc")])
 def test_proof_bytes_match_oracle(circuit_k6, transcript, multiopen):
     circ, opk, advice, params, gpk = circuit_k6
     seed = pyref.seed_from_u64(42)

@@ -21,7 +21,7 @@ def small():
     return circ, pk, advice
 
 
-@pytest.mark.parametrize("kind,multiopen", [("blake2b", "shplonk"), ("keccak", "shplonk"), ("blake2b", "gwc"), ("keccak", "gwc")])
+@pytest.mark.parametrize("kind,multiopen", [("blake2b", "shplonk"), ("keccak", "shplonk"), ("blake2b", "gwc"), ("keccak", "gwc"), ("evm", "shplonk"), ("poseidon", "shplonk")])
 def test_oracle_proof_verifies(small, kind, multiopen):
     circ, pk, advice = small
     proof = plonk.create_proof(pk, advice, circ.instances, rng_for(7), kind, multiopen)
@@ -90,3 +90,22 @@ def test_lookup_value_outside_table_is_an_error(small):
 def test_fast_rng_gives_identical_proof(small):
     circ, pk, advice = small
     assert plonk.create_proof(pk, advice, circ.instances, rng_for(4)) == plonk.create_proof(pk, advice, circ.instances, fast_rng_for(4))
+
+
+def test_poseidon_grain_known_answers_and_host_spec():
+    """The Grain LFSR reproduces the published round constants of the (t = 3, R_F = 8, R_P = 57, BN254) instance
+    (the same parameters circomlib / iden3 ship), and the product's C++ restatement generates the same spec."""
+    from oracle import poseidon
+    c, m = poseidon.spec()
+    assert c[0] == [0x0ee9a592ba9a9518d05986d656f40c2114c4993c11bb29938d21d47304cd8e6e,
+                    0x00f1445235f2148c5986587169fc1bcd887b08d4d00868df5696fff40956e864,
+                    0x08dff3487e8ac99e1f29a058d0fa80b930c728730b7ab36ce879f3890ecf73f5]
+    assert len(c) == 65
+    hc, hm = pkg().api.poseidon_spec()
+    assert hc == c and hm == m
+    # sponge: duplex behaviour and padding rule
+    s1, s2 = poseidon.PoseidonSponge(), poseidon.PoseidonSponge()
+    s1.update([1, 2]); s2.update([1, 2, 0])
+    assert s1.squeeze() != s2.squeeze()
+    a = s1.squeeze()
+    assert a != s1.squeeze()
