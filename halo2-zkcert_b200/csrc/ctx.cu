@@ -202,7 +202,13 @@ int vec_op_impl(zkc_ctx* ctx, int op, const Fe<P>* a, const Fe<P>* b, Fe<P>* out
   return ZKC_OK;
 }
 
-int fr_batch_invert(zkc_ctx* ctx, const Fr* a, Fr* out, size_t n) { return vec_op_impl<FrP>(ctx, ZKC_OP_INV, a, nullptr, out, n); }
+int fr_batch_invert_scan(zkc_ctx* ctx, const Fr* a, Fr* out, uint64_t n);   // poly.cu
+// small batches: per-thread Montgomery trick (one Fermat inversion per 8 elements); large ones: two product scans
+// and a single inversion (6 products per element instead of ~50)
+int fr_batch_invert(zkc_ctx* ctx, const Fr* a, Fr* out, size_t n) {
+  if (n >= (1u << 15)) return fr_batch_invert_scan(ctx, a, out, n);
+  return vec_op_impl<FrP>(ctx, ZKC_OP_INV, a, nullptr, out, n);
+}
 
 __global__ void k_mul_inplace(Fr* a, const Fr* b, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,6 +242,7 @@ extern "C" int zkc_field_vec_op_dev(zkc_ctx* ctx, int field, int op, const void*
   if ((op == ZKC_OP_ADD || op == ZKC_OP_SUB || op == ZKC_OP_MUL) && !b) return set_err(ctx, ZKC_ERR_BAD_ARG, "binary op needs b");
   if (op < 0 || op > ZKC_OP_NEG) return set_err(ctx, ZKC_ERR_BAD_ARG, "unknown op");
   CtxLock lock(ctx);
+  if (field == 0 && op == ZKC_OP_INV) return fr_batch_invert(ctx, (const Fr*)a, (Fr*)out, n);
   if (field == 0) return vec_op_impl<FrP>(ctx, op, (const Fr*)a, (const Fr*)b, (Fr*)out, n);
   if (field == 1) return vec_op_impl<FqP>(ctx, op, (const Fq*)a, (const Fq*)b, (Fq*)out, n);
   return set_err(ctx, ZKC_ERR_BAD_ARG, "field must be 0 (Fr) or 1 (Fq)");

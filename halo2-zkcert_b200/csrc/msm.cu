@@ -532,13 +532,16 @@ extern "C" int zkc_srs_setup(zkc_ctx* ctx, uint32_t k, const zkc_fr* s_abi, zkc_
   ZKC_TRY(srs_alloc(ctx, k, &s));
   const uint64_t n = s->n;
   Fr sec; memcpy(sec.v, s_abi, 32);
-  Fr *pw, *den;
-  G1Affine* tab;
-  int st = scratch_reserve(ctx, SCR_MISC, n * sizeof(Fr), (void**)&pw);
-  if (st == ZKC_OK) st = scratch_reserve(ctx, SCR_MISC2, n * sizeof(Fr), (void**)&den);
-  if (st == ZKC_OK) st = scratch_reserve(ctx, SCR_MISC3, 32 * 256 * sizeof(G1Affine), (void**)&tab);
-  if (st != ZKC_OK) { zkc_srs_free(s); return st; }
+  // private temporaries: the helpers called below (batch inversion -> scans) own the ctx scratch arenas
+  Fr *pw = nullptr, *den = nullptr;
+  G1Affine* tab = nullptr;
   cudaStream_t stream = ctx->stream;
+  int st = ZKC_OK;
+  if (cudaMallocAsync((void**)&pw, n * sizeof(Fr), stream) != cudaSuccess || cudaMallocAsync((void**)&den, n * sizeof(Fr), stream) != cudaSuccess ||
+      cudaMallocAsync((void**)&tab, 32 * 256 * sizeof(G1Affine), stream) != cudaSuccess)
+    st = set_err(ctx, ZKC_ERR_OOM, "zkc_srs_setup: out of memory");
+  auto release = [&]() { if (pw) cudaFreeAsync(pw, stream); if (den) cudaFreeAsync(den, stream); if (tab) cudaFreeAsync(tab, stream); };
+  if (st != ZKC_OK) { release(); zkc_srs_free(s); return st; }
   const unsigned gb = (unsigned)((n + 127) / 128), gp = (unsigned)(((n + 63) / 64 + 127) / 128);
   k_fixed_base_table<<<64, 128, 0, stream>>>(tab); ctx->launches++;
   // g[i] = [s^i] G
@@ -557,6 +560,7 @@ extern "C" int zkc_srs_setup(zkc_ctx* ctx, uint32_t k, const zkc_fr* s_abi, zkc_
     if (e != cudaSuccess) st = set_err(ctx, ZKC_ERR_CUDA, cudaGetErrorString(e));
   }
   if (st == ZKC_OK) st = srs_expand(ctx, s);
+  release();
   if (st != ZKC_OK) { zkc_srs_free(s); return st; }
   *out = s;
   return ZKC_OK;

@@ -67,24 +67,75 @@ __global__ void k_scan_apply(const Fr* in, Fr* out, const Fr* tot, uint64_t n, i
   }
 }
 
+// chunk totals beyond this count are scanned by a recursive pass instead of the single-CTA kernel
+#define SCAN_SINGLE_MAX 32768
+static int fr_scan_impl(zkc_ctx* ctx, const Fr* in, Fr* out, uint64_t n, int op, int reverse, const Fr& start, Fr* scratch) {
+  const uint64_t nchunks = (n + SCAN_CH - 1) / SCAN_CH;
+  Fr* tot = scratch;
+  const unsigned grid = (unsigned)((nchunks + 127) / 128);
+  cudaStream_t st = ctx->stream;
+  if (op == SCAN_MUL) { k_scan_chunk_totals<SCAN_MUL><<<grid, 128, 0, st>>>(in, tot, n, reverse); }
+  else { k_scan_chunk_totals<SCAN_ADD><<<grid, 128, 0, st>>>(in, tot, n, reverse); }
+  ZKC_LAUNCH_CHECK(ctx);
+  if (nchunks > SCAN_SINGLE_MAX) {
+    // totals are already in scan order: a forward exclusive scan (with the start value folded in) one level up
+    ZKC_TRY(fr_scan_impl(ctx, tot, tot, nchunks, op, 0, start, scratch + nchunks));
+  } else {
+    if (op == SCAN_MUL) { k_scan_totals<SCAN_MUL><<<1, 1024, 1024 * sizeof(Fr), st>>>(tot, nchunks, start); }
+    else { k_scan_totals<SCAN_ADD><<<1, 1024, 1024 * sizeof(Fr), st>>>(tot, nchunks, start); }
+    ZKC_LAUNCH_CHECK(ctx);
+  }
+  if (op == SCAN_MUL) { k_scan_apply<SCAN_MUL><<<grid, 128, 0, st>>>(in, out, tot, n, reverse); }
+  else { k_scan_apply<SCAN_ADD><<<grid, 128, 0, st>>>(in, out, tot, n, reverse); }
+  ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
 int fr_scan(zkc_ctx* ctx, const Fr* in, Fr* out, uint64_t n, int op, int reverse, const Fr& start) {
   if (n == 0) return ZKC_OK;
   ProfScope _p(ctx, op == SCAN_MUL ? "scan.mul" : "scan.add");
-  const uint64_t nchunks = (n + SCAN_CH - 1) / SCAN_CH;
-  Fr* tot;
-  ZKC_TRY(scratch_reserve(ctx, SCR_MISC, nchunks * sizeof(Fr), (void**)&tot));
-  const unsigned grid = (unsigned)((nchunks + 127) / 128);
+  uint64_t need = 0;
+  for (uint64_t m = n; ; ) { m = (m + SCAN_CH - 1) / SCAN_CH; need += m; if (m <= SCAN_SINGLE_MAX) break; }
+  Fr* scratch;
+  ZKC_TRY(scratch_reserve(ctx, SCR_MISC, need * sizeof(Fr), (void**)&scratch));
+  return fr_scan_impl(ctx, in, out, n, op, reverse, start, scratch);
+}
+
+// ---- batch inversion by two scans: inv_i = (prod_{j<i} a_j) (prod_{j>i} a_j) / prod_j a_j, zeros passed through ----
+__global__ void k_bi_prep(const Fr* a, Fr* t, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr v = fe_load(a + i);
+  fe_store(t + i, fe_is_zero(v) ? fe_one<FrP>() : v);
+}
+__global__ void k_bi_total_inv(const Fr* prefix, const Fr* t, uint64_t n, Fr* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) fe_store(out, fe_inv(fe_mul(fe_load(prefix + n - 1), fe_load(t + n - 1))));
+}
+__global__ void k_bi_finish(const Fr* a, const Fr* prefix, const Fr* suffix, const Fr* tinv, Fr* out, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fr v = fe_load(a + i);
+  if (fe_is_zero(v)) { fe_store(out + i, v); return; }
+  fe_store(out + i, fe_mul(fe_mul(fe_load(prefix + i), fe_load(suffix + i)), fe_load_nc(tinv)));
+}
+int fr_batch_invert_scan(zkc_ctx* ctx, const Fr* a, Fr* out, uint64_t n) {
+  ProfScope _p(ctx, "batch_invert");
+  Fr* buf = nullptr;
   cudaStream_t st = ctx->stream;
-  if (op == SCAN_MUL) {
-    k_scan_chunk_totals<SCAN_MUL><<<grid, 128, 0, st>>>(in, tot, n, reverse); ZKC_LAUNCH_CHECK(ctx);
-    k_scan_totals<SCAN_MUL><<<1, 1024, 1024 * sizeof(Fr), st>>>(tot, nchunks, start); ZKC_LAUNCH_CHECK(ctx);
-    k_scan_apply<SCAN_MUL><<<grid, 128, 0, st>>>(in, out, tot, n, reverse); ZKC_LAUNCH_CHECK(ctx);
-  } else {
-    k_scan_chunk_totals<SCAN_ADD><<<grid, 128, 0, st>>>(in, tot, n, reverse); ZKC_LAUNCH_CHECK(ctx);
-    k_scan_totals<SCAN_ADD><<<1, 1024, 1024 * sizeof(Fr), st>>>(tot, nchunks, start); ZKC_LAUNCH_CHECK(ctx);
-    k_scan_apply<SCAN_ADD><<<grid, 128, 0, st>>>(in, out, tot, n, reverse); ZKC_LAUNCH_CHECK(ctx);
+  ZKC_CUDA_TRY(ctx, cudaMallocAsync((void**)&buf, (3 * n + 1) * sizeof(Fr), st));
+  Fr *t = buf, *pf = buf + n, *sf = buf + 2 * n, *tinv = buf + 3 * n;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  int status = ZKC_OK;
+  k_bi_prep<<<grid, 256, 0, st>>>(a, t, n); ctx->launches++;
+  status = fr_scan(ctx, t, pf, n, SCAN_MUL, 0, fe_one<FrP>());
+  if (status == ZKC_OK) status = fr_scan(ctx, t, sf, n, SCAN_MUL, 1, fe_one<FrP>());
+  if (status == ZKC_OK) {
+    k_bi_total_inv<<<1, 32, 0, st>>>(pf, t, n, tinv); ctx->launches++;
+    k_bi_finish<<<grid, 256, 0, st>>>(a, pf, sf, tinv, out, n); ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) status = set_err(ctx, ZKC_ERR_CUDA, cudaGetErrorString(e));
   }
-  return ZKC_OK;
+  cudaFreeAsync(buf, st);
+  return status;
 }
 
 // u32 exclusive scan: three phases with 1024-element chunks per CTA
@@ -370,40 +421,38 @@ int fr_kate_division_batch(zkc_ctx* ctx, const std::vector<Fr*>& polys, const st
 // the point (16-coefficient Horner per thread, then a shared-memory tree with x^(16*2^l) factors).
 #define EV_PER_THREAD 16
 #define EV_THREADS 256
-struct EvalJob { const Fr* poly; Fr x; };
+struct EvalJob { const Fr* poly; Fr x; Fr xp[8]; Fr X; Fr X32; };   // xp[l] = x^(16 * 2^l), X = x^4096, X32 = X^32
 __global__ void __launch_bounds__(EV_THREADS) k_eval_slices(const EvalJob* jobs, uint64_t n, Fr* partial, uint32_t blocks_per_poly) {
   __shared__ uint4 smraw[EV_THREADS * 2];
   Fr* sm = reinterpret_cast<Fr*>(smraw);
-  const EvalJob job = jobs[blockIdx.y];
-  const Fr x = job.x;
+  const EvalJob* job = jobs + blockIdx.y;
+  const Fr x = fe_load_nc(&job->x);
+  const Fr* poly = job->poly;
   const uint64_t base = ((uint64_t)blockIdx.x * EV_THREADS + threadIdx.x) * EV_PER_THREAD;
   Fr acc = fe_zero<FrP>();
   for (int e = EV_PER_THREAD - 1; e >= 0; --e) {
     const uint64_t i = base + e;
-    Fr c = i < n ? fe_load(job.poly + i) : fe_zero<FrP>();
+    Fr c = i < n ? fe_load(poly + i) : fe_zero<FrP>();
     acc = fe_add(fe_mul(acc, x), c);
   }
   fe_store(sm + threadIdx.x, acc);
   __syncthreads();
-  Fr xp = fe_pow_u64(x, EV_PER_THREAD);   // x^16, squared each level
-  for (uint32_t d = 1; d < EV_THREADS; d <<= 1) {
+  int l = 0;
+  for (uint32_t d = 1; d < EV_THREADS; d <<= 1, ++l) {
     if ((threadIdx.x & (2 * d - 1)) == 0) {
       Fr lo = fe_load(sm + threadIdx.x), hi = fe_load(sm + threadIdx.x + d);
-      fe_store(sm + threadIdx.x, fe_add(lo, fe_mul(hi, xp)));
+      fe_store(sm + threadIdx.x, fe_add(lo, fe_mul(hi, fe_load_nc(&job->xp[l]))));
     }
-    xp = fe_sqr(xp);
     __syncthreads();
   }
   if (threadIdx.x == 0) fe_store(partial + (uint64_t)blockIdx.y * blocks_per_poly + blockIdx.x, fe_load(sm));
 }
-// one warp per evaluation: sum_b X^b * partial[b], X = x^4096, by strided Horner + shuffle-free tree in smem
+// one warp per evaluation: sum_b X^b * partial[b], X = x^4096: lane l folds blocks l, l+32, ... by Horner in X^32
 __global__ void __launch_bounds__(32) k_eval_combine(const EvalJob* jobs, const Fr* partial, uint32_t blocks_per_poly, Fr* out) {
   __shared__ uint4 smraw[32 * 2];
   Fr* sm = reinterpret_cast<Fr*>(smraw);
-  const Fr X = fe_pow_u64(jobs[blockIdx.x].x, (u64)EV_THREADS * EV_PER_THREAD);
+  const Fr X = fe_load_nc(&jobs[blockIdx.x].X), X32 = fe_load_nc(&jobs[blockIdx.x].X32);
   const Fr* p = partial + (uint64_t)blockIdx.x * blocks_per_poly;
-  // lane l handles blocks b = l, l+32, ...: value_l = sum_m p[l + 32m] (X^32)^m
-  const Fr X32 = fe_pow_u64(X, 32);
   Fr acc = fe_zero<FrP>();
   int cnt = ((int)blocks_per_poly - (int)threadIdx.x + 31) / 32;
   for (int m = cnt - 1; m >= 0; --m) acc = fe_add(fe_mul(acc, X32), fe_load(p + threadIdx.x + 32 * m));
@@ -422,7 +471,16 @@ int fr_eval_batch(zkc_ctx* ctx, const std::vector<const Fr*>& polys, uint64_t n,
   ProfScope _p(ctx, "eval_batch");
   const uint32_t bpp = (uint32_t)((n + EV_THREADS * EV_PER_THREAD - 1) / (EV_THREADS * EV_PER_THREAD));
   std::vector<EvalJob> jobs(m);
-  for (size_t i = 0; i < m; ++i) { jobs[i].poly = polys[i]; jobs[i].x = points[i]; }
+  for (size_t i = 0; i < m; ++i) {
+    jobs[i].poly = polys[i]; jobs[i].x = points[i];
+    bool reuse = false;   // many queries share a point: copy the power table of the previous identical point
+    for (size_t j = i; j-- > 0 && !reuse;) if (fe_eq(points[j], points[i])) { memcpy(jobs[i].xp, jobs[j].xp, sizeof(jobs[i].xp)); jobs[i].X = jobs[j].X; jobs[i].X32 = jobs[j].X32; reuse = true; }
+    if (reuse) continue;
+    Fr pw = fe_pow_u64(points[i], EV_PER_THREAD);
+    for (int l = 0; l < 8; ++l) { jobs[i].xp[l] = pw; pw = fe_sqr(pw); }
+    jobs[i].X = pw;                       // x^(16 * 2^8) = x^4096
+    jobs[i].X32 = fe_pow_u64(pw, 32);
+  }
   char* base;
   const size_t o_jobs = 0, o_part = (m * sizeof(EvalJob) + 255) & ~(size_t)255, o_out = o_part + ((m * bpp * sizeof(Fr) + 255) & ~(size_t)255);
   ZKC_TRY(scratch_reserve(ctx, SCR_MISC3, o_out + m * sizeof(Fr), (void**)&base));

@@ -138,3 +138,19 @@ def test_batch_invert_assigned():
     want = orc.field_op("fr", "mul", num, orc.field_op("fr", "inv", den))
     assert np.array_equal(to_host(out), want)
     assert not to_host(out)[3].any() and np.array_equal(to_host(out)[10], num[10])
+
+
+def test_large_batch_inversion_and_scan_paths():
+    """n >= 2^15 takes the two-scan batch inversion; n > 16 * 32768 takes the recursive scan"""
+    import torch
+    ctx = gpu_ctx()
+    n = (1 << 20) + 12345
+    a = random_fr_mont(n, 77)
+    a[0] = 0
+    a[n - 1] = 0
+    a[4097] = 0
+    out = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    ctx.field_vec_op_dev("fr", "inv", to_dev(a), None, out)
+    ctx.sync()
+    got = to_host(out)
+    assert np.array_equal(got, orc.batch_invert(a))
