@@ -324,7 +324,7 @@ class ParamsKZG:
 # ---- ProvingKey / create_proof --------------------------------------------------------------------
 class ProveOpts(C.Structure):
     _fields_ = [("transcript", C.c_int), ("multiopen", C.c_int), ("advice_blinding", C.c_int), ("blind_draws", C.c_int),
-                ("point_format", C.c_int), ("rng_seed", C.c_uint8 * 32)]
+                ("point_format", C.c_int), ("rng_kind", C.c_int), ("rng_seed", C.c_uint8 * 32)]
 
 
 class ProvingKey:
@@ -365,7 +365,7 @@ class ProvingKey:
 
 
 def create_proof(pk, advice, instances, rng_seed, transcript="blake2b", multiopen="shplonk", advice_blinding="axiom", blind_draws=False,
-                 point_format=0):
+                 point_format=0, rng="chacha20"):
     """plonk::create_proof for one circuit.  advice: (num_advice * n, 4) Montgomery, numpy (host) or
     torch CUDA tensor (already resident); instances: list of (len, 4) Montgomery arrays; rng_seed: 32
     bytes for ChaCha20Rng::from_seed.  Returns the proof bytes."""
@@ -376,6 +376,7 @@ def create_proof(pk, advice, instances, rng_seed, transcript="blake2b", multiope
     o.advice_blinding = {"axiom": 0, "pse": 1}[advice_blinding]
     o.blind_draws = 1 if blind_draws else 0
     o.point_format = point_format
+    o.rng_kind = {"chacha20": 0, "std": 1, "chacha12": 1}[rng]
     o.rng_seed[:] = list(rng_seed)
     on_dev = hasattr(advice, "is_cuda")
     if on_dev:
@@ -425,7 +426,7 @@ class CompactAdvice:
 
 
 def create_proof_compact(pk, compact, instances, rng_seed, transcript="blake2b", multiopen="shplonk", advice_blinding="axiom",
-                         blind_draws=False, point_format=0):
+                         blind_draws=False, point_format=0, rng="chacha20"):
     """create_proof with the witness handed over in compact host form (CompactAdvice)"""
     ctx = pk.ctx
     o = ProveOpts()
@@ -434,6 +435,7 @@ def create_proof_compact(pk, compact, instances, rng_seed, transcript="blake2b",
     o.advice_blinding = {"axiom": 0, "pse": 1}[advice_blinding]
     o.blind_draws = 1 if blind_draws else 0
     o.point_format = point_format
+    o.rng_kind = {"chacha20": 0, "std": 1, "chacha12": 1}[rng]
     o.rng_seed[:] = list(rng_seed)
     cols = (AdviceColumn * max(len(compact.columns), 1))()
     for i, (kind, arr) in enumerate(compact.columns):
@@ -455,11 +457,11 @@ def seed_from_u64(state):
     return bytes(out)
 
 
-def fr_random_stream(seed, count, skip=0):
-    """Fr::random draws of ChaCha20Rng::from_seed(seed) as (count, 4) Montgomery limbs (host-side helper)"""
+def fr_random_stream(seed, count, skip=0, rng="chacha20"):
+    """Fr::random draws of ChaCha20Rng / StdRng ::from_seed(seed) as (count, 4) Montgomery limbs (host-side helper)"""
     out = np.zeros((count, 4), dtype=np.uint64)
     s = (C.c_uint8 * 32)(*list(seed))
-    st = lib().zkc_rng_fr_random(s, C.c_uint64(skip), _hp(out), C.c_size_t(count))
+    st = lib().zkc_rng_fr_random(s, C.c_int(0 if rng == "chacha20" else 1), C.c_uint64(skip), _hp(out), C.c_size_t(count))
     if st != 0:
         raise ZkcError(st, "zkc_rng_fr_random")
     return out

@@ -108,8 +108,8 @@ void keccak256(const uint8_t* in, size_t len, uint8_t out[32]) {
 
 // ---- ChaCha20 -----------------------------------------------------------------------------------------------
 static inline uint32_t rotl32(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
-ChaCha20Rng::ChaCha20Rng(const uint8_t seed[32]) : counter(0), pos(16) { memcpy(key, seed, 32); }
-static void chacha_block(const uint32_t key[8], uint64_t counter, uint32_t out[16]) {
+ChaCha20Rng::ChaCha20Rng(const uint8_t seed[32], int dr) : counter(0), pos(16), double_rounds(dr) { memcpy(key, seed, 32); }
+static void chacha_block(const uint32_t key[8], uint64_t counter, uint32_t out[16], int double_rounds) {
   uint32_t s[16] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
                     (uint32_t)counter, (uint32_t)(counter >> 32), 0, 0};
   uint32_t x[16];
@@ -117,7 +117,7 @@ static void chacha_block(const uint32_t key[8], uint64_t counter, uint32_t out[1
 #define QR(a, b, c, d) \
   x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 12); \
   x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 7);
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < double_rounds; ++i) {
     QR(0, 4, 8, 12) QR(1, 5, 9, 13) QR(2, 6, 10, 14) QR(3, 7, 11, 15)
     QR(0, 5, 10, 15) QR(1, 6, 11, 12) QR(2, 7, 8, 13) QR(3, 4, 9, 14)
   }
@@ -125,7 +125,7 @@ static void chacha_block(const uint32_t key[8], uint64_t counter, uint32_t out[1
   for (int i = 0; i < 16; ++i) out[i] = x[i] + s[i];
 }
 uint32_t ChaCha20Rng::next_u32() {
-  if (pos >= 16) { chacha_block(key, counter++, block); pos = 0; }
+  if (pos >= 16) { chacha_block(key, counter++, block, double_rounds); pos = 0; }
   return block[pos++];
 }
 uint64_t ChaCha20Rng::next_u64() {

@@ -36,7 +36,8 @@ struct ChaCha20Rng {
   uint64_t counter;
   uint32_t block[16];
   int pos;  // next unread word in block; 16 = empty
-  explicit ChaCha20Rng(const uint8_t seed[32]);
+  int double_rounds;   // 10 = ChaCha20Rng, 6 = ChaCha12Rng (rand 0.8 StdRng)
+  explicit ChaCha20Rng(const uint8_t seed[32], int double_rounds = 10);
   uint32_t next_u32();
   uint64_t next_u64();
   Fr fr_random();   // halo2curves Fr::random: 8 x next_u64 as a 512-bit LE integer, reduced mod r

@@ -361,12 +361,13 @@ struct Rng {
   host::ChaCha20Rng cpu;
   ChaChaKey key;
   uint64_t drawn = 0;
-  explicit Rng(const uint8_t seed[32]) : cpu(seed) { memcpy(key.k, seed, 32); }
+  int double_rounds;
+  Rng(const uint8_t seed[32], int dr) : cpu(seed, dr), double_rounds(dr) { memcpy(key.k, seed, 32); }
   Fr draw() { ++drawn; return cpu.fr_random(); }
   // draws [first, first + n) of the stream generated on the device (the host cursor is not moved)
   int bulk_at(zkc_ctx* ctx, Fr* out, uint64_t first, uint64_t n) {
     if (!n) return ZKC_OK;
-    k_chacha_fr<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(out, key, first, n);
+    k_chacha_fr<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(out, key, first, n, double_rounds);
     ZKC_LAUNCH_CHECK(ctx);
     return ZKC_OK;
   }
@@ -464,7 +465,8 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   const uint32_t rot_scale = 1u << (pk->ext_k - cs.k);
   cudaStream_t st = ctx->stream;
   Pool pool(ctx);
-  Rng rng(opts->rng_seed);
+  if (opts->rng_kind < 0 || opts->rng_kind > 1) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_prove: unknown rng_kind");
+  Rng rng(opts->rng_seed, opts->rng_kind == 1 ? 6 : 10);
   if (opts->transcript < 0 || opts->transcript > 3 || opts->multiopen < 0 || opts->multiopen > 1)
     return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_prove: unknown transcript / multiopen");
   Transcript tr(opts->transcript, opts->point_format);
@@ -944,9 +946,9 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
 }
 
 // Fr::random stream exposed for hosts that want to cross-check their RNG restatement
-extern "C" int zkc_rng_fr_random(const uint8_t seed[32], uint64_t skip, zkc_fr* out, size_t count) {
-  if (!seed || !out) return ZKC_ERR_BAD_ARG;
-  host::ChaCha20Rng r(seed);
+extern "C" int zkc_rng_fr_random(const uint8_t seed[32], int rng_kind, uint64_t skip, zkc_fr* out, size_t count) {
+  if (!seed || !out || rng_kind < 0 || rng_kind > 1) return ZKC_ERR_BAD_ARG;
+  host::ChaCha20Rng r(seed, rng_kind == 1 ? 6 : 10);
   r.counter = skip; r.pos = 16;
   for (size_t i = 0; i < count; ++i) { Fr f = r.fr_random(); memcpy(&out[i], f.v, 32); }
   return ZKC_OK;

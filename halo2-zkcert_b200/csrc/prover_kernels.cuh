@@ -11,7 +11,7 @@ namespace zkc {
 // ---- Fr::random in bulk: draw #i of the proof's ChaCha20 stream is keystream block (first_block + i) ----
 __device__ __forceinline__ uint32_t rotl32_d(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
 struct ChaChaKey { uint32_t k[8]; };
-__global__ void k_chacha_fr(Fr* out, ChaChaKey key, uint64_t first_block, uint64_t count) {
+__global__ void k_chacha_fr(Fr* out, ChaChaKey key, uint64_t first_block, uint64_t count, int double_rounds) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const uint64_t ctr = first_block + i;
@@ -24,7 +24,7 @@ __global__ void k_chacha_fr(Fr* out, ChaChaKey key, uint64_t first_block, uint64
   x[a] += x[b]; x[d] = rotl32_d(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl32_d(x[b] ^ x[c], 12); \
   x[a] += x[b]; x[d] = rotl32_d(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl32_d(x[b] ^ x[c], 7);
 #pragma unroll 1
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < double_rounds; ++r) {
     ZKC_QR(0, 4, 8, 12) ZKC_QR(1, 5, 9, 13) ZKC_QR(2, 6, 10, 14) ZKC_QR(3, 7, 11, 15)
     ZKC_QR(0, 5, 10, 15) ZKC_QR(1, 6, 11, 12) ZKC_QR(2, 7, 8, 13) ZKC_QR(3, 4, 9, 14)
   }

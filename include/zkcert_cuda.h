@@ -179,7 +179,8 @@ typedef struct {
   int advice_blinding;  /* SURVEY OPEN-1: 0 = axiom (last row := 1, no draws), 1 = PSE (unusable rows random) */
   int blind_draws;      /* SURVEY OPEN-2: 1 = one Fr::random per commitment for the (unused) KZG blind */
   int point_format;     /* SURVEY OPEN-5: 0 = y-sign in bit 7; 1 = y-sign in bit 6, identity flag in bit 7 */
-  uint8_t rng_seed[32]; /* ChaCha20Rng::from_seed; every draw is Fr::random (one 64-byte keystream block) */
+  int rng_kind;         /* 0 = rand_chacha::ChaCha20Rng, 1 = rand::rngs::StdRng (ChaCha12; what the SDK's `StdRng` is — OPEN-6) */
+  uint8_t rng_seed[32]; /* SeedableRng::from_seed; every draw is Fr::random (one 64-byte keystream block) */
 } zkc_prove_opts;
 
 /* create_proof(params, pk, &[circuit], &[instances], rng, &mut transcript) for ONE circuit.
@@ -197,9 +198,9 @@ typedef struct { int kind; const void* data; } zkc_advice_column;
 int zkc_prove_compact(zkc_ctx* ctx, const zkc_pk* pk, const zkc_advice_column* cols /* num_advice */, const zkc_fr* const* instances,
                       const size_t* instance_lens, const zkc_prove_opts* opts, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
 
-/* host-side helpers mirrored for cross-checking a caller's RNG: Fr::random stream of ChaCha20Rng::from_seed(seed)
+/* host-side helpers mirrored for cross-checking a caller's RNG: Fr::random stream of ChaCha20Rng / StdRng ::from_seed(seed)
  * starting at draw `skip`; rand_core's SeedableRng::seed_from_u64. */
-int zkc_rng_fr_random(const uint8_t seed[32], uint64_t skip, zkc_fr* out, size_t count);
+int zkc_rng_fr_random(const uint8_t seed[32], int rng_kind, uint64_t skip, zkc_fr* out, size_t count);
 void zkc_seed_from_u64(uint64_t state, uint8_t seed[32]);
 /* Grain-generated Poseidon parameters of transcript kind 3 (canonical little-endian): 65 x 3 round constants, 3 x 3 MDS. */
 int zkc_poseidon_spec(zkc_fr* constants, zkc_fr* mds);

@@ -269,14 +269,15 @@ def powers(base, n, first=None):
 class ChaCha20Rng:
     """rand_chacha::ChaCha20Rng restricted to Fr::random draws (each consumes one 64-byte keystream block)."""
 
-    def __init__(self, seed32: bytes):
+    def __init__(self, seed32: bytes, rounds=20):
         self.seed = bytes(seed32)
+        self.rounds = rounds          # 20 = ChaCha20Rng, 12 = StdRng (rand 0.8)
         self.drawn = 0
 
     def fr_random_bulk(self, n):
         """n draws as an (n, 4) Montgomery array"""
         out = np.empty((n, 4), dtype=np.uint64)
-        lib().orc_chacha_fr_random(C.c_char_p(self.seed), C.c_uint64(self.drawn), C.c_size_t(n), _p(out))
+        lib().orc_chacha_fr_random(C.c_char_p(self.seed), C.c_int(self.rounds // 2), C.c_uint64(self.drawn), C.c_size_t(n), _p(out))
         self.drawn += n
         return out
 

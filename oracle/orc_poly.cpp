@@ -113,7 +113,7 @@ void orc_powers(const uint64_t* base, const uint64_t* first, size_t n, uint64_t*
 // 512-bit little-endian integer and reduced mod r.  Pinned against tests/pyref.py's pure-Python restatement
 // and the known answers of SURVEY §8c-4.
 static inline uint32_t rotl32(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
-extern "C" void orc_chacha_fr_random(const uint8_t* seed, uint64_t skip, size_t count, uint64_t* out) {
+extern "C" void orc_chacha_fr_random(const uint8_t* seed, int double_rounds, uint64_t skip, size_t count, uint64_t* out) {
   uint32_t key[8]; memcpy(key, seed, 32);
   parallel_chunks(count, default_threads(), [&](size_t lo, size_t hi, int) {
     for (size_t i = lo; i < hi; ++i) {
@@ -124,7 +124,7 @@ extern "C" void orc_chacha_fr_random(const uint8_t* seed, uint64_t skip, size_t 
 #define ORC_QR(a, b, c, d) \
   x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 12); \
   x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 7);
-      for (int r = 0; r < 10; ++r) {
+      for (int r = 0; r < double_rounds; ++r) {
         ORC_QR(0, 4, 8, 12) ORC_QR(1, 5, 9, 13) ORC_QR(2, 6, 10, 14) ORC_QR(3, 7, 11, 15)
         ORC_QR(0, 5, 10, 15) ORC_QR(1, 6, 11, 12) ORC_QR(2, 7, 8, 13) ORC_QR(3, 4, 9, 14)
       }

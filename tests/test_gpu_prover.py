@@ -219,3 +219,13 @@ def test_generic_paths_multi_lookup(k, with_perm):
     with pytest.raises(pkg().ZkcError) as e:
         pkg().create_proof(gpk, np.concatenate(bad), inst, s)
     assert e.value.code == 11
+
+
+def test_std_rng_chacha12(circuit_k6):
+    """rng_kind = 1: rand 0.8 `StdRng` (ChaCha12), what snark-verifier-sdk constructs (SURVEY OPEN-6)"""
+    circ, opk, advice, params, gpk = circuit_k6
+    seed = pyref.seed_from_u64(77)
+    inst = [orc.fr_from_ints(c) for c in circ.instances]
+    want = plonk.create_proof(opk, advice, circ.instances, orc.ChaCha20Rng(seed, rounds=12), "poseidon")
+    got = pkg().create_proof(gpk, np.concatenate(advice), inst, seed, "poseidon", rng="std")
+    assert got == want and got != pkg().create_proof(gpk, np.concatenate(advice), inst, seed, "poseidon")

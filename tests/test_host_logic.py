@@ -46,6 +46,10 @@ def test_host_rng_helpers_match_known_answers():
     to_int = lambda row: sum(int(row[i]) << (64 * i) for i in range(4)) * rinv % R_MOD
     assert to_int(s[0]) == 0x1c59a59b6cff4308740943526ade1d8c09f71b337a67269cc89586bcdd6dfcba   # gen_srs secret
     assert np.array_equal(p.api.fr_random_stream(bytes(32), 1, skip=1), s[1:2])
+    from tests import pyref
+    std = pyref.ChaChaRng(p.seed_from_u64(9), 12)
+    got = p.api.fr_random_stream(p.seed_from_u64(9), 3, rng="std")
+    assert [to_int(r) for r in got] == [std.fr_random() for _ in range(3)]
 
 
 def test_constraint_system_numbers_and_wire_format():

@@ -192,3 +192,11 @@ def test_oracle_chacha_stream_matches_python_restatement():
     assert [fast.fr_random() for _ in range(3)] == want[:3]
     assert orc.fr_to_ints(fast.fr_random_bulk(37)) == want[3:]
     assert orc.ChaCha20Rng(bytes(32)).fr_random() == 0x1c59a59b6cff4308740943526ade1d8c09f71b337a67269cc89586bcdd6dfcba
+
+
+def test_std_rng_chacha12_stream():
+    seed = pyref.seed_from_u64(5)
+    slow = pyref.ChaChaRng(seed, 12)
+    want = [slow.fr_random() for _ in range(6)]
+    assert orc.fr_to_ints(orc.ChaCha20Rng(seed, rounds=12).fr_random_bulk(6)) == want
+    assert want != [pyref.ChaChaRng(seed, 20).fr_random() for _ in range(6)]
