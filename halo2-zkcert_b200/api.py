@@ -109,6 +109,12 @@ class Context:
         self.check(lib().zkc_profile_report(self._h, buf, C.c_size_t(len(buf))))
         return json.loads(buf.value.decode() or "{}")
 
+    def profile_timeline(self):
+        import json
+        buf = C.create_string_buffer(1 << 20)
+        self.check(lib().zkc_profile_timeline(self._h, buf, C.c_size_t(len(buf))))
+        return json.loads(buf.value.decode() or "[]")
+
     def close(self):
         if self._h:
             lib().zkc_ctx_destroy(self._h)

@@ -114,6 +114,30 @@ extern "C" int zkc_profile_report(zkc_ctx* c, char* buf, size_t cap) {
   return ZKC_OK;
 }
 
+// Timeline of the phases recorded since profiling was enabled / last reported: [["name", start_ms, duration_ms], ...]
+// relative to the first phase.  Consumes the pending records like zkc_profile_report.
+extern "C" int zkc_profile_timeline(zkc_ctx* c, char* buf, size_t cap) {
+  if (!c || !buf || cap == 0) return ZKC_ERR_BAD_ARG;
+  CtxLock lock(c);
+  ZKC_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (c->side_stream) ZKC_CUDA_TRY(c, cudaStreamSynchronize(c->side_stream));
+  std::string js = "[";
+  bool first = true;
+  for (auto& r : c->prof_pending) {
+    float start = 0, dur = 0;
+    if (cudaEventElapsedTime(&start, c->prof_pending[0].e0, r.e0) == cudaSuccess && cudaEventElapsedTime(&dur, r.e0, r.e1) == cudaSuccess) {
+      char tmp[256];
+      snprintf(tmp, sizeof tmp, "%s[\"%s\", %.4f, %.4f]", first ? "" : ", ", r.name.c_str(), start, dur);
+      js += tmp; first = false;
+    }
+    c->prof_pool.push_back(r.e0); c->prof_pool.push_back(r.e1);
+  }
+  c->prof_pending.clear();
+  js += "]";
+  snprintf(buf, cap, "%s", js.c_str());
+  return ZKC_OK;
+}
+
 extern "C" int zkc_dev_alloc(zkc_ctx* c, size_t bytes, void** dptr) {
   if (!c || !dptr) return ZKC_ERR_BAD_ARG;
   CtxLock lock(c);

@@ -260,8 +260,11 @@ extern "C" int zkc_pk_load(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_b
   // l0, l_last, l_blind -> cosets; l_active = 1 - l_last - l_blind
   {
     ZKC_TRY(dev_alloc(ctx, P, &P->l0, en)); ZKC_TRY(dev_alloc(ctx, P, &P->l_last, en)); ZKC_TRY(dev_alloc(ctx, P, &P->l_active, en));
-    Fr* tmp;   // three Lagrange columns
-    ZKC_CUDA_TRY(ctx, cudaMalloc(&tmp, 3 * n * sizeof(Fr)));
+    struct DevTmp { void* p = nullptr; ~DevTmp() { if (p) cudaFree(p); } } tmp_h, lb_h;   // freed on every exit path
+    ZKC_CUDA_TRY(ctx, cudaMalloc(&tmp_h.p, 3 * n * sizeof(Fr)));
+    ZKC_CUDA_TRY(ctx, cudaMalloc(&lb_h.p, en * sizeof(Fr)));
+    Fr* tmp = (Fr*)tmp_h.p;   // three Lagrange columns: l0, l_last, l_blind
+    Fr* lb = (Fr*)lb_h.p;
     ZKC_CUDA_TRY(ctx, cudaMemsetAsync(tmp, 0, 3 * n * sizeof(Fr), st));
     const Fr one = fe_one<FrP>();
     const uint32_t bf = cs.blinding_factors;
@@ -271,15 +274,11 @@ extern "C" int zkc_pk_load(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_b
     ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(tmp + 2 * n + (n - bf), ones.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, st));
     ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     int s1 = dom_lagrange_to_coeff(ctx, P->dom, tmp, 3);
-    Fr* lb = nullptr;
-    if (s1 == ZKC_OK && cudaMalloc(&lb, en * sizeof(Fr)) != cudaSuccess) s1 = set_err(ctx, ZKC_ERR_OOM, "zkc_pk_load: out of memory");
     if (s1 == ZKC_OK) s1 = dom_coeff_to_extended(ctx, P->dom, tmp, n, P->l0, 1);
     if (s1 == ZKC_OK) s1 = dom_coeff_to_extended(ctx, P->dom, tmp + n, n, P->l_last, 1);
     if (s1 == ZKC_OK) s1 = dom_coeff_to_extended(ctx, P->dom, tmp + 2 * n, n, lb, 1);
     if (s1 == ZKC_OK) { k_l_active<<<(unsigned)((en + 255) / 256), 256, 0, st>>>(P->l_last, lb, P->l_active, en); ctx->launches++; }
-    cudaStreamSynchronize(st);
-    cudaFree(tmp);
-    if (lb) cudaFree(lb);
+    cudaStreamSynchronize(st);   // the temporaries are released when this block ends
     ZKC_TRY(s1);
   }
   // omega^i

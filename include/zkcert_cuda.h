@@ -79,6 +79,8 @@ const char* zkc_version(void);
  * into buf (truncated to cap) and clears the accumulators. */
 int zkc_profile_enable(zkc_ctx* ctx, int on);
 int zkc_profile_report(zkc_ctx* ctx, char* buf, size_t cap);
+/* same records as a timeline: JSON [["phase", start_ms, duration_ms], ...] relative to the first phase */
+int zkc_profile_timeline(zkc_ctx* ctx, char* buf, size_t cap);
 
 /* ---- device memory helpers (so non-CUDA hosts can keep columns resident) ------------------- */
 int zkc_dev_alloc(zkc_ctx* ctx, size_t bytes, void** dptr);
