@@ -115,6 +115,34 @@ class Context:
         self.check(lib().zkc_profile_timeline(self._h, buf, C.c_size_t(len(buf))))
         return json.loads(buf.value.decode() or "[]")
 
+    # ---- team proving (zkc_team_*): one create_proof over the GPUs of a node ---------------------------------
+    def team_init(self, group=None):
+        """Join the NCCL team spanning the torch.distributed group (one process per GPU).  The NCCL id is
+        made on rank 0 and handed round with the group's own broadcast (torch.distributed is the plumbing)."""
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ident = (C.c_uint8 * 128)()
+        if rank == 0:
+            self.check(lib().zkc_team_unique_id(ident))
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        self.check(lib().zkc_team_init(self._h, C.c_int(rank), C.c_int(world), ident))
+        return rank, world
+
+    def team_emulate(self, world):
+        """all `world` shards of every partitioned step on this one GPU, collectives elided (tests)"""
+        self.check(lib().zkc_team_emulate(self._h, C.c_int(world)))
+
+    def team_leave(self):
+        self.check(lib().zkc_team_leave(self._h))
+
+    def team_info(self):
+        r, w, e = C.c_int(), C.c_int(), C.c_int()
+        self.check(lib().zkc_team_info(self._h, C.byref(r), C.byref(w), C.byref(e)))
+        return r.value, w.value, bool(e.value)
+
     def close(self):
         if self._h:
             lib().zkc_ctx_destroy(self._h)

@@ -46,6 +46,11 @@ struct zkc_ctx {
   std::vector<cudaEvent_t> prof_pool;
   std::map<std::string, std::pair<double, uint64_t>> prof_acc;
   std::map<std::string, uint64_t> stats;   // work counters (e.g. msm.madds), reported with the profile
+  // team proving (dist.cuh): this GPU's place among the GPUs that share one create_proof
+  int team_rank = 0, team_world = 1;
+  int team_rot = 0;                        // rank that takes the first column block of the next partitioned batch (load balance)
+  bool team_emulate = false;               // zkc_team_emulate: all shards run here, one after the other, no collectives
+  void* team_comm = nullptr;               // ncclComm_t
 };
 
 namespace zkc {

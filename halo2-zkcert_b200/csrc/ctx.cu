@@ -39,6 +39,7 @@ extern "C" void zkc_ctx_destroy(zkc_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->dev);
   cudaStreamSynchronize(c->stream);
+  zkc_team_leave(c);
   for (auto& b : c->scratch) if (b.p) cudaFree(b.p);
   for (auto& kv : c->twiddles) cudaFree(kv.second);
   for (int i = 0; i < 2; ++i) if (c->pinned[i]) cudaFreeHost(c->pinned[i]);

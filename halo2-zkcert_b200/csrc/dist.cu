@@ -1,0 +1,231 @@
+// Team plumbing of libzkcert_cuda.so: NCCL communicator per ctx (bound with dlopen), the partition helpers and the
+// four collectives the sharded create_proof needs (dist.cuh).  SURVEY.md §8e; the reference has no multi-GPU path —
+// its CPU `best_multiexp` splits by point range across rayon threads, which is the split kept here across GPUs.
+#include "dist.cuh"
+#include <dlfcn.h>
+#include <algorithm>
+#include <cstdlib>
+
+namespace zkc {
+namespace {
+
+// the slice of the NCCL ABI used here (nccl.h 2.x: stable since 2.7 for send/recv)
+struct NcclId { char internal[128]; };
+typedef void* NcclComm;
+enum { kNcclUint8 = 1 };
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+
+NcclApi& nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    // a process that already holds torch's bundled libnccl gets that copy (same soname); otherwise the system one
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) return;
+    bool all = true;
+    auto sym = [&](const char* n) { void* p = dlsym(api.handle, n); if (!p) all = false; return p; };
+    api.GetUniqueId = (int (*)(NcclId*))sym("ncclGetUniqueId");
+    api.CommInitRank = (int (*)(NcclComm*, int, NcclId, int))sym("ncclCommInitRank");
+    api.CommDestroy = (int (*)(NcclComm))sym("ncclCommDestroy");
+    api.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))sym("ncclAllGather");
+    api.Broadcast = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))sym("ncclBroadcast");
+    api.Send = (int (*)(const void*, size_t, int, int, NcclComm, cudaStream_t))sym("ncclSend");
+    api.Recv = (int (*)(void*, size_t, int, int, NcclComm, cudaStream_t))sym("ncclRecv");
+    api.GroupStart = (int (*)())sym("ncclGroupStart");
+    api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    api.ok = all;
+  });
+  return api;
+}
+
+int nccl_fail(zkc_ctx* ctx, const char* what, int rc) {
+  return set_err(ctx, ZKC_ERR_CUDA, std::string(what) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "nccl error"));
+}
+#define ZKC_NCCL_TRY(ctx, expr)                                 \
+  do {                                                          \
+    int _rc = (expr);                                           \
+    if (_rc != 0) return nccl_fail(ctx, #expr, _rc);            \
+  } while (0)
+
+bool real_comm(const zkc_ctx* ctx) { return ctx->team_world > 1 && !ctx->team_emulate; }
+
+}  // namespace
+
+std::vector<Segment> halo_segments(uint64_t en, uint64_t lo, uint64_t hi, uint64_t halo_lo, uint64_t halo_hi) {
+  std::vector<Segment> out;
+  if (hi <= lo) return out;
+  if ((hi - lo) + halo_lo + halo_hi >= en) { out.push_back({0, en}); return out; }
+  // the cyclic interval [lo - halo_lo, hi + halo_hi) has length < en: at most one wrap
+  const uint64_t start = (lo + en - halo_lo % en) % en, len = (hi - lo) + halo_lo + halo_hi;
+  if (start + len <= en) out.push_back({start, len});
+  else { out.push_back({0, start + len - en}); out.push_back({start, en - start}); }
+  return out;
+}
+
+std::vector<int> team_ranks(const zkc_ctx* ctx) {
+  std::vector<int> r;
+  if (ctx->team_emulate) for (int i = 0; i < ctx->team_world; ++i) r.push_back(i);
+  else r.push_back(ctx->team_rank);
+  return r;
+}
+
+int team_allgather(zkc_ctx* ctx, void* buf, size_t bytes_per_rank) {
+  if (!real_comm(ctx) || !bytes_per_rank) return ZKC_OK;
+  ZKC_NCCL_TRY(ctx, nccl().AllGather((char*)buf + (size_t)ctx->team_rank * bytes_per_rank, buf, bytes_per_rank, kNcclUint8, (NcclComm)ctx->team_comm,
+                                     ctx->stream));
+  return ZKC_OK;
+}
+
+int team_bcast_cols(zkc_ctx* ctx, Fr* base, uint64_t stride, uint64_t len, uint32_t ncols) {
+  if (!real_comm(ctx) || !ncols || !len) return ZKC_OK;
+  ProfScope _p(ctx, "team.bcast_cols");
+  ZKC_NCCL_TRY(ctx, nccl().GroupStart());
+  for (int r = 0; r < ctx->team_world; ++r) {
+    uint32_t c0, c1;
+    team_cols(ctx, ncols, r, &c0, &c1);
+    for (uint32_t c = c0; c < c1; ++c) {
+      Fr* p = base + (uint64_t)c * stride;
+      int rc = nccl().Broadcast(p, p, len * sizeof(Fr), kNcclUint8, r, (NcclComm)ctx->team_comm, ctx->stream);
+      if (rc != 0) { nccl().GroupEnd(); return nccl_fail(ctx, "ncclBroadcast", rc); }
+    }
+  }
+  ZKC_NCCL_TRY(ctx, nccl().GroupEnd());
+  return ZKC_OK;
+}
+
+int team_scatter_rows(zkc_ctx* ctx, Fr* base, uint64_t en, uint32_t ncols, uint64_t halo_lo, uint64_t halo_hi) {
+  if (!real_comm(ctx) || !ncols) return ZKC_OK;
+  ProfScope _p(ctx, "team.scatter_rows");
+  const int me = ctx->team_rank, W = ctx->team_world;
+  // one NCCL group per chunk of columns (every owner sends at once: full NVSwitch bisection), bounded op count per group
+  const uint32_t block = (ncols + (uint32_t)W - 1) / (uint32_t)W, CH = 16;
+  for (uint32_t j0 = 0; j0 < block; j0 += CH) {
+    ZKC_NCCL_TRY(ctx, nccl().GroupStart());
+    int rc = 0;
+    for (int owner = 0; owner < W && rc == 0; ++owner) {
+      uint32_t c0, c1;
+      team_cols(ctx, ncols, owner, &c0, &c1);
+      const uint32_t ca = std::min(c1, c0 + j0), cb = std::min(c1, c0 + j0 + CH);
+      for (int dst = 0; dst < W && rc == 0; ++dst) {
+        if (dst == owner || (me != owner && me != dst)) continue;
+        uint64_t lo, hi;
+        shard_range(en, W, dst, &lo, &hi);
+        const std::vector<Segment> segs = halo_segments(en, lo, hi, halo_lo, halo_hi);
+        for (uint32_t c = ca; c < cb && rc == 0; ++c)
+          for (const Segment& s : segs) {
+            Fr* p = base + (uint64_t)c * en + s.lo;
+            rc = me == owner ? nccl().Send(p, s.len * sizeof(Fr), kNcclUint8, dst, (NcclComm)ctx->team_comm, ctx->stream)
+                             : nccl().Recv(p, s.len * sizeof(Fr), kNcclUint8, owner, (NcclComm)ctx->team_comm, ctx->stream);
+            if (rc != 0) break;
+          }
+      }
+    }
+    if (rc != 0) { nccl().GroupEnd(); return nccl_fail(ctx, "ncclSend/ncclRecv", rc); }
+    ZKC_NCCL_TRY(ctx, nccl().GroupEnd());
+  }
+  return ZKC_OK;
+}
+
+int team_allgather_rows(zkc_ctx* ctx, Fr* col, uint64_t en) {
+  if (!real_comm(ctx)) return ZKC_OK;
+  ProfScope _p(ctx, "team.allgather_rows");
+  const int W = ctx->team_world;
+  if (en % (uint64_t)W == 0) return team_allgather(ctx, col, (size_t)(en / W) * sizeof(Fr));
+  ZKC_NCCL_TRY(ctx, nccl().GroupStart());
+  for (int r = 0; r < W; ++r) {
+    uint64_t lo, hi;
+    shard_range(en, W, r, &lo, &hi);
+    if (hi == lo) continue;
+    int rc = nccl().Broadcast(col + lo, col + lo, (hi - lo) * sizeof(Fr), kNcclUint8, r, (NcclComm)ctx->team_comm, ctx->stream);
+    if (rc != 0) { nccl().GroupEnd(); return nccl_fail(ctx, "ncclBroadcast", rc); }
+  }
+  ZKC_NCCL_TRY(ctx, nccl().GroupEnd());
+  return ZKC_OK;
+}
+
+}  // namespace zkc
+
+using namespace zkc;
+
+extern "C" int zkc_team_unique_id(uint8_t id[ZKC_TEAM_ID_BYTES]) {
+  if (!id) return ZKC_ERR_BAD_ARG;
+  if (!nccl().ok) return ZKC_ERR_CUDA;
+  NcclId nid;
+  if (nccl().GetUniqueId(&nid) != 0) return ZKC_ERR_CUDA;
+  memcpy(id, nid.internal, ZKC_TEAM_ID_BYTES);
+  return ZKC_OK;
+}
+
+extern "C" int zkc_team_init(zkc_ctx* ctx, int rank, int world, const uint8_t id[ZKC_TEAM_ID_BYTES]) {
+  if (!ctx || world < 1 || rank < 0 || rank >= world) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_team_init: bad rank / world");
+  CtxLock lock(ctx);
+  if (ctx->team_comm || ctx->team_world > 1) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_team_init: the context already belongs to a team");
+  if (world == 1) return ZKC_OK;
+  if (!id) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_team_init: null id");
+  if (!nccl().ok) return set_err(ctx, ZKC_ERR_CUDA, "zkc_team_init: libnccl.so.2 not found (team proving needs NCCL)");
+  NcclId nid;
+  memcpy(nid.internal, id, ZKC_TEAM_ID_BYTES);
+  NcclComm comm = nullptr;
+  ZKC_NCCL_TRY(ctx, nccl().CommInitRank(&comm, world, nid, rank));
+  ctx->team_comm = comm; ctx->team_rank = rank; ctx->team_world = world; ctx->team_emulate = false;
+  return ZKC_OK;
+}
+
+extern "C" int zkc_team_emulate(zkc_ctx* ctx, int world) {
+  if (!ctx || world < 1 || world > 64) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_team_emulate: bad world");
+  CtxLock lock(ctx);
+  if (ctx->team_comm) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_team_emulate: the context belongs to a real team");
+  ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->team_world = world; ctx->team_rank = 0; ctx->team_emulate = world > 1;
+  return ZKC_OK;
+}
+
+extern "C" int zkc_team_leave(zkc_ctx* ctx) {
+  if (!ctx) return ZKC_ERR_BAD_ARG;
+  CtxLock lock(ctx);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->team_comm) { nccl().CommDestroy((NcclComm)ctx->team_comm); ctx->team_comm = nullptr; }
+  ctx->team_world = 1; ctx->team_rank = 0; ctx->team_emulate = false;
+  return ZKC_OK;
+}
+
+extern "C" int zkc_team_info(const zkc_ctx* ctx, int* rank, int* world, int* emulated) {
+  if (!ctx) return ZKC_ERR_BAD_ARG;
+  if (rank) *rank = ctx->team_rank;
+  if (world) *world = ctx->team_world;
+  if (emulated) *emulated = ctx->team_emulate ? 1 : 0;
+  return ZKC_OK;
+}
+
+// The partition arithmetic, exposed for host-side planning and tests (no device work).
+extern "C" int zkc_team_shard_range(uint64_t total, int world, int rank, uint64_t* lo, uint64_t* hi) {
+  if (world < 1 || rank < 0 || rank >= world || !lo || !hi) return ZKC_ERR_BAD_ARG;
+  shard_range(total, world, rank, lo, hi);
+  return ZKC_OK;
+}
+extern "C" int zkc_team_row_segments(uint64_t rows, int world, int rank, uint64_t halo_lo, uint64_t halo_hi, uint64_t out_lo_len[4], int* nseg) {
+  if (world < 1 || rank < 0 || rank >= world || !out_lo_len || !nseg || rows == 0) return ZKC_ERR_BAD_ARG;
+  uint64_t lo, hi;
+  shard_range(rows, world, rank, &lo, &hi);
+  const std::vector<Segment> segs = halo_segments(rows, lo, hi, halo_lo, halo_hi);
+  *nseg = (int)segs.size();
+  for (size_t i = 0; i < segs.size() && i < 2; ++i) { out_lo_len[2 * i] = segs[i].lo; out_lo_len[2 * i + 1] = segs[i].len; }
+  return ZKC_OK;
+}

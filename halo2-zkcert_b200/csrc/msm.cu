@@ -19,6 +19,7 @@
 // With a resident SRS the bases are expanded once into W tables 2^(c*w) * P_i, so all windows of
 // all points share ONE bucket set per column and step 6 shrinks by a factor W.
 #include "msm.cuh"
+#include "dist.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -30,7 +31,7 @@ __global__ void k_msm_digits(const Fr* scalars, uint32_t* dig, uint32_t* counts,
   if (idx >= g.n * g.ncols) return;
   const uint32_t col = (uint32_t)(idx / g.n);
   const uint64_t i = idx - (uint64_t)col * g.n;
-  const Fr s = fe_to_canonical(fe_load(scalars + idx));
+  const Fr s = fe_to_canonical(fe_load(scalars + (uint64_t)col * g.sstride + i));
   uint32_t carry = 0;
   const uint32_t full = 1u << g.c;
   for (uint32_t w = 0; w < g.W; ++w) {
@@ -70,7 +71,7 @@ __global__ void k_msm_scatter(const uint32_t* dig, uint32_t* cursor, uint32_t* e
   if (lane == leader) basepos = atomicAdd(cursor + key, (uint32_t)__popc(peers));
   basepos = __shfl_sync(peers, basepos, leader);
   const uint32_t pos = basepos + (uint32_t)__popc(peers & ((1u << lane) - 1));
-  const uint64_t pt = g.sets == 1 ? (uint64_t)w * g.n + i : i;   // precomputed tables are laid out [w][i]
+  const uint64_t pt = g.sets == 1 ? (uint64_t)w * g.bstride + i : i;   // precomputed tables are laid out [w][i]
   ent_pt[pos] = (uint32_t)pt | (d & 0x80000000u);
   ent_key[pos] = (uint32_t)key;
 }
@@ -276,7 +277,7 @@ MsmGeom msm_geom(uint64_t n, uint32_t ncols, uint32_t c, bool precomputed) {
   MsmGeom g;
   g.W = (255 + c - 1) / c;
   c = (255 + g.W - 1) / g.W;   // same window count, evenly filled: a nearly empty top window would pile n/2^few entries on a handful of buckets
-  g.c = c; g.NB = 1u << (c - 1); g.sets = precomputed ? 1 : g.W; g.n = n; g.ncols = ncols;
+  g.c = c; g.NB = 1u << (c - 1); g.sets = precomputed ? 1 : g.W; g.n = n; g.ncols = ncols; g.sstride = n; g.bstride = n;
   const uint64_t e = g.emax();
   // entries per accumulate thread (B200 sweep): short chunks keep more warps in flight (T=8 reaches
   // 0.99 of the IMAD.WIDE peak) but multiply the partials the gather phase must fold; 32 / 64 minimise the sum
@@ -287,12 +288,12 @@ MsmGeom msm_geom(uint64_t n, uint32_t ncols, uint32_t c, bool precomputed) {
   return g;
 }
 
-// Enqueue one batch (all kernels + the async D2H of the c bit-plane sums per column) on ctx->stream.
-int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, uint32_t nc, uint32_t c, bool precomputed, MsmPending* pend,
-                int result_slot) {
-  MsmGeom g = msm_geom(n, nc, c, precomputed);
-  const uint64_t nbt = g.nbtot(), em = g.emax();
-  if (nbt + em / g.T + 1 >= (1ull << 32) || em >= (1ull << 32)) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: batch too large");
+// All kernels of one batch on ctx->stream: bit-plane sums to U_out[nc * sets * c], number of non-zero digits to *total_out.
+static int msm_kernels(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, const MsmGeom& g, G1Xyzz* U, uint32_t* total_out) {
+  const uint64_t n = g.n, nbt = g.nbtot(), em = g.emax();
+  const uint32_t nc = g.ncols;
+  if (nbt + em / g.T + 1 >= (1ull << 32) || em >= (1ull << 32) || (uint64_t)g.W * g.bstride >= (1ull << 31))
+    return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: batch too large");
   if ((uint64_t)nc * g.sets > 65535) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: too many bucket sets in one batch");
   const uint64_t nslots = nbt + (em + g.T - 1) / g.T + 1;
   size_t o = 0;
@@ -300,7 +301,6 @@ int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t
   const size_t o_counts = carve(nbt * 4), o_offsets = carve((nbt + 1) * 4), o_cursor = carve(nbt * 4), o_heavyc = carve(8),
                o_heavy = carve((nbt + MSM_GIANT_CAP) * 4), o_hpart = carve((size_t)MSM_GIANT_CAP * MSM_GIANT_SLICES * sizeof(G1Xyzz)), o_dig = carve(em * 4), o_pt = carve(em * 4), o_key = carve(em * 4),
                o_part = carve(nslots * sizeof(G1Xyzz)), o_bk = carve(nbt * sizeof(G1Xyzz)),
-               o_U = carve((size_t)nc * g.sets * g.c * sizeof(G1Xyzz)),
                o_redp = carve((size_t)nc * g.sets * g.c * ((g.NB + 1023) / 1024) * sizeof(G1Xyzz));
   char* base;
   ZKC_TRY(scratch_reserve(ctx, SCR_MSM, o, (void**)&base));
@@ -308,7 +308,7 @@ int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t
   uint32_t* cursor = (uint32_t*)(base + o_cursor); uint32_t* heavyc = (uint32_t*)(base + o_heavyc);
   uint32_t* heavy = (uint32_t*)(base + o_heavy); uint32_t* dig = (uint32_t*)(base + o_dig);
   uint32_t* ent_pt = (uint32_t*)(base + o_pt); uint32_t* ent_key = (uint32_t*)(base + o_key);
-  G1Xyzz* partial = (G1Xyzz*)(base + o_part); G1Xyzz* buckets = (G1Xyzz*)(base + o_bk); G1Xyzz* U = (G1Xyzz*)(base + o_U); G1Xyzz* redp = (G1Xyzz*)(base + o_redp); G1Xyzz* hpart = (G1Xyzz*)(base + o_hpart);
+  G1Xyzz* partial = (G1Xyzz*)(base + o_part); G1Xyzz* buckets = (G1Xyzz*)(base + o_bk); G1Xyzz* redp = (G1Xyzz*)(base + o_redp); G1Xyzz* hpart = (G1Xyzz*)(base + o_hpart);
   cudaStream_t st = ctx->stream;
   ZKC_CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, nbt * 4, st));
   ZKC_CUDA_TRY(ctx, cudaMemsetAsync(heavyc, 0, 8, st));
@@ -352,25 +352,68 @@ int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t
     k_msm_reduce2<<<g2, 32, 32 * sizeof(G1Xyzz), st>>>(redp, U, g, nchunks);
     ZKC_LAUNCH_CHECK(ctx);
   }
-  const size_t ubytes = (size_t)nc * g.sets * g.c * sizeof(G1Xyzz);
-  void* hU;
-  ZKC_TRY(pinned_reserve(ctx, ubytes + 16, &hU, result_slot));   // slot 1: a batch whose result is consumed later
-  ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(hU, U, ubytes, cudaMemcpyDeviceToHost, st));
-  ZKC_CUDA_TRY(ctx, cudaMemcpyAsync((char*)hU + ubytes, offsets + nbt, 4, cudaMemcpyDeviceToHost, st));
-  cudaEvent_t ev = result_slot ? ctx->ev_msm_side : ctx->ev_msm_main;
-  ZKC_CUDA_TRY(ctx, cudaEventRecord(ev, st));
-  pend->g = g; pend->nc = nc; pend->n = n; pend->hU = hU; pend->ubytes = ubytes; pend->done = ev; pend->active = true;
+  ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(total_out, offsets + nbt, 4, cudaMemcpyDeviceToDevice, st));
   return ZKC_OK;
 }
 
-// Wait for the batch, then the host-side epilogue (Horner over bit planes / windows, normalisation).
+// Enqueue one batch (all kernels + the async D2H of the c bit-plane sums per column) on ctx->stream.
+int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, uint32_t nc, uint32_t c, bool precomputed, MsmPending* pend,
+                int result_slot, bool team) {
+  team = team && team_active(ctx) && n >= (uint64_t)ctx->team_world;
+  const int shards = team ? ctx->team_world : 1;
+  const MsmGeom g0 = msm_geom(n, nc, c, precomputed);
+  const size_t ubytes = (size_t)nc * g0.sets * g0.c * sizeof(G1Xyzz), slot_bytes = (ubytes + 4 + 255) & ~(size_t)255;   // U, then the digit count
+  char* dU;
+  ZKC_TRY(scratch_reserve(ctx, SCR_MSM2, slot_bytes * shards, (void**)&dU));
+  if (!team) {
+    ZKC_TRY(msm_kernels(ctx, scalars, bases, g0, (G1Xyzz*)dU, (uint32_t*)(dU + ubytes)));
+  } else {
+    // point-range shards: rank r walks points [lo, hi) of every column against the same slice of every window table
+    for (int r : team_ranks(ctx)) {
+      uint64_t lo, hi;
+      shard_range(n, shards, r, &lo, &hi);
+      MsmGeom g = msm_geom(hi - lo, nc, c, precomputed);
+      g.sstride = n; g.bstride = n;
+      char* slot = dU + (size_t)r * slot_bytes;
+      ZKC_TRY(msm_kernels(ctx, scalars + lo, bases + lo, g, (G1Xyzz*)slot, (uint32_t*)(slot + ubytes)));
+    }
+    ProfScope _p(ctx, "team.msm_allgather");
+    ZKC_TRY(team_allgather(ctx, dU, slot_bytes));
+  }
+  void* hU;
+  ZKC_TRY(pinned_reserve(ctx, slot_bytes * shards, &hU, result_slot));   // slot 1: a batch whose result is consumed later
+  ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(hU, dU, slot_bytes * shards, cudaMemcpyDeviceToHost, ctx->stream));
+  cudaEvent_t ev = result_slot ? ctx->ev_msm_side : ctx->ev_msm_main;
+  ZKC_CUDA_TRY(ctx, cudaEventRecord(ev, ctx->stream));
+  pend->g = g0; pend->nc = nc; pend->n = n; pend->hU = hU; pend->ubytes = ubytes; pend->shards = shards; pend->done = ev; pend->active = true;
+  return ZKC_OK;
+}
+
+// Wait for the batch, then the host-side epilogue (sum of the shards' bit planes, Horner over bit planes / windows, normalisation).
 int msm_finish(zkc_ctx* ctx, MsmPending* pend, zkc_g1* out) {
   if (!pend->active) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm_finish: nothing pending");
   ZKC_CUDA_TRY(ctx, cudaEventSynchronize(pend->done));
   pend->active = false;
-  { uint32_t e; memcpy(&e, (char*)pend->hU + pend->ubytes, 4); ctx->stats["msm.madds"] += e; ctx->stats["msm.points"] += pend->n * pend->nc; }
+  const size_t slot_bytes = (pend->ubytes + 4 + 255) & ~(size_t)255;
+  const size_t per_col = (size_t)pend->g.sets * pend->g.c;
+  std::vector<G1Xyzz> sum;
+  const G1Xyzz* U = (const G1Xyzz*)pend->hU;
+  uint64_t madds = 0;
+  for (int r = 0; r < pend->shards; ++r) {
+    uint32_t e; memcpy(&e, (char*)pend->hU + (size_t)r * slot_bytes + pend->ubytes, 4);
+    if (ctx->team_emulate || pend->shards == 1 || r == ctx->team_rank) madds += e;    // this GPU's own work
+  }
+  ctx->stats["msm.madds"] += madds; ctx->stats["msm.points"] += pend->n * pend->nc;
+  if (pend->shards > 1) {
+    sum.assign(U, U + per_col * pend->nc);
+    for (int r = 1; r < pend->shards; ++r) {
+      const G1Xyzz* Ur = (const G1Xyzz*)((const char*)pend->hU + (size_t)r * slot_bytes);
+      for (size_t i = 0; i < sum.size(); ++i) xyzz_add(sum[i], Ur[i]);
+    }
+    U = sum.data();
+  }
   for (uint32_t col = 0; col < pend->nc; ++col) {
-    G1Xyzz r = host_combine((const G1Xyzz*)pend->hU + (size_t)col * pend->g.sets * pend->g.c, pend->g);
+    G1Xyzz r = host_combine(U + (size_t)col * per_col, pend->g);
     xyzz_to_abi(r, out + col);
   }
   return ZKC_OK;
@@ -378,7 +421,8 @@ int msm_finish(zkc_ctx* ctx, MsmPending* pend, zkc_g1* out) {
 
 // Core: `ncols` scalar columns (n each, contiguous) against `bases` (n points, or W tables of n when
 // precomputed).  Writes ncols results to `out` (host).
-int msm_run(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, uint32_t ncols, uint32_t c, bool precomputed, zkc_g1* out) {
+int msm_run(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, uint32_t ncols, uint32_t c, bool precomputed, zkc_g1* out,
+            bool team = false) {
   if (ncols == 0) return ZKC_OK;
   if (n == 0) {
     for (uint32_t i = 0; i < ncols; ++i) xyzz_to_abi(xyzz_identity(), out + i);
@@ -393,7 +437,7 @@ int msm_run(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, 
   for (uint32_t c0 = 0; c0 < ncols; c0 += chunk) {
     const uint32_t nc = std::min(chunk, ncols - c0);
     MsmPending pend;
-    ZKC_TRY(msm_enqueue(ctx, scalars + (uint64_t)c0 * n, bases, n, nc, c, precomputed, &pend, 0));
+    ZKC_TRY(msm_enqueue(ctx, scalars + (uint64_t)c0 * n, bases, n, nc, c, precomputed, &pend, 0, team));
     ZKC_TRY(msm_finish(ctx, &pend, out + c0));
   }
   return ZKC_OK;
@@ -578,12 +622,12 @@ namespace zkc {
 // asynchronous single-column commitment of a full-length polynomial (finish with msm_finish)
 int srs_commit_enqueue(zkc_ctx* ctx, const zkc_srs* s, int basis, const Fr* poly, uint64_t len, MsmPending* pend) {
   if (len != s->n) return set_err(ctx, ZKC_ERR_BAD_ARG, "srs_commit_enqueue: full-length polynomials only");
-  return msm_enqueue(ctx, poly, s->tab[basis], len, 1, s->c, true, pend, 1);
+  return msm_enqueue(ctx, poly, s->tab[basis], len, 1, s->c, true, pend, 1, true);
 }
 // commit `ncols` device-resident polynomials of `len` <= n coefficients (column stride = len)
 int srs_commit_dev(zkc_ctx* ctx, const zkc_srs* s, int basis, const Fr* polys, uint64_t len, uint32_t ncols, zkc_g1* out) {
   if (len > s->n) return set_err(ctx, ZKC_ERR_BAD_ARG, "commit: polynomial longer than the SRS");
-  if (len == s->n) return msm_run(ctx, polys, s->tab[basis], len, ncols, s->c, true, out);
+  if (len == s->n) return msm_run(ctx, polys, s->tab[basis], len, ncols, s->c, true, out, true);   // team: point-range shards
   // shorter polynomials: the window tables are laid out with stride n, so fall back to the generic
   // (non-precomputed) walk over the first `len` bases.
   return msm_run(ctx, polys, s->tab[basis], len, ncols, msm_pick_c(len, false), false, out);

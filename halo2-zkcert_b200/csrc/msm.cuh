@@ -13,6 +13,8 @@ struct MsmGeom {
   uint64_t n;          // points per column
   uint32_t ncols;
   uint32_t T;          // entries per accumulate thread
+  uint64_t sstride;    // distance between scalar columns (n, or the full column length when a point range is processed)
+  uint64_t bstride;    // distance between window tables (precomputed layout [w][i])
   ZKC_HD uint64_t nbtot() const { return (uint64_t)ncols * sets * NB; }
   ZKC_HD uint64_t emax() const { return (uint64_t)ncols * W * n; }
 };
@@ -24,13 +26,16 @@ struct MsmPending {
   uint32_t nc = 0;
   uint64_t n = 0;
   void* hU = nullptr;
-  size_t ubytes = 0;
+  size_t ubytes = 0;   // bytes of bit-plane sums per shard
+  int shards = 1;      // team proving: one block of `ubytes` per rank, summed on the host
   cudaEvent_t done = nullptr;
   bool active = false;
 };
 
+// `team`: the batch is a commitment against resident bases shared by a team (dist.cuh): each rank walks its point range
+// and the bit-plane sums are all-gathered before the D2H copy.
 int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, uint32_t nc, uint32_t c, bool precomputed, MsmPending* pend,
-                int result_slot);
+                int result_slot, bool team = false);
 int msm_finish(zkc_ctx* ctx, MsmPending* pend, zkc_g1* out);
 int srs_commit_enqueue(zkc_ctx* ctx, const zkc_srs* s, int basis, const Fr* poly, uint64_t len, MsmPending* pend);
 

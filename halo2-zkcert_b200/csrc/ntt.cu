@@ -168,9 +168,10 @@ __global__ void k_gen_twiddles(Fr* tw, Fr omega, uint64_t half_n) {
   for (uint64_t i = start; i < end; ++i) { fe_store(tw + i, w); w = fe_mul(w, omega); }
 }
 
-__global__ void k_scale_periodic(Fr* a, const Fr* t, uint32_t mask, uint64_t n) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__global__ void k_scale_periodic(Fr* a, const Fr* t, uint32_t mask, uint64_t row0, uint64_t cnt) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= cnt) return;
+  const uint64_t i = row0 + tid;
   fe_store(a + i, fe_mul(fe_load(a + i), fe_load_nc(t + (i & mask))));
 }
 
@@ -370,9 +371,9 @@ int dom_extended_to_coeff(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint32_t nco
   }
   return ZKC_OK;
 }
-int dom_divide_by_vanishing(zkc_ctx* ctx, const zkc_domain* d, Fr* a) {
-  const uint64_t en = 1ull << d->extended_k;
-  k_scale_periodic<<<(unsigned)((en + 255) / 256), 256, 0, ctx->stream>>>(a, d->t_inv_dev, (1u << (d->extended_k - d->k)) - 1, en);
+int dom_divide_by_vanishing(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint64_t row0, uint64_t cnt) {   // rows [row0, row0 + cnt)
+  if (cnt == 0) return ZKC_OK;
+  k_scale_periodic<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(a, d->t_inv_dev, (1u << (d->extended_k - d->k)) - 1, row0, cnt);
   ZKC_LAUNCH_CHECK(ctx);
   return ZKC_OK;
 }
@@ -432,7 +433,7 @@ extern "C" int zkc_extended_to_coeff_dev(zkc_ctx* ctx, const zkc_domain* d, zkc_
 }
 extern "C" int zkc_divide_by_vanishing_dev(zkc_ctx* ctx, const zkc_domain* d, zkc_fr* a) {
   if (!ctx || !d || !a) return set_err(ctx, ZKC_ERR_BAD_ARG, "null argument");
-  CtxLock lock(ctx); return dom_divide_by_vanishing(ctx, d, (Fr*)a);
+  CtxLock lock(ctx); return dom_divide_by_vanishing(ctx, d, (Fr*)a, 0, 1ull << d->extended_k);
 }
 
 extern "C" int zkc_lagrange_to_coeff(zkc_ctx* ctx, const zkc_domain* d, zkc_fr* a) {

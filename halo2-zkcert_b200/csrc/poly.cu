@@ -503,9 +503,10 @@ int fr_eval_batch(zkc_ctx* ctx, const std::vector<const Fr*>& polys, uint64_t n,
 // ---- constraint-system program interpreter ---------------------------------------------------------------------
 #define PROG_STACK 12
 __global__ void __launch_bounds__(128) k_eval_program(const uint32_t* words, uint32_t npairs, const Fr* consts, DevQueries q, Fr* out,
-                                                      uint64_t rows, uint32_t rot_scale, Fr mult, int accumulate) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows) return;
+                                                      uint64_t rows, uint32_t rot_scale, Fr mult, int accumulate, uint64_t row0, uint64_t cnt) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= cnt) return;
+  const uint64_t i = row0 + tid;
   Fr stack[PROG_STACK];
   int sp = 0;
   Fr acc = accumulate ? fe_load(out + i) : fe_zero<FrP>();
@@ -531,14 +532,16 @@ __global__ void __launch_bounds__(128) k_eval_program(const uint32_t* words, uin
   fe_store(out + i, acc);
 }
 int eval_program(zkc_ctx* ctx, const DevProgram& prog, const DevQueries& q, Fr* out, uint64_t rows, uint32_t rot_scale, const Fr& mult,
-                 int accumulate) {
+                 int accumulate, uint64_t row0, uint64_t cnt) {
   ProfScope _p(ctx, "eval_program");
+  if (cnt == UINT64_MAX) { row0 = 0; cnt = rows; }
+  if (cnt == 0) return ZKC_OK;
   if (prog.npairs == 0) {
-    if (!accumulate) ZKC_CUDA_TRY(ctx, cudaMemsetAsync(out, 0, rows * sizeof(Fr), ctx->stream));
+    if (!accumulate) ZKC_CUDA_TRY(ctx, cudaMemsetAsync(out + row0, 0, cnt * sizeof(Fr), ctx->stream));
     return ZKC_OK;
   }
-  k_eval_program<<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(prog.words, prog.npairs, prog.consts, q, out, rows, rot_scale, mult,
-                                                                           accumulate);
+  k_eval_program<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(prog.words, prog.npairs, prog.consts, q, out, rows, rot_scale, mult,
+                                                                          accumulate, row0, cnt);
   ZKC_LAUNCH_CHECK(ctx);
   return ZKC_OK;
 }

@@ -51,9 +51,10 @@ int fr_batch_invert(zkc_ctx* ctx, const Fr* a, Fr* out, size_t n);
 
 // postfix-program evaluation over `rows` rows: acc = 0; for each expression: acc = acc * mult + expr
 // (mult = theta for lookup compression, y for the custom-gate part of h(X)).  If `accumulate`, the
-// running value starts from out[i] instead of 0.
+// running value starts from out[i] instead of 0.  `rows` is the domain size (rotations wrap modulo it); only rows
+// [row0, row0 + cnt) are evaluated (default: all).
 int eval_program(zkc_ctx* ctx, const DevProgram& prog, const DevQueries& q, Fr* out, uint64_t rows, uint32_t rot_scale, const Fr& mult,
-                 int accumulate);
+                 int accumulate, uint64_t row0 = 0, uint64_t cnt = UINT64_MAX);
 
 // 256-bit ascending sort of canonical values (n a power of two)
 int sort_u256(zkc_ctx* ctx, Fr* keys, uint64_t n);

@@ -10,6 +10,7 @@
 // and only commitments (64 B), evaluations (32 B) and challenges cross PCIe.
 #include "prover_kernels.cuh"
 #include "msm.cuh"
+#include "dist.cuh"
 #include "host/hostutil.h"
 #include <algorithm>
 #include <functional>
@@ -21,7 +22,7 @@ int ntt_twiddles(zkc_ctx* ctx, uint32_t log_n, const Fr** out);
 int dom_lagrange_to_coeff(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint32_t ncols);
 int dom_coeff_to_extended(zkc_ctx* ctx, const zkc_domain* d, const Fr* in, uint64_t in_stride, Fr* out, uint32_t ncols);
 int dom_extended_to_coeff(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint32_t ncols);
-int dom_divide_by_vanishing(zkc_ctx* ctx, const zkc_domain* d, Fr* a);
+int dom_divide_by_vanishing(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint64_t row0, uint64_t cnt);
 int srs_commit_dev(zkc_ctx* ctx, const zkc_srs* s, int basis, const Fr* polys, uint64_t len, uint32_t ncols, zkc_g1* out);
 }  // namespace zkc
 
@@ -464,6 +465,45 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   const uint32_t rot_scale = 1u << (pk->ext_k - cs.k);
   cudaStream_t st = ctx->stream;
   Pool pool(ctx);
+  // Team proving (dist.cuh): the same driver runs on every rank; MSMs split by point range, column transforms by column,
+  // h(X) by extended-row block.  One stream: the collectives are ordered with the kernels they depend on.
+  const bool team = team_active(ctx);
+  struct OverlapGuard { zkc_ctx* c; bool saved; ~OverlapGuard() { c->overlap = saved; } } overlap_guard{ctx, ctx->overlap};
+  if (team) { ctx->overlap = false; ctx->team_rot = 0; }
+  uint64_t halo_lo = 0, halo_hi = 0;   // rows of rotation reach on the extended coset, before / after a row block
+  {
+    int64_t rmin = -(int64_t)(bf + 1), rmax = 1;   // z(omega X), z(omega^-(bf+1) X), a'(omega^-1 X)
+    for (auto* v : {&cs.aq, &cs.fq, &cs.iq}) for (auto& qq : *v) { rmin = std::min<int64_t>(rmin, qq.second); rmax = std::max<int64_t>(rmax, qq.second); }
+    halo_lo = (uint64_t)(-rmin) * rot_scale; halo_hi = (uint64_t)rmax * rot_scale;
+  }
+  // row blocks of the extended coset this process evaluates: the whole coset, or the block(s) of its team rank(s)
+  std::vector<Segment> my_rows;
+  if (!team) my_rows.push_back({0, en});
+  else for (int r : team_ranks(ctx)) { uint64_t lo, hi; shard_range(en, ctx->team_world, r, &lo, &hi); if (hi > lo) my_rows.push_back({lo, hi - lo}); }
+  // values -> coefficient form, `ncols` columns in place; team: the owner of a column transforms it and broadcasts the result
+  auto to_coeff = [&](Fr* polys, uint32_t ncols) -> int {
+    if (!team) return dom_lagrange_to_coeff(ctx, pk->dom, polys, ncols);
+    for (int r : team_ranks(ctx)) {
+      uint32_t c0, c1;
+      team_cols(ctx, ncols, r, &c0, &c1);
+      if (c1 > c0) ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, polys + (size_t)c0 * n, c1 - c0));
+    }
+    ZKC_TRY(team_bcast_cols(ctx, polys, n, n, ncols));
+    team_advance(ctx, ncols);
+    return ZKC_OK;
+  };
+  // coefficient form -> extended coset; team: the owner sends every rank the rows its block reads (block + rotation halo)
+  auto to_extended = [&](const Fr* polys, Fr* cosets, uint32_t ncols) -> int {
+    if (!team) return dom_coeff_to_extended(ctx, pk->dom, polys, n, cosets, ncols);
+    for (int r : team_ranks(ctx)) {
+      uint32_t c0, c1;
+      team_cols(ctx, ncols, r, &c0, &c1);
+      if (c1 > c0) ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, polys + (size_t)c0 * n, n, cosets + (size_t)c0 * en, c1 - c0));
+    }
+    ZKC_TRY(team_scatter_rows(ctx, cosets, en, ncols, halo_lo, halo_hi));
+    team_advance(ctx, ncols);
+    return ZKC_OK;
+  };
   if (opts->rng_kind < 0 || opts->rng_kind > 1) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_prove: unknown rng_kind");
   Rng rng(opts->rng_seed, opts->rng_kind == 1 ? 6 : 10);
   if (opts->transcript < 0 || opts->transcript > 3 || opts->multiopen < 0 || opts->multiopen > 1)
@@ -528,6 +568,11 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   Fr *adv_cosets, *inst_cosets, *pz_cosets, *lk_cosets;
   ZKC_TRY(pool.get(&adv_cosets, (size_t)A * en)); ZKC_TRY(pool.get(&inst_cosets, (size_t)I * en));
   ZKC_TRY(pool.get(&pz_cosets, (size_t)Pn * en)); ZKC_TRY(pool.get(&lk_cosets, (size_t)3 * L * en));
+  if (team && getenv("ZKC_TEAM_POISON")) {   // testing: rows a rank never receives must never be read
+    ZKC_CUDA_TRY(ctx, cudaMemsetAsync(adv_cosets, 0xff, (size_t)A * en * sizeof(Fr), st));
+    ZKC_CUDA_TRY(ctx, cudaMemsetAsync(pz_cosets, 0xff, (size_t)Pn * en * sizeof(Fr), st));
+    ZKC_CUDA_TRY(ctx, cudaMemsetAsync(lk_cosets, 0xff, (size_t)3 * L * en * sizeof(Fr), st));
+  }
   Fr *lk_comp, *lk_perm, *lk_perm_polys, *z_all, *z_all_polys;
   ZKC_TRY(pool.get(&lk_comp, (size_t)2 * L * n)); ZKC_TRY(pool.get(&lk_perm, (size_t)2 * L * n));
   ZKC_TRY(pool.get(&lk_perm_polys, (size_t)2 * L * n));
@@ -552,8 +597,8 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
     SideScope side(ctx);
     if (A) {
       ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(adv_polys, adv_values, (size_t)A * n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
-      ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, adv_polys, A));
-      ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, adv_polys, n, adv_cosets, A));
+      ZKC_TRY(to_coeff(adv_polys, A));
+      ZKC_TRY(to_extended(adv_polys, adv_cosets, A));
     }
     if (I) ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, inst_polys, n, inst_cosets, I));
   }
@@ -624,8 +669,8 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
         SideScope side(ctx);   // A', S' coefficient forms and cosets (needed at steps 10 / 13)
         Fr* pp = lk_perm_polys + (size_t)2 * l * n;
         ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(pp, ap, (size_t)2 * n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
-        ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, pp, 2));
-        ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, pp, n, lk_cosets + (size_t)3 * l * en + en, 2));
+        ZKC_TRY(to_coeff(pp, 2));
+        ZKC_TRY(to_extended(pp, lk_cosets + (size_t)3 * l * en + en, 2));
       }
       ZKC_TRY(commit_points(ctx, srs, 1, ap, n, 2, pts));
       ZKC_TRY(write_points(pts));
@@ -704,9 +749,9 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
     {
       SideScope side(ctx);   // z coefficient forms and cosets
       ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(z_all_polys, z_all, (size_t)(Pn + L) * n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
-      ZKC_TRY(dom_lagrange_to_coeff(ctx, pk->dom, z_all_polys, Pn + L));
-      if (Pn) ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, pz_polys, n, pz_cosets, Pn));
-      for (uint32_t l = 0; l < L; ++l) ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, lk_z_polys + (size_t)l * n, n, lk_cosets + (size_t)3 * l * en, 1));
+      ZKC_TRY(to_coeff(z_all_polys, Pn + L));
+      if (Pn) ZKC_TRY(to_extended(pz_polys, pz_cosets, Pn));
+      for (uint32_t l = 0; l < L; ++l) ZKC_TRY(to_extended(lk_z_polys + (size_t)l * n, lk_cosets + (size_t)3 * l * en, 1));
     }
     ZKC_TRY(commit_points(ctx, srs, 1, z_all, n, Pn + L, pts));
     ZKC_TRY(write_points(pts));
@@ -733,30 +778,35 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   side_join(ctx);   // every coset produced on the side stream is complete from here on
   {
     ProfScope _p(ctx, "prove.quotient");
-    ZKC_TRY(eval_program(ctx, pk->gates, qext, hval, en, rot_scale, y, 0));
-    if (Pn) {
-      PermFixedArgs fa; fa.nsets = Pn;
-      for (uint32_t s = 0; s < Pn; ++s) fa.z[s] = pz_cosets + (size_t)s * en;
-      const int64_t last_off = -(int64_t)(bf + 1) * rot_scale;
-      k_quot_perm_fixed<<<grid(en, 128), 128, 0, st>>>(hval, fa, pk->l0, pk->l_last, y, en, last_off); ZKC_LAUNCH_CHECK(ctx);
-      const Fr* tw_ext;
-      ZKC_TRY(ntt_twiddles(ctx, pk->ext_k, &tw_ext));
-      for (uint32_t s = 0; s < Pn; ++s) {
-        k_quot_perm_set<<<grid(en, 128), 128, 0, st>>>(hval, perm_args(s, true), pz_cosets + (size_t)s * en, pk->l_active, tw_ext, pk->ext_k, beta,
-                                                        gamma, y, en, rot_scale);
+    const Fr* tw_ext = nullptr;
+    if (Pn) ZKC_TRY(ntt_twiddles(ctx, pk->ext_k, &tw_ext));
+    for (const Segment& rb : my_rows) {
+      const uint64_t r0 = rb.lo, rc = rb.len;
+      ZKC_TRY(eval_program(ctx, pk->gates, qext, hval, en, rot_scale, y, 0, r0, rc));
+      if (Pn) {
+        PermFixedArgs fa; fa.nsets = Pn;
+        for (uint32_t s = 0; s < Pn; ++s) fa.z[s] = pz_cosets + (size_t)s * en;
+        const int64_t last_off = -(int64_t)(bf + 1) * rot_scale;
+        k_quot_perm_fixed<<<grid(rc, 128), 128, 0, st>>>(hval, fa, pk->l0, pk->l_last, y, en, last_off, r0, rc); ZKC_LAUNCH_CHECK(ctx);
+        for (uint32_t s = 0; s < Pn; ++s) {
+          k_quot_perm_set<<<grid(rc, 128), 128, 0, st>>>(hval, perm_args(s, true), pz_cosets + (size_t)s * en, pk->l_active, tw_ext, pk->ext_k, beta,
+                                                          gamma, y, en, rot_scale, r0, rc);
+          ZKC_LAUNCH_CHECK(ctx);
+        }
+      }
+      for (uint32_t l = 0; l < L; ++l) {
+        Fr* zc = lk_cosets + (size_t)3 * l * en; Fr* ac = zc + en; Fr* sc = ac + en;
+        ZKC_TRY(eval_program(ctx, pk->lookups[l].first, qext, lk_comp_cosets, en, rot_scale, theta, 0, r0, rc));
+        ZKC_TRY(eval_program(ctx, pk->lookups[l].second, qext, lk_comp_cosets + en, en, rot_scale, theta, 0, r0, rc));
+        k_quot_lookup<<<grid(rc, 128), 128, 0, st>>>(hval, zc, ac, sc, lk_comp_cosets, lk_comp_cosets + en, pk->l0, pk->l_last, pk->l_active, beta,
+                                                      gamma, y, en, rot_scale, r0, rc);
         ZKC_LAUNCH_CHECK(ctx);
       }
+      // 11. divide by X^n - 1 on the coset
+      ZKC_TRY(dom_divide_by_vanishing(ctx, pk->dom, hval, r0, rc));
     }
-    for (uint32_t l = 0; l < L; ++l) {
-      Fr* zc = lk_cosets + (size_t)3 * l * en; Fr* ac = zc + en; Fr* sc = ac + en;
-      ZKC_TRY(eval_program(ctx, pk->lookups[l].first, qext, lk_comp_cosets, en, rot_scale, theta, 0));
-      ZKC_TRY(eval_program(ctx, pk->lookups[l].second, qext, lk_comp_cosets + en, en, rot_scale, theta, 0));
-      k_quot_lookup<<<grid(en, 128), 128, 0, st>>>(hval, zc, ac, sc, lk_comp_cosets, lk_comp_cosets + en, pk->l0, pk->l_last, pk->l_active, beta,
-                                                    gamma, y, en, rot_scale);
-      ZKC_LAUNCH_CHECK(ctx);
-    }
-    // 11. divide by X^n - 1 on the coset, back to coefficients
-    ZKC_TRY(dom_divide_by_vanishing(ctx, pk->dom, hval));
+    //     ... (team: every rank needs the whole quotient) and back to coefficients
+    if (team) ZKC_TRY(team_allgather_rows(ctx, hval, en));
     ZKC_TRY(dom_extended_to_coeff(ctx, pk->dom, hval, 1));
   }
   const uint32_t q = cs.degree - 1;

@@ -149,9 +149,12 @@ __global__ void k_lookup_finish(const Fr* canon, const Fr* tail, Fr* out, uint64
 #define PERM_MAX_SETS 32
 struct PermFixedArgs { const Fr* z[PERM_MAX_SETS]; uint32_t nsets; };
 // value = value*y + l0*(1 - z_0);  value*y + l_last*(z_l^2 - z_l);  for s >= 1: value*y + l0*(z_s - z_{s-1}[i + last_rot])
-__global__ void k_quot_perm_fixed(Fr* value, PermFixedArgs a, const Fr* l0, const Fr* l_last, Fr y, uint64_t rows, int64_t last_off) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows) return;
+// (all h(X) kernels: `rows` is the size of the extended domain, [row0, row0 + cnt) the row block this launch evaluates)
+__global__ void k_quot_perm_fixed(Fr* value, PermFixedArgs a, const Fr* l0, const Fr* l_last, Fr y, uint64_t rows, int64_t last_off, uint64_t row0,
+                                  uint64_t cnt) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= cnt) return;
+  const uint64_t i = row0 + tid;
   Fr v = fe_load(value + i);
   const Fr L0 = fe_load(l0 + i), LL = fe_load(l_last + i);
   const Fr z0 = fe_load(a.z[0] + i);
@@ -168,9 +171,10 @@ __global__ void k_quot_perm_fixed(Fr* value, PermFixedArgs a, const Fr* l0, cons
 // value = value*y + l_active * ( z(wX) prod (v + beta sigma + gamma) - z(X) prod (v + delta_beta_t X + gamma) )
 // X = zeta * w_ext^i is folded into delta_beta (zeta) and the twiddle table (w_ext^i).
 __global__ void k_quot_perm_set(Fr* value, PermSetArgs a, const Fr* z, const Fr* l_active, const Fr* tw_ext, uint32_t ext_k, Fr beta,
-                                Fr gamma, Fr y, uint64_t rows, uint32_t rot_scale) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows) return;
+                                Fr gamma, Fr y, uint64_t rows, uint32_t rot_scale, uint64_t row0, uint64_t cnt) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= cnt) return;
+  const uint64_t i = row0 + tid;
   const uint64_t half = rows >> 1;
   Fr w = fe_load_nc(tw_ext + (i >= half ? i - half : i));
   if (i >= half) w = fe_neg(w);
@@ -186,9 +190,11 @@ __global__ void k_quot_perm_set(Fr* value, PermSetArgs a, const Fr* z, const Fr*
 }
 // the five lookup terms (A.7 / evaluation.rs order)
 __global__ void k_quot_lookup(Fr* value, const Fr* zc, const Fr* ac, const Fr* sc, const Fr* comp_in, const Fr* comp_tab, const Fr* l0,
-                              const Fr* l_last, const Fr* l_active, Fr beta, Fr gamma, Fr y, uint64_t rows, uint32_t rot_scale) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows) return;
+                              const Fr* l_last, const Fr* l_active, Fr beta, Fr gamma, Fr y, uint64_t rows, uint32_t rot_scale, uint64_t row0,
+                              uint64_t cnt) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= cnt) return;
+  const uint64_t i = row0 + tid;
   Fr v = fe_load(value + i);
   const Fr L0 = fe_load(l0 + i), LL = fe_load(l_last + i), LA = fe_load(l_active + i);
   const Fr z = fe_load(zc + i), zn = fe_load(zc + ((i + rot_scale) & (rows - 1)));

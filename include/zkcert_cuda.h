@@ -207,6 +207,25 @@ void zkc_seed_from_u64(uint64_t state, uint8_t seed[32]);
 /* Grain-generated Poseidon parameters of transcript kind 3 (canonical little-endian): 65 x 3 round constants, 3 x 3 MDS. */
 int zkc_poseidon_spec(zkc_fr* constants, zkc_fr* mds);
 
+/* ---- team proving: ONE create_proof over the GPUs of a node ---------------------------------------------
+ * One process (and one zkc_ctx) per GPU.  After zkc_team_init every rank calls zkc_srs_*, zkc_pk_load and zkc_prove with
+ * IDENTICAL arguments; the library partitions the device work (MSM by point range — the split halo2's best_multiexp makes
+ * across rayon threads —, column transforms by column, h(X) by extended-row block) and exchanges results with NCCL on the
+ * ctx stream.  Every rank returns the same proof bytes, identical to the single-GPU proof.  The id comes from
+ * zkc_team_unique_id on one rank and reaches the others through the host's own channel (torch.distributed, MPI, a file).
+ * zkc_team_emulate(world) runs all `world` shards on this one GPU sequentially with the collectives elided (testing). */
+#define ZKC_TEAM_ID_BYTES 128
+int zkc_team_unique_id(uint8_t id[ZKC_TEAM_ID_BYTES]);
+int zkc_team_init(zkc_ctx* ctx, int rank, int world, const uint8_t id[ZKC_TEAM_ID_BYTES]);
+int zkc_team_emulate(zkc_ctx* ctx, int world);
+int zkc_team_leave(zkc_ctx* ctx);
+int zkc_team_info(const zkc_ctx* ctx, int* rank, int* world, int* emulated);
+/* the partition arithmetic (host only): contiguous share [lo, hi) of `total` items for `rank`; and the <= 2 row segments
+ * {lo, len} of a cyclic column of `rows` rows that `rank` reads when evaluating its row block with rotations reaching
+ * halo_lo rows back and halo_hi rows forward */
+int zkc_team_shard_range(uint64_t total, int world, int rank, uint64_t* lo, uint64_t* hi);
+int zkc_team_row_segments(uint64_t rows, int world, int rank, uint64_t halo_lo, uint64_t halo_hi, uint64_t out_lo_len[4], int* nseg);
+
 #ifdef __cplusplus
 }
 #endif

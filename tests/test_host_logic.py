@@ -220,3 +220,33 @@ def test_g1_sum_host_epilogue():
     neg = orc.g1_from_ints([pyref.ec_neg(orc.g1_to_ints(pts[0:1])[0])])
     two = np.concatenate([np.concatenate([pts[0:1], one], axis=1), np.concatenate([neg, one], axis=1)])
     assert orc.fq_to_ints(p.api.g1_sum(two).reshape(3, 4)) == [0, 1, 0]
+
+
+def test_team_partition_arithmetic():
+    """zkc_team_shard_range / zkc_team_row_segments (dist.cu): blocks tile the range; the segments a rank receives
+    cover exactly the rows its block reads under every rotation in [-halo_lo, +halo_hi] (cyclic)."""
+    import ctypes as C
+    L = pkg().lib()
+    for total, world in [(10, 3), (7, 8), (1 << 12, 4), (0, 2), (5, 5)]:
+        prev = 0
+        for r in range(world):
+            lo, hi = C.c_uint64(), C.c_uint64()
+            assert L.zkc_team_shard_range(C.c_uint64(total), world, r, C.byref(lo), C.byref(hi)) == 0
+            assert lo.value == prev and hi.value - lo.value in (total // world, total // world + 1)
+            prev = hi.value
+        assert prev == total
+    for rows, world, hl, hh in [(64, 2, 28, 12), (64, 4, 28, 12), (256, 3, 28, 12), (1 << 10, 8, 40, 4), (32, 2, 28, 12), (16, 4, 0, 0)]:
+        for r in range(world):
+            lo, hi = C.c_uint64(), C.c_uint64()
+            L.zkc_team_shard_range(C.c_uint64(rows), world, r, C.byref(lo), C.byref(hi))
+            out, nseg = (C.c_uint64 * 4)(), C.c_int()
+            assert L.zkc_team_row_segments(C.c_uint64(rows), world, r, C.c_uint64(hl), C.c_uint64(hh), out, C.byref(nseg)) == 0
+            got = set()
+            for i in range(nseg.value):
+                assert out[2 * i] + out[2 * i + 1] <= rows
+                seg = set(range(out[2 * i], out[2 * i] + out[2 * i + 1]))
+                assert not (got & seg)
+                got |= seg
+            want = {(i + d) % rows for i in range(lo.value, hi.value) for d in range(-hl, hh + 1)}
+            assert got == want if len(want) < rows else got == set(range(rows))
+    assert L.zkc_team_shard_range(C.c_uint64(4), 2, 2, None, None) != 0
