@@ -50,7 +50,7 @@ struct zkc_ctx {
   int team_rank = 0, team_world = 1;
   int team_rot = 0;                        // rank that takes the first column block of the next partitioned batch (load balance)
   bool team_emulate = false;               // zkc_team_emulate: all shards run here, one after the other, no collectives
-  void* team_comm = nullptr;               // ncclComm_t
+  void* team_comm[2] = {nullptr, nullptr}; // ncclComm_t: [0] collectives issued on the main stream, [1] on the side stream
 };
 
 namespace zkc {

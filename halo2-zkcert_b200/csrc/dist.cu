@@ -65,6 +65,8 @@ int nccl_fail(zkc_ctx* ctx, const char* what, int rc) {
   } while (0)
 
 bool real_comm(const zkc_ctx* ctx) { return ctx->team_world > 1 && !ctx->team_emulate; }
+// one communicator per stream: collectives of the two streams may be in flight at the same time
+NcclComm comm_of(const zkc_ctx* ctx) { return (NcclComm)ctx->team_comm[ctx->side_stream && ctx->stream == ctx->side_stream ? 1 : 0]; }
 
 }  // namespace
 
@@ -88,7 +90,7 @@ std::vector<int> team_ranks(const zkc_ctx* ctx) {
 
 int team_allgather(zkc_ctx* ctx, void* buf, size_t bytes_per_rank) {
   if (!real_comm(ctx) || !bytes_per_rank) return ZKC_OK;
-  ZKC_NCCL_TRY(ctx, nccl().AllGather((char*)buf + (size_t)ctx->team_rank * bytes_per_rank, buf, bytes_per_rank, kNcclUint8, (NcclComm)ctx->team_comm,
+  ZKC_NCCL_TRY(ctx, nccl().AllGather((char*)buf + (size_t)ctx->team_rank * bytes_per_rank, buf, bytes_per_rank, kNcclUint8, comm_of(ctx),
                                      ctx->stream));
   return ZKC_OK;
 }
@@ -102,7 +104,7 @@ int team_bcast_cols(zkc_ctx* ctx, Fr* base, uint64_t stride, uint64_t len, uint3
     team_cols(ctx, ncols, r, &c0, &c1);
     for (uint32_t c = c0; c < c1; ++c) {
       Fr* p = base + (uint64_t)c * stride;
-      int rc = nccl().Broadcast(p, p, len * sizeof(Fr), kNcclUint8, r, (NcclComm)ctx->team_comm, ctx->stream);
+      int rc = nccl().Broadcast(p, p, len * sizeof(Fr), kNcclUint8, r, comm_of(ctx), ctx->stream);
       if (rc != 0) { nccl().GroupEnd(); return nccl_fail(ctx, "ncclBroadcast", rc); }
     }
   }
@@ -131,8 +133,8 @@ int team_scatter_rows(zkc_ctx* ctx, Fr* base, uint64_t en, uint32_t ncols, uint6
         for (uint32_t c = ca; c < cb && rc == 0; ++c)
           for (const Segment& s : segs) {
             Fr* p = base + (uint64_t)c * en + s.lo;
-            rc = me == owner ? nccl().Send(p, s.len * sizeof(Fr), kNcclUint8, dst, (NcclComm)ctx->team_comm, ctx->stream)
-                             : nccl().Recv(p, s.len * sizeof(Fr), kNcclUint8, owner, (NcclComm)ctx->team_comm, ctx->stream);
+            rc = me == owner ? nccl().Send(p, s.len * sizeof(Fr), kNcclUint8, dst, comm_of(ctx), ctx->stream)
+                             : nccl().Recv(p, s.len * sizeof(Fr), kNcclUint8, owner, comm_of(ctx), ctx->stream);
             if (rc != 0) break;
           }
       }
@@ -153,7 +155,7 @@ int team_allgather_rows(zkc_ctx* ctx, Fr* col, uint64_t en) {
     uint64_t lo, hi;
     shard_range(en, W, r, &lo, &hi);
     if (hi == lo) continue;
-    int rc = nccl().Broadcast(col + lo, col + lo, (hi - lo) * sizeof(Fr), kNcclUint8, r, (NcclComm)ctx->team_comm, ctx->stream);
+    int rc = nccl().Broadcast(col + lo, col + lo, (hi - lo) * sizeof(Fr), kNcclUint8, r, comm_of(ctx), ctx->stream);
     if (rc != 0) { nccl().GroupEnd(); return nccl_fail(ctx, "ncclBroadcast", rc); }
   }
   ZKC_NCCL_TRY(ctx, nccl().GroupEnd());
@@ -176,22 +178,38 @@ extern "C" int zkc_team_unique_id(uint8_t id[ZKC_TEAM_ID_BYTES]) {
 extern "C" int zkc_team_init(zkc_ctx* ctx, int rank, int world, const uint8_t id[ZKC_TEAM_ID_BYTES]) {
   if (!ctx || world < 1 || rank < 0 || rank >= world) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_team_init: bad rank / world");
   CtxLock lock(ctx);
-  if (ctx->team_comm || ctx->team_world > 1) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_team_init: the context already belongs to a team");
+  if (ctx->team_comm[0] || ctx->team_world > 1) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_team_init: the context already belongs to a team");
   if (world == 1) return ZKC_OK;
   if (!id) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_team_init: null id");
   if (!nccl().ok) return set_err(ctx, ZKC_ERR_CUDA, "zkc_team_init: libnccl.so.2 not found (team proving needs NCCL)");
   NcclId nid;
   memcpy(nid.internal, id, ZKC_TEAM_ID_BYTES);
-  NcclComm comm = nullptr;
+  NcclComm comm = nullptr, comm2 = nullptr;
   ZKC_NCCL_TRY(ctx, nccl().CommInitRank(&comm, world, nid, rank));
-  ctx->team_comm = comm; ctx->team_rank = rank; ctx->team_world = world; ctx->team_emulate = false;
+  // second communicator (side stream): its id travels over the first one
+  NcclId nid2;
+  memset(&nid2, 0, sizeof nid2);
+  if (rank == 0 && nccl().GetUniqueId(&nid2) != 0) { nccl().CommDestroy(comm); return set_err(ctx, ZKC_ERR_CUDA, "zkc_team_init: ncclGetUniqueId failed"); }
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof nid2);
+  if (e == cudaSuccess) e = cudaMemcpy(d, &nid2, sizeof nid2, cudaMemcpyHostToDevice);
+  int rc = e == cudaSuccess ? nccl().Broadcast(d, d, sizeof nid2, kNcclUint8, 0, comm, ctx->stream) : 0;
+  if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && rc == 0) e = cudaMemcpy(&nid2, d, sizeof nid2, cudaMemcpyDeviceToHost);
+  if (d) cudaFree(d);
+  if (e == cudaSuccess && rc == 0) rc = nccl().CommInitRank(&comm2, world, nid2, rank);
+  if (e != cudaSuccess || rc != 0) {
+    nccl().CommDestroy(comm);
+    return e != cudaSuccess ? set_err(ctx, ZKC_ERR_CUDA, std::string("zkc_team_init: ") + cudaGetErrorString(e)) : nccl_fail(ctx, "zkc_team_init (second communicator)", rc);
+  }
+  ctx->team_comm[0] = comm; ctx->team_comm[1] = comm2; ctx->team_rank = rank; ctx->team_world = world; ctx->team_emulate = false;
   return ZKC_OK;
 }
 
 extern "C" int zkc_team_emulate(zkc_ctx* ctx, int world) {
   if (!ctx || world < 1 || world > 64) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_team_emulate: bad world");
   CtxLock lock(ctx);
-  if (ctx->team_comm) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_team_emulate: the context belongs to a real team");
+  if (ctx->team_comm[0]) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_team_emulate: the context belongs to a real team");
   ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->team_world = world; ctx->team_rank = 0; ctx->team_emulate = world > 1;
   return ZKC_OK;
@@ -201,7 +219,8 @@ extern "C" int zkc_team_leave(zkc_ctx* ctx) {
   if (!ctx) return ZKC_ERR_BAD_ARG;
   CtxLock lock(ctx);
   cudaStreamSynchronize(ctx->stream);
-  if (ctx->team_comm) { nccl().CommDestroy((NcclComm)ctx->team_comm); ctx->team_comm = nullptr; }
+  if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
+  for (auto& c : ctx->team_comm) if (c) { nccl().CommDestroy((NcclComm)c); c = nullptr; }
   ctx->team_world = 1; ctx->team_rank = 0; ctx->team_emulate = false;
   return ZKC_OK;
 }

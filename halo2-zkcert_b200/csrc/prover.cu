@@ -466,10 +466,10 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   cudaStream_t st = ctx->stream;
   Pool pool(ctx);
   // Team proving (dist.cuh): the same driver runs on every rank; MSMs split by point range, column transforms by column,
-  // h(X) by extended-row block.  One stream: the collectives are ordered with the kernels they depend on.
+  // h(X) by extended-row block.  Collectives are issued on the stream of the kernels they depend on (one communicator per
+  // stream), in the same host order on every rank, so the column exchanges of the side stream hide under the MSM phases.
   const bool team = team_active(ctx);
-  struct OverlapGuard { zkc_ctx* c; bool saved; ~OverlapGuard() { c->overlap = saved; } } overlap_guard{ctx, ctx->overlap};
-  if (team) { ctx->overlap = false; ctx->team_rot = 0; }
+  if (team) ctx->team_rot = 0;
   uint64_t halo_lo = 0, halo_hi = 0;   // rows of rotation reach on the extended coset, before / after a row block
   {
     int64_t rmin = -(int64_t)(bf + 1), rmax = 1;   // z(omega X), z(omega^-(bf+1) X), a'(omega^-1 X)
@@ -849,7 +849,27 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   }
   const size_t i_h = want(h_poly, x);
   std::vector<Fr> ev;
-  ZKC_TRY(fr_eval_batch(ctx, ev_polys, n, ev_points, ev));
+  if (!team) {
+    ZKC_TRY(fr_eval_batch(ctx, ev_polys, n, ev_points, ev));
+  } else {
+    // the (polynomial, point) pairs are independent: each rank evaluates a contiguous share, 32-byte results all-gathered
+    const size_t m = ev_polys.size(), W = (size_t)ctx->team_world, per = (m + W - 1) / W;
+    Fr* ev_dev;
+    ZKC_TRY(pool.get(&ev_dev, per * W));
+    std::vector<Fr> all(per * W, ZERO);
+    for (int r : team_ranks(ctx)) {
+      const size_t j0 = std::min(m, (size_t)r * per), j1 = std::min(m, j0 + per);
+      std::vector<Fr> part;
+      ZKC_TRY(fr_eval_batch(ctx, std::vector<const Fr*>(ev_polys.begin() + j0, ev_polys.begin() + j1), n,
+                            std::vector<Fr>(ev_points.begin() + j0, ev_points.begin() + j1), part));
+      std::copy(part.begin(), part.end(), all.begin() + j0);
+    }
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(ev_dev, all.data(), all.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    ZKC_TRY(team_allgather(ctx, ev_dev, per * sizeof(Fr)));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(all.data(), ev_dev, all.size() * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    ev.assign(all.begin(), all.begin() + m);
+  }
   // transcript order (A.9): advice, fixed, random, sigma, permutation products, lookups
   for (size_t i : i_adv) tr.write_scalar(ev[i]);
   for (size_t i : i_fix) tr.write_scalar(ev[i]);
