@@ -203,6 +203,24 @@ extern "C" int zkc_team_init(zkc_ctx* ctx, int rank, int world, const uint8_t id
     return e != cudaSuccess ? set_err(ctx, ZKC_ERR_CUDA, std::string("zkc_team_init: ") + cudaGetErrorString(e)) : nccl_fail(ctx, "zkc_team_init (second communicator)", rc);
   }
   ctx->team_comm[0] = comm; ctx->team_comm[1] = comm2; ctx->team_rank = rank; ctx->team_world = world; ctx->team_emulate = false;
+  // NCCL connects peers lazily at the first collective of each kind: do that here, on both communicators, not inside a proof
+  void* w = nullptr;
+  if (cudaMalloc(&w, 256 * (size_t)world * 2) == cudaSuccess) {
+    cudaMemset(w, 0, 256 * (size_t)world * 2);
+    for (NcclComm cm : {comm, comm2}) {
+      nccl().AllGather((char*)w + 256 * (size_t)rank, w, 256, kNcclUint8, cm, ctx->stream);
+      nccl().Broadcast(w, w, 256, kNcclUint8, 0, cm, ctx->stream);
+      nccl().GroupStart();
+      for (int p = 0; p < world; ++p) {
+        if (p == rank) continue;
+        nccl().Send((char*)w + 256 * (size_t)rank, 256, kNcclUint8, p, cm, ctx->stream);
+        nccl().Recv((char*)w + 256 * ((size_t)world + p), 256, kNcclUint8, p, cm, ctx->stream);
+      }
+      nccl().GroupEnd();
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(w);
+  }
   return ZKC_OK;
 }
 

@@ -416,6 +416,24 @@ int fr_kate_division_batch(zkc_ctx* ctx, const std::vector<Fr*>& polys, const st
   return ZKC_OK;
 }
 
+// q[j] += C * z^(len-1-j): the contribution of everything above a coefficient slice to its synthetic-division
+// quotient (team proving: each rank divides its own slice, the tails' values arrive as one field element)
+__global__ void k_add_geometric(Fr* q, uint64_t len, Fr C, Fr z) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t hi = len - (t * 64 < len ? t * 64 : len);    // this thread covers j in (hi - 64, hi], walking down from exponent t*64
+  if (hi == 0) return;
+  Fr w = fe_mul(C, fe_pow_u64(z, t * 64));
+  const uint64_t lo = hi > 64 ? hi - 64 : 0;
+  for (uint64_t j = hi; j-- > lo;) { fe_store(q + j, fe_add(fe_load(q + j), w)); w = fe_mul(w, z); }
+}
+int fr_add_geometric(zkc_ctx* ctx, Fr* q, uint64_t len, const Fr& C, const Fr& z) {
+  if (len == 0 || fe_is_zero(C)) return ZKC_OK;
+  const uint64_t threads = (len + 63) / 64;
+  k_add_geometric<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(q, len, C, z);
+  ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+
 // ---- batched polynomial evaluation ---------------------------------------------------------------------------
 // grid = (blocks_per_poly, n_evals); each CTA of 256 threads evaluates a 4096-coefficient slice at
 // the point (16-coefficient Horner per thread, then a shared-memory tree with x^(16*2^l) factors).

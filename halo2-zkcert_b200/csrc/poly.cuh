@@ -44,6 +44,8 @@ int fr_kate_division(zkc_ctx* ctx, const Fr* a, Fr* q, uint64_t n, const Fr& z, 
 // in-place batch: polys[j] <- polys[j] / (X - roots[j]) for independent jobs, one set of launches (tmp: n elements)
 #define KD_MAX_JOBS 16
 int fr_kate_division_batch(zkc_ctx* ctx, const std::vector<Fr*>& polys, const std::vector<Fr>& roots, uint64_t n, Fr* tmp);
+// q[j] += C * z^(len-1-j), j < len
+int fr_add_geometric(zkc_ctx* ctx, Fr* q, uint64_t len, const Fr& C, const Fr& z);
 // evaluate polys[j] (n coefficients each) at points[j]; results to host `out`
 int fr_eval_batch(zkc_ctx* ctx, const std::vector<const Fr*>& polys, uint64_t n, const std::vector<Fr>& points, std::vector<Fr>& out);
 // batch inversion (zeros pass through)

@@ -544,7 +544,17 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   ZKC_TRY(pool.get(&adv_values, (size_t)A * n)); ZKC_TRY(pool.get(&adv_polys, (size_t)A * n));
   if (A) {
     ProfScope _p(ctx, "prove.advice_h2d");
-    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(adv_values, advice, (size_t)A * n * sizeof(Fr), advice_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    const size_t cells = (size_t)A * n;
+    if (team && !advice_on_device && cells % (size_t)ctx->team_world == 0) {
+      // every rank holds the same host witness: each uploads 1/world of it over its own PCIe link and the shares are
+      // all-gathered over NVLink (world x less host-to-device traffic per rank)
+      const size_t per = cells / (size_t)ctx->team_world;
+      for (int r : team_ranks(ctx))
+        ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(adv_values + (size_t)r * per, (const Fr*)advice + (size_t)r * per, per * sizeof(Fr), cudaMemcpyHostToDevice, st));
+      ZKC_TRY(team_allgather(ctx, adv_values, per * sizeof(Fr)));
+    } else {
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(adv_values, advice, cells * sizeof(Fr), advice_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    }
   }
   {
     std::vector<Fr> tail;
@@ -901,6 +911,68 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
 
   Fr *acc, *tmp1, *tmp2, *tmp3;
   ZKC_TRY(pool.get(&acc, n)); ZKC_TRY(pool.get(&tmp1, n)); ZKC_TRY(pool.get(&tmp2, n)); ZKC_TRY(pool.get(&tmp3, n));
+  // Team proving, SHPLONK: a point-range MSM reads only coefficients [lo, hi) of the polynomial it commits, so the
+  // quotient polynomials are built slice by slice on the rank that will commit the slice: linear combinations are
+  // element-wise, and a synthetic division of a slice needs one field element from the slices above it (the value of
+  // their tail at the root), exchanged with a 32-byte-per-job all-gather.
+  const bool sliced = team && opts->multiopen == 0 && n >= 16ull * (uint64_t)ctx->team_world;
+  std::vector<std::pair<int, Segment>> my_coeffs;   // (team rank, coefficient slice)
+  if (sliced) for (int r : team_ranks(ctx)) { uint64_t lo, hi; shard_range(n, ctx->team_world, r, &lo, &hi); my_coeffs.push_back({r, {lo, hi - lo}}); }
+  else my_coeffs.push_back({0, {0, n}});
+  auto lincomb_s = [&](Fr* out, const std::vector<const Fr*>& ps, const std::vector<Fr>& cf) -> int {
+    for (auto& sl : my_coeffs) {
+      std::vector<const Fr*> shifted(ps);
+      for (auto& q : shifted) q += sl.second.lo;
+      ZKC_TRY(fr_lincomb(ctx, out + sl.second.lo, sl.second.len, shifted, cf));
+    }
+    return ZKC_OK;
+  };
+  auto sub_low_s = [&](Fr* a, const std::vector<Fr>& low) -> int {
+    for (auto& sl : my_coeffs) if (sl.second.lo == 0) ZKC_TRY(fr_sub_low(ctx, a, low));
+    return ZKC_OK;
+  };
+  auto scale_s = [&](Fr* a, const Fr& f) -> int {
+    for (auto& sl : my_coeffs) ZKC_TRY(fr_scale(ctx, a + sl.second.lo, sl.second.len, f));
+    return ZKC_OK;
+  };
+  Fr* kd_exchange = nullptr;
+  if (sliced) ZKC_TRY(pool.get(&kd_exchange, (size_t)ctx->team_world * KD_MAX_JOBS));
+  auto kate_s = [&](const std::vector<Fr*>& ps, const std::vector<Fr>& roots, Fr* tmp) -> int {
+    if (!sliced) return fr_kate_division_batch(ctx, ps, roots, n, tmp);
+    const size_t W = (size_t)ctx->team_world;
+    for (size_t off = 0; off < ps.size(); off += KD_MAX_JOBS) {
+      const size_t J = std::min<size_t>(KD_MAX_JOBS, ps.size() - off);
+      const std::vector<Fr> rt(roots.begin() + off, roots.begin() + off + J);
+      // value of every slice at the root, taken before the in-place divisions
+      std::vector<Fr> E(W * KD_MAX_JOBS, ZERO);
+      for (auto& sl : my_coeffs) {
+        std::vector<const Fr*> cp(J);
+        for (size_t j = 0; j < J; ++j) cp[j] = ps[off + j] + sl.second.lo;
+        std::vector<Fr> ev;
+        ZKC_TRY(fr_eval_batch(ctx, cp, sl.second.len, rt, ev));
+        std::copy(ev.begin(), ev.end(), E.begin() + (size_t)sl.first * KD_MAX_JOBS);
+      }
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(kd_exchange, E.data(), E.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+      ZKC_TRY(team_allgather(ctx, kd_exchange, KD_MAX_JOBS * sizeof(Fr)));
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(E.data(), kd_exchange, E.size() * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+      ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      for (auto& sl : my_coeffs) {
+        std::vector<Fr*> cp(J);
+        for (size_t j = 0; j < J; ++j) cp[j] = ps[off + j] + sl.second.lo;
+        ZKC_TRY(fr_kate_division_batch(ctx, cp, rt, sl.second.len, tmp));
+        for (size_t j = 0; j < J; ++j) {
+          Fr C = ZERO;   // value at the root of everything above this slice: C_{q-1} = E_q + z^(len_q) C_q
+          for (int q = (int)W - 1; q > sl.first; --q) {
+            uint64_t lo, hi;
+            shard_range(n, (int)W, q, &lo, &hi);
+            C = fe_add(E[(size_t)q * KD_MAX_JOBS + j], fe_mul(fe_pow_u64(rt[j], hi - lo), C));
+          }
+          ZKC_TRY(fr_add_geometric(ctx, cp[j], sl.second.len, C, rt[j]));
+        }
+      }
+    }
+    return ZKC_OK;
+  };
   if (opts->multiopen == 0) {
     // ---- SHPLONK (A.11) ----
     ProfScope _p(ctx, "prove.shplonk");
@@ -924,20 +996,20 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
         for (size_t i = 0; i < low.size(); ++i) low[i] = fe_add(low[i], fe_mul(py, rcoef[s][p][i]));
         py = fe_mul(py, yy);
       }
-      ZKC_TRY(fr_lincomb(ctx, setbuf + s * n, n, sets[s].polys, cf));
-      ZKC_TRY(fr_sub_low(ctx, setbuf + s * n, low));
+      ZKC_TRY(lincomb_s(setbuf + s * n, sets[s].polys, cf));
+      ZKC_TRY(sub_low_s(setbuf + s * n, low));
       max_roots = std::max(max_roots, sets[s].points.size());
     }
     for (size_t r = 0; r < max_roots; ++r) {
       std::vector<Fr*> jp; std::vector<Fr> jr;
       for (size_t s = 0; s < sets.size(); ++s) if (sets[s].points.size() > r) { jp.push_back(setbuf + s * n); jr.push_back(sets[s].points[r]); }
-      ZKC_TRY(fr_kate_division_batch(ctx, jp, jr, n, tmp2));
+      ZKC_TRY(kate_s(jp, jr, tmp2));
     }
     {
       std::vector<const Fr*> ps; std::vector<Fr> cf;
       Fr pv = ONE;
       for (size_t s = 0; s < sets.size(); ++s) { ps.push_back(setbuf + s * n); cf.push_back(pv); pv = fe_mul(pv, v); }
-      ZKC_TRY(fr_lincomb(ctx, acc, n, ps, cf));
+      ZKC_TRY(lincomb_s(acc, ps, cf));
     }
     ZKC_TRY(commit_points(ctx, srs, 0, acc, n, 1, pts));
     ZKC_TRY(write_points(pts));
@@ -968,11 +1040,12 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
     }
     const Fr zt = vanishing_eval(super_points, u);
     ps.push_back(acc); cf.push_back(fe_neg(zt));
-    ZKC_TRY(fr_lincomb(ctx, tmp1, n, ps, cf));
-    ZKC_TRY(fr_sub_low(ctx, tmp1, {cst}));
-    ZKC_TRY(fr_kate_division(ctx, tmp1, tmp1, n, u, tmp2, tmp3));
+    ZKC_TRY(lincomb_s(tmp1, ps, cf));
+    ZKC_TRY(sub_low_s(tmp1, {cst}));
+    if (sliced) ZKC_TRY(kate_s({tmp1}, {u}, tmp2));
+    else ZKC_TRY(fr_kate_division(ctx, tmp1, tmp1, n, u, tmp2, tmp3));
     if (fe_is_zero(z0)) return set_err(ctx, ZKC_ERR_OPENING, "shplonk: z_diff of the first rotation set is zero");
-    ZKC_TRY(fr_scale(ctx, tmp1, n, fe_inv(z0)));
+    ZKC_TRY(scale_s(tmp1, fe_inv(z0)));
     ZKC_TRY(commit_points(ctx, srs, 0, tmp1, n, 1, pts));
     ZKC_TRY(write_points(pts));
   } else {
