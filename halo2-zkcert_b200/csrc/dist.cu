@@ -148,6 +148,11 @@ int team_scatter_rows(zkc_ctx* ctx, Fr* base, uint64_t en, uint32_t ncols, uint6
 int team_allgather_rows(zkc_ctx* ctx, Fr* col, uint64_t en) {
   if (!real_comm(ctx)) return ZKC_OK;
   ProfScope _p(ctx, "team.allgather_rows");
+  return team_allgather_flat(ctx, col, en);
+}
+
+int team_allgather_flat(zkc_ctx* ctx, Fr* col, uint64_t en) {
+  if (!real_comm(ctx)) return ZKC_OK;
   const int W = ctx->team_world;
   if (en % (uint64_t)W == 0) return team_allgather(ctx, col, (size_t)(en / W) * sizeof(Fr));
   ZKC_NCCL_TRY(ctx, nccl().GroupStart());

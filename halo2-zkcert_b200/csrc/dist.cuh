@@ -41,6 +41,8 @@ int team_bcast_cols(zkc_ctx* ctx, Fr* base, uint64_t stride, uint64_t len, uint3
 int team_scatter_rows(zkc_ctx* ctx, Fr* base, uint64_t en, uint32_t ncols, uint64_t halo_lo, uint64_t halo_hi);
 // in-place all-gather of the row blocks of one length-en column
 int team_allgather_rows(zkc_ctx* ctx, Fr* col, uint64_t en);
+// in-place all-gather of a flat array split with shard_range(total, world, r)
+int team_allgather_flat(zkc_ctx* ctx, Fr* base, uint64_t total);
 // columns [c0, c1) of a batch of `ncols` that rank `r` transforms
 // (blocks are dealt starting at rank ctx->team_rot, which team_advance moves past the ranks that just received the
 // larger blocks, so that batches of few columns do not all land on rank 0)

@@ -722,24 +722,42 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
     const size_t perm_len = Pn ? (size_t)Pn * U + 1 : 0, lk_len = U + 1, total = perm_len + (size_t)L * lk_len;
     Fr *num, *den, *tails;
     ZKC_TRY(pool.get(&num, total)); ZKC_TRY(pool.get(&den, total)); ZKC_TRY(pool.get(&tails, (size_t)(Pn + L) * bf));
-    for (uint32_t s = 0; s < Pn; ++s) {
-      k_perm_num_den<<<grid(U, 128), 128, 0, st>>>(perm_args(s, false), pk->omega_pows, beta, gamma, num + (size_t)s * U, den + (size_t)s * U, U);
-      ZKC_LAUNCH_CHECK(ctx);
-    }
+    // rows are independent up to the scan: a team splits the flat [0, total) range, each rank builds and inverts its part
+    std::vector<Segment> flat;
+    if (team) for (int r : team_ranks(ctx)) { uint64_t lo, hi; shard_range(total, ctx->team_world, r, &lo, &hi); if (hi > lo) flat.push_back({lo, hi - lo}); }
+    else flat.push_back({0, total});
+    auto clip = [](const Segment& f, uint64_t base, uint64_t len, uint64_t* r0, uint64_t* rc) {   // rows of [base, base + len) inside f
+      const uint64_t a = std::max(f.lo, base), b = std::min(f.lo + f.len, base + len);
+      *r0 = a > base ? a - base : 0; *rc = b > a ? b - a : 0;
+    };
     if (Pn) {
       ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(num + perm_len - 1, &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));
       ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(den + perm_len - 1, &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));
     }
     for (uint32_t l = 0; l < L; ++l) {
-      const Fr* comp_in = lk_comp + (size_t)2 * l * n; const Fr* comp_tab = comp_in + n;
-      const Fr* ap = lk_perm + (size_t)2 * l * n; const Fr* sp = ap + n;
-      Fr* nl = num + perm_len + (size_t)l * lk_len; Fr* dl = den + perm_len + (size_t)l * lk_len;
-      k_lookup_num_den<<<grid(U, 128), 128, 0, st>>>(comp_in, comp_tab, ap, sp, beta, gamma, nl, dl, U); ZKC_LAUNCH_CHECK(ctx);
-      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(nl + U, &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));
-      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(dl + U, &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(num + perm_len + (size_t)l * lk_len + U, &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(den + perm_len + (size_t)l * lk_len + U, &ONE, sizeof(Fr), cudaMemcpyHostToDevice, st));
     }
-    ZKC_TRY(fr_batch_invert(ctx, den, den, total));
-    k_pk_mul_vec<<<grid(total, 256), 256, 0, st>>>(num, den, num, total); ZKC_LAUNCH_CHECK(ctx);
+    for (const Segment& f : flat) {
+      uint64_t r0, rc;
+      for (uint32_t s = 0; s < Pn; ++s) {
+        clip(f, (uint64_t)s * U, U, &r0, &rc);
+        if (!rc) continue;
+        k_perm_num_den<<<grid(rc, 128), 128, 0, st>>>(perm_args(s, false), pk->omega_pows, beta, gamma, num + (size_t)s * U, den + (size_t)s * U, r0, rc);
+        ZKC_LAUNCH_CHECK(ctx);
+      }
+      for (uint32_t l = 0; l < L; ++l) {
+        const Fr* comp_in = lk_comp + (size_t)2 * l * n; const Fr* comp_tab = comp_in + n;
+        const Fr* ap = lk_perm + (size_t)2 * l * n; const Fr* sp = ap + n;
+        Fr* nl = num + perm_len + (size_t)l * lk_len; Fr* dl = den + perm_len + (size_t)l * lk_len;
+        clip(f, perm_len + (uint64_t)l * lk_len, U, &r0, &rc);
+        if (!rc) continue;
+        k_lookup_num_den<<<grid(rc, 128), 128, 0, st>>>(comp_in, comp_tab, ap, sp, beta, gamma, nl, dl, r0, rc); ZKC_LAUNCH_CHECK(ctx);
+      }
+      ZKC_TRY(fr_batch_invert(ctx, den + f.lo, den + f.lo, f.len));
+      k_pk_mul_vec<<<grid(f.len, 256), 256, 0, st>>>(num + f.lo, den + f.lo, num + f.lo, f.len); ZKC_LAUNCH_CHECK(ctx);
+    }
+    if (team) ZKC_TRY(team_allgather_flat(ctx, num, total));
     if (Pn) ZKC_TRY(fr_scan(ctx, num, den, perm_len, SCAN_MUL, 0, ONE));
     for (uint32_t l = 0; l < L; ++l)
       ZKC_TRY(fr_scan(ctx, num + perm_len + (size_t)l * lk_len, den + perm_len + (size_t)l * lk_len, lk_len, SCAN_MUL, 0, ONE));

@@ -47,9 +47,11 @@ struct PermSetArgs {
   uint32_t m;
 };
 // rows i < U:  num[i] = prod_t (v_t + delta_beta_t * omega^i + gamma),  den[i] = prod_t (v_t + beta * sigma_t + gamma)
-__global__ void k_perm_num_den(PermSetArgs a, const Fr* omega_pows, Fr beta, Fr gamma, Fr* num, Fr* den, uint64_t U) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= U) return;
+// (rows [row0, row0 + cnt) of the set; team proving splits the rows across ranks)
+__global__ void k_perm_num_den(PermSetArgs a, const Fr* omega_pows, Fr beta, Fr gamma, Fr* num, Fr* den, uint64_t row0, uint64_t cnt) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= cnt) return;
+  const uint64_t i = row0 + tid;
   const Fr w = fe_load_nc(omega_pows + i);
   Fr nacc = fe_one<FrP>(), dacc = fe_one<FrP>();
   for (uint32_t t = 0; t < a.m; ++t) {
@@ -61,9 +63,11 @@ __global__ void k_perm_num_den(PermSetArgs a, const Fr* omega_pows, Fr beta, Fr 
   fe_store(den + i, dacc);
 }
 // lookup: num = (a + beta)(s + gamma), den = (a' + beta)(s' + gamma)
-__global__ void k_lookup_num_den(const Fr* a, const Fr* s, const Fr* ap, const Fr* sp, Fr beta, Fr gamma, Fr* num, Fr* den, uint64_t U) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= U) return;
+__global__ void k_lookup_num_den(const Fr* a, const Fr* s, const Fr* ap, const Fr* sp, Fr beta, Fr gamma, Fr* num, Fr* den, uint64_t row0,
+                                 uint64_t cnt) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= cnt) return;
+  const uint64_t i = row0 + tid;
   fe_store(num + i, fe_mul(fe_add(fe_load(a + i), beta), fe_add(fe_load(s + i), gamma)));
   fe_store(den + i, fe_mul(fe_add(fe_load(ap + i), beta), fe_add(fe_load(sp + i), gamma)));
 }
