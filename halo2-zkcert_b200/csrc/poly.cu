@@ -641,4 +641,69 @@ int sort_u256(zkc_ctx* ctx, Fr* keys, uint64_t n) {
   return ZKC_OK;
 }
 
+
+// ---- counting sort for small keys --------------------------------------------------------------------------------
+// Range-check lookups (halo2-base RangeChip: values < 2^lookup_bits, /root/reference/src/bin/cli.rs:421) sort columns whose
+// canonical values fit a few dozen bits.  keys[0..U) are canonical values, keys[U..n) the all-ones sentinel written by
+// k_lookup_prepare (already in final position).  If every value is below 2^24 the sort is histogram -> scan -> expand;
+// otherwise the generic bitonic network runs.  Same output either way.
+#define COUNT_SORT_MAX_BITS 24
+__global__ void k_sort_probe(const Fr* keys, uint64_t U, uint32_t* probe /* [0] max low limb, [1] OR of the high limbs */) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t lo = 0, hi = 0;
+  if (i < U) {
+    const Fr v = fe_load(keys + i);
+    lo = v.v[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) hi |= v.v[j];
+  }
+  lo = __reduce_max_sync(0xffffffffu, lo);
+  hi = __reduce_or_sync(0xffffffffu, hi);
+  if ((threadIdx.x & 31) == 0) { if (lo) atomicMax(probe, lo); if (hi) atomicOr(probe + 1, hi); }
+}
+__global__ void k_count_hist(const Fr* keys, uint64_t U, uint32_t* hist) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= U) return;
+  const uint32_t key = keys[i].v[0];
+  const uint32_t peers = __match_any_sync(__activemask(), key);
+  if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(hist + key, (uint32_t)__popc(peers));
+}
+__global__ void k_count_expand(const uint32_t* offsets, uint32_t bins, Fr* keys, uint64_t U) {
+  const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= U) return;
+  uint32_t lo = 0, hi = bins;          // first bin whose exclusive offset exceeds pos
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (offsets[mid] > pos) hi = mid; else lo = mid + 1;
+  }
+  Fr v = fe_zero<FrP>();
+  v.v[0] = lo - 1;
+  fe_store(keys + pos, v);
+}
+int sort_u256_padded(zkc_ctx* ctx, Fr* keys, uint64_t n, uint64_t U) {
+  if (U > n) return set_err(ctx, ZKC_ERR_BAD_ARG, "sort_u256_padded: U > n");
+  if (U < 2048 || U >= (1ull << 32)) return sort_u256(ctx, keys, n);
+  cudaStream_t st = ctx->stream;
+  uint32_t* w;
+  ZKC_TRY(scratch_reserve(ctx, SCR_MISC3, 256, (void**)&w));
+  uint32_t probe[2];
+  {
+    ProfScope _p(ctx, "sort_u256");
+    ZKC_CUDA_TRY(ctx, cudaMemsetAsync(w, 0, 8, st));
+    k_sort_probe<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(keys, U, w); ZKC_LAUNCH_CHECK(ctx);
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(probe, w, 8, cudaMemcpyDeviceToHost, st));
+    ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  }
+  if (probe[1] || probe[0] >= (1u << COUNT_SORT_MAX_BITS)) return sort_u256(ctx, keys, n);
+  ProfScope _p(ctx, "sort_u256");
+  const uint32_t bins = probe[0] + 1;
+  ZKC_TRY(scratch_reserve(ctx, SCR_MISC3, 256 + 2 * (size_t)bins * 4, (void**)&w));
+  uint32_t* hist = w + 64; uint32_t* offsets = hist + bins;
+  ZKC_CUDA_TRY(ctx, cudaMemsetAsync(hist, 0, (size_t)bins * 4, st));
+  k_count_hist<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(keys, U, hist); ZKC_LAUNCH_CHECK(ctx);
+  ZKC_TRY(u32_scan(ctx, hist, offsets, bins, nullptr));
+  k_count_expand<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(offsets, bins, keys, U); ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+
 }  // namespace zkc

@@ -60,5 +60,7 @@ int eval_program(zkc_ctx* ctx, const DevProgram& prog, const DevQueries& q, Fr* 
 
 // 256-bit ascending sort of canonical values (n a power of two)
 int sort_u256(zkc_ctx* ctx, Fr* keys, uint64_t n);
+// the same for keys[0..U) canonical + keys[U..n) all-ones sentinel; counting sort when every value is < 2^24
+int sort_u256_padded(zkc_ctx* ctx, Fr* keys, uint64_t n, uint64_t U);
 
 }  // namespace zkc

@@ -653,8 +653,8 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
       ZKC_TRY(eval_program(ctx, pk->lookups[l].second, qlag, comp_tab, n, 1, theta, 0));
       k_lookup_prepare<<<grid(n, 256), 256, 0, st>>>(comp_in, ca, U, n); ZKC_LAUNCH_CHECK(ctx);
       k_lookup_prepare<<<grid(n, 256), 256, 0, st>>>(comp_tab, ct, U, n); ZKC_LAUNCH_CHECK(ctx);
-      ZKC_TRY(sort_u256(ctx, ca, n));
-      ZKC_TRY(sort_u256(ctx, ct, n));
+      ZKC_TRY(sort_u256_padded(ctx, ca, n, U));
+      ZKC_TRY(sort_u256_padded(ctx, ct, n, U));
       ZKC_CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, 16, st));
       k_lookup_flags<<<grid(U, 128), 128, 0, st>>>(ca, ct, flags, flags + n, counts, U); ZKC_LAUNCH_CHECK(ctx);
       ZKC_TRY(u32_scan(ctx, flags, ranks, U, counts + 2));
