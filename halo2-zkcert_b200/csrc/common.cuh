@@ -27,6 +27,8 @@ struct zkc_ctx {
   cudaStream_t own_stream = nullptr;  // created with the ctx
   cudaStream_t side_stream = nullptr; // second stream: work that is not on the Fiat-Shamir critical path (SideScope)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_msm_main = nullptr, ev_msm_side = nullptr;
+  cudaStream_t copy_stream = nullptr; // staged witness upload (zkc_prove): host-to-device copies that run under the first MSMs
+  std::vector<cudaEvent_t> ev_copy;
   bool side_pending = false;
   bool overlap = true;                // zkc_ctx_set_overlap: 0 serialises side work on the main stream (clean per-kernel timing)
   std::string err;

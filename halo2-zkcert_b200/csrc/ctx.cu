@@ -43,6 +43,8 @@ extern "C" void zkc_ctx_destroy(zkc_ctx* c) {
   for (auto& b : c->scratch) if (b.p) cudaFree(b.p);
   for (auto& kv : c->twiddles) cudaFree(kv.second);
   for (int i = 0; i < 2; ++i) if (c->pinned[i]) cudaFreeHost(c->pinned[i]);
+  for (auto e : c->ev_copy) cudaEventDestroy(e);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->ev_msm_main) cudaEventDestroy(c->ev_msm_main);
   if (c->ev_msm_side) cudaEventDestroy(c->ev_msm_side);
   for (auto& r : c->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }

@@ -344,6 +344,7 @@ struct Pool {
   ~Pool() {
     // error paths may leave side-stream work in flight: drain it before the buffers go back to the pool
     if (ctx->side_pending) { cudaStreamSynchronize(ctx->side_stream); ctx->side_pending = false; }
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);   // a staged upload may still be writing into a pool buffer
     for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
   }
   template <class T> int get(T** out, size_t count) {
@@ -542,6 +543,9 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   // 2. advice: upload, blinding policy, commit (Lagrange basis), to coefficient form
   Fr *adv_values, *adv_polys;
   ZKC_TRY(pool.get(&adv_values, (size_t)A * n)); ZKC_TRY(pool.get(&adv_polys, (size_t)A * n));
+  std::vector<std::pair<uint32_t, uint32_t>> staged;   // column groups of a staged upload, in flight on the copy stream
+  size_t stage_min_bytes = (size_t)256 << 20;   // ZKC_STAGE_MIN_BYTES overrides (tests force the staged path on small circuits)
+  if (const char* e = getenv("ZKC_STAGE_MIN_BYTES")) stage_min_bytes = (size_t)strtoull(e, nullptr, 10);
   if (A) {
     ProfScope _p(ctx, "prove.advice_h2d");
     const size_t cells = (size_t)A * n;
@@ -552,6 +556,24 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
       for (int r : team_ranks(ctx))
         ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(adv_values + (size_t)r * per, (const Fr*)advice + (size_t)r * per, per * sizeof(Fr), cudaMemcpyHostToDevice, st));
       ZKC_TRY(team_allgather(ctx, adv_values, per * sizeof(Fr)));
+    } else if (!team && !advice_on_device && ctx->overlap && cells * sizeof(Fr) >= stage_min_bytes) {
+      // Staged upload of a large host witness: groups of columns travel on a copy stream while the random polynomial is
+      // generated and committed and the first groups are already being committed.  The copies skip the rows the blinding
+      // policy overwrites, so they need no ordering against those writes.
+      if (!ctx->copy_stream) ZKC_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      const uint32_t ngroups = std::min<uint32_t>(A, 6);
+      while (ctx->ev_copy.size() < ngroups) { cudaEvent_t e; ZKC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_copy.push_back(e); }
+      ZKC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));                       // adv_values is allocated in stream order on `st`
+      ZKC_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+      const uint64_t keep = opts->advice_blinding == 0 ? n - 1 : U;              // rows taken from the host
+      for (uint32_t g = 0; g < ngroups; ++g) {
+        uint64_t c0, c1;
+        shard_range(A, (int)ngroups, (int)g, &c0, &c1);
+        ZKC_CUDA_TRY(ctx, cudaMemcpy2DAsync(adv_values + c0 * n, n * sizeof(Fr), (const Fr*)advice + c0 * n, n * sizeof(Fr), keep * sizeof(Fr), c1 - c0,
+                                            cudaMemcpyHostToDevice, ctx->copy_stream));
+        ZKC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[g], ctx->copy_stream));
+        staged.push_back({(uint32_t)c0, (uint32_t)c1});
+      }
     } else {
       ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(adv_values, advice, cells * sizeof(Fr), advice_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     }
@@ -605,6 +627,7 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
     // off the Fiat-Shamir critical path: coefficient forms and extended cosets of advice / instance columns are
     // not needed before step 10, so they run on the side stream underneath the latency-bound MSM phases
     SideScope side(ctx);
+    if (!staged.empty()) ZKC_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[staged.size() - 1], 0));   // whole witness resident
     if (A) {
       ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(adv_polys, adv_values, (size_t)A * n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
       ZKC_TRY(to_coeff(adv_polys, A));
@@ -612,8 +635,17 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
     }
     if (I) ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, inst_polys, n, inst_cosets, I));
   }
-  if (A) {
+  if (A && staged.empty()) {
     ZKC_TRY(commit_points(ctx, srs, 1, adv_values, n, A, pts));
+    ZKC_TRY(write_points(pts));
+  } else if (A) {
+    std::vector<G1Affine> part;
+    pts.clear();
+    for (size_t g = 0; g < staged.size(); ++g) {   // commit each group as soon as it has landed
+      ZKC_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_copy[g], 0));
+      ZKC_TRY(commit_points(ctx, srs, 1, adv_values + (size_t)staged[g].first * n, n, staged[g].second - staged[g].first, part));
+      pts.insert(pts.end(), part.begin(), part.end());
+    }
     ZKC_TRY(write_points(pts));
   }
   {

@@ -229,3 +229,20 @@ def test_std_rng_chacha12(circuit_k6):
     want = plonk.create_proof(opk, advice, circ.instances, orc.ChaCha20Rng(seed, rounds=12), "poseidon")
     got = pkg().create_proof(gpk, np.concatenate(advice), inst, seed, "poseidon", rng="std")
     assert got == want and got != pkg().create_proof(gpk, np.concatenate(advice), inst, seed, "poseidon")
+
+
+@pytest.mark.parametrize("blinding", ["axiom", "pse"])
+def test_staged_witness_upload(circuit_k6, monkeypatch, blinding):
+    """large host witnesses travel on a copy stream in column groups (zkc_prove staged upload); forced here on a small circuit"""
+    circ, opk, advice, params, gpk = circuit_k6
+    seed = pyref.seed_from_u64(55)
+    inst = [orc.fr_from_ints(c) for c in circ.instances]
+    kw = dict(advice_blinding=blinding) if blinding != "axiom" else {}
+    want = pkg().create_proof(gpk, np.concatenate(advice), inst, seed, **kw)
+    monkeypatch.setenv("ZKC_STAGE_MIN_BYTES", "1")
+    assert pkg().create_proof(gpk, np.concatenate(advice), inst, seed, **kw) == want
+    w = pkg().workload.build(gpu_ctx(), 12, 7, seed=2)
+    monkeypatch.delenv("ZKC_STAGE_MIN_BYTES")
+    ref = pkg().create_proof(w.pk, w.advice_dev, w.instances, seed)
+    monkeypatch.setenv("ZKC_STAGE_MIN_BYTES", "1")
+    assert pkg().create_proof(w.pk, w.advice_host, w.instances, seed) == ref
