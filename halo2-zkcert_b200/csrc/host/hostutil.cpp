@@ -358,3 +358,21 @@ void Transcript::write_scalar(const Fr& s) {
 
 }  // namespace host
 }  // namespace zkc
+
+// Host hashes of the transcripts, exposed so that they can be pinned against published vectors (RFC 7693, Keccak team
+// test vectors) and hashlib without a GPU.  kind 0: Blake2b-512 with a 16-byte personalisation (null = none), 64 bytes
+// out; kind 1: Keccak-256 (pre-NIST padding), 32 bytes out.
+extern "C" int zkc_host_hash(int kind, const uint8_t* personal16, const uint8_t* data, size_t len, uint8_t* out) {
+  if (!out || (len && !data)) return 1;
+  if (kind == 0) {
+    char pers[16] = {0};
+    if (personal16) memcpy(pers, personal16, 16);
+    zkc::host::Blake2b b;
+    b.init(pers);
+    if (len) b.update(data, len);
+    b.finalize(out);
+    return 0;
+  }
+  if (kind == 1) { zkc::host::keccak256(data, len, out); return 0; }
+  return 1;
+}

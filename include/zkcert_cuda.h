@@ -204,6 +204,9 @@ int zkc_prove_compact(zkc_ctx* ctx, const zkc_pk* pk, const zkc_advice_column* c
  * starting at draw `skip`; rand_core's SeedableRng::seed_from_u64. */
 int zkc_rng_fr_random(const uint8_t seed[32], int rng_kind, uint64_t skip, zkc_fr* out, size_t count);
 void zkc_seed_from_u64(uint64_t state, uint8_t seed[32]);
+/* the transcripts' host hashes: kind 0 = Blake2b-512 with a 16-byte personalisation (NULL = none; halo2 uses
+ * "Halo2-Transcript"), 64 bytes out; kind 1 = Keccak-256, 32 bytes out.  No device work. */
+int zkc_host_hash(int kind, const uint8_t* personal16, const uint8_t* data, size_t len, uint8_t* out);
 /* Grain-generated Poseidon parameters of transcript kind 3 (canonical little-endian): 65 x 3 round constants, 3 x 3 MDS. */
 int zkc_poseidon_spec(zkc_fr* constants, zkc_fr* mds);
 

@@ -143,3 +143,14 @@ def test_commit_coeff_equals_commit_lagrange_k17():
     sparse[idx] = orc.fr_from_ints(vals)
     ps = sum(v * pow(s_int, i, R_MOD) for i, v in zip(idx, vals)) % R_MOD
     assert orc.g1_to_ints(affine(params.commit(sparse)))[0] == pyref.ec_mul(pyref.G1_GEN, ps)
+
+
+def test_published_eip196_known_answer():
+    """EIP-196 (alt_bn128) ecAdd vector (1, 2) + (1, 2), through zkc_msm_g1 with scalars [1, 1] and [2] on the generator"""
+    from tests.test_oracle_ops import EIP196_2G
+    p = pkg()
+    ctx = gpu_ctx()
+    G = orc.g1_generator()
+    both = np.concatenate([G, G])
+    assert orc.g1_to_ints(affine(ctx.msm(orc.fr_from_ints([1, 1]), both)))[0] == EIP196_2G
+    assert orc.g1_to_ints(affine(ctx.msm(orc.fr_from_ints([2]), G)))[0] == EIP196_2G

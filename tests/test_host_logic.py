@@ -250,3 +250,36 @@ def test_team_partition_arithmetic():
             want = {(i + d) % rows for i in range(lo.value, hi.value) for d in range(-hl, hh + 1)}
             assert got == want if len(want) < rows else got == set(range(rows))
     assert L.zkc_team_shard_range(C.c_uint64(4), 2, 2, None, None) != 0
+
+
+def test_host_hashes_match_published_vectors():
+    """The product's own Blake2b-512 / Keccak-256 (csrc/host/hostutil.cpp; what Blake2bWrite / Keccak256Write hash with)
+    against RFC 7693 Appendix A, the Keccak team's vectors and hashlib (personalised, multi-block, empty)."""
+    import ctypes as C
+    import hashlib
+    L = pkg().lib()
+
+    def h(kind, data, person=None):
+        out = (C.c_uint8 * (64 if kind == 0 else 32))()
+        buf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data or b"\0")
+        pers = None if person is None else (C.c_uint8 * 16).from_buffer_copy(person)
+        assert L.zkc_host_hash(kind, pers, buf, C.c_size_t(len(data)), out) == 0
+        return bytes(out)
+    assert h(0, b"abc").hex() == ("ba80a53f981c4d0d6a2797b69f12f6e94c212f14685ac4b74b12bb6fdbffa2d1"
+                                  "7d87c5392aab792dc252d5de4533cc9518d38aa8dbf1925ab92386edd4009923")          # RFC 7693 App. A
+    assert h(1, b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert h(1, b"abc").hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"
+    person = b"Halo2-Transcript"
+    rng = np.random.default_rng(0)
+    for n in [0, 1, 63, 64, 127, 128, 129, 135, 136, 137, 255, 256, 1000, 4097]:
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert h(0, data, person) == hashlib.blake2b(data, digest_size=64, person=person).digest()
+        assert h(0, data) == hashlib.blake2b(data, digest_size=64).digest()
+    try:
+        from Crypto.Hash import keccak as _k   # optional cross-check when pycryptodome exists
+    except Exception:
+        _k = None
+    if _k is not None:
+        for n in [135, 136, 137, 500]:
+            data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+            assert h(1, data) == _k.new(digest_bits=256, data=data).digest()

@@ -67,6 +67,10 @@ def test_chacha_known_answers():
     assert enc.update(bytes(64)) == stream
 
 
+EIP196_2G = (1368015179489954701390400359078579693043519447331113978918064868415326638035,
+             9918110051302171585080402603319702774565515993150576347155970296011118125764)
+
+
 def test_g1_ops():
     rng = random.Random(3)
     G = orc.g1_generator()
@@ -81,6 +85,9 @@ def test_g1_ops():
         assert got == pyref.ec_add(a, b)
     assert orc.g1_on_curve(orc.g1_from_ints([P]))
     assert not orc.g1_on_curve(orc.g1_from_ints([(P[0], P[1] + 1)]))
+    # published known answer: EIP-196 (alt_bn128 ecAdd) (1, 2) + (1, 2)
+    assert orc.g1_to_ints(orc.g1_mul(G, orc.fr_from_ints([2])))[0] == EIP196_2G
+    assert orc.g1_to_ints(orc.g1_add(G, G))[0] == EIP196_2G
 
 
 def _points(n, seed):
