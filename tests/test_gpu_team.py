@@ -63,3 +63,19 @@ def test_emulated_team_full_size(team_ctx):
     single = p.create_proof(w.pk, w.advice_dev, w.instances, seed)
     team_ctx.team_emulate(8)
     assert p.create_proof(w.pk, w.advice_dev, w.instances, seed) == single
+
+
+def test_aggregation_shape_k20_verifies_and_team_matches(team_ctx):
+    """BASELINE config-5 shape (BaseConfig, 17 gate columns + lookup, 20 permutation columns) reduced to k=20 (the k=22
+    build needs ~65 GB): the proof verifies under the independent verifier, host-buffer (staged upload) == device-resident,
+    and the 4-shard team proof has the same bytes."""
+    from tests.test_gpu_prover import _verify_workload
+    p = pkg()
+    w = p.workload.build(team_ctx, 20, 17, seed=100, shape="base_fast")
+    seed = pyref.seed_from_u64(20)
+    proof = p.create_proof(w.pk, w.advice_dev, w.instances, seed)
+    assert _verify_workload(w, proof)
+    assert p.create_proof(w.pk, w.advice_host, w.instances, seed) == proof      # 604 MB witness: staged upload path
+    team_ctx.team_emulate(4)
+    assert p.create_proof(w.pk, w.advice_dev, w.instances, seed) == proof
+    assert p.create_proof(w.pk, w.advice_host, w.instances, seed) == proof      # team: 1/W upload shares
