@@ -194,10 +194,11 @@ def main():
 
     # untimed setup: gen_srs + gen_pk + witness (each rank proves its own certificate: different seed)
     team = args.team and world > 1
+    if team:
+        ctx.team_init()      # every rank proves the SAME certificate together (zkc_team_init: NCCL over NVLink); joined before
+                             # the SRS is built so that its window tables are sized for the per-rank point range
     w = pkg.workload.build(ctx, wl["k"], wl["gate_cols"], seed=100 + (0 if team else rank), shape=wl.get("shape", "base"))
     seeds = [pkg.seed_from_u64(1000 * (0 if team else rank) + i) for i in range(W + K)]
-    if team:
-        ctx.team_init()      # every rank now proves the SAME certificate together (zkc_team_init: NCCL over NVLink)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def barrier():

@@ -532,7 +532,10 @@ static int srs_expand(zkc_ctx* ctx, zkc_srs* s) {
 static int srs_alloc(zkc_ctx* ctx, uint32_t k, zkc_srs** out) {
   zkc_srs* s = new zkc_srs();
   s->ctx = ctx; s->k = k; s->n = 1ull << k;
-  s->c = msm_pick_c(s->n, true);
+  // window width from the points ONE GPU walks: a team rank sees n / world points per commitment (point-range shards), and
+  // the bucket phases (gather, reduce) do not shrink with the shard, so a team wants narrower windows than a single GPU
+  const uint64_t n_eff = team_active(ctx) ? std::max<uint64_t>(s->n / (uint64_t)ctx->team_world, 1024) : s->n;
+  s->c = msm_pick_c(n_eff, true);
   s->W = (255 + s->c - 1) / s->c;
   for (int b = 0; b < 2; ++b) {
     cudaError_t e = cudaMalloc(&s->tab[b], (size_t)s->W * s->n * sizeof(G1Affine));

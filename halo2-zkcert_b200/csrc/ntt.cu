@@ -16,6 +16,7 @@
 // extended domain and the 1/n scaling of inverse transforms are fused into the first load / last
 // store.  One twiddle table w_N^i (i < N/2) per size serves forward and inverse transforms.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace zkc {
 
@@ -202,6 +203,7 @@ struct NttOpts {
 };
 
 static const uint32_t LOG_TILE = 11;  // 2^11 elements = 64 KiB of shared memory per CTA
+#define NTT_TWO_PASS_MAX 20   // B200 sweep (tools/nttsweep.py): 2^19-2^20 gain 4-5 % from the saved pass, 2^21-2^22 break even
 
 static int launch_pass(zkc_ctx* ctx, bool last, const NttPass& p, uint32_t grid_x, uint32_t ncols) {
 
@@ -247,6 +249,11 @@ int ntt_run(zkc_ctx* ctx, const Fr* src, uint64_t src_stride, Fr* dst, uint64_t 
     p.s = log_n; p.logC = 0; p.logN1 = 0; p.logN2 = 0;
     return launch_pass(ctx, true, p, 1, ncols);
   }
+  // Two passes up to 2^two_pass_max, three above.  A pass boundary costs one twiddle product per element and one trip
+  // through HBM; a tile is 2^11 elements, so two passes of a 2^22 transform read single 32-byte elements at large
+  // strides (one DRAM sector each) — affordable because the transform is bound by the integer pipe, not by HBM.
+  uint32_t two_pass_max = NTT_TWO_PASS_MAX;
+  if (const char* e = getenv("ZKC_NTT_TWO_PASS_MAX")) { const int v = atoi(e); if (v >= 12 && v <= 2 * (int)LOG_TILE) two_pass_max = (uint32_t)v; }
   // bound the scratch: process columns in chunks of <= 1 GiB
   uint32_t chunk = (uint32_t)std::max<uint64_t>(1, (1ull << 30) / (N * sizeof(Fr)));
   if (chunk > ncols) chunk = ncols;
@@ -256,7 +263,7 @@ int ntt_run(zkc_ctx* ctx, const Fr* src, uint64_t src_stride, Fr* dst, uint64_t 
     const uint32_t nc = std::min(chunk, ncols - c0);
     const Fr* csrc = src + (uint64_t)c0 * src_stride;
     Fr* cdst = dst + (uint64_t)c0 * dst_stride;
-    if (log_n <= 2 * 9) {
+    if (log_n <= two_pass_max) {
       const uint32_t s1 = (log_n + 1) / 2, s2 = log_n - s1;
       NttPass p1 = base; first(p1); p1.src = csrc;
       p1.dst = tmp; p1.dst_stride = N; p1.s = s1; p1.logB = s2; p1.logC = std::min(3u, std::min(LOG_TILE - s1, s2));
