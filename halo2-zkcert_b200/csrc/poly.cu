@@ -68,7 +68,7 @@ __global__ void k_scan_apply(const Fr* in, Fr* out, const Fr* tot, uint64_t n, i
 }
 
 // chunk totals beyond this count are scanned by a recursive pass instead of the single-CTA kernel
-#define SCAN_SINGLE_MAX 32768
+#define SCAN_SINGLE_MAX 2048   // (one 1024-thread CTA is one SM: beyond a few totals per thread a parallel level is faster)
 static int fr_scan_impl(zkc_ctx* ctx, const Fr* in, Fr* out, uint64_t n, int op, int reverse, const Fr& start, Fr* scratch) {
   const uint64_t nchunks = (n + SCAN_CH - 1) / SCAN_CH;
   Fr* tot = scratch;
@@ -107,31 +107,35 @@ __global__ void k_bi_prep(const Fr* a, Fr* t, uint64_t n) {
   Fr v = fe_load(a + i);
   fe_store(t + i, fe_is_zero(v) ? fe_one<FrP>() : v);
 }
-__global__ void k_bi_total_inv(const Fr* prefix, const Fr* t, uint64_t n, Fr* out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) fe_store(out, fe_inv(fe_mul(fe_load(prefix + n - 1), fe_load(t + n - 1))));
-}
-__global__ void k_bi_finish(const Fr* a, const Fr* prefix, const Fr* suffix, const Fr* tinv, Fr* out, uint64_t n) {
+__global__ void k_bi_finish(const Fr* a, const Fr* prefix, const Fr* suffix, Fr tinv, Fr* out, uint64_t n) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Fr v = fe_load(a + i);
   if (fe_is_zero(v)) { fe_store(out + i, v); return; }
-  fe_store(out + i, fe_mul(fe_mul(fe_load(prefix + i), fe_load(suffix + i)), fe_load_nc(tinv)));
+  fe_store(out + i, fe_mul(fe_mul(fe_load(prefix + i), fe_load(suffix + i)), tinv));
 }
 int fr_batch_invert_scan(zkc_ctx* ctx, const Fr* a, Fr* out, uint64_t n) {
   ProfScope _p(ctx, "batch_invert");
   Fr* buf = nullptr;
   cudaStream_t st = ctx->stream;
-  ZKC_CUDA_TRY(ctx, cudaMallocAsync((void**)&buf, (3 * n + 1) * sizeof(Fr), st));
-  Fr *t = buf, *pf = buf + n, *sf = buf + 2 * n, *tinv = buf + 3 * n;
+  ZKC_CUDA_TRY(ctx, cudaMallocAsync((void**)&buf, 3 * n * sizeof(Fr), st));
+  Fr *t = buf, *pf = buf + n, *sf = buf + 2 * n;
   const unsigned grid = (unsigned)((n + 255) / 256);
   int status = ZKC_OK;
   k_bi_prep<<<grid, 256, 0, st>>>(a, t, n); ctx->launches++;
   status = fr_scan(ctx, t, pf, n, SCAN_MUL, 0, fe_one<FrP>());
   if (status == ZKC_OK) status = fr_scan(ctx, t, sf, n, SCAN_MUL, 1, fe_one<FrP>());
   if (status == ZKC_OK) {
-    k_bi_total_inv<<<1, 32, 0, st>>>(pf, t, n, tinv); ctx->launches++;
-    k_bi_finish<<<grid, 256, 0, st>>>(a, pf, sf, tinv, out, n); ctx->launches++;
-    cudaError_t e = cudaGetLastError();
+    // the one true inversion runs on the host: a lone GPU thread needs ~380 dependent products (160 us) for it, the
+    // host 10 us plus a 64-byte round trip
+    Fr last[2];
+    cudaError_t e = cudaMemcpyAsync(&last[0], pf + n - 1, sizeof(Fr), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&last[1], t + n - 1, sizeof(Fr), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) {
+      k_bi_finish<<<grid, 256, 0, st>>>(a, pf, sf, fe_inv(fe_mul(last[0], last[1])), out, n); ctx->launches++;
+      e = cudaGetLastError();
+    }
     if (e != cudaSuccess) status = set_err(ctx, ZKC_ERR_CUDA, cudaGetErrorString(e));
   }
   cudaFreeAsync(buf, st);
@@ -276,68 +280,15 @@ int fr_mul_add(zkc_ctx* ctx, Fr* a, const Fr* b, uint64_t n, const Fr& s) {
 }
 
 // ---- kate division: q_j = sum_{i>j} a_i z^(i-j-1), blocked synthetic division -----------------------------
-// phase 1: per 16-coefficient chunk P_c = sum_e a[c0+e] z^e; phase 2 (one CTA): carry_c = value of all
+// phase 1: per 16-coefficient chunk P_c = sum_e a[c0+e] z^e; phase 2 (one CTA per job, or a recursion): carry_c = value of all
 // higher chunks at z (a linear recurrence with constant multiplier Z = z^16, solved by a Hillis-Steele
 // scan over Z^(per*2^s)); phase 3: q_{i-1} = a_i + z q_i inside each chunk starting from its carry.
 #define KD_CH 16
-__global__ void k_kd_chunk(const Fr* a, Fr* P, uint64_t n, Fr z) {
-  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t lo = t * KD_CH;
-  if (lo >= n) return;
-  const uint64_t hi = lo + KD_CH < n ? lo + KD_CH : n;
-  Fr acc = fe_zero<FrP>();
-  for (uint64_t i = hi; i-- > lo;) acc = fe_add(fe_mul(acc, z), fe_load(a + i));
-  fe_store(P + t, acc);
-}
-__global__ void __launch_bounds__(1024) k_kd_carry(Fr* P, uint64_t nchunks, Fr Z) {
-  extern __shared__ uint4 smraw[];
-  Fr* sm = reinterpret_cast<Fr*>(smraw);
-  const uint32_t t = threadIdx.x;
-  const uint64_t per = (nchunks + 1023) / 1024;
-  const uint64_t lo = (uint64_t)t * per, hi = lo + per < nchunks ? lo + per : nchunks;
-  Fr L = fe_zero<FrP>();                      // sum_{c in [lo,hi)} Z^(c-lo) P_c
-  for (uint64_t c = hi; c-- > lo && hi > lo;) L = fe_add(fe_mul(L, Z), fe_load(P + c));
-  fe_store(sm + t, L);
-  __syncthreads();
-  Fr M = fe_pow_u64(Z, per);                  // multiplier between neighbouring threads
-  for (uint32_t d = 1; d < 1024; d <<= 1) {
-    Fr v = fe_zero<FrP>();
-    const bool act = t + d < 1024;
-    if (act) v = fe_load(sm + t + d);
-    __syncthreads();
-    if (act) fe_store(sm + t, fe_add(fe_load(sm + t), fe_mul(M, v)));
-    M = fe_sqr(M);
-    __syncthreads();
-  }
-  Fr carry = t + 1 < 1024 ? fe_load(sm + t + 1) : fe_zero<FrP>();   // value of everything above this thread's range
-  for (uint64_t c = hi; c-- > lo && hi > lo;) {
-    const Fr pc = fe_load(P + c);
-    fe_store(P + c, carry);
-    carry = fe_add(pc, fe_mul(Z, carry));
-  }
-}
-__global__ void k_kd_apply(const Fr* a, Fr* q, const Fr* carry, uint64_t n, Fr z) {
-  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t lo = t * KD_CH;
-  if (lo >= n) return;
-  const uint64_t hi = lo + KD_CH < n ? lo + KD_CH : n;
-  Fr r = fe_load(carry + t);
-  for (uint64_t i = hi; i-- > lo;) {
-    const Fr ai = fe_load(a + i);
-    fe_store(q + i, r);
-    r = fe_add(ai, fe_mul(z, r));
-  }
-}
 int fr_kate_division(zkc_ctx* ctx, const Fr* a, Fr* q, uint64_t n, const Fr& z, Fr* tmp1, Fr* tmp2) {
   (void)tmp2;
   if (n == 0) return ZKC_OK;
-  ProfScope _p(ctx, "kate_division");
-  const uint64_t nchunks = (n + KD_CH - 1) / KD_CH;   // tmp1 (n elements) holds the nchunks partials
-  const unsigned grid = (unsigned)((nchunks + 127) / 128);
-  k_kd_chunk<<<grid, 128, 0, ctx->stream>>>(a, tmp1, n, z); ZKC_LAUNCH_CHECK(ctx);
-  k_kd_carry<<<1, 1024, 1024 * sizeof(Fr), ctx->stream>>>(tmp1, nchunks, fe_pow_u64(z, KD_CH)); ZKC_LAUNCH_CHECK(ctx);
-  k_kd_apply<<<grid, 128, 0, ctx->stream>>>(a, q, tmp1, n, z); ZKC_LAUNCH_CHECK(ctx);
-  return ZKC_OK;
+  if (a != q) ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(q, a, n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+  return fr_kate_division_batch(ctx, std::vector<Fr*>{q}, std::vector<Fr>{z}, n, tmp1);
 }
 
 // Several independent in-place divisions (different polynomials, different roots) in one set of launches:
@@ -399,19 +350,34 @@ __global__ void k_kd_apply_b(KdBatch b, const Fr* carry, uint64_t n, uint64_t nc
     r = fe_add(ai, fe_mul(z, r));
   }
 }
-int fr_kate_division_batch(zkc_ctx* ctx, const std::vector<Fr*>& polys, const std::vector<Fr>& roots, uint64_t n, Fr* tmp /* n elements */) {
-  if (n == 0 || polys.empty()) return ZKC_OK;
-  ProfScope _p(ctx, "kate_division");
+// The carries of the 16-coefficient chunks are themselves a synthetic division — of the chunk values P_c by (X - z^16) —
+// so large inputs recurse (every level is a grid-wide launch) and only the last <= KD_SINGLE_MAX partials go through the
+// single-CTA scan.  `tmp` holds the partials of all levels: njobs * n / 15 elements at most (callers pass n + n / 8).
+#define KD_SINGLE_MAX 2048
+static int kd_batch_level(zkc_ctx* ctx, KdBatch b, uint64_t n, Fr* tmp) {
   const uint64_t nchunks = (n + KD_CH - 1) / KD_CH;
   const unsigned gx = (unsigned)((nchunks + 127) / 128);
+  dim3 grid(gx, b.njobs);
+  k_kd_chunk_b<<<grid, 128, 0, ctx->stream>>>(b, tmp, n, nchunks); ZKC_LAUNCH_CHECK(ctx);
+  if (nchunks > KD_SINGLE_MAX) {
+    KdBatch up;
+    up.njobs = b.njobs;
+    for (uint32_t j = 0; j < b.njobs; ++j) { up.a[j] = tmp + (uint64_t)j * nchunks; up.z[j] = b.Z[j]; up.Z[j] = fe_pow_u64(b.Z[j], KD_CH); }
+    ZKC_TRY(kd_batch_level(ctx, up, nchunks, tmp + (uint64_t)b.njobs * nchunks));
+  } else {
+    k_kd_carry_b<<<b.njobs, 1024, 1024 * sizeof(Fr), ctx->stream>>>(b, tmp, nchunks); ZKC_LAUNCH_CHECK(ctx);
+  }
+  k_kd_apply_b<<<grid, 128, 0, ctx->stream>>>(b, tmp, n, nchunks); ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+int fr_kate_division_batch(zkc_ctx* ctx, const std::vector<Fr*>& polys, const std::vector<Fr>& roots, uint64_t n, Fr* tmp /* n + n / 8 elements */) {
+  if (n == 0 || polys.empty()) return ZKC_OK;
+  ProfScope _p(ctx, "kate_division");
   for (size_t off = 0; off < polys.size(); off += KD_MAX_JOBS) {
     KdBatch b;
-    b.njobs = (uint32_t)std::min<size_t>(KD_MAX_JOBS, polys.size() - off);   // KD_MAX_JOBS * nchunks <= n
+    b.njobs = (uint32_t)std::min<size_t>(KD_MAX_JOBS, polys.size() - off);   // KD_MAX_JOBS * n / 15 <= n + n / 8
     for (uint32_t j = 0; j < b.njobs; ++j) { b.a[j] = polys[off + j]; b.z[j] = roots[off + j]; b.Z[j] = fe_pow_u64(roots[off + j], KD_CH); }
-    dim3 grid(gx, b.njobs);
-    k_kd_chunk_b<<<grid, 128, 0, ctx->stream>>>(b, tmp, n, nchunks); ZKC_LAUNCH_CHECK(ctx);
-    k_kd_carry_b<<<b.njobs, 1024, 1024 * sizeof(Fr), ctx->stream>>>(b, tmp, nchunks); ZKC_LAUNCH_CHECK(ctx);
-    k_kd_apply_b<<<grid, 128, 0, ctx->stream>>>(b, tmp, n, nchunks); ZKC_LAUNCH_CHECK(ctx);
+    ZKC_TRY(kd_batch_level(ctx, b, n, tmp));
   }
   return ZKC_OK;
 }

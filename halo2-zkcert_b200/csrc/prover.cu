@@ -960,7 +960,7 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   add_q(i_rand);
 
   Fr *acc, *tmp1, *tmp2, *tmp3;
-  ZKC_TRY(pool.get(&acc, n)); ZKC_TRY(pool.get(&tmp1, n)); ZKC_TRY(pool.get(&tmp2, n)); ZKC_TRY(pool.get(&tmp3, n));
+  ZKC_TRY(pool.get(&acc, n)); ZKC_TRY(pool.get(&tmp1, n)); ZKC_TRY(pool.get(&tmp2, n + n / 8 + 64)); ZKC_TRY(pool.get(&tmp3, n));   // tmp2: chunk partials of every level of the synthetic divisions
   // Team proving, SHPLONK: a point-range MSM reads only coefficients [lo, hi) of the polynomial it commits, so the
   // quotient polynomials are built slice by slice on the rank that will commit the slice: linear combinations are
   // element-wise, and a synthetic division of a slice needs one field element from the slices above it (the value of
