@@ -76,13 +76,24 @@ __global__ void k_msm_scatter(const uint32_t* dig, uint32_t* cursor, uint32_t* e
   ent_key[pos] = (uint32_t)key;
 }
 
+// Entries per accumulate thread for THIS batch: g.T when the batch fills the machine, halved (down to 4) while the actual
+// number of non-zero digits E leaves fewer than MSM_MIN_THREADS chains — witness columns of bits / bytes / small limbs
+// have a fraction of the worst-case entries, and a short batch is bound by the length of the dependent chain, not by work.
+#define MSM_MIN_THREADS (148u * 512u)
+__device__ __forceinline__ uint32_t msm_T(const MsmGeom& g, uint64_t E) {
+  uint32_t T = g.T;
+  while (T > 4 && E / T < MSM_MIN_THREADS) T >>= 1;
+  return T;
+}
+
 __global__ void __launch_bounds__(128) k_msm_accum(const G1Affine* bases, const uint32_t* ent_pt, const uint32_t* ent_key,
                                                    const uint32_t* offsets, G1Xyzz* partial, MsmGeom g) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t E = offsets[g.nbtot()];
-  const uint64_t p0 = t * g.T;
+  const uint32_t T = msm_T(g, E);
+  const uint64_t p0 = t * T;
   if (p0 >= E) return;
-  const uint64_t p1 = p0 + g.T < E ? p0 + g.T : E;
+  const uint64_t p1 = p0 + T < E ? p0 + T : E;
   G1Xyzz acc = xyzz_identity();
   uint32_t cur = ent_key[p0];
   // software pipeline: the next entry's base point is requested before the current mixed add is issued
@@ -123,7 +134,8 @@ __global__ void __launch_bounds__(128) k_msm_gather(const uint32_t* offsets, con
   uint32_t off = 0, cnt = 0;
   if (valid) { off = offsets[key]; cnt = offsets[key + 1] - off; }
   uint64_t first = 0, np = 0;
-  if (cnt) { first = key + off / g.T; np = key + (off + cnt - 1) / g.T - first + 1; }
+  const uint32_t T = msm_T(g, offsets[g.nbtot()]);
+  if (cnt) { first = key + off / T; np = key + (off + cnt - 1) / T - first + 1; }
   const bool heavy = np > (uint64_t)MSM_HEAVY_PER_LANE * G;
   G1Xyzz acc = xyzz_identity();
   if (cnt && !heavy)
@@ -164,10 +176,11 @@ __global__ void __launch_bounds__(128) k_msm_gather_heavy(const uint32_t* offset
   extern __shared__ uint4 smraw[];
   G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smraw);
   const uint32_t nh = *heavy_count;
+  const uint32_t T = msm_T(g, offsets[g.nbtot()]);
   for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
     const uint64_t key = heavy_list[h];
     const uint32_t off = offsets[key], cnt = offsets[key + 1] - off;
-    const uint64_t first = key + off / g.T, last = key + (off + cnt - 1) / g.T;
+    const uint64_t first = key + off / T, last = key + (off + cnt - 1) / T;
     G1Xyzz acc = xyzz_identity();
     for (uint64_t s = first + threadIdx.x; s <= last; s += blockDim.x) xyzz_add(acc, xyzz_load(partial + s));
     G1Xyzz r = block_reduce_xyzz(acc, sm);
@@ -181,10 +194,11 @@ __global__ void __launch_bounds__(128) k_msm_gather_giant1(const uint32_t* offse
   extern __shared__ uint4 smraw[];
   G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smraw);
   const uint32_t ng = min(heavy_count[1], (uint32_t)MSM_GIANT_CAP);
+  const uint32_t T = msm_T(g, offsets[g.nbtot()]);
   for (uint32_t gi = blockIdx.y; gi < ng; gi += gridDim.y) {
     const uint64_t key = heavy_list[g.nbtot() + gi];
     const uint32_t off = offsets[key], cnt = offsets[key + 1] - off;
-    const uint64_t first = key + off / g.T, np = key + (off + cnt - 1) / g.T - first + 1;
+    const uint64_t first = key + off / T, np = key + (off + cnt - 1) / T - first + 1;
     const uint64_t per = (np + MSM_GIANT_SLICES - 1) / MSM_GIANT_SLICES;
     const uint64_t lo = (uint64_t)blockIdx.x * per, hi = lo + per < np ? lo + per : np;
     G1Xyzz acc = xyzz_identity();
@@ -206,17 +220,32 @@ __global__ void __launch_bounds__(MSM_GIANT_SLICES) k_msm_gather_giant2(const G1
 }
 
 // Level 1: P[set][t][chunk] = sum of buckets b of the chunk whose index has bit t set.  grid = (c, nchunks, nsets)
-#define RED_CHUNK 1024
+// A chunk is the aligned range b in [ch * 1024, ch * 1024 + 1024); the buckets with bit t set are ENUMERATED (the j-th one
+// directly), not filtered: every lane adds in every iteration, where a filter would leave half of each warp idle and
+// double the dependent chain.  b = NB = 2^(c-1), the one bucket outside the aligned ranges, has only the top bit.
+#define RED_LOG 10
+#define RED_CHUNK (1u << RED_LOG)
 __global__ void __launch_bounds__(64) k_msm_reduce1(const G1Xyzz* buckets, G1Xyzz* P, MsmGeom g, uint32_t nchunks) {
   extern __shared__ uint4 smraw[];
   G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smraw);
   const uint32_t t = blockIdx.x, ch = blockIdx.y;
   const uint64_t set = blockIdx.z;
-  const G1Xyzz* bk = buckets + set * g.NB;
+  const G1Xyzz* bk = buckets + set * g.NB;     // bucket b lives at bk[b - 1]
   G1Xyzz acc = xyzz_identity();
-  const uint32_t lo = ch * RED_CHUNK, hi = min(g.NB, lo + RED_CHUNK);
-  for (uint32_t b = lo + threadIdx.x + 1; b <= hi; b += blockDim.x)
-    if ((b >> t) & 1) xyzz_add(acc, xyzz_load(bk + (b - 1)));
+  const uint32_t lo = ch * RED_CHUNK;
+  if (t < RED_LOG) {
+    for (uint32_t j = threadIdx.x; j < RED_CHUNK / 2; j += blockDim.x) {
+      const uint32_t b = lo + (((j >> t) << (t + 1)) | (1u << t) | (j & ((1u << t) - 1)));
+      if (b < g.NB) xyzz_add(acc, xyzz_load(bk + (b - 1)));
+    }
+  } else {
+    // whole chunks qualify or not: the two CTAs of a chunk pair (ch with / without bit t) take half of the qualifying chunk each
+    const uint32_t bit = 1u << (t - RED_LOG);
+    const uint32_t base = (ch | bit) * RED_CHUNK + ((ch & bit) ? RED_CHUNK / 2 : 0);
+    for (uint32_t j = threadIdx.x; j < RED_CHUNK / 2; j += blockDim.x)
+      if (base + j < g.NB) xyzz_add(acc, xyzz_load(bk + (base + j - 1)));
+  }
+  if (ch == 0 && threadIdx.x == 0 && t == g.c - 1) xyzz_add(acc, xyzz_load(bk + (g.NB - 1)));
   G1Xyzz r = block_reduce_xyzz(acc, sm);
   if (threadIdx.x == 0) xyzz_store(P + (set * g.c + t) * nchunks + ch, r);
 }
@@ -292,10 +321,13 @@ MsmGeom msm_geom(uint64_t n, uint32_t ncols, uint32_t c, bool precomputed) {
 static int msm_kernels(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, const MsmGeom& g, G1Xyzz* U, uint32_t* total_out) {
   const uint64_t n = g.n, nbt = g.nbtot(), em = g.emax();
   const uint32_t nc = g.ncols;
-  if (nbt + em / g.T + 1 >= (1ull << 32) || em >= (1ull << 32) || (uint64_t)g.W * g.bstride >= (1ull << 31))
+  if (nbt + em / g.T + 2ull * MSM_MIN_THREADS + 1 >= (1ull << 32) || em >= (1ull << 32) || (uint64_t)g.W * g.bstride >= (1ull << 31))
     return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: batch too large");
   if ((uint64_t)nc * g.sets > 65535) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: too many bucket sets in one batch");
-  const uint64_t nslots = nbt + (em + g.T - 1) / g.T + 1;
+  // accumulate threads / partial slots: worst case em / T chains; a sparse batch runs shorter chains (msm_T), never more
+  // than 2 * MSM_MIN_THREADS of them
+  const uint64_t nthreads = std::max<uint64_t>((em + g.T - 1) / g.T, 2ull * MSM_MIN_THREADS);
+  const uint64_t nslots = nbt + nthreads + 1;
   size_t o = 0;
   auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
   const size_t o_counts = carve(nbt * 4), o_offsets = carve((nbt + 1) * 4), o_cursor = carve(nbt * 4), o_heavyc = carve(8),
@@ -322,7 +354,6 @@ static int msm_kernels(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, c
   { ProfScope _p(ctx, "msm.scatter");
     k_msm_scatter<<<(unsigned)((em + 255) / 256), 256, 0, st>>>(dig, cursor, ent_pt, ent_key, g);
     ZKC_LAUNCH_CHECK(ctx); }
-  const uint64_t nthreads = (em + g.T - 1) / g.T;
   { ProfScope _p(ctx, "msm.accum");
     k_msm_accum<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(bases, ent_pt, ent_key, offsets, partial, g);
     ZKC_LAUNCH_CHECK(ctx); }
