@@ -544,7 +544,7 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
   Fr *adv_values, *adv_polys;
   ZKC_TRY(pool.get(&adv_values, (size_t)A * n)); ZKC_TRY(pool.get(&adv_polys, (size_t)A * n));
   std::vector<std::pair<uint32_t, uint32_t>> staged;   // column groups of a staged upload, in flight on the copy stream
-  size_t stage_min_bytes = (size_t)256 << 20;   // ZKC_STAGE_MIN_BYTES overrides (tests force the staged path on small circuits)
+  size_t stage_min_bytes = (size_t)4 << 20;     // ZKC_STAGE_MIN_BYTES overrides (tests force the staged path on small circuits)
   if (const char* e = getenv("ZKC_STAGE_MIN_BYTES")) stage_min_bytes = (size_t)strtoull(e, nullptr, 10);
   if (A) {
     ProfScope _p(ctx, "prove.advice_h2d");
@@ -561,7 +561,7 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
       // generated and committed and the first groups are already being committed.  The copies skip the rows the blinding
       // policy overwrites, so they need no ordering against those writes.
       if (!ctx->copy_stream) ZKC_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-      const uint32_t ngroups = std::min<uint32_t>(A, 6);
+      const uint32_t ngroups = (uint32_t)std::min<size_t>(std::min<size_t>(A, 6), std::max<size_t>(1, cells * sizeof(Fr) >> 27));   // >= 128 MB each
       while (ctx->ev_copy.size() < ngroups) { cudaEvent_t e; ZKC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_copy.push_back(e); }
       ZKC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));                       // adv_values is allocated in stream order on `st`
       ZKC_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));

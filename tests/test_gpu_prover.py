@@ -246,3 +246,30 @@ def test_staged_witness_upload(circuit_k6, monkeypatch, blinding):
     ref = pkg().create_proof(w.pk, w.advice_dev, w.instances, seed)
     monkeypatch.setenv("ZKC_STAGE_MIN_BYTES", "1")
     assert pkg().create_proof(w.pk, w.advice_host, w.instances, seed) == ref
+
+
+def test_repeated_and_concurrent_proofs_are_stable(circuit_k6):
+    """50 proofs leave device memory where it was (pool reuse, no leak); two host threads sharing one context
+    (upstream calls from rayon workers) get serialised by the library and both obtain the right bytes."""
+    import threading
+    import torch
+    circ, opk, advice, params, gpk = circuit_k6
+    inst = [orc.fr_from_ints(c) for c in circ.instances]
+    adv = np.concatenate(advice)
+    seeds = [pyref.seed_from_u64(1000 + i) for i in range(4)]
+    want = [pkg().create_proof(gpk, adv, inst, s) for s in seeds]
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for i in range(50):
+        assert pkg().create_proof(gpk, adv, inst, seeds[i % 4]) == want[i % 4]
+    torch.cuda.synchronize()
+    assert abs(torch.cuda.mem_get_info()[0] - free0) < (64 << 20)
+    got = {}
+
+    def work(tid):
+        got[tid] = [pkg().create_proof(gpk, adv, inst, seeds[(tid + j) % 4]) for j in range(8)]
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for tid in range(2):
+        assert got[tid] == [want[(tid + j) % 4] for j in range(8)]
