@@ -10,4 +10,4 @@ The directory name contains a hyphen, so import it through `__graft_entry__.load
 """
 from . import api, circuit, dist, synth, workload  # noqa: F401
 from .api import (CompactAdvice, ZkcError, Context, create_proof_compact, EvaluationDomain, ParamsKZG, ProvingKey, best_fft, best_multiexp, create_proof,  # noqa: F401
-                  default_context, lib, lib_path, seed_from_u64)
+                  default_context, lib, lib_path, seed_from_u64, verify_proof)

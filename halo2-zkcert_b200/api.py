@@ -428,6 +428,58 @@ def create_proof(pk, advice, instances, rng_seed, transcript="blake2b", multiope
     return bytes(buf[:plen.value])
 
 
+# ---- verify_proof (host only) --------------------------------------------------------------------------------------
+def g2_generator():
+    """(1, 16) uint64: halo2curves G2Affine::generator() (x.c0, x.c1, y.c0, y.c1; Montgomery limbs)"""
+    out = np.zeros((1, 16), dtype=np.uint64)
+    assert lib().zkc_g2_generator(_hp(out)) == 0
+    return out
+
+
+def g2_mul(point, scalar):
+    """[scalar]P on G2 (scalar: (1, 4) Montgomery Fr) — ParamsKZG::setup's s_g2 = [s]G2"""
+    out = np.zeros((1, 16), dtype=np.uint64)
+    st = lib().zkc_g2_mul(_hp(_np(point, 16)), _hp(_np(scalar, 4)), _hp(out))
+    if st != 0:
+        raise ZkcError(st, "zkc_g2_mul")
+    return out
+
+
+def pairing_check(g1s, g2s):
+    """prod_i e(g1s[i], g2s[i]) == 1 ; g1s (m, 8) affine, g2s (m, 16)"""
+    g1s, g2s = _np(g1s, 8), _np(g2s, 16)
+    assert g1s.shape[0] == g2s.shape[0]
+    ok = C.c_int(0)
+    st = lib().zkc_pairing_check(_hp(g1s), _hp(g2s), C.c_size_t(g1s.shape[0]), C.byref(ok))
+    if st != 0:
+        raise ZkcError(st, "zkc_pairing_check: point not on the curve")
+    return bool(ok.value)
+
+
+def verify_proof(cs, fixed_commitments, sigma_commitments, transcript_repr, g1_gen, g2, s_g2, instances, proof,
+                 transcript="blake2b", multiopen="shplonk", point_format=0):
+    """plonk::verify_proof (zkc_verify, host only).  cs: circuit.ConstraintSystem; commitments: (m, 8) affine Montgomery
+    arrays (ProvingKey.commitments()); transcript_repr (1, 4); g1_gen (1, 8) = params.g[0]; g2 / s_g2 (1, 16);
+    instances: list of (len, 4) Montgomery arrays.  Returns True iff the proof is accepted."""
+    blob = cs.serialize()
+    f = _np(fixed_commitments, 8) if cs.num_fixed else np.zeros((0, 8), dtype=np.uint64)
+    sg = _np(sigma_commitments, 8) if cs.permutation else np.zeros((0, 8), dtype=np.uint64)
+    inst = [_np(i, 4) if len(i) else np.zeros((0, 4), dtype=np.uint64) for i in instances]
+    ptrs = (C.c_void_p * max(len(inst), 1))(*[i.ctypes.data for i in inst])
+    lens = (C.c_size_t * max(len(inst), 1))(*[i.shape[0] for i in inst])
+    o = ProveOpts()
+    o.transcript = {"blake2b": 0, "keccak": 1, "evm": 2, "poseidon": 3}[transcript]
+    o.multiopen = {"shplonk": 0, "gwc": 1}[multiopen]
+    o.point_format = point_format
+    buf = (C.c_uint8 * max(len(proof), 1)).from_buffer_copy(bytes(proof) or b"\0")
+    ok = C.c_int(0)
+    st = lib().zkc_verify(blob, C.c_size_t(len(blob)), _hp(f), _hp(sg), _hp(_np(transcript_repr, 4)), _hp(_np(g1_gen, 8)), _hp(_np(g2, 16)),
+                          _hp(_np(s_g2, 16)), ptrs, lens, buf, C.c_size_t(len(proof)), C.byref(o), C.byref(ok))
+    if st != 0:
+        raise ZkcError(st, "zkc_verify")
+    return bool(ok.value)
+
+
 class AdviceColumn(C.Structure):
     _fields_ = [("kind", C.c_int), ("data", C.c_void_p)]
 

@@ -356,6 +356,66 @@ void Transcript::write_scalar(const Fr& s) {
   proof.insert(proof.end(), b, b + 32);
 }
 
+
+// ---- reader side ---------------------------------------------------------------------------------------------------
+bool g1_decompress(const Fq& x, int y_is_odd, Fq* y) {
+  static const unsigned long long SQRT_EXP[4] = {0x4f082305b61f3f52ull, 0x65e05aa45a1c72a3ull, 0x6e14116da0605617ull, 0x0c19139cb84c680aull};   // (p + 1) / 4
+  Fq three = fe_zero<FqP>(); three.v[0] = 3; three = fe_from_canonical(three);
+  const Fq y2 = fe_add(fe_mul(fe_sqr(x), x), three);
+  Fq acc = fe_one<FqP>();
+  for (int w = 3; w >= 0; --w)
+    for (int b = 63; b >= 0; --b) { acc = fe_sqr(acc); if ((SQRT_EXP[w] >> b) & 1) acc = fe_mul(acc, y2); }
+  if (!fe_eq(fe_sqr(acc), y2)) return false;
+  if ((int)(fe_to_canonical(acc).v[0] & 1) != y_is_odd) acc = fe_neg(acc);
+  *y = acc;
+  return true;
+}
+static bool fq_from_repr(const uint8_t b[32], Fq* out) {   // canonical little-endian, must be < p
+  Fq v; memcpy(v.v, b, 32);
+  if (geq_mod<FqP>(v.v)) return false;
+  *out = fe_from_canonical(v);
+  return true;
+}
+int Transcript::read_point(G1Affine* out) {
+  G1Affine p;
+  if (kind == 2) {   // 64 bytes, big-endian x then y
+    if (in_pos + 64 > in_len) return 1;
+    uint8_t xb[32], yb[32];
+    memcpy(xb, in + in_pos, 32); memcpy(yb, in + in_pos + 32, 32);
+    in_pos += 64;
+    reverse32(xb); reverse32(yb);
+    if (!fq_from_repr(xb, &p.x) || !fq_from_repr(yb, &p.y)) return 1;
+    Fq three = fe_zero<FqP>(); three.v[0] = 3; three = fe_from_canonical(three);
+    if (!fe_eq(fe_sqr(p.y), fe_add(fe_mul(fe_sqr(p.x), p.x), three))) return 1;
+  } else {
+    if (in_pos + 32 > in_len) return 1;
+    uint8_t xb[32];
+    memcpy(xb, in + in_pos, 32);
+    in_pos += 32;
+    int sign;
+    if (point_format == 0) { sign = xb[31] >> 7; xb[31] &= 0x7f; }
+    else { if (xb[31] & 0x80) return 1; sign = (xb[31] >> 6) & 1; xb[31] &= 0x3f; }
+    if (!fq_from_repr(xb, &p.x)) return 1;
+    if (fe_is_zero(p.x) && sign == 0 && point_format == 0) return 1;   // the identity encoding
+    if (!g1_decompress(p.x, sign, &p.y)) return 1;
+  }
+  if (common_point(p)) return 1;
+  *out = p;
+  return 0;
+}
+int Transcript::read_scalar(Fr* out) {
+  if (in_pos + 32 > in_len) return 1;
+  uint8_t b[32];
+  memcpy(b, in + in_pos, 32);
+  in_pos += 32;
+  if (kind == 2) reverse32(b);
+  Fr v; memcpy(v.v, b, 32);
+  if (geq_mod<FrP>(v.v)) return 1;
+  *out = fe_from_canonical(v);
+  common_scalar(*out);
+  return 0;
+}
+
 }  // namespace host
 }  // namespace zkc
 

@@ -80,7 +80,15 @@ struct Transcript {
   void common_scalar(const Fr& s);
   int write_point(const G1Affine& p);
   void write_scalar(const Fr& s);
+  // reader side (TranscriptRead of the same four kinds): elements are taken from `in`, absorbed, and returned
+  const uint8_t* in = nullptr;
+  size_t in_len = 0, in_pos = 0;
+  void set_input(const uint8_t* p, size_t n) { in = p; in_len = n; in_pos = 0; }
+  int read_point(G1Affine* out);   // nonzero: truncated input, non-canonical coordinate, not on the curve, or identity
+  int read_scalar(Fr* out);        // nonzero: truncated input or non-canonical scalar
 };
+// y with y^2 = x^3 + 3 and the given parity; false if x^3 + 3 is not a square
+bool g1_decompress(const Fq& x, int y_is_odd, Fq* y);
 
 }  // namespace host
 }  // namespace zkc

@@ -12,6 +12,8 @@
 #include "msm.cuh"
 #include "dist.cuh"
 #include "host/hostutil.h"
+#include "host/cs.h"
+#include "host/small_poly.h"
 #include <algorithm>
 #include <functional>
 #include <memory>
@@ -29,68 +31,14 @@ int srs_commit_dev(zkc_ctx* ctx, const zkc_srs* s, int basis, const Fr* polys, u
 using namespace zkc;
 using zkc::host::Transcript;
 
-#define PROG_STACK_HOST_MAX 12   // must not exceed PROG_STACK of the device interpreter (poly.cu)
 extern "C" uint32_t zkc_srs_k(const zkc_srs* srs);
 
-// ---- parsed constraint system --------------------------------------------------------------------------
-namespace {
-
-struct HostProgram {
-  std::vector<uint32_t> words;     // (op, arg) pairs
-  std::vector<Fr> consts;          // Montgomery
-  uint32_t nexprs = 0;
-  std::vector<uint32_t> degrees;   // per expression
-};
-
-struct Cs {
-  uint32_t k = 0, num_advice = 0, num_fixed = 0, num_instance = 0, min_degree = 0;
-  std::vector<std::pair<uint32_t, int32_t>> aq, fq, iq;
-  std::vector<std::pair<uint32_t, uint32_t>> perm;   // (kind, column)
-  HostProgram gates;
-  std::vector<std::pair<HostProgram, HostProgram>> lookups;
-  uint32_t blinding_factors = 0, degree = 0, chunk_len = 0;
-  uint64_t n() const { return 1ull << k; }
-  uint64_t usable() const { return n() - (blinding_factors + 1); }
-  uint32_t nsets() const { return perm.empty() ? 0 : (uint32_t)((perm.size() + chunk_len - 1) / chunk_len); }
-};
-
-struct Reader {
-  const uint8_t* p; size_t len, pos = 0; bool ok = true;
-  uint32_t u32() { if (pos + 4 > len) { ok = false; return 0; } uint32_t v; memcpy(&v, p + pos, 4); pos += 4; return v; }
-  void bytes(void* out, size_t n) { if (pos + n > len) { ok = false; memset(out, 0, n); return; } memcpy(out, p + pos, n); pos += n; }
-};
-
-bool parse_program(Reader& r, uint32_t nexprs, HostProgram& out) {
-  out.nexprs = nexprs;
-  const uint32_t npairs = r.u32();
-  if (!r.ok || (size_t)npairs * 8 > r.len) return false;
-  out.words.resize((size_t)npairs * 2);
-  for (auto& w : out.words) w = r.u32();
-  const uint32_t nconsts = r.u32();
-  if (!r.ok || (size_t)nconsts * 32 > r.len) return false;
-  out.consts.resize(nconsts);
-  for (auto& c : out.consts) { Fr raw; r.bytes(raw.v, 32); c = fe_from_canonical(raw); }
-  // degrees (and a structural check) by abstract interpretation of the postfix stream
-  std::vector<uint32_t> st;
-  uint32_t ends = 0;
-  for (uint32_t i = 0; i < npairs; ++i) {
-    const uint32_t op = out.words[2 * i], arg = out.words[2 * i + 1];
-    switch (op) {
-      case 0: if (arg >= nconsts) return false; st.push_back(0); break;
-      case 1: case 2: case 3: st.push_back(1); break;
-      case 4: if (st.empty()) return false; break;
-      case 5: if (st.size() < 2) return false; { uint32_t b = st.back(); st.pop_back(); st.back() = std::max(st.back(), b); } break;
-      case 6: if (st.size() < 2) return false; { uint32_t b = st.back(); st.pop_back(); st.back() += b; } break;
-      case 7: if (st.empty() || arg >= nconsts) return false; break;
-      case 8: if (st.size() != 1) return false; out.degrees.push_back(st.back()); st.clear(); ++ends; break;
-      default: return false;
-    }
-    if (st.size() > PROG_STACK_HOST_MAX) return false;
-  }
-  return r.ok && ends == nexprs && st.empty();
-}
-
-}  // namespace
+using zkc::host::Cs;
+using zkc::host::HostProgram;
+using zkc::host::rotate_omega;
+using zkc::host::lagrange_interpolate;
+using zkc::host::eval_small;
+using zkc::host::vanishing_eval;
 
 // ---- proving key -------------------------------------------------------------------------------------------
 struct zkc_pk {
@@ -167,66 +115,12 @@ extern "C" int zkc_pk_load(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_b
   std::unique_ptr<zkc_pk, void (*)(zkc_pk*)> pk(new zkc_pk(), zkc_pk_free);
   pk->ctx = ctx; pk->srs = srs;
   Cs& cs = pk->cs;
-  Reader r{cs_blob, cs_len};
-  uint8_t magic[4]; r.bytes(magic, 4);
-  if (memcmp(magic, "ZKCS", 4) != 0 || r.u32() != 1) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: bad constraint-system blob");
-  cs.k = r.u32(); cs.num_advice = r.u32(); cs.num_fixed = r.u32(); cs.num_instance = r.u32(); cs.min_degree = r.u32();
-  if (!r.ok || cs.k > 26 || cs.k != zkc_srs_k(srs)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: k does not match the SRS");
-  auto read_queries = [&](std::vector<std::pair<uint32_t, int32_t>>& q, uint32_t ncols) {
-    const uint32_t m = r.u32();
-    if (!r.ok || m > (1u << 20)) { r.ok = false; return; }
-    q.resize(m);
-    for (auto& e : q) { e.first = r.u32(); e.second = (int32_t)r.u32(); if (e.first >= ncols) r.ok = false; }
-  };
-  read_queries(cs.aq, cs.num_advice); read_queries(cs.fq, cs.num_fixed); read_queries(cs.iq, cs.num_instance);
-  const uint32_t nperm = r.u32();
-  if (!r.ok || nperm > (1u << 16)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: truncated blob");
-  cs.perm.resize(nperm);
-  for (auto& e : cs.perm) {
-    e.first = r.u32(); e.second = r.u32();
-    const uint32_t lim = e.first == 0 ? cs.num_advice : (e.first == 1 ? cs.num_fixed : cs.num_instance);
-    if (e.first > 2 || e.second >= lim) r.ok = false;
-  }
-  const uint32_t npolys = r.u32();
-  if (!r.ok || !parse_program(r, npolys, cs.gates)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: bad gate program");
-  const uint32_t nlk = r.u32();
-  if (!r.ok || nlk > 4096) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: truncated blob");
-  cs.lookups.resize(nlk);
-  for (auto& lk : cs.lookups) {
-    const uint32_t ni = r.u32();
-    if (!r.ok || !parse_program(r, ni, lk.first)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: bad lookup input program");
-    const uint32_t nt = r.u32();
-    if (!r.ok || !parse_program(r, nt, lk.second)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: bad lookup table program");
-  }
-  // query indices inside programs must be in range
-  auto check_prog = [&](const HostProgram& h) {
-    for (size_t i = 0; i < h.words.size(); i += 2) {
-      const uint32_t op = h.words[i], arg = h.words[i + 1];
-      if ((op == 1 && arg >= cs.aq.size()) || (op == 2 && arg >= cs.fq.size()) || (op == 3 && arg >= cs.iq.size())) return false;
-    }
-    return true;
-  };
-  bool okp = check_prog(cs.gates);
-  for (auto& lk : cs.lookups) okp = okp && check_prog(lk.first) && check_prog(lk.second);
-  if (!okp) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: query index out of range");
-  // A.5 numbers
   {
-    std::vector<uint32_t> per_col(cs.num_advice, 0);
-    for (auto& q : cs.aq) per_col[q.first]++;
-    uint32_t f = 3;
-    for (uint32_t c : per_col) f = std::max(f, c);
-    cs.blinding_factors = f + 2;
-    uint32_t d = 3;
-    for (auto& lk : cs.lookups) {
-      uint32_t di = 1, dt = 1;
-      for (uint32_t x : lk.first.degrees) di = std::max(di, x);
-      for (uint32_t x : lk.second.degrees) dt = std::max(dt, x);
-      d = std::max(d, std::max(4u, 2 + di + dt));
-    }
-    for (uint32_t x : cs.gates.degrees) d = std::max(d, x);
-    cs.degree = std::max(d, std::max(cs.min_degree, 1u));
-    cs.chunk_len = cs.degree - 2;
+    std::string perr;
+    if (!zkc::host::parse_cs(cs_blob, cs_len, cs, perr)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: " + perr);
+    if (cs.k != zkc_srs_k(srs)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: k does not match the SRS");
   }
+  const uint32_t nperm = (uint32_t)cs.perm.size();
   const uint64_t n = cs.n();
   if (n < cs.blinding_factors + 3) return set_err(ctx, ZKC_ERR_NOT_ENOUGH_ROWS, "zkc_pk_load: not enough rows for the blinding factors");
   if (cs.chunk_len > PERM_MAX_CHUNK) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: permutation chunk longer than PERM_MAX_CHUNK");
@@ -376,44 +270,6 @@ struct Rng {
 };
 
 struct Query { const Fr* poly; Fr point; Fr eval; };
-
-Fr rotate_omega(const Fr& x, const Fr& omega, const Fr& omega_inv, int32_t rot) {
-  return rot >= 0 ? fe_mul(x, fe_pow_u64(omega, (u64)rot)) : fe_mul(x, fe_pow_u64(omega_inv, (u64)(-(int64_t)rot)));
-}
-
-// coefficients of the interpolation polynomial through (points[i], evals[i])
-std::vector<Fr> lagrange_interpolate(const std::vector<Fr>& pts, const std::vector<Fr>& evals) {
-  const size_t m = pts.size();
-  std::vector<Fr> coeffs(m, fe_zero<FrP>());
-  if (m == 1) { coeffs[0] = evals[0]; return coeffs; }
-  for (size_t j = 0; j < m; ++j) {
-    std::vector<Fr> num(1, fe_one<FrP>());
-    Fr den = fe_one<FrP>();
-    for (size_t kx = 0; kx < m; ++kx) {
-      if (kx == j) continue;
-      std::vector<Fr> nxt(num.size() + 1, fe_zero<FrP>());
-      for (size_t i = 0; i < num.size(); ++i) {
-        nxt[i + 1] = fe_add(nxt[i + 1], num[i]);
-        nxt[i] = fe_sub(nxt[i], fe_mul(pts[kx], num[i]));
-      }
-      num.swap(nxt);
-      den = fe_mul(den, fe_sub(pts[j], pts[kx]));
-    }
-    const Fr scale = fe_mul(evals[j], fe_inv(den));
-    for (size_t i = 0; i < m; ++i) coeffs[i] = fe_add(coeffs[i], fe_mul(num[i], scale));
-  }
-  return coeffs;
-}
-Fr eval_small(const std::vector<Fr>& c, const Fr& x) {
-  Fr acc = fe_zero<FrP>();
-  for (size_t i = c.size(); i-- > 0;) acc = fe_add(fe_mul(acc, x), c[i]);
-  return acc;
-}
-Fr vanishing_eval(const std::vector<Fr>& roots, const Fr& z) {
-  Fr acc = fe_one<FrP>();
-  for (auto& r : roots) acc = fe_mul(acc, fe_sub(z, r));
-  return acc;
-}
 
 struct RotationSet {
   std::vector<Fr> points;                       // ascending canonical order (BTreeSet<Fr>)

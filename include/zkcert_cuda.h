@@ -210,6 +210,23 @@ int zkc_host_hash(int kind, const uint8_t* personal16, const uint8_t* data, size
 /* Grain-generated Poseidon parameters of transcript kind 3 (canonical little-endian): 65 x 3 round constants, 3 x 3 MDS. */
 int zkc_poseidon_spec(zkc_fr* constants, zkc_fr* mds);
 
+/* ---- verify_proof (host only, no device) ---------------------------------------------------------------------------------
+ * plonk::verify_proof::<KZGCommitmentScheme<Bn256>, VerifierSHPLONK / VerifierGWC, Challenge255, TranscriptRead, SingleStrategy>:
+ * the self-check snark-verifier-sdk's gen_snark_shplonk runs after create_proof (/root/reference/src/helpers.rs:233,299) and what
+ * the reference's tests assert (src/tests/x509_aggregation.rs:64-105).  `cs_blob` as for zkc_pk_load; fixed / sigma commitments
+ * as returned by zkc_pk_get_commitments (= the VerifyingKey); g1_gen = params.g[0], g2 / s_g2 = params.g2() / params.s_g2()
+ * (halo2curves G2Affine: x.c0, x.c1, y.c0, y.c1, Montgomery limbs).  Only opts->transcript, multiopen and point_format are read.
+ * *ok = 1 iff the proof is accepted (a malformed proof is a rejected proof: return value ZKC_OK, *ok = 0). */
+typedef struct { zkc_fq x_c0, x_c1, y_c0, y_c1; } zkc_g2_affine;
+int zkc_verify(const uint8_t* cs_blob, size_t cs_len, const zkc_g1_affine* fixed_comm, const zkc_g1_affine* sigma_comm,
+               const zkc_fr* transcript_repr, const zkc_g1_affine* g1_gen, const zkc_g2_affine* g2, const zkc_g2_affine* s_g2,
+               const zkc_fr* const* instances, const size_t* instance_lens, const uint8_t* proof, size_t proof_len,
+               const zkc_prove_opts* opts, int* ok);
+/* G2 pieces of ParamsKZG::setup and the pairing behind the final check: generator of G2, [scalar]P, prod e(g1s[i], g2s[i]) == 1 */
+int zkc_g2_generator(zkc_g2_affine* out);
+int zkc_g2_mul(const zkc_g2_affine* p, const zkc_fr* scalar, zkc_g2_affine* out);
+int zkc_pairing_check(const zkc_g1_affine* g1s, const zkc_g2_affine* g2s, size_t npairs, int* is_one);
+
 /* ---- team proving: ONE create_proof over the GPUs of a node ---------------------------------------------
  * One process (and one zkc_ctx) per GPU.  After zkc_team_init every rank calls zkc_srs_*, zkc_pk_load and zkc_prove with
  * IDENTICAL arguments; the library partitions the device work (MSM by point range — the split halo2's best_multiexp makes

@@ -151,6 +151,28 @@ def _verify_workload(w, proof, **kw):
     return verifier.verify_proof(vk, pyref.G1_GEN, w.circ.instances, proof, verifier.trapdoor_check(SRS_SECRET), **kw)
 
 
+def _product_verify(w, proof, **kw):
+    """the product's own host verifier (zkc_verify, C++ pairing) on a GPU-built workload: no oracle code involved"""
+    api = pkg().api
+    f, s = w.pk.commitments()
+    s_g2 = api.g2_mul(api.g2_generator(), orc.fr_from_ints([SRS_SECRET]))
+    return api.verify_proof(w.circ.cs, f, s, orc.fr_from_ints([w.circ.transcript_repr()]), w.params.get_g(0)[:1], api.g2_generator(), s_g2,
+                            w.instances, proof, **kw)
+
+
+@pytest.mark.parametrize("transcript,multiopen", [("blake2b", "shplonk"), ("keccak", "gwc"), ("evm", "shplonk"), ("poseidon", "shplonk")])
+def test_product_verifier_accepts_gpu_proofs(transcript, multiopen):
+    """prove on the GPU, verify with zkc_verify on the host: the drop-in's create_proof -> verify_proof loop"""
+    w = pkg().workload.build(gpu_ctx(), 10, 3, seed=12)
+    seed = pyref.seed_from_u64(8)
+    proof = pkg().create_proof(w.pk, w.advice_dev, w.instances, seed, transcript, multiopen)
+    assert _product_verify(w, proof, transcript=transcript, multiopen=multiopen)
+    assert _verify_workload(w, proof, transcript_kind=transcript, multiopen=multiopen)
+    bad = bytearray(proof)
+    bad[-5] ^= 2
+    assert not _product_verify(w, bytes(bad), transcript=transcript, multiopen=multiopen)
+
+
 @pytest.mark.parametrize("k,cols,shape", [(17, 3, "base"), (15, 12, "base"), (15, 112, "sha_bit")])
 def test_full_size_proofs_verify(k, cols, shape):
     """BASELINE.json sizes (config 1: RSA k=17; config 2: k=15 with 12 gate columns; config 3 shape at k=15):
@@ -162,6 +184,7 @@ def test_full_size_proofs_verify(k, cols, shape):
     seed = pyref.seed_from_u64(k)
     proof = pkg().create_proof(w.pk, w.advice_dev, w.instances, seed)
     assert _verify_workload(w, proof)
+    assert _product_verify(w, proof)
     assert pkg().create_proof(w.pk, w.advice_host, w.instances, seed) == proof
     ctx.set_overlap(False)
     try:
