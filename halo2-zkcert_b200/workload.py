@@ -75,6 +75,7 @@ def build(ctx, k, num_gate_cols, seed=0, circ=None, params=None, shape="base"):
     ctx.sync()
     sigma = table[torch.from_numpy(mapping).cuda(ctx.device)]
     tr = to_host(to_mont_dev(ctx, [w.circ.transcript_repr()]))
+    w.transcript_repr = tr          # (1, 4) Montgomery: vk.transcript_repr, also what verify_proof absorbs first
     w.pk = api.ProvingKey(params, cs, to_host(fixed), to_host(sigma), tr)
     # pinned host copy of the witness for the end-to-end (host-buffer) path
     w.advice_pinned = w.advice_dev.cpu().pin_memory()
