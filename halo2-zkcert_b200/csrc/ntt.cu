@@ -16,6 +16,7 @@
 // extended domain and the 1/n scaling of inverse transforms are fused into the first load / last
 // store.  One twiddle table w_N^i (i < N/2) per size serves forward and inverse transforms.
 #include "common.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace zkc {
@@ -216,6 +217,13 @@ static int launch_pass(zkc_ctx* ctx, bool last, const NttPass& p, uint32_t grid_
 
   }
   dim3 grid(grid_x, ncols);
+  {
+    // field products of this pass (the roofline numerator of bench.py): N/2 per butterfly stage, N inter-pass twiddles after a
+    // strided pass, N for a fused post-scaling, ~2/3 n_in for the coset pre-scaling
+    const uint64_t N = 1ull << p.log_n;
+    ctx->stats["ntt.muls"] += (uint64_t)ncols * ((N >> 1) * p.s + (last ? 0 : N) + (p.post ? N : 0) + (p.pre ? (p.n_in * 2) / 3 : 0));
+    ctx->stats["ntt.bytes"] += (uint64_t)ncols * (std::min<uint64_t>(p.n_in, N) + N) * sizeof(Fr);   // read the valid inputs, write N
+  }
   ProfScope _p(ctx, last ? "ntt.last" : "ntt.strided");
   if (last) k_ntt_last<<<grid, NTT_THREADS, smem, ctx->stream>>>(p);
   else k_ntt_strided<<<grid, NTT_THREADS, smem, ctx->stream>>>(p);
