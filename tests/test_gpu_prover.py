@@ -296,3 +296,22 @@ def test_repeated_and_concurrent_proofs_are_stable(circuit_k6):
     [t.join() for t in ts]
     for tid in range(2):
         assert got[tid] == [want[(tid + j) % 4] for j in range(8)]
+
+
+def test_gpu_prover_reproduces_golden_fixtures():
+    """tests/golden/proofs.json: the CUDA prover emits the committed bytes (no oracle prover run in this test; the oracle is
+    only used to lay out the synthetic circuit's key material)"""
+    import hashlib
+    from tests import golden_util
+    for name, entry in golden_util.load().items():
+        circ = golden_util.circuit_of(entry)
+        opk, advice = oracle_setup(circ)
+        params, gpk = gpu_setup(circ, opk)
+        f, s = gpk.commitments()
+        assert orc.g1_to_ints(f) == golden_util.points_of(entry["fixed_commitments"])
+        assert orc.g1_to_ints(s) == golden_util.points_of(entry["sigma_commitments"])
+        inst = [orc.fr_from_ints(c) for c in circ.instances]
+        for combo, rec in entry["proofs"].items():
+            t, m = combo.split("/")
+            proof = pkg().create_proof(gpk, np.concatenate(advice), inst, pyref.seed_from_u64(entry["rng_seed_u64"]), t, m)
+            assert hashlib.sha256(proof).hexdigest() == rec["sha256"], (name, combo)

@@ -106,3 +106,25 @@ def test_product_verifier_other_shapes_and_point_format():
     proof = plonk.create_proof(opk, advice, circ.instances, pyref.ChaChaRng(pyref.seed_from_u64(6), 20), opts=plonk.ProverOptions(point_format=1))
     assert _verify(circ, opk, s_g2, circ.instances, proof, point_format=1)
     assert not _verify(circ, opk, s_g2, circ.instances, proof, point_format=0)
+
+
+def test_product_verifier_accepts_golden_proofs():
+    """the committed fixture bytes (tests/golden/proofs.json) verify under zkc_verify against the committed vk commitments —
+    no prover runs in this test"""
+    from tests import golden_util
+    api = pkg().api
+    s_g2 = api.g2_mul(api.g2_generator(), orc.fr_from_ints([SRS_SECRET]))
+    n = 0
+    for name, entry in golden_util.load().items():
+        circ = golden_util.circuit_of(entry)
+        f = orc.g1_from_ints(golden_util.points_of(entry["fixed_commitments"]))
+        s = orc.g1_from_ints(golden_util.points_of(entry["sigma_commitments"]))
+        for combo, rec in entry["proofs"].items():
+            if "hex" not in rec:
+                continue
+            t, m = combo.split("/")
+            ok = api.verify_proof(circ.cs, f, s, orc.fr_from_ints([circ.transcript_repr()]), orc.g1_from_ints([pyref.G1_GEN]), api.g2_generator(),
+                                  s_g2, [orc.fr_from_ints(c) for c in circ.instances], bytes.fromhex(rec["hex"]), transcript=t, multiopen=m)
+            assert ok, (name, combo)
+            n += 1
+    assert n >= 10

@@ -109,3 +109,21 @@ def test_poseidon_grain_known_answers_and_host_spec():
     assert s1.squeeze() != s2.squeeze()
     a = s1.squeeze()
     assert a != s1.squeeze()
+
+
+def test_oracle_reproduces_golden_fixtures():
+    """tests/golden/proofs.json (tools/make_golden.py): the oracle's keygen commitments and proof bytes have not drifted"""
+    import hashlib
+    from tests import golden_util
+    from tests.circuits import oracle_setup
+    for name, entry in golden_util.load().items():
+        circ = golden_util.circuit_of(entry)
+        opk, advice = oracle_setup(circ)
+        assert opk.fixed_commitments == golden_util.points_of(entry["fixed_commitments"]), name
+        assert opk.sigma_commitments == golden_util.points_of(entry["sigma_commitments"]), name
+        for combo, rec in entry["proofs"].items():
+            t, m = combo.split("/")
+            proof = plonk.create_proof(opk, advice, circ.instances, pyref.ChaChaRng(pyref.seed_from_u64(entry["rng_seed_u64"]), 20), t, m)
+            assert len(proof) == rec["len"] and hashlib.sha256(proof).hexdigest() == rec["sha256"], (name, combo)
+            if "hex" in rec:
+                assert proof.hex() == rec["hex"]
