@@ -332,6 +332,20 @@ class ParamsKZG:
         except Exception:
             pass
 
+    def write(self, path, s_g2, g2=None):
+        """ParamsKZG::write: kzg_bn254_{k}.srs in RawBytes form (g, g_lagrange from the device; g2 / s_g2 live on the host)"""
+        data = params_to_bytes(self.k, self.get_g(0), self.get_g(1), g2_generator() if g2 is None else g2, s_g2)
+        with open(path, "wb") as f:
+            f.write(data)
+        return len(data)
+
+    @classmethod
+    def read(cls, path, ctx=None, checked=True):
+        """ParamsKZG::read: loads the file and uploads g / g_lagrange; returns (params, g2, s_g2)"""
+        with open(path, "rb") as f:
+            k, g, gl, g2, s_g2 = params_from_bytes(f.read(), checked)
+        return cls(k, g=g, g_lagrange=gl, ctx=ctx), g2, s_g2
+
     def get_g(self, basis=0):
         out = np.empty((self.n, 8), dtype=np.uint64)
         self.ctx.check(lib().zkc_srs_get(self.ctx._h, self._h, C.c_int(basis), _hp(out)))
@@ -426,6 +440,34 @@ def create_proof(pk, advice, instances, rng_seed, transcript="blake2b", multiope
     plen = C.c_size_t(0)
     ctx.check(lib().zkc_prove(ctx._h, pk._h, adv_ptr, C.c_int(1 if on_dev else 0), ptrs, lens, C.byref(o), buf, C.c_size_t(cap), C.byref(plen)))
     return bytes(buf[:plen.value])
+
+
+# ---- ParamsKZG files (host only) -----------------------------------------------------------------------------------
+def params_to_bytes(k, g, g_lagrange, g2, s_g2):
+    """ParamsKZG::write (SerdeFormat::RawBytes): the bytes of a kzg_bn254_{k}.srs file"""
+    lib().zkc_params_size.restype = C.c_size_t
+    size = lib().zkc_params_size(C.c_uint32(k))
+    buf = np.zeros(size, dtype=np.uint8)
+    st = lib().zkc_params_write(C.c_uint32(k), _hp(_np(g, 8)), _hp(_np(g_lagrange, 8)), _hp(_np(g2, 16)), _hp(_np(s_g2, 16)), _hp(buf), C.c_size_t(size))
+    if st != 0:
+        raise ZkcError(st, "zkc_params_write")
+    return buf.tobytes()
+
+
+def params_from_bytes(data, checked=True):
+    """ParamsKZG::read: (k, g, g_lagrange, g2, s_g2) as numpy arrays; checked=True validates every point (RawBytes)"""
+    raw = np.frombuffer(data, dtype=np.uint8)
+    k = C.c_uint32(0)
+    st = lib().zkc_params_read(_hp(raw), C.c_size_t(raw.size), C.c_int(0), C.byref(k), None, None, None, None)
+    if st != 0:
+        raise ZkcError(st, "zkc_params_read: not a ParamsKZG RawBytes file (size does not match k)")
+    n = 1 << k.value
+    g, gl = np.zeros((n, 8), dtype=np.uint64), np.zeros((n, 8), dtype=np.uint64)
+    g2, s_g2 = np.zeros((1, 16), dtype=np.uint64), np.zeros((1, 16), dtype=np.uint64)
+    st = lib().zkc_params_read(_hp(raw), C.c_size_t(raw.size), C.c_int(1 if checked else 0), C.byref(k), _hp(g), _hp(gl), _hp(g2), _hp(s_g2))
+    if st != 0:
+        raise ZkcError(st, "zkc_params_read: invalid point in the file")
+    return k.value, g, gl, g2, s_g2
 
 
 # ---- verify_proof (host only) --------------------------------------------------------------------------------------

@@ -227,6 +227,16 @@ int zkc_g2_generator(zkc_g2_affine* out);
 int zkc_g2_mul(const zkc_g2_affine* p, const zkc_fr* scalar, zkc_g2_affine* out);
 int zkc_pairing_check(const zkc_g1_affine* g1s, const zkc_g2_affine* g2s, size_t npairs, int* is_one);
 
+/* ---- ParamsKZG files (host only) ------------------------------------------------------------------------------------------
+ * `kzg_bn254_{k}.srs` as ParamsKZG::write / read lay it out in SerdeFormat::RawBytes[Unchecked] (SURVEY OPEN-8):
+ * u32 k (LE) | g[n] | g_lagrange[n] | g2 | s_g2, points as raw Montgomery limbs (64 B / 128 B).  The arrays read here go to
+ * zkc_srs_load (device) and zkc_verify (g2, s_g2).  `checked` != 0 validates every point (RawBytes), 0 trusts the file. */
+size_t zkc_params_size(uint32_t k);
+int zkc_params_write(uint32_t k, const zkc_g1_affine* g, const zkc_g1_affine* g_lagrange, const zkc_g2_affine* g2, const zkc_g2_affine* s_g2,
+                     uint8_t* out, size_t cap);
+int zkc_params_read(const uint8_t* in, size_t len, int checked, uint32_t* k, zkc_g1_affine* g, zkc_g1_affine* g_lagrange, zkc_g2_affine* g2,
+                    zkc_g2_affine* s_g2);
+
 /* ---- team proving: ONE create_proof over the GPUs of a node ---------------------------------------------
  * One process (and one zkc_ctx) per GPU.  After zkc_team_init every rank calls zkc_srs_*, zkc_pk_load and zkc_prove with
  * IDENTICAL arguments; the library partitions the device work (MSM by point range — the split halo2's best_multiexp makes

@@ -154,3 +154,24 @@ def test_published_eip196_known_answer():
     both = np.concatenate([G, G])
     assert orc.g1_to_ints(affine(ctx.msm(orc.fr_from_ints([1, 1]), both)))[0] == EIP196_2G
     assert orc.g1_to_ints(affine(ctx.msm(orc.fr_from_ints([2]), G)))[0] == EIP196_2G
+
+
+def test_params_file_write_read_on_device(tmp_path):
+    """ParamsKZG::write / read through kzg_bn254_{k}.srs (RawBytes): device SRS -> file -> device SRS, same commitments"""
+    from tests.circuits import SRS_SECRET
+    p = pkg()
+    ctx = gpu_ctx()
+    k = 8
+    params = p.ParamsKZG.setup(k, orc.fr_from_ints([SRS_SECRET]), ctx=ctx)
+    s_g2 = p.api.g2_mul(p.api.g2_generator(), orc.fr_from_ints([SRS_SECRET]))
+    path = str(tmp_path / ("kzg_bn254_%d.srs" % k))
+    assert params.write(path, s_g2) == 4 + 2 * 64 * (1 << k) + 256
+    back, g2, s_g2_back = p.ParamsKZG.read(path, ctx=ctx)
+    assert back.k == k and np.array_equal(back.get_g(0), params.get_g(0)) and np.array_equal(back.get_g(1), params.get_g(1))
+    assert np.array_equal(g2, p.api.g2_generator()) and np.array_equal(s_g2_back, s_g2)
+    poly = random_fr_mont(1 << k, 3)
+    assert np.array_equal(back.commit(poly), params.commit(poly)) and np.array_equal(back.commit_lagrange(poly), params.commit_lagrange(poly))
+    # e(g[1], G2) == e(g[0], s_g2): the file's G1 and G2 halves belong to the same secret
+    g = back.get_g(0)
+    neg_g0 = orc.g1_from_ints([pyref.ec_neg(orc.g1_to_ints(g[:1])[0])])
+    assert p.api.pairing_check(np.concatenate([g[1:2], neg_g0]), np.concatenate([g2, s_g2_back]))

@@ -128,3 +128,29 @@ def test_product_verifier_accepts_golden_proofs():
             assert ok, (name, combo)
             n += 1
     assert n >= 10
+
+
+def test_params_file_round_trip_and_validation():
+    """kzg_bn254_{k}.srs codec (zkc_params_write / zkc_params_read, RawBytes layout): round trip, size law, point validation"""
+    from tests.circuits import oracle_srs
+    api = pkg().api
+    k = 6
+    g, gl = oracle_srs(k)
+    g2 = api.g2_generator()
+    s_g2 = api.g2_mul(g2, orc.fr_from_ints([SRS_SECRET]))
+    data = api.params_to_bytes(k, g, gl, g2, s_g2)
+    assert len(data) == 4 + 2 * 64 * (1 << k) + 256 and data[:4] == (k).to_bytes(4, "little")
+    assert data[4:68] == g[0].tobytes()                      # raw Montgomery limbs of g[0] = the generator
+    k2, g_r, gl_r, g2_r, s_g2_r = api.params_from_bytes(data)
+    assert k2 == k and np.array_equal(g_r, g) and np.array_equal(gl_r, gl) and np.array_equal(g2_r, g2) and np.array_equal(s_g2_r, s_g2)
+    bad = bytearray(data)
+    bad[4 + 64 * 5 + 3] ^= 1                                 # g[5] leaves the curve
+    with pytest.raises(pkg().ZkcError):
+        api.params_from_bytes(bytes(bad))
+    assert api.params_from_bytes(bytes(bad), checked=False)[0] == k     # RawBytesUnchecked trusts the file
+    with pytest.raises(pkg().ZkcError):
+        api.params_from_bytes(data[:-1])
+    bad = bytearray(data)
+    bad[-1] ^= 0x40                                          # s_g2.y.c1 out of range / off the curve
+    with pytest.raises(pkg().ZkcError):
+        api.params_from_bytes(bytes(bad))
