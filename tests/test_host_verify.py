@@ -154,3 +154,32 @@ def test_params_file_round_trip_and_validation():
     bad[-1] ^= 0x40                                          # s_g2.y.c1 out of range / off the curve
     with pytest.raises(pkg().ZkcError):
         api.params_from_bytes(bytes(bad))
+
+
+def test_verifier_rejects_random_mutations_without_crashing(setup_k6):
+    """fuzz: random byte strings and 150 single-byte mutations of a valid proof are all rejected (never accepted, never a crash);
+    malformed constraint-system blobs are an error, not a verdict"""
+    circ, opk, advice, s_g2 = setup_k6
+    rng = np.random.default_rng(7)
+    for multiopen in ("shplonk", "gwc"):
+        proof = plonk.create_proof(opk, advice, circ.instances, pyref.ChaChaRng(pyref.seed_from_u64(11), 20), multiopen=multiopen)
+        assert _verify(circ, opk, s_g2, circ.instances, proof, multiopen=multiopen)
+        for _ in range(75):
+            bad = bytearray(proof)
+            pos = int(rng.integers(0, len(bad)))
+            bad[pos] ^= int(rng.integers(1, 256))
+            assert not _verify(circ, opk, s_g2, circ.instances, bytes(bad), multiopen=multiopen), pos
+        for n in [0, 1, 31, 32, 33, 64, len(proof) // 2, len(proof) + 32]:
+            assert not _verify(circ, opk, s_g2, circ.instances, rng.integers(0, 256, n, dtype=np.uint8).tobytes(), multiopen=multiopen)
+    # truncated / corrupted constraint system: ZkcError (BAD_ARG), not a crash
+    import ctypes as C
+    api = pkg().api
+    blob = circ.cs.serialize()
+    ok = C.c_int(0)
+    o = api.ProveOpts()
+    one = orc.fr_from_ints([1])
+    for cut in [0, 3, 8, 40, len(blob) // 2, len(blob) - 1]:
+        b = blob[:cut]
+        st = api.lib().zkc_verify(b, C.c_size_t(len(b)), None, None, api._hp(one), api._hp(orc.g1_from_ints([pyref.G1_GEN])), api._hp(api.g2_generator()),
+                                  api._hp(s_g2), None, None, proof, C.c_size_t(len(proof)), C.byref(o), C.byref(ok))
+        assert st != 0 and ok.value == 0
