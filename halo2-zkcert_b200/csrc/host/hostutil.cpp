@@ -436,3 +436,23 @@ extern "C" int zkc_host_hash(int kind, const uint8_t* personal16, const uint8_t*
   if (kind == 1) { zkc::host::keccak256(data, len, out); return 0; }
   return 1;
 }
+
+// Host field inversion exposed for tests: which = 0 the product's host fe_inv (binary extended Euclid), 1 the Fermat ladder;
+// field = 0 Fr, 1 Fq.  Montgomery in, Montgomery out.
+extern "C" int zkc_host_fe_inv(int field, int which, const uint64_t* in, uint64_t* out, size_t n) {
+  if (!in || !out || field < 0 || field > 1 || which < 0 || which > 1) return 1;
+  for (size_t i = 0; i < n; ++i) {
+    if (field == 0) {
+      zkc::Fr a; memcpy(a.v, in + 4 * i, 32);
+      if (zkc::geq_mod<zkc::FrP>(a.v)) return 1;
+      const zkc::Fr r = which ? zkc::fe_inv_fermat_host(a) : zkc::fe_inv(a);
+      memcpy(out + 4 * i, r.v, 32);
+    } else {
+      zkc::Fq a; memcpy(a.v, in + 4 * i, 32);
+      if (zkc::geq_mod<zkc::FqP>(a.v)) return 1;
+      const zkc::Fq r = which ? zkc::fe_inv_fermat_host(a) : zkc::fe_inv(a);
+      memcpy(out + 4 * i, r.v, 32);
+    }
+  }
+  return 0;
+}

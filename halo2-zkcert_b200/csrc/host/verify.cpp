@@ -347,8 +347,9 @@ extern "C" int zkc_verify(const uint8_t* cs_blob, size_t cs_len, const zkc_g1_af
       }
       G1Affine inner = g1_identity();
       Fr r_inner = ZERO, py = ONE;
+      const std::vector<std::vector<Fr>> basis = lagrange_basis(sets[i].points);
       for (size_t c = 0; c < sets[i].ids.size(); ++c) {
-        const std::vector<Fr> r_x = lagrange_interpolate(sets[i].points, sets[i].evals[c]);
+        const std::vector<Fr> r_x = interpolate_with_basis(basis, sets[i].evals[c]);
         r_inner = fe_add(r_inner, fe_mul(py, eval_small(r_x, u)));
         inner = g1_add(inner, g1_mul(comms[sets[i].ids[c]], py));
         py = fe_mul(py, yy);

@@ -887,8 +887,10 @@ extern "C" int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, i
     build_rotation_sets(queries, sets, super_points);
     const Fr v = tr.squeeze_challenge();
     std::vector<std::vector<std::vector<Fr>>> rcoef(sets.size());   // [set][poly] -> r(X) coefficients
-    for (size_t s = 0; s < sets.size(); ++s)
-      for (size_t p = 0; p < sets[s].polys.size(); ++p) rcoef[s].push_back(lagrange_interpolate(sets[s].points, sets[s].evals[p]));
+    for (size_t s = 0; s < sets.size(); ++s) {
+      const std::vector<std::vector<Fr>> basis = zkc::host::lagrange_basis(sets[s].points);   // one inversion per point, shared by the set
+      for (size_t p = 0; p < sets[s].polys.size(); ++p) rcoef[s].push_back(zkc::host::interpolate_with_basis(basis, sets[s].evals[p]));
+    }
     // h(X) = sum_i v^i * ( sum_j y^j (p_ij - r_ij) ) / Z_i: numerators per set, then one batched division
     // launch per "round" (the r-th root of every set that still has one), then one linear combination
     Fr* setbuf;

@@ -207,6 +207,9 @@ void zkc_seed_from_u64(uint64_t state, uint8_t seed[32]);
 /* the transcripts' host hashes: kind 0 = Blake2b-512 with a 16-byte personalisation (NULL = none; halo2 uses
  * "Halo2-Transcript"), 64 bytes out; kind 1 = Keccak-256, 32 bytes out.  No device work. */
 int zkc_host_hash(int kind, const uint8_t* personal16, const uint8_t* data, size_t len, uint8_t* out);
+/* host field inversion (Montgomery in / out), for cross-checks: field 0 = Fr, 1 = Fq; which 0 = the host driver's fe_inv (binary
+ * extended Euclid), 1 = the Fermat ladder.  Returns non-zero on a non-canonical input. */
+int zkc_host_fe_inv(int field, int which, const uint64_t* in, uint64_t* out, size_t n);
 /* Grain-generated Poseidon parameters of transcript kind 3 (canonical little-endian): 65 x 3 round constants, 3 x 3 MDS. */
 int zkc_poseidon_spec(zkc_fr* constants, zkc_fr* mds);
 
