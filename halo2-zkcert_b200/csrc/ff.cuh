@@ -296,27 +296,51 @@ template <class P> ZKC_HD Fe<P> fe_pow_u64(Fe<P> x, u64 e) {
 // sets).  Works on the Montgomery residue as a plain integer: (aR)^-1 = a^-1 R^-1, then two products by R^2 give a^-1 R.
 template <class P> inline Fe<P> fe_inv_host(const Fe<P>& a) {
   if (fe_is_zero(a)) return a;
+  typedef unsigned __int128 u128;
   struct U { uint64_t l[4]; };
   auto load = [](const uint32_t* v) { U r; for (int i = 0; i < 4; ++i) r.l[i] = (uint64_t)v[2 * i] | ((uint64_t)v[2 * i + 1] << 32); return r; };
   auto is_one = [](const U& x) { return x.l[0] == 1 && !(x.l[1] | x.l[2] | x.l[3]); };
   auto geq = [](const U& x, const U& y) { for (int i = 3; i >= 0; --i) { if (x.l[i] != y.l[i]) return x.l[i] > y.l[i]; } return true; };
-  auto sub = [](U& x, const U& y) { unsigned __int128 bw = 0; for (int i = 0; i < 4; ++i) { unsigned __int128 d = (unsigned __int128)x.l[i] - y.l[i] - (uint64_t)bw; x.l[i] = (uint64_t)d; bw = (d >> 64) & 1; } };
-  auto add = [](U& x, const U& y) { unsigned __int128 c = 0; for (int i = 0; i < 4; ++i) { c += (unsigned __int128)x.l[i] + y.l[i]; x.l[i] = (uint64_t)c; c >>= 64; } };
-  auto shr1 = [](U& x) { for (int i = 0; i < 3; ++i) x.l[i] = (x.l[i] >> 1) | (x.l[i + 1] << 63); x.l[3] >>= 1; };
+  auto sub = [](U& x, const U& y) { uint64_t bw = 0; for (int i = 0; i < 4; ++i) { const u128 d = (u128)x.l[i] - y.l[i] - bw; x.l[i] = (uint64_t)d; bw = (uint64_t)(d >> 64) & 1; } };
+  auto add = [](U& x, const U& y) { u128 c = 0; for (int i = 0; i < 4; ++i) { c += (u128)x.l[i] + y.l[i]; x.l[i] = (uint64_t)c; c >>= 64; } };
   uint32_t mw[8];
   for (int i = 0; i < 8; ++i) mw[i] = P::M(i);
   const U m = load(mw);
+  // -m^-1 mod 2^64 (one Newton step from the 32-bit Montgomery constant)
+  uint64_t minv = (uint64_t)0 - (uint64_t)P::INV;
+  minv = minv * (2 - m.l[0] * minv);
+  const uint64_t neg_minv = (uint64_t)0 - minv;
+  // x >>= t for 1 <= t <= 63
+  auto shr = [](U& x, int t) { for (int i = 0; i < 3; ++i) x.l[i] = (x.l[i] >> t) | (x.l[i + 1] << (64 - t)); x.l[3] >>= t; };
+  // x / 2^t mod m for x < m: add the multiple k*m that clears the low t bits, then shift (the sum stays below 2^t * m)
+  auto div2t = [&](U& x, int t) {
+    const uint64_t k = (x.l[0] * neg_minv) & (((uint64_t)1 << t) - 1);
+    uint64_t w[5];
+    u128 c = 0;
+    for (int i = 0; i < 4; ++i) { c += (u128)k * m.l[i] + x.l[i]; w[i] = (uint64_t)c; c >>= 64; }
+    w[4] = (uint64_t)c;
+    for (int i = 0; i < 4; ++i) x.l[i] = (w[i] >> t) | (w[i + 1] << (64 - t));
+  };
+  // strip the factors of two of an even, non-zero u, keeping x * a = u (mod m)
+  auto make_odd = [&](U& u, U& x) {
+    while (!(u.l[0] & 1)) {
+      int t = u.l[0] ? __builtin_ctzll(u.l[0]) : 63;
+      if (t > 63) t = 63;
+      shr(u, t);
+      div2t(x, t);
+    }
+  };
+  auto sub_mod = [&](U& x, const U& y) { if (!geq(x, y)) add(x, m); sub(x, y); };   // x - y mod m for x, y < m
   U u = load(a.v), v = m, x1{{1, 0, 0, 0}}, x2{{0, 0, 0, 0}};
-  auto halve_mod = [&](U& x) { if (x.l[0] & 1) add(x, m); shr1(x); };          // x / 2 mod m (m < 2^254: no overflow)
-  auto sub_mod = [&](U& x, const U& y) { if (!geq(x, y)) add(x, m); sub(x, y); };  // x - y mod m for x, y < m
-  while (!is_one(u) && !is_one(v)) {
-    while (!(u.l[0] & 1)) { shr1(u); halve_mod(x1); }
-    while (!(v.l[0] & 1)) { shr1(v); halve_mod(x2); }
-    if (geq(u, v)) { sub(u, v); sub_mod(x1, x2); } else { sub(v, u); sub_mod(x2, x1); }
+  make_odd(u, x1);
+  for (;;) {
+    if (is_one(u)) break;
+    if (is_one(v)) { x1 = x2; break; }
+    if (geq(u, v)) { sub(u, v); sub_mod(x1, x2); make_odd(u, x1); }
+    else { sub(v, u); sub_mod(x2, x1); make_odd(v, x2); }
   }
-  const U& x = is_one(u) ? x1 : x2;
   Fe<P> t;
-  for (int i = 0; i < 4; ++i) { t.v[2 * i] = (uint32_t)x.l[i]; t.v[2 * i + 1] = (uint32_t)(x.l[i] >> 32); }
+  for (int i = 0; i < 4; ++i) { t.v[2 * i] = (uint32_t)x1.l[i]; t.v[2 * i + 1] = (uint32_t)(x1.l[i] >> 32); }
   const Fe<P> r2 = fe_r2<P>();
   return fe_mul(fe_mul(t, r2), r2);
 }
