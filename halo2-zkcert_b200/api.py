@@ -375,6 +375,20 @@ class ProveOpts(C.Structure):
                 ("point_format", C.c_int), ("rng_kind", C.c_int), ("rng_seed", C.c_uint8 * 32)]
 
 
+def _prove_opts(transcript="blake2b", multiopen="shplonk", advice_blinding="axiom", blind_draws=False, point_format=0, rng="chacha20",
+                rng_seed=bytes(32)):
+    """zkc_prove_opts from the reference's vocabulary (transcript / multiopen names, OPEN switches of SURVEY 8c)"""
+    o = ProveOpts()
+    o.transcript = {"blake2b": 0, "keccak": 1, "evm": 2, "poseidon": 3}[transcript]
+    o.multiopen = {"shplonk": 0, "gwc": 1}[multiopen]
+    o.advice_blinding = {"axiom": 0, "pse": 1}[advice_blinding]
+    o.blind_draws = 1 if blind_draws else 0
+    o.point_format = point_format
+    o.rng_kind = {"chacha20": 0, "std": 1, "chacha12": 1}[rng]
+    o.rng_seed[:] = list(rng_seed)
+    return o
+
+
 class ProvingKey:
     """halo2_proofs::plonk::ProvingKey resident on the device (zkc_pk).
 
@@ -418,14 +432,7 @@ def create_proof(pk, advice, instances, rng_seed, transcript="blake2b", multiope
     torch CUDA tensor (already resident); instances: list of (len, 4) Montgomery arrays; rng_seed: 32
     bytes for ChaCha20Rng::from_seed.  Returns the proof bytes."""
     ctx = pk.ctx
-    o = ProveOpts()
-    o.transcript = {"blake2b": 0, "keccak": 1, "evm": 2, "poseidon": 3}[transcript]
-    o.multiopen = {"shplonk": 0, "gwc": 1}[multiopen]
-    o.advice_blinding = {"axiom": 0, "pse": 1}[advice_blinding]
-    o.blind_draws = 1 if blind_draws else 0
-    o.point_format = point_format
-    o.rng_kind = {"chacha20": 0, "std": 1, "chacha12": 1}[rng]
-    o.rng_seed[:] = list(rng_seed)
+    o = _prove_opts(transcript, multiopen, advice_blinding, blind_draws, point_format, rng, rng_seed)
     on_dev = hasattr(advice, "is_cuda")
     if on_dev:
         adv_ptr = _dp(advice)
@@ -509,10 +516,7 @@ def verify_proof(cs, fixed_commitments, sigma_commitments, transcript_repr, g1_g
     inst = [_np(i, 4) if len(i) else np.zeros((0, 4), dtype=np.uint64) for i in instances]
     ptrs = (C.c_void_p * max(len(inst), 1))(*[i.ctypes.data for i in inst])
     lens = (C.c_size_t * max(len(inst), 1))(*[i.shape[0] for i in inst])
-    o = ProveOpts()
-    o.transcript = {"blake2b": 0, "keccak": 1, "evm": 2, "poseidon": 3}[transcript]
-    o.multiopen = {"shplonk": 0, "gwc": 1}[multiopen]
-    o.point_format = point_format
+    o = _prove_opts(transcript, multiopen, point_format=point_format)
     buf = (C.c_uint8 * max(len(proof), 1)).from_buffer_copy(bytes(proof) or b"\0")
     ok = C.c_int(0)
     st = lib().zkc_verify(blob, C.c_size_t(len(blob)), _hp(f), _hp(sg), _hp(_np(transcript_repr, 4)), _hp(_np(g1_gen, 8)), _hp(_np(g2, 16)),
@@ -557,14 +561,7 @@ def create_proof_compact(pk, compact, instances, rng_seed, transcript="blake2b",
                          blind_draws=False, point_format=0, rng="chacha20"):
     """create_proof with the witness handed over in compact host form (CompactAdvice)"""
     ctx = pk.ctx
-    o = ProveOpts()
-    o.transcript = {"blake2b": 0, "keccak": 1, "evm": 2, "poseidon": 3}[transcript]
-    o.multiopen = {"shplonk": 0, "gwc": 1}[multiopen]
-    o.advice_blinding = {"axiom": 0, "pse": 1}[advice_blinding]
-    o.blind_draws = 1 if blind_draws else 0
-    o.point_format = point_format
-    o.rng_kind = {"chacha20": 0, "std": 1, "chacha12": 1}[rng]
-    o.rng_seed[:] = list(rng_seed)
+    o = _prove_opts(transcript, multiopen, advice_blinding, blind_draws, point_format, rng, rng_seed)
     cols = (AdviceColumn * max(len(compact.columns), 1))()
     for i, (kind, arr) in enumerate(compact.columns):
         cols[i].kind = kind
