@@ -302,3 +302,22 @@ def test_host_field_inversion_matches_bigint_and_fermat():
         assert L.zkc_host_fe_inv(field, 1, a.ctypes.data_as(C.c_void_p), out1.ctypes.data_as(C.c_void_p), C.c_size_t(len(vals))) == 0
         assert np.array_equal(out0, out1)
         assert back(out0) == [pow(v, -1, mod) if v else 0 for v in vals]
+
+
+def test_rust_bindings_are_in_sync_with_the_header():
+    """integration/zkcert_cuda_sys.rs (tools/gen_rust_bindings.py) declares every function of include/zkcert_cuda.h with the
+    committed text equal to a fresh generation"""
+    import importlib.util
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_gen_rs", os.path.join(root, "tools", "gen_rust_bindings.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    committed = open(os.path.join(root, "integration", "zkcert_cuda_sys.rs")).read()
+    assert committed == gen.generate()
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "zkcert_cuda.h")).read(), flags=re.S)
+    names = set(re.findall(r"\b(zkc_[a-z0-9_]+)\s*\(", header))
+    declared = set(re.findall(r"pub fn (zkc_[a-z0-9_]+)\(", committed))
+    assert names == declared
+    assert "instances: *const *const Fr" in committed and "-> *const c_char" in committed
