@@ -6,6 +6,11 @@ commitments are independent, and an MSM splits by point range exactly as the CPU
 splits across threads.  The only exchange is the gather of results: proof bytes (a few KB) or one
 partial sum per rank (96 B), done with all_gather on whatever backend the group uses (NCCL on the
 GPUs, gloo in the CPU tests).
+
+ONE proof spread over several GPUs (MSM by point range, transforms by column, h(X) by row block) is not
+orchestrated from here: it lives inside the library (`csrc/dist.cu`, `zkc_team_*`, `Context.team_init`),
+where the collectives run on the streams of the kernels they depend on.  The helpers below remain the
+operator-level building blocks (sharded MSM, four-step NTT) and the proof-chain distributor.
 """
 import torch.distributed as dist
 
