@@ -321,3 +321,23 @@ def test_rust_bindings_are_in_sync_with_the_header():
     declared = set(re.findall(r"pub fn (zkc_[a-z0-9_]+)\(", committed))
     assert names == declared
     assert "instances: *const *const Fr" in committed and "-> *const c_char" in committed
+
+
+def test_c_client_links_and_runs_host_entry_points(tmp_path):
+    """include/zkcert_cuda.h is plain C99 and libzkcert_cuda.so links from C: tests/cabi_host.c calls the host entry points and
+    checks that the device ones fail loudly here (no GPU, no CPU fallback)"""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    pkg().lib()
+    libdir = os.path.join(root, "halo2-zkcert_b200")
+    exe = str(tmp_path / "cabi_host")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", os.path.join(root, "tests", "cabi_host.c"), "-o", exe,
+                           "-L" + libdir, "-lzkcert_cuda", "-Wl,-rpath," + libdir])
+    import torch
+    args = [exe] + (["--gpu"] if torch.cuda.is_available() else [])
+    out = subprocess.run(args, capture_output=True, text=True)
+    assert out.returncode == 0 and "cabi_host ok" in out.stdout, out.stderr
