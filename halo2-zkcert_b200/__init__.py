@@ -9,5 +9,5 @@ The directory name contains a hyphen, so import it through `__graft_entry__.load
 `importlib`), which registers it as the module `halo2_zkcert_b200`.
 """
 from . import api, circuit, dist, synth, workload  # noqa: F401
-from .api import (CompactAdvice, ZkcError, Context, create_proof_compact, EvaluationDomain, ParamsKZG, ProvingKey, best_fft, best_multiexp, create_proof,  # noqa: F401
+from .api import (CompactAdvice, ProverSession, RandomPolySpec, ZkcError, Context, create_proof_compact, EvaluationDomain, ParamsKZG, ProvingKey, best_fft, best_multiexp, create_proof,  # noqa: F401
                   default_context, lib, lib_path, seed_from_u64, verify_proof)

@@ -47,6 +47,8 @@ def lib():
         _lib.zkc_ctx_launch_count.restype = C.c_uint64
         _lib.zkc_ctx_destroy.restype = None
         _lib.zkc_domain_free.restype = None
+        _lib.zkc_prove_end.restype = None
+        _lib.zkc_prove_end.argtypes = [C.c_void_p]
         if hasattr(_lib, "zkc_srs_free"):
             _lib.zkc_srs_free.restype = None
     return _lib
@@ -94,6 +96,11 @@ class Context:
 
     def sync(self):
         self.check(lib().zkc_ctx_sync(self._h))
+
+    def set_tunable(self, name, value):
+        """debug / sweep override on this ctx (zkc_ctx_set_tunable): msm_c, msm_c_pre, msm_T, ntt_two_pass_max,
+        stage_min_bytes (-1 = default), team_poison"""
+        self.check(lib().zkc_ctx_set_tunable(self._h, name.encode(), C.c_int64(int(value))))
 
     @property
     def launches(self):
@@ -372,11 +379,22 @@ class ParamsKZG:
 # ---- ProvingKey / create_proof --------------------------------------------------------------------
 class ProveOpts(C.Structure):
     _fields_ = [("transcript", C.c_int), ("multiopen", C.c_int), ("advice_blinding", C.c_int), ("blind_draws", C.c_int),
-                ("point_format", C.c_int), ("rng_kind", C.c_int), ("rng_seed", C.c_uint8 * 32)]
+                ("point_format", C.c_int), ("rng_kind", C.c_int), ("rng_seed", C.c_uint8 * 32), ("lookup_fill", C.c_int),
+                ("random_poly", C.c_int), ("random_poly_threads", C.c_uint32)]
+
+
+class RandomPoly(C.Structure):
+    """zkc_random_poly: the vanishing argument's random polynomial as the step API takes it"""
+    _fields_ = [("kind", C.c_int), ("scalars", C.c_void_p), ("seed", C.c_uint8 * 32), ("rng_kind", C.c_int), ("first_word", C.c_uint64),
+                ("seeds", C.c_void_p), ("nseeds", C.c_uint32), ("chunk_len", C.c_uint64)]
+
+
+LOOKUP_FILL = {"pse": 0, "axiom": 1}
+RANDOM_POLY = {"serial": 0, "chunked": 1}
 
 
 def _prove_opts(transcript="blake2b", multiopen="shplonk", advice_blinding="axiom", blind_draws=False, point_format=0, rng="chacha20",
-                rng_seed=bytes(32)):
+                rng_seed=bytes(32), lookup_fill="pse", random_poly="serial", random_poly_threads=1):
     """zkc_prove_opts from the reference's vocabulary (transcript / multiopen names, OPEN switches of SURVEY 8c)"""
     o = ProveOpts()
     o.transcript = {"blake2b": 0, "keccak": 1, "evm": 2, "poseidon": 3}[transcript]
@@ -386,7 +404,18 @@ def _prove_opts(transcript="blake2b", multiopen="shplonk", advice_blinding="axio
     o.point_format = point_format
     o.rng_kind = {"chacha20": 0, "std": 1, "chacha12": 1}[rng]
     o.rng_seed[:] = list(rng_seed)
+    o.lookup_fill = LOOKUP_FILL[lookup_fill]
+    o.random_poly = RANDOM_POLY[random_poly]
+    o.random_poly_threads = int(random_poly_threads)
     return o
+
+
+def _instances(cs, instances):
+    """ctypes views of the instance columns; upstream's Error::InvalidInstances when their number is not cs.num_instance_columns"""
+    inst = [_np(i, 4) if len(i) else np.zeros((0, 4), dtype=np.uint64) for i in instances]
+    ptrs = (C.c_void_p * max(len(inst), 1))(*[i.ctypes.data for i in inst])
+    lens = (C.c_size_t * max(len(inst), 1))(*[i.shape[0] for i in inst])
+    return inst, ptrs, lens, C.c_size_t(len(inst))
 
 
 class ProvingKey:
@@ -426,27 +455,128 @@ class ProvingKey:
         return f, s
 
 
-def create_proof(pk, advice, instances, rng_seed, transcript="blake2b", multiopen="shplonk", advice_blinding="axiom", blind_draws=False,
-                 point_format=0, rng="chacha20"):
-    """plonk::create_proof for one circuit.  advice: (num_advice * n, 4) Montgomery, numpy (host) or
-    torch CUDA tensor (already resident); instances: list of (len, 4) Montgomery arrays; rng_seed: 32
-    bytes for ChaCha20Rng::from_seed.  Returns the proof bytes."""
-    ctx = pk.ctx
-    o = _prove_opts(transcript, multiopen, advice_blinding, blind_draws, point_format, rng, rng_seed)
+def _advice_ptr(pk, advice):
     on_dev = hasattr(advice, "is_cuda")
     if on_dev:
-        adv_ptr = _dp(advice)
-    else:
-        advice = _np(advice, 4)
-        adv_ptr = _hp(advice)
-    inst = [_np(i, 4) if len(i) else np.zeros((0, 4), dtype=np.uint64) for i in instances]
-    ptrs = (C.c_void_p * max(len(inst), 1))(*[i.ctypes.data for i in inst])
-    lens = (C.c_size_t * max(len(inst), 1))(*[i.shape[0] for i in inst])
+        if advice.shape[0] != pk.cs.num_advice * pk.cs.n:
+            raise ValueError("advice: expected num_advice * n rows")
+        return advice, _dp(advice), 1
+    advice = _np(advice, 4)
+    if advice.shape[0] != pk.cs.num_advice * pk.cs.n:
+        raise ValueError("advice: expected num_advice * n rows")
+    return advice, _hp(advice), 0
+
+
+def create_proof(pk, advice, instances, rng_seed, transcript="blake2b", multiopen="shplonk", advice_blinding="axiom", blind_draws=False,
+                 point_format=0, rng="chacha20", lookup_fill="pse", random_poly="serial", random_poly_threads=1, ctx=None):
+    """plonk::create_proof for one circuit.  advice: (num_advice * n, 4) Montgomery, numpy (host) or
+    torch CUDA tensor (already resident); instances: list of (len, 4) Montgomery arrays; rng_seed: 32
+    bytes for ChaCha20Rng::from_seed.  Returns the proof bytes.  `ctx`: run on another zkc_ctx of the SAME device than the one
+    the key was loaded through (its own streams and scratch; the resident SRS / key are only read) — several proofs in flight."""
+    ctx = ctx or pk.ctx
+    o = _prove_opts(transcript, multiopen, advice_blinding, blind_draws, point_format, rng, rng_seed, lookup_fill, random_poly, random_poly_threads)
+    advice, adv_ptr, on_dev = _advice_ptr(pk, advice)
+    inst, ptrs, lens, ninst = _instances(pk.cs, instances)
     cap = 1 << 20
     buf = (C.c_uint8 * cap)()
     plen = C.c_size_t(0)
-    ctx.check(lib().zkc_prove(ctx._h, pk._h, adv_ptr, C.c_int(1 if on_dev else 0), ptrs, lens, C.byref(o), buf, C.c_size_t(cap), C.byref(plen)))
+    ctx.check(lib().zkc_prove(ctx._h, pk._h, adv_ptr, C.c_int(on_dev), ptrs, lens, ninst, C.byref(o), buf, C.c_size_t(cap), C.byref(plen)))
     return bytes(buf[:plen.value])
+
+
+class ProverSession:
+    """The step API of create_proof (zkc_prove_begin ... zkc_prove_end): the caller keeps the Fiat-Shamir transcript and the
+    RNG, the library does the O(n) work of each round.  Scalars go in and out as (m, 4) Montgomery arrays, points come back as
+    (m, 8) affine arrays (identity = zeros)."""
+
+    def __init__(self, pk, advice, instances, advice_tails=None, early_random=None):
+        self.pk, self.ctx = pk, pk.ctx
+        cs = pk.cs
+        advice, adv_ptr, on_dev = _advice_ptr(pk, advice)
+        inst, ptrs, lens, ninst = _instances(cs, instances)
+        tails = None if advice_tails is None else _np(advice_tails, 4)
+        self._keep = [advice, inst, tails, early_random]
+        self._h = C.c_void_p()
+        out = np.zeros((cs.num_advice, 8), dtype=np.uint64)
+        self.ctx.check(lib().zkc_prove_begin(self.ctx._h, pk._h, adv_ptr, C.c_int(on_dev), ptrs, lens, ninst, None if tails is None else _hp(tails),
+                                             None if early_random is None else C.byref(early_random._c), C.byref(self._h), _hp(out)))
+        self.advice_commitments = out
+
+    def lookups(self, theta, tails, lookup_fill="pse"):
+        out = np.zeros((2 * self.pk.num_lookups, 8), dtype=np.uint64)
+        tails = _np(tails, 4) if self.pk.num_lookups else np.zeros((1, 4), dtype=np.uint64)
+        self.ctx.check(lib().zkc_prove_lookups(self._h, _hp(_np(theta, 4)), _hp(tails), C.c_int(LOOKUP_FILL[lookup_fill]), _hp(out)))
+        return out
+
+    def products(self, beta, gamma, tails):
+        m = self.pk.num_sets + self.pk.num_lookups
+        out = np.zeros((m, 8), dtype=np.uint64)
+        tails = _np(tails, 4) if m else np.zeros((1, 4), dtype=np.uint64)
+        self.ctx.check(lib().zkc_prove_products(self._h, _hp(_np(beta, 4)), _hp(_np(gamma, 4)), _hp(tails), _hp(out)))
+        return out
+
+    def vanishing(self, random=None):
+        out = np.zeros((1, 8), dtype=np.uint64)
+        self._keep.append(random)
+        self.ctx.check(lib().zkc_prove_vanishing(self._h, None if random is None else C.byref(random._c), _hp(out)))
+        return out
+
+    def quotient(self, y):
+        out = np.zeros((self.pk.degree - 1, 8), dtype=np.uint64)
+        self.ctx.check(lib().zkc_prove_quotient(self._h, _hp(_np(y, 4)), _hp(out)))
+        return out
+
+    def evals(self, x):
+        cap = 1 << 14
+        out = np.zeros((cap, 4), dtype=np.uint64)
+        cnt = C.c_size_t(0)
+        self.ctx.check(lib().zkc_prove_evals(self._h, _hp(_np(x, 4)), _hp(out), C.c_size_t(cap), C.byref(cnt)))
+        return out[:cnt.value].copy()
+
+    def open_shplonk_h(self, y, v):
+        out = np.zeros((1, 8), dtype=np.uint64)
+        self.ctx.check(lib().zkc_prove_open_shplonk_h(self._h, _hp(_np(y, 4)), _hp(_np(v, 4)), _hp(out)))
+        return out
+
+    def open_shplonk_w(self, u):
+        out = np.zeros((1, 8), dtype=np.uint64)
+        self.ctx.check(lib().zkc_prove_open_shplonk_w(self._h, _hp(_np(u, 4)), _hp(out)))
+        return out
+
+    def open_gwc(self, v):
+        cap = 256
+        out = np.zeros((cap, 8), dtype=np.uint64)
+        cnt = C.c_size_t(0)
+        self.ctx.check(lib().zkc_prove_open_gwc(self._h, _hp(_np(v, 4)), _hp(out), C.c_size_t(cap), C.byref(cnt)))
+        return out[:cnt.value].copy()
+
+    def end(self):
+        if self._h:
+            lib().zkc_prove_end(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.end()
+        except Exception:
+            pass
+
+
+class RandomPolySpec:
+    """zkc_random_poly builder: scalars (n, 4) | keystream (seed, rng, first_word) | chunk seeds (list of 32-byte seeds, chunk_len)"""
+
+    def __init__(self, scalars=None, seed=None, rng="chacha20", first_word=0, seeds=None, chunk_len=0):
+        c = RandomPoly()
+        if scalars is not None:
+            self._a = _np(scalars, 4)
+            c.kind, c.scalars = 0, self._a.ctypes.data
+        elif seeds is not None:
+            self._a = np.frombuffer(b"".join(seeds), dtype=np.uint8).copy()
+            c.kind, c.seeds, c.nseeds, c.chunk_len = 2, self._a.ctypes.data, len(seeds), int(chunk_len)
+        else:
+            c.kind, c.rng_kind, c.first_word = 1, (0 if rng == "chacha20" else 1), int(first_word)
+            c.seed[:] = list(seed)
+        self._c = c
 
 
 # ---- ParamsKZG files (host only) -----------------------------------------------------------------------------------
@@ -513,16 +643,14 @@ def verify_proof(cs, fixed_commitments, sigma_commitments, transcript_repr, g1_g
     blob = cs.serialize()
     f = _np(fixed_commitments, 8) if cs.num_fixed else np.zeros((0, 8), dtype=np.uint64)
     sg = _np(sigma_commitments, 8) if cs.permutation else np.zeros((0, 8), dtype=np.uint64)
-    inst = [_np(i, 4) if len(i) else np.zeros((0, 4), dtype=np.uint64) for i in instances]
-    ptrs = (C.c_void_p * max(len(inst), 1))(*[i.ctypes.data for i in inst])
-    lens = (C.c_size_t * max(len(inst), 1))(*[i.shape[0] for i in inst])
+    inst, ptrs, lens, ninst = _instances(cs, instances)
     o = _prove_opts(transcript, multiopen, point_format=point_format)
     buf = (C.c_uint8 * max(len(proof), 1)).from_buffer_copy(bytes(proof) or b"\0")
     ok = C.c_int(0)
     st = lib().zkc_verify(blob, C.c_size_t(len(blob)), _hp(f), _hp(sg), _hp(_np(transcript_repr, 4)), _hp(_np(g1_gen, 8)), _hp(_np(g2, 16)),
-                          _hp(_np(s_g2, 16)), ptrs, lens, buf, C.c_size_t(len(proof)), C.byref(o), C.byref(ok))
+                          _hp(_np(s_g2, 16)), ptrs, lens, ninst, buf, C.c_size_t(len(proof)), C.byref(o), C.byref(ok))
     if st != 0:
-        raise ZkcError(st, "zkc_verify")
+        raise ZkcError(st, "zkc_verify: instances.len() != cs.num_instance_columns" if st == 10 else "zkc_verify")
     return bool(ok.value)
 
 
@@ -558,21 +686,21 @@ class CompactAdvice:
 
 
 def create_proof_compact(pk, compact, instances, rng_seed, transcript="blake2b", multiopen="shplonk", advice_blinding="axiom",
-                         blind_draws=False, point_format=0, rng="chacha20"):
+                         blind_draws=False, point_format=0, rng="chacha20", lookup_fill="pse", random_poly="serial", random_poly_threads=1):
     """create_proof with the witness handed over in compact host form (CompactAdvice)"""
     ctx = pk.ctx
-    o = _prove_opts(transcript, multiopen, advice_blinding, blind_draws, point_format, rng, rng_seed)
+    if len(compact.columns) != pk.cs.num_advice:
+        raise ValueError("compact witness: expected num_advice columns")
+    o = _prove_opts(transcript, multiopen, advice_blinding, blind_draws, point_format, rng, rng_seed, lookup_fill, random_poly, random_poly_threads)
     cols = (AdviceColumn * max(len(compact.columns), 1))()
     for i, (kind, arr) in enumerate(compact.columns):
         cols[i].kind = kind
         cols[i].data = arr.ctypes.data
-    inst = [_np(i, 4) if len(i) else np.zeros((0, 4), dtype=np.uint64) for i in instances]
-    ptrs = (C.c_void_p * max(len(inst), 1))(*[i.ctypes.data for i in inst])
-    lens = (C.c_size_t * max(len(inst), 1))(*[i.shape[0] for i in inst])
+    inst, ptrs, lens, ninst = _instances(pk.cs, instances)
     cap = 1 << 20
     buf = (C.c_uint8 * cap)()
     plen = C.c_size_t(0)
-    ctx.check(lib().zkc_prove_compact(ctx._h, pk._h, cols, ptrs, lens, C.byref(o), buf, C.c_size_t(cap), C.byref(plen)))
+    ctx.check(lib().zkc_prove_compact(ctx._h, pk._h, cols, ptrs, lens, ninst, C.byref(o), buf, C.c_size_t(cap), C.byref(plen)))
     return bytes(buf[:plen.value])
 
 

@@ -18,6 +18,15 @@ struct DevBuf {
   size_t bytes = 0;
 };
 
+// Debug / sweep overrides, per ctx.  The environment (ZKC_MSM_C, ZKC_MSM_C_PRE, ZKC_MSM_T, ZKC_NTT_TWO_PASS_MAX,
+// ZKC_STAGE_MIN_BYTES, ZKC_TEAM_POISON) is read ONCE, when the ctx is created — never on the proving path; tests and the
+// sweeps under tools/ change a value on a live ctx with zkc_ctx_set_tunable.
+struct Tunables {
+  int msm_c = 0, msm_c_pre = 0, msm_T = 0, ntt_two_pass_max = 0;   // 0 = library default
+  size_t stage_min_bytes = (size_t)4 << 20;   // host witnesses at least this large are uploaded in stages on a copy stream
+  bool team_poison = false;                   // team proving: rows a rank never receives are filled with 0xff
+};
+
 }  // namespace zkc
 
 // The opaque context: one per GPU.  All public calls lock `mu` (thread-safe per ctx).
@@ -32,6 +41,8 @@ struct zkc_ctx {
   bool side_pending = false;
   bool overlap = true;                // zkc_ctx_set_overlap: 0 serialises side work on the main stream (clean per-kernel timing)
   std::string err;
+  zkc::Tunables tune;
+  struct zkc_prover* active_prover = nullptr;   // step API: one create_proof session per ctx at a time
   uint64_t launches = 0;
   std::recursive_mutex mu;
   int sm_count = 148;

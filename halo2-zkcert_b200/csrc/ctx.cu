@@ -1,9 +1,36 @@
 // Context, device-memory helpers and element-wise Fr/Fq vector kernels of libzkcert_cuda.so.
 #include "common.cuh"
 
+#include <cstdlib>
+
 using namespace zkc;
 
-extern "C" const char* zkc_version(void) { return "halo2-zkcert_b200 0.1 (sm_100a)"; }
+namespace {
+int env_int(const char* name, int lo, int hi) { const char* e = getenv(name); if (!e) return 0; const int x = atoi(e); return x >= lo && x <= hi ? x : 0; }
+void tunables_from_env(Tunables& v) {
+  v.msm_c = env_int("ZKC_MSM_C", 3, 20); v.msm_c_pre = env_int("ZKC_MSM_C_PRE", 3, 20); v.msm_T = env_int("ZKC_MSM_T", 4, 128);
+  v.ntt_two_pass_max = env_int("ZKC_NTT_TWO_PASS_MAX", 12, 22);
+  if (const char* e = getenv("ZKC_STAGE_MIN_BYTES")) v.stage_min_bytes = (size_t)strtoull(e, nullptr, 10);
+  v.team_poison = getenv("ZKC_TEAM_POISON") != nullptr;
+}
+}  // namespace
+
+extern "C" int zkc_ctx_set_tunable(zkc_ctx* c, const char* name, int64_t value) {
+  if (!c || !name) return ZKC_ERR_BAD_ARG;
+  CtxLock lock(c);
+  const std::string n(name);
+  Tunables& t = c->tune;
+  if (n == "msm_c") t.msm_c = (int)value;
+  else if (n == "msm_c_pre") t.msm_c_pre = (int)value;
+  else if (n == "msm_T") t.msm_T = (int)value;
+  else if (n == "ntt_two_pass_max") t.ntt_two_pass_max = (int)value;
+  else if (n == "stage_min_bytes") t.stage_min_bytes = value < 0 ? ((size_t)4 << 20) : (size_t)value;
+  else if (n == "team_poison") t.team_poison = value != 0;
+  else return set_err(c, ZKC_ERR_BAD_ARG, "zkc_ctx_set_tunable: unknown name " + n);
+  return ZKC_OK;
+}
+
+extern "C" const char* zkc_version(void) { return "halo2-zkcert_b200 0.2 (sm_100a)"; }
 
 extern "C" int zkc_ctx_create(int device, zkc_ctx** out) {
   if (!out) return ZKC_ERR_BAD_ARG;
@@ -15,6 +42,7 @@ extern "C" int zkc_ctx_create(int device, zkc_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) return ZKC_ERR_CUDA;
   zkc_ctx* c = new zkc_ctx();
   c->dev = device;
+  tunables_from_env(c->tune);
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ZKC_ERR_CUDA; }
   c->stream = c->own_stream;
   if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||

@@ -138,6 +138,13 @@ Fr ChaCha20Rng::fr_random() {
   for (int i = 0; i < 8; ++i) { uint64_t v = next_u64(); memcpy(b + 8 * i, &v, 8); }
   return fr_from_u512_le(b);
 }
+void ChaCha20Rng::seek(uint64_t word) {
+  counter = word / 16; pos = 16;
+  if (word % 16) { chacha_block(key, counter++, block, double_rounds); pos = (int)(word % 16); }
+}
+void ChaCha20Rng::fill_bytes(uint8_t* out, size_t nbytes) {
+  for (size_t i = 0; i + 4 <= nbytes; i += 4) { const uint32_t w = next_u32(); memcpy(out + i, &w, 4); }
+}
 void seed_from_u64(uint64_t state, uint8_t seed[32]) {
   const uint64_t MUL = 6364136223846793005ULL, INC = 11634580027462260723ULL;
   for (int i = 0; i < 8; ++i) {

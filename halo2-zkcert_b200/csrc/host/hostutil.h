@@ -41,6 +41,11 @@ struct ChaCha20Rng {
   uint32_t next_u32();
   uint64_t next_u64();
   Fr fr_random();   // halo2curves Fr::random: 8 x next_u64 as a 512-bit LE integer, reduced mod r
+  // The generator is a linear stream of 32-bit keystream words (rand_core BlockRng): next_u64 takes two, Fr::random
+  // sixteen, fill_bytes(32) eight.  word_pos() is the index of the next unread word; seek() moves there.
+  uint64_t word_pos() const { return counter * 16 - (uint64_t)(16 - pos); }
+  void seek(uint64_t word);
+  void fill_bytes(uint8_t* out, size_t nbytes);   // nbytes a multiple of 4 (whole words)
 };
 // rand_core SeedableRng::seed_from_u64 (PCG32 expansion)
 void seed_from_u64(uint64_t state, uint8_t seed[32]);

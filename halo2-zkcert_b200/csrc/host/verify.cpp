@@ -28,6 +28,7 @@ Fr fr_u64(uint64_t x) { Fr t = fe_zero<FrP>(); t.v[0] = (uint32_t)x; t.v[1] = (u
 G1Affine g1_mul(const G1Affine& p, const Fr& k_mont) {
   const Fr k = fe_to_canonical(k_mont);
   G1Xyzz acc = xyzz_identity();
+  if (affine_is_identity(p) || fe_is_zero(k)) return xyzz_to_affine(acc);   // xyzz_madd's contract: the affine operand is not the identity
   for (int i = 255; i >= 0; --i) {
     acc = xyzz_dbl(acc);
     if ((k.v[i >> 5] >> (i & 31)) & 1) xyzz_madd(acc, p, false);
@@ -117,8 +118,8 @@ extern "C" int zkc_pairing_check(const zkc_g1_affine* g1s, const zkc_g2_affine* 
 
 extern "C" int zkc_verify(const uint8_t* cs_blob, size_t cs_len, const zkc_g1_affine* fixed_comm, const zkc_g1_affine* sigma_comm,
                           const zkc_fr* transcript_repr, const zkc_g1_affine* g1_gen, const zkc_g2_affine* g2_abi, const zkc_g2_affine* s_g2_abi,
-                          const zkc_fr* const* instances, const size_t* instance_lens, const uint8_t* proof, size_t proof_len,
-                          const zkc_prove_opts* opts, int* ok) {
+                          const zkc_fr* const* instances, const size_t* instance_lens, size_t num_instance_columns, const uint8_t* proof,
+                          size_t proof_len, const zkc_prove_opts* opts, int* ok) {
   if (!cs_blob || !transcript_repr || !g1_gen || !g2_abi || !s_g2_abi || !proof || !opts || !ok) return ZKC_ERR_BAD_ARG;
   *ok = 0;
   if (opts->transcript < 0 || opts->transcript > 3 || opts->multiopen < 0 || opts->multiopen > 1) return ZKC_ERR_BAD_ARG;
@@ -126,6 +127,7 @@ extern "C" int zkc_verify(const uint8_t* cs_blob, size_t cs_len, const zkc_g1_af
   std::string perr;
   if (!parse_cs(cs_blob, cs_len, cs, perr)) return ZKC_ERR_BAD_ARG;
   if ((cs.num_fixed && !fixed_comm) || (!cs.perm.empty() && !sigma_comm) || (cs.num_instance && (!instances || !instance_lens))) return ZKC_ERR_BAD_ARG;
+  if (num_instance_columns != cs.num_instance) return ZKC_ERR_INVALID_INSTANCES;   // plonk::Error::InvalidInstances upstream
   const uint64_t n = cs.n();
   const uint32_t bf = cs.blinding_factors, nsets = cs.nsets(), L = (uint32_t)cs.lookups.size();
   if (n < bf + 3) return ZKC_ERR_NOT_ENOUGH_ROWS;
@@ -392,7 +394,9 @@ extern "C" int zkc_verify(const uint8_t* cs_blob, size_t cs_len, const zkc_g1_af
       pu = fe_mul(pu, u);
     }
   }
-  if (tr.in_pos != proof_len) return ZKC_OK;   // trailing bytes
+  // Deliberately stricter than upstream: halo2's verify_proof never checks that the transcript is exhausted; a byte stream
+  // with trailing garbage is rejected here (documented in DESIGN.md / INTEGRATION.md).
+  if (tr.in_pos != proof_len) return ZKC_OK;
   std::vector<std::pair<G1Affine, G2Affine>> pairs;
   pairs.push_back({left, s_g2});
   pairs.push_back({g1_neg(right), g2});

@@ -285,11 +285,8 @@ static void xyzz_to_abi(const G1Xyzz& p, zkc_g1* out) {
 
 int u32_scan(zkc_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* total_dev);   // poly.cu
 
-uint32_t msm_pick_c(uint64_t n, bool precomputed) {
-  if (const char* e = getenv(precomputed ? "ZKC_MSM_C_PRE" : "ZKC_MSM_C")) {
-    int v = atoi(e);
-    if (v >= 3 && v <= 20) { const int W = (255 + v - 1) / v; return (uint32_t)((255 + W - 1) / W); }
-  }
+uint32_t msm_pick_c(const zkc_ctx* ctx, uint64_t n, bool precomputed) {
+  if (const int v = precomputed ? ctx->tune.msm_c_pre : ctx->tune.msm_c) { const int W = (255 + v - 1) / v; return (uint32_t)((255 + W - 1) / W); }
   uint32_t lg = 0;
   while ((1ull << (lg + 1)) <= n) ++lg;
   // measured on B200: shared-bucket (precomputed) layout wants ~4-8 partials per bucket for the
@@ -302,7 +299,7 @@ uint32_t msm_pick_c(uint64_t n, bool precomputed) {
   return (uint32_t)((255 + W - 1) / W);   // same number of windows, evenly filled (see msm_geom)
 }
 
-MsmGeom msm_geom(uint64_t n, uint32_t ncols, uint32_t c, bool precomputed) {
+MsmGeom msm_geom(const zkc_ctx* ctx, uint64_t n, uint32_t ncols, uint32_t c, bool precomputed) {
   MsmGeom g;
   g.W = (255 + c - 1) / c;
   c = (255 + g.W - 1) / g.W;   // same window count, evenly filled: a nearly empty top window would pile n/2^few entries on a handful of buckets
@@ -311,7 +308,7 @@ MsmGeom msm_geom(uint64_t n, uint32_t ncols, uint32_t c, bool precomputed) {
   // entries per accumulate thread (B200 sweep): short chunks keep more warps in flight (T=8 reaches
   // 0.99 of the IMAD.WIDE peak) but multiply the partials the gather phase must fold; 32 / 64 minimise the sum
   uint32_t T = e >= (1ull << 26) ? 64 : 32;
-  if (const char* ev = getenv("ZKC_MSM_T")) { int v = atoi(ev); if (v >= 4 && v <= 128) T = (uint32_t)v; }
+  if (ctx->tune.msm_T) T = (uint32_t)ctx->tune.msm_T;
   while (T > 4 && e / T < 148ull * 512) T >>= 1;
   g.T = T;
   return g;
@@ -392,7 +389,7 @@ int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t
                 int result_slot, bool team) {
   team = team && team_active(ctx) && n >= (uint64_t)ctx->team_world;
   const int shards = team ? ctx->team_world : 1;
-  const MsmGeom g0 = msm_geom(n, nc, c, precomputed);
+  const MsmGeom g0 = msm_geom(ctx, n, nc, c, precomputed);
   const size_t ubytes = (size_t)nc * g0.sets * g0.c * sizeof(G1Xyzz), slot_bytes = (ubytes + 4 + 255) & ~(size_t)255;   // U, then the digit count
   char* dU;
   ZKC_TRY(scratch_reserve(ctx, SCR_MSM2, slot_bytes * shards, (void**)&dU));
@@ -403,7 +400,7 @@ int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t
     for (int r : team_ranks(ctx)) {
       uint64_t lo, hi;
       shard_range(n, shards, r, &lo, &hi);
-      MsmGeom g = msm_geom(hi - lo, nc, c, precomputed);
+      MsmGeom g = msm_geom(ctx, hi - lo, nc, c, precomputed);
       g.sstride = n; g.bstride = n;
       char* slot = dU + (size_t)r * slot_bytes;
       ZKC_TRY(msm_kernels(ctx, scalars + lo, bases + lo, g, (G1Xyzz*)slot, (uint32_t*)(slot + ubytes)));
@@ -461,7 +458,7 @@ int msm_run(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, 
   }
   if (n >= (1ull << 31) / 32) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: n too large");
   // bound memory: process columns in chunks
-  MsmGeom g1 = msm_geom(n, 1, c, precomputed);
+  MsmGeom g1 = msm_geom(ctx, n, 1, c, precomputed);
   const uint64_t per_col = g1.emax() * 12 + g1.nbtot() * (128 + 12) + (g1.nbtot() + g1.emax() / g1.T + 1) * 128;
   uint32_t chunk = (uint32_t)std::max<uint64_t>(1, (3ull << 30) / per_col);
   chunk = std::min(chunk, ncols);
@@ -566,7 +563,7 @@ static int srs_alloc(zkc_ctx* ctx, uint32_t k, zkc_srs** out) {
   // window width from the points ONE GPU walks: a team rank sees n / world points per commitment (point-range shards), and
   // the bucket phases (gather, reduce) do not shrink with the shard, so a team wants narrower windows than a single GPU
   const uint64_t n_eff = team_active(ctx) ? std::max<uint64_t>(s->n / (uint64_t)ctx->team_world, 1024) : s->n;
-  s->c = msm_pick_c(n_eff, true);
+  s->c = msm_pick_c(ctx, n_eff, true);
   s->W = (255 + s->c - 1) / s->c;
   for (int b = 0; b < 2; ++b) {
     cudaError_t e = cudaMalloc(&s->tab[b], (size_t)s->W * s->n * sizeof(G1Affine));
@@ -664,7 +661,7 @@ int srs_commit_dev(zkc_ctx* ctx, const zkc_srs* s, int basis, const Fr* polys, u
   if (len == s->n) return msm_run(ctx, polys, s->tab[basis], len, ncols, s->c, true, out, true);   // team: point-range shards
   // shorter polynomials: the window tables are laid out with stride n, so fall back to the generic
   // (non-precomputed) walk over the first `len` bases.
-  return msm_run(ctx, polys, s->tab[basis], len, ncols, msm_pick_c(len, false), false, out);
+  return msm_run(ctx, polys, s->tab[basis], len, ncols, msm_pick_c(ctx, len, false), false, out);
 }
 }  // namespace zkc
 
@@ -685,7 +682,7 @@ extern "C" int zkc_commit(zkc_ctx* ctx, const zkc_srs* s, int basis, const zkc_f
 extern "C" int zkc_msm_g1_dev(zkc_ctx* ctx, const zkc_fr* scalars, const zkc_g1_affine* bases, size_t n, uint32_t ncols, zkc_g1* out) {
   if (!ctx || !out || (n && (!scalars || !bases))) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_msm_g1_dev: bad arguments");
   CtxLock lock(ctx);
-  return msm_run(ctx, (const Fr*)scalars, (const G1Affine*)bases, n, ncols, msm_pick_c(n ? n : 1, false), false, out);
+  return msm_run(ctx, (const Fr*)scalars, (const G1Affine*)bases, n, ncols, msm_pick_c(ctx, n ? n : 1, false), false, out);
 }
 extern "C" int zkc_msm_g1(zkc_ctx* ctx, const zkc_fr* scalars, const zkc_g1_affine* bases, size_t n, zkc_g1* out) {
   if (!ctx || !out || (n && (!scalars || !bases))) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_msm_g1: bad arguments");
@@ -697,7 +694,7 @@ extern "C" int zkc_msm_g1(zkc_ctx* ctx, const zkc_fr* scalars, const zkc_g1_affi
     ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(ds, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(db, bases, n * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
   }
-  return msm_run(ctx, (const Fr*)ds, (const G1Affine*)db, n, 1, msm_pick_c(n ? n : 1, false), false, out);
+  return msm_run(ctx, (const Fr*)ds, (const G1Affine*)db, n, 1, msm_pick_c(ctx, n ? n : 1, false), false, out);
 }
 
 // Host-side epilogue of a point-sharded MSM: sum of `n` normalised Jacobian partial results,

@@ -261,7 +261,7 @@ int ntt_run(zkc_ctx* ctx, const Fr* src, uint64_t src_stride, Fr* dst, uint64_t 
   // through HBM; a tile is 2^11 elements, so two passes of a 2^22 transform read single 32-byte elements at large
   // strides (one DRAM sector each) — affordable because the transform is bound by the integer pipe, not by HBM.
   uint32_t two_pass_max = NTT_TWO_PASS_MAX;
-  if (const char* e = getenv("ZKC_NTT_TWO_PASS_MAX")) { const int v = atoi(e); if (v >= 12 && v <= 2 * (int)LOG_TILE) two_pass_max = (uint32_t)v; }
+  if (const int v = ctx->tune.ntt_two_pass_max) { if (v <= 2 * (int)LOG_TILE) two_pass_max = (uint32_t)v; }
   // bound the scratch: process columns in chunks of <= 1 GiB
   uint32_t chunk = (uint32_t)std::max<uint64_t>(1, (1ull << 30) / (N * sizeof(Fr)));
   if (chunk > ncols) chunk = ncols;
@@ -382,7 +382,9 @@ int dom_extended_to_coeff(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint32_t nco
   // upstream truncates to n*(j-1) coefficients; the buffer keeps its size, so zero the tail
   const uint64_t keep = (1ull << d->k) * (d->j - 1);
   if (keep < en) {
-    ZKC_CUDA_TRY(ctx, cudaMemset2DAsync(a + keep, en * sizeof(Fr), 0, (en - keep) * sizeof(Fr), ncols, ctx->stream));
+    // per column: a 2-D memset's pitch is limited to cudaDeviceProp::memPitch (2^31 - 1), which en * 32 bytes exceeds from extended_k = 26
+    for (uint32_t c = 0; c < ncols; ++c)
+      ZKC_CUDA_TRY(ctx, cudaMemsetAsync(a + (uint64_t)c * en + keep, 0, (en - keep) * sizeof(Fr), ctx->stream));
   }
   return ZKC_OK;
 }

@@ -8,15 +8,16 @@ namespace zkc {
 
 #define PERM_MAX_CHUNK 8
 
-// ---- Fr::random in bulk: draw #i of the proof's ChaCha20 stream is keystream block (first_block + i) ----
+// ---- Fr::random in bulk -------------------------------------------------------------------------------------
+// rand_chacha hands its keystream out word by word (rand_core BlockRng): Fr::random (halo2curves from_u512 of 8 x
+// next_u64) takes 16 consecutive words, fill_bytes(32) eight.  Draw #i of a run that starts at keystream word
+// `first_word` covers words [first_word + 16 i, first_word + 16 i + 16): one block when the run is block aligned, the
+// upper half of one block and the lower half of the next when it starts 8 words in (after an odd number of 32-byte seeds).
 __device__ __forceinline__ uint32_t rotl32_d(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
 struct ChaChaKey { uint32_t k[8]; };
-__global__ void k_chacha_fr(Fr* out, ChaChaKey key, uint64_t first_block, uint64_t count, int double_rounds) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const uint64_t ctr = first_block + i;
-  uint32_t s[16] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574, key.k[0], key.k[1], key.k[2], key.k[3], key.k[4], key.k[5], key.k[6],
-                    key.k[7], (uint32_t)ctr, (uint32_t)(ctr >> 32), 0, 0};
+__device__ __forceinline__ void chacha_block_dev(const uint32_t* key, uint64_t ctr, int double_rounds, uint32_t* out) {
+  uint32_t s[16] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574, key[0], key[1], key[2], key[3], key[4], key[5], key[6],
+                    key[7], (uint32_t)ctr, (uint32_t)(ctr >> 32), 0, 0};
   uint32_t x[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) x[j] = s[j];
@@ -29,14 +30,50 @@ __global__ void k_chacha_fr(Fr* out, ChaChaKey key, uint64_t first_block, uint64
     ZKC_QR(0, 5, 10, 15) ZKC_QR(1, 6, 11, 12) ZKC_QR(2, 7, 8, 13) ZKC_QR(3, 4, 9, 14)
   }
 #undef ZKC_QR
-  Fr lo, hi;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { lo.v[j] = x[j] + s[j]; hi.v[j] = x[8 + j] + s[8 + j]; }
-  // from_u512: lo * R^2 / R + hi * R^3 / R.  The row multiplier (second operand) of fe_mul may be any
-  // 256-bit value: each CIOS row adds a * b_i with a < r, so the running value stays < 2r.
+  for (int j = 0; j < 16; ++j) out[j] = x[j] + s[j];
+}
+// from_u512: lo * R^2 / R + hi * R^3 / R.  The row multiplier (second operand) of fe_mul may be any
+// 256-bit value: each CIOS row adds a * b_i with a < r, so the running value stays < 2r.
+__device__ __forceinline__ Fr fr_from_u512_dev(const Fr& lo, const Fr& hi) {
   const Fr r2 = fe_r2<FrP>();
   const Fr r3 = fe_mul(r2, r2);
-  fe_store(out + i, fe_add(fe_mul(r2, lo), fe_mul(r3, hi)));
+  return fe_add(fe_mul(r2, lo), fe_mul(r3, hi));
+}
+// first_word % 16 must be 0 or 8 (the host falls back to its own generator otherwise)
+__global__ void k_chacha_fr(Fr* out, ChaChaKey key, uint64_t first_word, uint64_t count, int double_rounds) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint64_t w = first_word + 16 * i;
+  uint32_t b0[16];
+  chacha_block_dev(key.k, w >> 4, double_rounds, b0);
+  Fr lo, hi;
+  if ((w & 15) == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { lo.v[j] = b0[j]; hi.v[j] = b0[8 + j]; }
+  } else {
+    uint32_t b1[16];
+    chacha_block_dev(key.k, (w >> 4) + 1, double_rounds, b1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { lo.v[j] = b0[8 + j]; hi.v[j] = b1[j]; }
+  }
+  fe_store(out + i, fr_from_u512_dev(lo, hi));
+}
+// chunk j of `chunk_len` elements is the Fr::random stream of ChaCha20Rng::from_seed(keys[j]) from its start
+// (the per-thread generators of the vanishing argument's random polynomial; SURVEY OPEN-3)
+__global__ void k_chacha_fr_chunked(Fr* out, const ChaChaKey* keys, uint64_t chunk_len, uint64_t count) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint64_t c = i / chunk_len;
+  uint32_t key[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) key[j] = keys[c].k[j];
+  uint32_t b0[16];
+  chacha_block_dev(key, i - c * chunk_len, 10, b0);
+  Fr lo, hi;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { lo.v[j] = b0[j]; hi.v[j] = b0[8 + j]; }
+  fe_store(out + i, fr_from_u512_dev(lo, hi));
 }
 
 // ---- permutation argument: numerators / denominators of the grand-product ratio ------------------------
@@ -131,15 +168,16 @@ __global__ void k_lookup_replist(const uint32_t* rep, const uint32_t* rep_rank, 
   if (rep[i]) replist[rep_rank[i]] = (uint32_t)i;
 }
 // S'[i] = A[i] on first occurrences; the l-th leftover table value (ascending) goes to the (R-1-l)-th repeated row
+// (PSE: `repeated_input_rows.pop()`), or to the l-th repeated row when `ascending` (axiom fork's rayon variant; SURVEY OPEN-9)
 __global__ void k_lookup_assign(const Fr* A, const Fr* T, const uint32_t* rep, const uint32_t* left, const uint32_t* left_rank,
-                                const uint32_t* replist, const uint32_t* totals /* [R] */, Fr* Sp, uint64_t U) {
+                                const uint32_t* replist, const uint32_t* totals /* [R] */, Fr* Sp, uint64_t U, int ascending) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= U) return;
   if (!rep[i]) fe_store(Sp + i, fe_load(A + i));
   if (left[i]) {
     const uint32_t R = totals[0];
     const uint32_t l = left_rank[i];
-    if (l < R) fe_store(Sp + replist[R - 1 - l], fe_load(T + i));
+    if (l < R) fe_store(Sp + replist[ascending ? l : R - 1 - l], fe_load(T + i));
   }
 }
 // canonical -> Montgomery for rows < U, tails (already Montgomery) for rows >= U
@@ -233,6 +271,15 @@ __global__ void k_expand_compact(const uint8_t* src, Fr* out, uint64_t n, int ki
   else if (v == 1) r = fe_one<FrP>();
   else { Fr c = fe_zero<FrP>(); c.v[0] = (uint32_t)v; c.v[1] = (uint32_t)(v >> 32); r = fe_from_canonical(c); }
   fe_store(out + i, r);
+}
+
+// rows [row0, row0 + rows) of each of `ncols` columns (stride n) := tails[c * rows + r] (or `value` when tails is null):
+// the advice blinding policies of create_proof (SURVEY OPEN-1)
+__global__ void k_fill_rows(Fr* cols, uint64_t n, uint64_t row0, uint32_t rows, uint32_t ncols, const Fr* tails, Fr value) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (uint64_t)rows * ncols) return;
+  const uint64_t c = idx / rows, r = idx - c * rows;
+  fe_store(cols + c * n + row0 + r, tails ? fe_load(tails + idx) : value);
 }
 
 // l_active = 1 - l_last - l_blind (extended coset)

@@ -18,9 +18,11 @@
  *     NO CPU fallback: without a CUDA device every compute call returns ZKC_ERR_CUDA.
  *   - `*_dev` variants take device pointers (data already resident in HBM); the plain variants
  *     take host pointers and include the host<->device copies.
- *   - Randomness and the Fiat-Shamir transcript never cross this boundary except through the
- *     `zkc_prover_*` session, which mirrors `plonk::create_proof` and takes the RNG seed and the
- *     transcript kind from the caller.
+ *   - Tier B comes in two forms.  The STEP API (zkc_prove_begin ... zkc_prove_end) keeps randomness and the
+ *     Fiat-Shamir transcript on the caller's side of the boundary: every step takes the challenges and the
+ *     scalars the caller drew and returns points / evaluations for the caller's own TranscriptWrite.
+ *     zkc_prove is a convenience driver over the same steps that owns a transcript and an RNG restated
+ *     from upstream (seed and kinds chosen through zkc_prove_opts).
  *   - One zkc_ctx per GPU; calls on one ctx are serialised internally (thread-safe per ctx).
  */
 #ifndef ZKCERT_CUDA_H
@@ -70,6 +72,10 @@ int zkc_ctx_sync(zkc_ctx* ctx);
  * stream underneath the latency-bound MSM phases.  on = 0 serialises everything on one stream (used when timing
  * individual kernels); results are identical either way. */
 int zkc_ctx_set_overlap(zkc_ctx* ctx, int on);
+/* Debug / sweep overrides on a live ctx: "msm_c", "msm_c_pre", "msm_T", "ntt_two_pass_max" (0 = library default),
+ * "stage_min_bytes" (-1 = default), "team_poison".  The ZKC_* environment variables of the same names are read once, when the
+ * ctx is created; nothing reads the environment on the proving path. */
+int zkc_ctx_set_tunable(zkc_ctx* ctx, const char* name, int64_t value);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 uint64_t zkc_ctx_launch_count(const zkc_ctx* ctx);
 const char* zkc_version(void);
@@ -182,7 +188,12 @@ typedef struct {
   int blind_draws;      /* SURVEY OPEN-2: 1 = one Fr::random per commitment for the (unused) KZG blind */
   int point_format;     /* SURVEY OPEN-5: 0 = y-sign in bit 7; 1 = y-sign in bit 6, identity flag in bit 7 */
   int rng_kind;         /* 0 = rand_chacha::ChaCha20Rng, 1 = rand::rngs::StdRng (ChaCha12; what the SDK's `StdRng` is — OPEN-6) */
-  uint8_t rng_seed[32]; /* SeedableRng::from_seed; every draw is Fr::random (one 64-byte keystream block) */
+  uint8_t rng_seed[32]; /* SeedableRng::from_seed; Fr::random takes 16 keystream words, fill_bytes(32) eight */
+  int lookup_fill;      /* SURVEY OPEN-9: 0 = PSE permute_expression_pair (leftover table values go to the repeated rows from the
+                           last one backwards), 1 = the axiom fork's rayon variant (ascending rows) */
+  int random_poly;      /* SURVEY OPEN-3: 0 = n serial Fr::random draws from the caller's rng; 1 = per-thread ChaCha20Rng instances
+                           seeded by rng.fill_bytes, chunks of n / threads coefficients (thread-count dependent upstream) */
+  uint32_t random_poly_threads; /* rayon::current_num_threads() of the machine being reproduced (random_poly = 1 only) */
 } zkc_prove_opts;
 
 /* create_proof(params, pk, &[circuit], &[instances], rng, &mut transcript) for ONE circuit.
@@ -191,14 +202,64 @@ typedef struct {
  * the usable range are overwritten by the blinding policy.  instances[c] has instance_lens[c] values.
  * The proof bytes (commitments compressed to 32 B, evaluations 32 B) are written to proof_out. */
 int zkc_prove(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, int advice_on_device, const zkc_fr* const* instances,
-              const size_t* instance_lens, const zkc_prove_opts* opts, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+              const size_t* instance_lens, size_t num_instance_columns /* != cs.num_instance_columns -> InvalidInstances */,
+              const zkc_prove_opts* opts, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
 
 /* Compact witness columns: kind 0 = zkc_fr[n] (Montgomery), 1 = bit-packed (1 bit per cell, LSB first,
  * ceil(n/8) bytes), 2 = uint8[n], 3 = uint16[n], 4 = uint64[n] (canonical small integers).  Host pointers.  The proof is
  * byte-identical to zkc_prove on the expanded columns; the H2D volume of a SHA256-bit witness drops ~250x. */
 typedef struct { int kind; const void* data; } zkc_advice_column;
 int zkc_prove_compact(zkc_ctx* ctx, const zkc_pk* pk, const zkc_advice_column* cols /* num_advice */, const zkc_fr* const* instances,
-                      const size_t* instance_lens, const zkc_prove_opts* opts, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+                      const size_t* instance_lens, size_t num_instance_columns, const zkc_prove_opts* opts, uint8_t* proof_out,
+                      size_t proof_cap, size_t* proof_len);
+
+/* ---- create_proof, STEP API (Tier B) -------------------------------------------------------------------------
+ * One call per prover round of plonk::create_proof (halo2_proofs 0.2.0 @4b42325 src/plonk/prover.rs; reached from
+ * /root/reference/src/helpers.rs:233,299 through gen_snark_shplonk).  The caller keeps its own `TranscriptWrite` (Blake2b,
+ * Keccak, snark-verifier's Poseidon / EVM transcripts - whatever it instantiates) and its own RNG: it writes the returned
+ * points / scalars to the transcript, squeezes the challenges and hands them to the next step together with the scalars it
+ * drew where upstream draws from `rng`.  Nothing here hashes or draws; given the same inputs the library is deterministic.
+ * Order is fixed: begin, lookups, products, vanishing, quotient, evals, then open_shplonk_h + open_shplonk_w or open_gwc, end.
+ * A step called out of order returns ZKC_ERR_BAD_ARG; after an error only zkc_prove_end is valid.  One session per ctx at
+ * a time.  Points are returned affine, identity = (0, 0) (upstream's write_point then fails on the caller's side).
+ * Team proving: every rank runs the same sequence with identical arguments. */
+typedef struct zkc_prover zkc_prover;
+/* the vanishing argument's random polynomial (n coefficients), described so that it can be produced on the device */
+typedef struct {
+  int kind;               /* 0 = `scalars`: n host scalars the caller drew (Fr::random, upstream order)
+                             1 = the Fr::random draws of ChaCha20Rng / StdRng ::from_seed(seed) that start at keystream word
+                                 `first_word` (16 words per draw)
+                             2 = chunk j of `chunk_len` coefficients = the Fr::random stream of ChaCha20Rng::from_seed(seeds + 32 j)
+                                 (SURVEY OPEN-3: the caller drew the seeds with rng.fill_bytes) */
+  const zkc_fr* scalars;
+  uint8_t seed[32]; int rng_kind; uint64_t first_word;
+  const uint8_t* seeds; uint32_t nseeds; uint64_t chunk_len;
+} zkc_random_poly;
+/* Round 1.  advice / instances as for zkc_prove.  advice_tails = NULL: axiom policy (last row := 1; SURVEY OPEN-1); else
+ * num_advice * (blinding_factors + 1) scalars for the unusable rows of each column (PSE policy, drawn column by column).
+ * early_random (optional): the random polynomial, if the caller can already describe it (a seeded RNG whose position at the
+ * vanishing argument is known) - it is then generated and committed underneath the first rounds. */
+int zkc_prove_begin(zkc_ctx* ctx, const zkc_pk* pk, const zkc_fr* advice, int advice_on_device, const zkc_fr* const* instances,
+                    const size_t* instance_lens, size_t num_instance_columns, const zkc_fr* advice_tails,
+                    const zkc_random_poly* early_random, zkc_prover** out, zkc_g1_affine* advice_commitments /* num_advice */);
+/* Round 2 (after theta).  tails: per lookup, blinding_factors + 1 scalars for A' then as many for S'.  out: A'_0, S'_0, A'_1, ... */
+int zkc_prove_lookups(zkc_prover* p, const zkc_fr* theta, const zkc_fr* tails, int lookup_fill, zkc_g1_affine* out /* 2 * #lookups */);
+/* Round 3 (after beta, gamma).  tails: blinding_factors scalars per permutation set, then per lookup product (upstream draw
+ * order).  out: the permutation product commitments, then the lookup product commitments. */
+int zkc_prove_products(zkc_prover* p, const zkc_fr* beta, const zkc_fr* gamma, const zkc_fr* tails, zkc_g1_affine* out /* #sets + #lookups */);
+/* Round 4a: commitment to the random polynomial (random = NULL if it was given to zkc_prove_begin). */
+int zkc_prove_vanishing(zkc_prover* p, const zkc_random_poly* random, zkc_g1_affine* out /* 1 */);
+/* Round 4b (after y): h(X) on the extended coset, divided by X^n - 1, split into degree - 1 pieces.  out: their commitments. */
+int zkc_prove_quotient(zkc_prover* p, const zkc_fr* y, zkc_g1_affine* out /* cs.degree() - 1 */);
+/* Round 5 (after x): every evaluation, in the order upstream writes them to the transcript (advice, fixed, random, sigma,
+ * permutation products, lookups).  *count receives the number (also when cap is too small: ZKC_ERR_BAD_ARG). */
+int zkc_prove_evals(zkc_prover* p, const zkc_fr* x, zkc_fr* out, size_t cap, size_t* count);
+/* Multiopen, ProverSHPLONK: y and v are squeezed back to back; the caller writes *out, squeezes u, and calls _w. */
+int zkc_prove_open_shplonk_h(zkc_prover* p, const zkc_fr* y, const zkc_fr* v, zkc_g1_affine* out /* 1 */);
+int zkc_prove_open_shplonk_w(zkc_prover* p, const zkc_fr* u, zkc_g1_affine* out /* 1 */);
+/* Multiopen, ProverGWC: one witness commitment per distinct evaluation point, first-appearance order. */
+int zkc_prove_open_gwc(zkc_prover* p, const zkc_fr* v, zkc_g1_affine* out, size_t cap, size_t* count);
+void zkc_prove_end(zkc_prover* p);
 
 /* host-side helpers mirrored for cross-checking a caller's RNG: Fr::random stream of ChaCha20Rng / StdRng ::from_seed(seed)
  * starting at draw `skip`; rand_core's SeedableRng::seed_from_u64. */
@@ -223,8 +284,8 @@ int zkc_poseidon_spec(zkc_fr* constants, zkc_fr* mds);
 typedef struct { zkc_fq x_c0, x_c1, y_c0, y_c1; } zkc_g2_affine;
 int zkc_verify(const uint8_t* cs_blob, size_t cs_len, const zkc_g1_affine* fixed_comm, const zkc_g1_affine* sigma_comm,
                const zkc_fr* transcript_repr, const zkc_g1_affine* g1_gen, const zkc_g2_affine* g2, const zkc_g2_affine* s_g2,
-               const zkc_fr* const* instances, const size_t* instance_lens, const uint8_t* proof, size_t proof_len,
-               const zkc_prove_opts* opts, int* ok);
+               const zkc_fr* const* instances, const size_t* instance_lens, size_t num_instance_columns, const uint8_t* proof,
+               size_t proof_len, const zkc_prove_opts* opts, int* ok);
 /* G2 pieces of ParamsKZG::setup and the pairing behind the final check: generator of G2, [scalar]P, prod e(g1s[i], g2s[i]) == 1 */
 int zkc_g2_generator(zkc_g2_affine* out);
 int zkc_g2_mul(const zkc_g2_affine* p, const zkc_fr* scalar, zkc_g2_affine* out);

@@ -267,19 +267,38 @@ def powers(base, n, first=None):
 
 
 class ChaCha20Rng:
-    """rand_chacha::ChaCha20Rng restricted to Fr::random draws (each consumes one 64-byte keystream block)."""
+    """rand_chacha::ChaCha{20,12}Rng as a linear stream of 32-bit keystream words (rand_core BlockRng): Fr::random
+    (halo2curves from_u512 of 8 x next_u64) consumes 16 words, fill_bytes(32) eight.  Aligned bulk draws run in C++."""
 
     def __init__(self, seed32: bytes, rounds=20):
         self.seed = bytes(seed32)
         self.rounds = rounds          # 20 = ChaCha20Rng, 12 = StdRng (rand 0.8)
-        self.drawn = 0
+        self.word = 0                 # next unread keystream word
+
+    @property
+    def drawn(self):
+        return self.word // 16
+
+    def _words(self, count):
+        out = np.empty(count, dtype=np.uint32)
+        lib().orc_chacha_words(C.c_char_p(self.seed), C.c_int(self.rounds // 2), C.c_uint64(self.word), C.c_size_t(count), _p(out))
+        self.word += count
+        return out
+
+    def fill_bytes(self, nbytes):
+        """RngCore::fill_bytes for a multiple of 4 bytes (whole words are consumed)"""
+        assert nbytes % 4 == 0
+        return self._words(nbytes // 4).tobytes()
 
     def fr_random_bulk(self, n):
         """n draws as an (n, 4) Montgomery array"""
-        out = np.empty((n, 4), dtype=np.uint64)
-        lib().orc_chacha_fr_random(C.c_char_p(self.seed), C.c_int(self.rounds // 2), C.c_uint64(self.drawn), C.c_size_t(n), _p(out))
-        self.drawn += n
-        return out
+        if self.word % 16 == 0:
+            out = np.empty((n, 4), dtype=np.uint64)
+            lib().orc_chacha_fr_random(C.c_char_p(self.seed), C.c_int(self.rounds // 2), C.c_uint64(self.word // 16), C.c_size_t(n), _p(out))
+            self.word += 16 * n
+            return out
+        w = self._words(16 * n).astype(object).reshape(n, 16)
+        return fr_from_ints([sum(int(row[j]) << (32 * j) for j in range(16)) % R_MOD for row in w])
 
     def fr_random(self):
         """one draw as a canonical int"""

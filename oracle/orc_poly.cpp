@@ -136,3 +136,25 @@ extern "C" void orc_chacha_fr_random(const uint8_t* seed, int double_rounds, uin
     }
   });
 }
+
+// raw keystream words [first_word, first_word + count) of the same stream (BlockRng hands the stream out word by word:
+// next_u64 = two consecutive words, fill_bytes(32) = eight words) — used where draws are not 16-word aligned (SURVEY OPEN-3)
+extern "C" void orc_chacha_words(const uint8_t* seed, int double_rounds, uint64_t first_word, size_t count, uint32_t* out) {
+  uint32_t key[8]; memcpy(key, seed, 32);
+  size_t done = 0;
+  while (done < count) {
+    const uint64_t w = first_word + done, ctr = w / 16;
+    uint32_t s[16] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                      (uint32_t)ctr, (uint32_t)(ctr >> 32), 0, 0};
+    uint32_t x[16]; memcpy(x, s, sizeof x);
+#define ORC_QR(a, b, c, d) \
+  x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 12); \
+  x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 7);
+    for (int r = 0; r < double_rounds; ++r) {
+      ORC_QR(0, 4, 8, 12) ORC_QR(1, 5, 9, 13) ORC_QR(2, 6, 10, 14) ORC_QR(3, 7, 11, 15)
+      ORC_QR(0, 5, 10, 15) ORC_QR(1, 6, 11, 12) ORC_QR(2, 7, 8, 13) ORC_QR(3, 4, 9, 14)
+    }
+#undef ORC_QR
+    for (size_t j = (size_t)(w % 16); j < 16 && done < count; ++j) out[done++] = x[j] + s[j];
+  }
+}

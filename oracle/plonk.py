@@ -33,10 +33,13 @@ def I(a):
 
 
 class ProverOptions:
-    def __init__(self, advice_blinding="axiom", blind_draws=False, random_poly="serial", point_format=0, zeta_choice=0):
+    def __init__(self, advice_blinding="axiom", blind_draws=False, random_poly="serial", point_format=0, zeta_choice=0,
+                 lookup_fill="pse", random_poly_threads=1):
         self.advice_blinding = advice_blinding   # OPEN-1: "axiom" (last row := 1) | "pse" (last u rows random)
         self.blind_draws = blind_draws           # OPEN-2: per-commitment Blind(Fr::random) draws
-        self.random_poly = random_poly           # OPEN-3: "serial"
+        self.random_poly = random_poly           # OPEN-3: "serial" (n draws from the caller's rng) | "chunked" (one ChaCha20Rng per
+        self.random_poly_threads = random_poly_threads   # rayon thread, seeded by rng.fill_bytes; thread-count dependent)
+        self.lookup_fill = lookup_fill           # OPEN-9: "pse" (leftovers pop repeated rows from the end) | "axiom" (ascending rows)
         self.point_format = point_format         # OPEN-5: 0 = sign in bit 7, identity all-zero; 1 = sign bit 6, identity bit 7
         self.zeta_choice = zeta_choice           # OPEN-4 (does not change proof bytes)
 
@@ -255,7 +258,12 @@ def rotate_rows(a, rot, scale=1):
 
 
 # ---- lookup permutation (A.6, PSE form) ---------------------------------------------------------------
-def permute_expression_pair(cs, inp, tab, draw):
+def permute_expression_pair(cs, inp, tab, draw, fill="pse"):
+    """fill = "pse": halo2 (PSE) permute_expression_pair — the leftover table values, ascending, are written to
+    `repeated_input_rows.pop()`, i.e. to the repeated rows from the LAST one backwards.
+    fill = "axiom": the rayon variant of the axiom fork as recalled (SURVEY OPEN-9) — first occurrences take their own value,
+    every other row takes the next leftover table value (sorted table entries that are duplicates of their predecessor or
+    absent from the input), ascending, in ascending row order.  Same multisets, different row assignment."""
     n, bf = cs.n, cs.blinding_factors()
     U = n - (bf + 1)
     a = orc.fr_to_ints(inp[:U])
@@ -276,6 +284,8 @@ def permute_expression_pair(cs, inp, tab, draw):
             left[v] = c - 1
         else:
             repeated.append(row)
+    if fill == "axiom":
+        repeated.reverse()        # pop() now yields the repeated rows in ascending order
     for v in sorted(left):
         for _ in range(left[v]):
             s_perm[repeated.pop()] = v
@@ -445,6 +455,24 @@ def gwc_prove(pk, transcript, polys, queries):
         transcript.write_point(commit(w, pk.g))
 
 
+def chunked_random_poly(rng, n, threads):
+    """vanishing::Argument::commit of halo2 >= v2023_04 / the axiom fork as recalled (SURVEY OPEN-3): n_chunks =
+    threads + (n % threads != 0) ChaCha20Rng instances, each seeded with 32 bytes of rng.fill_bytes (in order), fill
+    consecutive chunks of n / threads coefficients with Fr::random.  Thread-count dependent by construction."""
+    chunk = n // threads
+    if chunk == 0:
+        raise ValueError("more threads than coefficients")
+    n_chunks = threads + (1 if n % threads else 0)
+    if (n + chunk - 1) // chunk != n_chunks:
+        raise ValueError("zip_eq length mismatch (upstream panics for this thread count)")
+    seeds = [rng.fill_bytes(32) for _ in range(n_chunks)]
+    parts = []
+    for c, seed in enumerate(seeds):
+        cnt = min(chunk, n - c * chunk)
+        parts.append(orc.ChaCha20Rng(seed, 20).fr_random_bulk(cnt))
+    return np.concatenate(parts)
+
+
 # ---- create_proof (§3.2) -----------------------------------------------------------------------------
 def create_proof(pk, advice_mont, instances, rng, transcript_kind="blake2b", multiopen="shplonk", opts=None, trace=None):
     """advice_mont: list of (n, 4) Montgomery columns as synthesised (rows >= usable are overwritten by
@@ -510,7 +538,7 @@ def create_proof(pk, advice_mont, instances, rng, transcript_kind="blake2b", mul
                 acc = orc.vec_vec("add", orc.vec_scalar("mul", acc, M(theta)), eval_expr_cols(e, lagrange_query, n))
             return acc
         comp_in, comp_tab = compress(inp_exprs), compress(tab_exprs)
-        perm_in, perm_tab = permute_expression_pair(cs, comp_in, comp_tab, draw)
+        perm_in, perm_tab = permute_expression_pair(cs, comp_in, comp_tab, draw, opts.lookup_fill)
         if opts.blind_draws:
             draw()
         tr.write_point(commit(perm_in, pk.g_lagrange))
@@ -569,7 +597,10 @@ def create_proof(pk, advice_mont, instances, rng, transcript_kind="blake2b", mul
         lk["z_poly"] = orc.lagrange_to_coeff(j, k, z)
 
     # 8. vanishing: random polynomial
-    random_poly = rng.fr_random_bulk(n) if hasattr(rng, "fr_random_bulk") else orc.fr_from_ints([draw() for _ in range(n)])
+    if opts.random_poly == "chunked":
+        random_poly = chunked_random_poly(rng, n, opts.random_poly_threads)
+    else:
+        random_poly = rng.fr_random_bulk(n) if hasattr(rng, "fr_random_bulk") else orc.fr_from_ints([draw() for _ in range(n)])
     if opts.blind_draws:
         draw()
     tr.write_point(commit(random_poly, pk.g))

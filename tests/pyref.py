@@ -114,6 +114,11 @@ class ChaChaRng:
             v |= self.next_u64() << (64 * i)
         return v % R_MOD
 
+    def fill_bytes(self, nbytes):
+        """rand_core BlockRng::fill_bytes for a multiple of 4 bytes: whole keystream words, little-endian"""
+        assert nbytes % 4 == 0
+        return b"".join(self.next_u32().to_bytes(4, "little") for _ in range(nbytes // 4))
+
 
 def seed_from_u64(state):
     """rand_core SeedableRng::seed_from_u64: PCG32 expansion into a 32-byte seed."""

@@ -56,7 +56,12 @@ def test_proof_bytes_match_oracle(circuit_k6, transcript, multiopen):
 
 
 @pytest.mark.parametrize("opts", [dict(advice_blinding="pse"), dict(blind_draws=True), dict(point_format=1),
-                                  dict(advice_blinding="pse", blind_draws=True)])
+                                  dict(advice_blinding="pse", blind_draws=True),
+                                  dict(lookup_fill="axiom"),                                          # SURVEY OPEN-9
+                                  dict(random_poly="chunked", random_poly_threads=4),                 # SURVEY OPEN-3
+                                  dict(random_poly="chunked", random_poly_threads=3, blind_draws=True),
+                                  dict(random_poly="chunked", random_poly_threads=1, blind_draws=True, advice_blinding="pse"),
+                                  dict(random_poly="chunked", random_poly_threads=64, lookup_fill="axiom", blind_draws=True)])
 def test_open_switches_match_oracle(circuit_k6, opts):
     circ, opk, advice, params, gpk = circuit_k6
     seed = pyref.seed_from_u64(7)
@@ -173,12 +178,35 @@ def test_product_verifier_accepts_gpu_proofs(transcript, multiopen):
     assert not _product_verify(w, bytes(bad), transcript=transcript, multiopen=multiopen)
 
 
+@pytest.mark.parametrize("k,cols", [(17, 3), (15, 12)])
+def test_full_size_proof_bytes_match_oracle(k, cols):
+    """BASELINE.json configs 1 and 2 at their real sizes (RSA k=17 with 3 + 1 advice columns; k=15 with 12 + 1): the proof bytes
+    of the device prover equal the CPU oracle's for the same circuit, witness and seed — also with the axiom-fork variants of
+    the lookup fill order and the random polynomial switched on (SURVEY OPEN-9 / OPEN-3) and through GWC + Keccak."""
+    ctx = gpu_ctx()
+    circ = pkg().synth.make_base_circuit(k, cols, seed=11)
+    opk, advice = oracle_setup(circ)
+    w = pkg().workload.build(ctx, k, cols, circ=circ)
+    f, sg = w.pk.commitments()
+    assert orc.g1_to_ints(f) == opk.fixed_commitments and orc.g1_to_ints(sg) == opk.sigma_commitments
+    seed = pyref.seed_from_u64(1000 + k)
+    want = plonk.create_proof(opk, advice, circ.instances, orc.ChaCha20Rng(seed))
+    got = pkg().create_proof(w.pk, w.advice_dev, w.instances, seed)
+    assert got == want
+    assert pkg().create_proof(w.pk, w.advice_host, w.instances, seed) == want
+    assert _product_verify(w, got)
+    o = plonk.ProverOptions(lookup_fill="axiom", random_poly="chunked", random_poly_threads=16)
+    want2 = plonk.create_proof(opk, advice, circ.instances, orc.ChaCha20Rng(seed), "keccak", "gwc", opts=o)
+    assert want2 != want
+    assert pkg().create_proof(w.pk, w.advice_dev, w.instances, seed, "keccak", "gwc", lookup_fill="axiom", random_poly="chunked",
+                              random_poly_threads=16) == want2
+
+
 @pytest.mark.parametrize("k,cols,shape", [(17, 3, "base"), (15, 12, "base"), (15, 112, "sha_bit")])
 def test_full_size_proofs_verify(k, cols, shape):
-    """BASELINE.json sizes (config 1: RSA k=17; config 2: k=15 with 12 gate columns; config 3 shape at k=15):
-    too large for the CPU oracle prover inside a test, so parity is checked through the size-independent
-    property the reference's own tests use — the proof verifies — plus determinism and
-    device-resident == host-buffer."""
+    """BASELINE.json sizes (config 1: RSA k=17; config 2: k=15 with 12 gate columns; config 3 shape at k=15) through the
+    size-independent property the reference's own tests use — the proof verifies — plus determinism and
+    device-resident == host-buffer.  (Byte parity with the oracle at these sizes: test_full_size_proof_bytes_match_oracle.)"""
     ctx = gpu_ctx()
     w = pkg().workload.build(ctx, k, cols, seed=11, shape=shape)
     seed = pyref.seed_from_u64(k)
@@ -255,20 +283,24 @@ def test_std_rng_chacha12(circuit_k6):
 
 
 @pytest.mark.parametrize("blinding", ["axiom", "pse"])
-def test_staged_witness_upload(circuit_k6, monkeypatch, blinding):
+def test_staged_witness_upload(circuit_k6, blinding):
     """large host witnesses travel on a copy stream in column groups (zkc_prove staged upload); forced here on a small circuit"""
     circ, opk, advice, params, gpk = circuit_k6
     seed = pyref.seed_from_u64(55)
     inst = [orc.fr_from_ints(c) for c in circ.instances]
     kw = dict(advice_blinding=blinding) if blinding != "axiom" else {}
     want = pkg().create_proof(gpk, np.concatenate(advice), inst, seed, **kw)
-    monkeypatch.setenv("ZKC_STAGE_MIN_BYTES", "1")
-    assert pkg().create_proof(gpk, np.concatenate(advice), inst, seed, **kw) == want
-    w = pkg().workload.build(gpu_ctx(), 12, 7, seed=2)
-    monkeypatch.delenv("ZKC_STAGE_MIN_BYTES")
-    ref = pkg().create_proof(w.pk, w.advice_dev, w.instances, seed)
-    monkeypatch.setenv("ZKC_STAGE_MIN_BYTES", "1")
-    assert pkg().create_proof(w.pk, w.advice_host, w.instances, seed) == ref
+    ctx = gpu_ctx()
+    try:
+        ctx.set_tunable("stage_min_bytes", 1)
+        assert pkg().create_proof(gpk, np.concatenate(advice), inst, seed, **kw) == want
+        w = pkg().workload.build(ctx, 12, 7, seed=2)
+        ctx.set_tunable("stage_min_bytes", -1)
+        ref = pkg().create_proof(w.pk, w.advice_dev, w.instances, seed)
+        ctx.set_tunable("stage_min_bytes", 1)
+        assert pkg().create_proof(w.pk, w.advice_host, w.instances, seed) == ref
+    finally:
+        ctx.set_tunable("stage_min_bytes", -1)
 
 
 def test_repeated_and_concurrent_proofs_are_stable(circuit_k6):

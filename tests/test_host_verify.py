@@ -181,5 +181,35 @@ def test_verifier_rejects_random_mutations_without_crashing(setup_k6):
     for cut in [0, 3, 8, 40, len(blob) // 2, len(blob) - 1]:
         b = blob[:cut]
         st = api.lib().zkc_verify(b, C.c_size_t(len(b)), None, None, api._hp(one), api._hp(orc.g1_from_ints([pyref.G1_GEN])), api._hp(api.g2_generator()),
-                                  api._hp(s_g2), None, None, proof, C.c_size_t(len(proof)), C.byref(o), C.byref(ok))
+                                  api._hp(s_g2), None, None, C.c_size_t(0), proof, C.c_size_t(len(proof)), C.byref(o), C.byref(ok))
         assert st != 0 and ok.value == 0
+
+
+def test_instance_column_count_is_checked(setup_k6):
+    """plonk::Error::InvalidInstances when instances.len() != cs.num_instance_columns: too few would make the C side read past
+    the caller's arrays, extra columns would be silently ignored."""
+    circ, opk, advice, s_g2 = setup_k6
+    proof = plonk.create_proof(opk, advice, circ.instances, pyref.ChaChaRng(pyref.seed_from_u64(3), 20))
+    assert _verify(circ, opk, s_g2, circ.instances, proof)
+    for bad in ([], list(circ.instances) + [[1, 2, 3]]):
+        with pytest.raises(pkg().ZkcError) as e:
+            _verify(circ, opk, s_g2, bad, proof)
+        assert e.value.code == 10
+
+
+def test_identity_commitments_in_the_verifying_key():
+    """all selectors off: the vk's selector commitments are the point at infinity; the host verifier multiplies and adds them
+    like any other commitment (g1_mul on the identity)."""
+    circ = pkg().synth.make_base_circuit(6, 2, seed=5, fill=0.0)
+    assert not any(circ.fixed[0]) and not any(circ.fixed[1])
+    opk, advice = oracle_setup(circ)
+    assert opk.fixed_commitments[0] is None and opk.fixed_commitments[1] is None
+    api = pkg().api
+    s_g2 = api.g2_mul(api.g2_generator(), orc.fr_from_ints([SRS_SECRET]))
+    for multiopen in ("shplonk", "gwc"):
+        proof = plonk.create_proof(opk, advice, circ.instances, pyref.ChaChaRng(pyref.seed_from_u64(4), 20), multiopen=multiopen)
+        assert verifier.verify_proof(verifier.VerifyingKey(circ.cs, opk.fixed_commitments, opk.sigma_commitments, opk.transcript_repr),
+                                     pyref.G1_GEN, circ.instances, proof, verifier.trapdoor_check(SRS_SECRET), multiopen=multiopen)
+        assert _verify(circ, opk, s_g2, circ.instances, proof, multiopen=multiopen)
+        bad = bytearray(proof); bad[7] ^= 1
+        assert not _verify(circ, opk, s_g2, circ.instances, bytes(bad), multiopen=multiopen)

@@ -61,6 +61,49 @@ def test_open_switches(small, opts):
                                  point_format=o.point_format)
 
 
+@pytest.mark.parametrize("opts", [dict(lookup_fill="axiom"), dict(random_poly="chunked", random_poly_threads=4),
+                                  dict(random_poly="chunked", random_poly_threads=3, blind_draws=True),      # 3 + 1 seeds: even, aligned
+                                  dict(random_poly="chunked", random_poly_threads=1, blind_draws=True, advice_blinding="pse"),  # 1 seed: half a block off
+                                  dict(lookup_fill="axiom", random_poly="chunked", random_poly_threads=8)])
+def test_open9_open3_switches(small, opts):
+    """SURVEY OPEN-9 (lookup fill order) and OPEN-3 (per-thread random polynomial): both variants give valid proofs that
+    differ from the default ones; the pure-Python RNG and the C++ stream agree on the word-granular draws."""
+    circ, pk, advice = small
+    o = plonk.ProverOptions(**opts)
+    proof = plonk.create_proof(pk, advice, circ.instances, rng_for(13), opts=o)
+    assert verifier.verify_proof(_vk(pk), pyref.G1_GEN, circ.instances, proof, verifier.trapdoor_check(SRS_SECRET))
+    base = {k: v for k, v in opts.items() if k in ("blind_draws", "advice_blinding")}
+    assert proof != plonk.create_proof(pk, advice, circ.instances, rng_for(13), opts=plonk.ProverOptions(**base))
+    assert proof == plonk.create_proof(pk, advice, circ.instances, fast_rng_for(13), opts=o)
+
+
+def test_lookup_fill_orders():
+    """permute_expression_pair: same A' and the same multiset in S' for both fill orders; S'[row] = A'[row] on first occurrences;
+    PSE writes the leftovers to the repeated rows from the last one backwards, the axiom variant forwards."""
+    from oracle import orc
+
+    class Cs:
+        n = 16
+        def blinding_factors(self):
+            return 5
+    U = 10
+    inp = [3, 3, 3, 1, 1, 2, 2, 2, 2, 5]
+    tab = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9]
+    pad = [0] * 6
+    draw = iter(range(100, 200)).__next__
+    a_p, s_p = plonk.permute_expression_pair(Cs(), orc.fr_from_ints(inp + pad), orc.fr_from_ints(tab + pad), draw, "pse")
+    a_a, s_a = plonk.permute_expression_pair(Cs(), orc.fr_from_ints(inp + pad), orc.fr_from_ints(tab + pad), draw, "axiom")
+    A = orc.fr_to_ints(a_p)[:U]
+    assert A == sorted(inp) == orc.fr_to_ints(a_a)[:U]
+    SP, SA = orc.fr_to_ints(s_p)[:U], orc.fr_to_ints(s_a)[:U]
+    assert sorted(SP) == sorted(SA) == tab
+    firsts = [i for i in range(U) if i == 0 or A[i] != A[i - 1]]
+    reps = [i for i in range(U) if i not in firsts]
+    assert all(SP[i] == A[i] == SA[i] for i in firsts)
+    left = sorted(set(tab) - set(inp))
+    assert [SA[i] for i in reps] == left and [SP[i] for i in reversed(reps)] == left
+
+
 def test_zeta_choice_does_not_change_proof(small):
     """h(X) is unique whatever coset it is evaluated on."""
     circ, pk, advice = small

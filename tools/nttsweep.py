@@ -45,7 +45,7 @@ for k, ncols in [(17, 16), (19, 32), (20, 8), (22, 4)]:
     a0 = rand_fr(n * ncols, 2)
     outs = {}
     for setting in ("18", "20", "22"):
-        os.environ["ZKC_NTT_TWO_PASS_MAX"] = setting
+        ctx.set_tunable("ntt_two_pass_max", int(setting))
         a = a0.clone()
         ext = torch.empty((en * ce, 4), dtype=torch.int64, device="cuda")
         r = {}
