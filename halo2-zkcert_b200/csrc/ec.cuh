@@ -121,6 +121,57 @@ ZKC_HD G1Affine xyzz_to_affine(const G1Xyzz& p) {
 }
 
 #if defined(__CUDACC__)
+// ---- cooperative addition: FOUR lanes of a warp (an aligned quad) share one XYZZ addition ----------------------------------
+// The back end of an MSM (bucket sums, the bit-plane tree) is a chain of dependent additions on a machine that is mostly idle:
+// what counts there is the latency of ONE addition (14 Montgomery products in a row for a lone thread), not throughput.  The
+// products of add-2008-s fall into four independent groups { u1, u2, s1, s2 } -> { pp, r^2, zz1 zz2, zzz1 zzz2 } ->
+// { ppp, qq, zz } -> { r (qq - x3), s1 ppp, zzz }; a quad computes one group per step, one product per lane, and exchanges the
+// results with shuffles: 4 product latencies instead of 14.  All four lanes hold the same p and q on entry and the same sum
+// on exit.
+ZKC_D Fq fq_quad_bcast(const Fq& v, int src, unsigned qmask) {
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = __shfl_sync(qmask, v.v[i], src, 4);
+  return r;
+}
+// a_role, selected with bit masks: a chain of ?: on the role compiles to a divergent branch region PER WORD, which serialises
+// the four roles and costs more than the products it feeds
+ZKC_D Fq fq_sel4(int role, const Fq& a0, const Fq& a1, const Fq& a2, const Fq& a3) {
+  const uint32_t m0 = role == 0 ? 0xffffffffu : 0u, m1 = role == 1 ? 0xffffffffu : 0u, m2 = role == 2 ? 0xffffffffu : 0u,
+                 m3 = role == 3 ? 0xffffffffu : 0u;
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = (a0.v[i] & m0) | (a1.v[i] & m1) | (a2.v[i] & m2) | (a3.v[i] & m3);
+  return r;
+}
+// Every lane of the WARP must call this together (the shuffles name the full warp: a shuffle with a run-time sub-mask costs a
+// WARPSYNC each, which is what made a quad-masked variant no faster than a lone thread); quads with nothing to add pass the
+// identity for q.  The exceptional cases are resolved by selection after the common path, so the warp never diverges around
+// a shuffle.
+ZKC_D void xyzz_add_quad(G1Xyzz& p, const G1Xyzz& q) {
+  const unsigned FULL = 0xffffffffu;
+  const int role = threadIdx.x & 3;
+  const bool q_id = xyzz_is_identity(q), p_id = xyzz_is_identity(p);
+  Fq m = fe_mul(fq_sel4(role, p.x, q.x, p.y, q.y), fq_sel4(role, q.zz, p.zz, q.zzz, p.zzz));
+  const Fq u1 = fq_quad_bcast(m, 0, FULL), u2 = fq_quad_bcast(m, 1, FULL), s1 = fq_quad_bcast(m, 2, FULL), s2 = fq_quad_bcast(m, 3, FULL);
+  const Fq pp_ = fe_sub(u2, u1), r = fe_sub(s2, s1);
+  m = fe_mul(fq_sel4(role, pp_, r, p.zz, p.zzz), fq_sel4(role, pp_, r, q.zz, q.zzz));
+  const Fq pp = fq_quad_bcast(m, 0, FULL), rr = fq_quad_bcast(m, 1, FULL), zz12 = fq_quad_bcast(m, 2, FULL), zzz12 = fq_quad_bcast(m, 3, FULL);
+  m = fe_mul(fq_sel4(role, pp_, u1, zz12, zz12), pp);
+  const Fq ppp = fq_quad_bcast(m, 0, FULL), qq = fq_quad_bcast(m, 1, FULL), zz3 = fq_quad_bcast(m, 2, FULL);
+  const Fq x3 = fe_sub(fe_sub(rr, ppp), fe_dbl(qq));
+  m = fe_mul(fq_sel4(role, r, s1, zzz12, zzz12), fq_sel4(role, fe_sub(qq, x3), ppp, ppp, ppp));
+  const Fq y1 = fq_quad_bcast(m, 0, FULL), y2 = fq_quad_bcast(m, 1, FULL), zzz3 = fq_quad_bcast(m, 2, FULL);
+  if (q_id) return;                       // p + 0
+  if (p_id) { p = q; return; }            // 0 + q
+  if (fe_is_zero(pp_)) {                  // same x: P + P or P - P (no shuffles below: lanes may diverge freely)
+    if (fe_is_zero(r)) p = xyzz_dbl(p);
+    else p = xyzz_identity();
+    return;
+  }
+  p.x = x3; p.y = fe_sub(y1, y2); p.zz = zz3; p.zzz = zzz3;
+}
+
 ZKC_D G1Affine affine_load_nc(const G1Affine* p) { G1Affine r; r.x = fe_load_nc(&p->x); r.y = fe_load_nc(&p->y); return r; }
 ZKC_D G1Xyzz xyzz_load(const G1Xyzz* p) { G1Xyzz r; r.x = fe_load(&p->x); r.y = fe_load(&p->y); r.zz = fe_load(&p->zz); r.zzz = fe_load(&p->zzz); return r; }
 ZKC_D void xyzz_store(G1Xyzz* p, const G1Xyzz& r) { fe_store(&p->x, r.x); fe_store(&p->y, r.y); fe_store(&p->zz, r.zz); fe_store(&p->zzz, r.zzz); }

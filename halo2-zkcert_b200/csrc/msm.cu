@@ -14,8 +14,9 @@
 //                    limb-valued witness columns (a few giant buckets) run as fast as uniform scalars.
 //   5 k_msm_gather   one thread per bucket sums its (usually 1-3) partials; buckets with many
 //                    partials are queued and reduced by a whole CTA (k_msm_gather_heavy).
-//   6 k_msm_reduce1/2 sum_b b*S_b per window as c independent two-level tree reductions U_t = sum of
-//                    buckets whose index has bit t set (no serial running sum), then 2^t weights by Horner.
+//   6 k_msm_tree     sum_b b*S_b per bucket set as c bit-plane sums U_t = sum of buckets whose index has bit t set,
+//                    computed by ONE binary tree over the bucket indices whose nodes carry (U_0..U_{t-1}, S): about two
+//                    additions per bucket, depth c - 1, no serial running sum; the 2^t weights are applied by Horner on the host.
 // With a resident SRS the bases are expanded once into W tables 2^(c*w) * P_i, so all windows of
 // all points share ONE bucket set per column and step 6 shrinks by a factor W.
 #include "msm.cuh"
@@ -79,41 +80,13 @@ __global__ void k_msm_scatter(const uint32_t* dig, uint32_t* cursor, uint32_t* e
 // Entries per accumulate thread for THIS batch: g.T when the batch fills the machine, halved (down to 4) while the actual
 // number of non-zero digits E leaves fewer than MSM_MIN_THREADS chains — witness columns of bits / bytes / small limbs
 // have a fraction of the worst-case entries, and a short batch is bound by the length of the dependent chain, not by work.
-#define MSM_MIN_THREADS (148u * 512u)
+#define MSM_MIN_THREADS (148u * 256u)
 __device__ __forceinline__ uint32_t msm_T(const MsmGeom& g, uint64_t E) {
   uint32_t T = g.T;
   while (T > 4 && E / T < MSM_MIN_THREADS) T >>= 1;
   return T;
 }
 
-__global__ void __launch_bounds__(128) k_msm_accum(const G1Affine* bases, const uint32_t* ent_pt, const uint32_t* ent_key,
-                                                   const uint32_t* offsets, G1Xyzz* partial, MsmGeom g) {
-  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t E = offsets[g.nbtot()];
-  const uint32_t T = msm_T(g, E);
-  const uint64_t p0 = t * T;
-  if (p0 >= E) return;
-  const uint64_t p1 = p0 + T < E ? p0 + T : E;
-  G1Xyzz acc = xyzz_identity();
-  uint32_t cur = ent_key[p0];
-  // software pipeline: the next entry's base point is requested before the current mixed add is issued
-  uint32_t e = ent_pt[p0];
-  G1Affine q = affine_load_nc(bases + (e & 0x7fffffffu));
-  for (uint64_t p = p0; p < p1; ++p) {
-    const uint32_t k = ent_key[p];
-    const uint32_t e_cur = e;
-    const G1Affine q_cur = q;
-    if (p + 1 < p1) { e = ent_pt[p + 1]; q = affine_load_nc(bases + (e & 0x7fffffffu)); }
-    if (k != cur) { xyzz_store(partial + cur + t, acc); acc = xyzz_identity(); cur = k; }
-    if (!affine_is_identity(q_cur)) xyzz_madd(acc, q_cur, (e_cur >> 31) != 0);
-  }
-  xyzz_store(partial + cur + t, acc);
-}
-
-#define MSM_HEAVY_PER_LANE 12
-#define MSM_GIANT 4096        // partials: above this a bucket is sliced over MSM_GIANT_SLICES CTAs
-#define MSM_GIANT_SLICES 64
-#define MSM_GIANT_CAP 512
 __device__ __forceinline__ G1Xyzz xyzz_shfl_xor(const G1Xyzz& p, int mask) {
   G1Xyzz r;
 #pragma unroll
@@ -125,23 +98,79 @@ __device__ __forceinline__ G1Xyzz xyzz_shfl_xor(const G1Xyzz& p, int mask) {
   }
   return r;
 }
+
+__global__ void __launch_bounds__(128) k_msm_accum(const G1Affine* bases, const uint32_t* ent_pt, const uint32_t* ent_key,
+                                                   const uint32_t* offsets, G1Xyzz* partial, MsmGeom g) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t E = offsets[g.nbtot()];
+  const uint32_t T = msm_T(g, E);
+  const uint64_t p0 = t * T;
+  const bool active = p0 < E;
+  const uint64_t p1 = !active ? p0 : (p0 + T < E ? p0 + T : E);
+  G1Xyzz acc = xyzz_identity();
+  uint32_t cur = 0xffffffffu;
+  bool single = true;     // the thread's whole range lies in one bucket
+  if (active) {
+    cur = ent_key[p0];
+    // software pipeline: the next entry's base point is requested before the current mixed add is issued
+    uint32_t e = ent_pt[p0];
+    G1Affine q = affine_load_nc(bases + (e & 0x7fffffffu));
+    for (uint64_t p = p0; p < p1; ++p) {
+      const uint32_t k = ent_key[p];
+      const uint32_t e_cur = e;
+      const G1Affine q_cur = q;
+      if (p + 1 < p1) { e = ent_pt[p + 1]; q = affine_load_nc(bases + (e & 0x7fffffffu)); }
+      if (k != cur) { xyzz_store(partial + cur + t, acc); acc = xyzz_identity(); cur = k; single = false; }
+      if (!affine_is_identity(q_cur)) xyzz_madd(acc, q_cur, (e_cur >> 31) != 0);
+    }
+  }
+  // A warp that sits entirely inside ONE bucket (bit / byte valued witness columns and the top window of range-checked
+  // cells pile thousands of entries on a few buckets) folds its 32 partials with a shuffle tree and leaves the identity in
+  // the other 31 slots, so such a bucket hands 32x fewer non-trivial partials to the bucket-sum kernels: their dependent
+  // chain is what costs there, and adding the identity is free.
+  const uint32_t k0 = __shfl_sync(0xffffffffu, cur, 0);
+  if (__all_sync(0xffffffffu, active && single && cur == k0)) {
+#pragma unroll 1
+    for (int d = 16; d > 0; d >>= 1) { const G1Xyzz o = xyzz_shfl_xor(acc, d); xyzz_add(acc, o); }
+    if (threadIdx.x & 31) acc = xyzz_identity();
+  }
+  if (active) xyzz_store(partial + cur + t, acc);
+}
+
+// ---- bucket sums: the partials of a bucket are folded by QUADS of lanes (xyzz_add_quad: this phase is a chain of dependent
+// additions on a mostly idle machine, so four lanes share each addition).  A bucket gets G quads (G from the expected number of
+// partials); buckets with more than MSM_HEAVY_PER_QUAD * G partials are queued for a whole CTA, above MSM_GIANT partials they
+// are sliced over MSM_GIANT_SLICES CTAs.
+#define MSM_HEAVY_PER_QUAD 6
+#define MSM_GIANT 1024        // partials: above this a bucket is sliced over MSM_GIANT_SLICES CTAs
+#define MSM_GIANT_SLICES 32
+#define MSM_GIANT_CAP 1024
 __global__ void __launch_bounds__(128) k_msm_gather(const uint32_t* offsets, const G1Xyzz* partial, G1Xyzz* buckets,
                                                     uint32_t* heavy_list, uint32_t* heavy_count, MsmGeom g, uint32_t logG) {
-  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t key = tid >> logG;
-  const uint32_t G = 1u << logG, lane = (uint32_t)tid & (G - 1);
+  const uint64_t qd = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;      // quad index
+  const uint64_t key = qd >> logG;
+  const uint32_t G = 1u << logG, slot = (uint32_t)qd & (G - 1);
   const bool valid = key < g.nbtot();     // whole groups are valid or not (nbtot * G is a multiple of the warp's group span)
   uint32_t off = 0, cnt = 0;
   if (valid) { off = offsets[key]; cnt = offsets[key + 1] - off; }
-  uint64_t first = 0, np = 0;
+  uint64_t first = 0;
+  uint32_t np = 0;
   const uint32_t T = msm_T(g, offsets[g.nbtot()]);
-  if (cnt) { first = key + off / T; np = key + (off + cnt - 1) / T - first + 1; }
-  const bool heavy = np > (uint64_t)MSM_HEAVY_PER_LANE * G;
+  if (cnt) { first = key + off / T; np = (uint32_t)(key + (off + cnt - 1) / T - first + 1); }
+  const bool heavy = np > (uint32_t)MSM_HEAVY_PER_QUAD * G;
+  // the additions are warp-wide collectives: every quad of the warp makes the same number of steps (the longest chain among
+  // its buckets, at most MSM_HEAVY_PER_QUAD), quads that have run out add the identity
+  const uint32_t mine = heavy ? 0 : np;
+  const uint32_t steps = (__reduce_max_sync(0xffffffffu, mine) + G - 1) >> logG;
   G1Xyzz acc = xyzz_identity();
-  if (cnt && !heavy)
-    for (uint64_t s = lane; s < np; s += G) xyzz_add(acc, xyzz_load(partial + first + s));
-  for (uint32_t d = G >> 1; d > 0; d >>= 1) { G1Xyzz o = xyzz_shfl_xor(acc, (int)d); xyzz_add(acc, o); }
-  if (valid && lane == 0) {
+  for (uint32_t it = 0; it < steps; ++it) {
+    const uint32_t sidx = it * G + slot;
+    G1Xyzz o = xyzz_identity();
+    if (sidx < mine) o = xyzz_load(partial + first + sidx);
+    xyzz_add_quad(acc, o);
+  }
+  for (uint32_t d = G >> 1; d > 0; d >>= 1) { G1Xyzz o = xyzz_shfl_xor(acc, (int)(d << 2)); xyzz_add_quad(acc, o); }
+  if (valid && slot == 0 && (threadIdx.x & 3) == 0) {
     if (heavy) {
       // heavy_count[0] / heavy_list[0..nbt): one CTA per bucket; heavy_count[1] / giant list (after nbt): sliced over many CTAs
       if (np > MSM_GIANT && heavy_count[1] < MSM_GIANT_CAP) {
@@ -157,20 +186,70 @@ __global__ void __launch_bounds__(128) k_msm_gather(const uint32_t* offsets, con
   }
 }
 
-// block-wide XYZZ tree reduction through shared memory; result valid in thread 0
-__device__ __forceinline__ G1Xyzz block_reduce_xyzz(G1Xyzz acc, G1Xyzz* sm) {
-  const uint32_t t = threadIdx.x;
-  xyzz_store(sm + t, acc);
-  __syncthreads();
-  for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
-    if (t < d) { G1Xyzz a = xyzz_load(sm + t); xyzz_add(a, xyzz_load(sm + t + d)); xyzz_store(sm + t, a); }
-    __syncthreads();
+// The same with ONE lane per slot (plain additions): when a batch has enough buckets to fill the machine the bucket sums are bound
+// by multiplier throughput, where the quad variant's four-fold lane count loses; the launcher picks by grid size.
+__global__ void __launch_bounds__(128) k_msm_gather_plain(const uint32_t* offsets, const G1Xyzz* partial, G1Xyzz* buckets,
+                                                          uint32_t* heavy_list, uint32_t* heavy_count, MsmGeom g, uint32_t logG) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t key = tid >> logG;
+  const uint32_t G = 1u << logG, lane = (uint32_t)tid & (G - 1);
+  const bool valid = key < g.nbtot();     // whole groups are valid or not (nbtot * G is a multiple of the warp's group span)
+  uint32_t off = 0, cnt = 0;
+  if (valid) { off = offsets[key]; cnt = offsets[key + 1] - off; }
+  uint64_t first = 0, np = 0;
+  const uint32_t T = msm_T(g, offsets[g.nbtot()]);
+  if (cnt) { first = key + off / T; np = key + (off + cnt - 1) / T - first + 1; }
+  const bool heavy = np > (uint64_t)MSM_HEAVY_PER_QUAD * G;
+  G1Xyzz acc = xyzz_identity();
+  if (cnt && !heavy)
+    for (uint64_t s = lane; s < np; s += G) xyzz_add(acc, xyzz_load(partial + first + s));
+  for (uint32_t d = G >> 1; d > 0; d >>= 1) { G1Xyzz o = xyzz_shfl_xor(acc, (int)d); xyzz_add(acc, o); }
+  if (valid && lane == 0) {
+    if (heavy) {
+      if (np > MSM_GIANT && heavy_count[1] < MSM_GIANT_CAP) {
+        const uint32_t gi = atomicAdd(heavy_count + 1, 1u);
+        if (gi < MSM_GIANT_CAP) heavy_list[g.nbtot() + gi] = (uint32_t)key;
+        else heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)key;
+      } else {
+        heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)key;
+      }
+    } else {
+      xyzz_store(buckets + key, acc);
+    }
   }
-  G1Xyzz r = xyzz_load(sm);
-  __syncthreads();
-  return r;
 }
 
+// CTA-wide XYZZ sum of one value per QUAD (the four lanes of a quad hold the same value): shuffle tree inside the warps,
+// shared memory across them; every step is a quad addition.  Result valid in thread 0.  blockDim.x a multiple of 32, <= 256.
+__device__ __forceinline__ G1Xyzz block_reduce_quads(G1Xyzz acc, G1Xyzz* sm) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll 1
+  for (int d = 4; d < 32; d <<= 1) { const G1Xyzz o = xyzz_shfl_xor(acc, d); xyzz_add_quad(acc, o); }
+  if (nwarps == 1) return acc;
+  if (lane == 0) xyzz_store(sm + warp, acc);
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t q = lane >> 2;
+    acc = q < nwarps ? xyzz_load(sm + q) : xyzz_identity();
+#pragma unroll 1
+    for (uint32_t d = 4; (d >> 2) < nwarps; d <<= 1) { const G1Xyzz o = xyzz_shfl_xor(acc, (int)d); xyzz_add_quad(acc, o); }
+  }
+  __syncthreads();
+  return acc;
+}
+// sum of partial[first + lo .. first + hi) by the CTA's quads: each quad walks a strided share (uniform trip count), then the tree
+__device__ __forceinline__ G1Xyzz block_sum_partials(const G1Xyzz* partial, uint64_t first, uint64_t lo, uint64_t hi, G1Xyzz* sm) {
+  const uint32_t nq = blockDim.x >> 2, qd = threadIdx.x >> 2;
+  G1Xyzz acc = xyzz_identity();
+  for (uint64_t base = lo; base < hi; base += nq) {
+    G1Xyzz o = xyzz_identity();
+    if (base + qd < hi) o = xyzz_load(partial + first + base + qd);
+    xyzz_add_quad(acc, o);
+  }
+  return block_reduce_quads(acc, sm);
+}
+
+// heavy buckets (a few dozen to MSM_GIANT partials): one CTA per bucket, its quads walk the partials, then the tree
 __global__ void __launch_bounds__(128) k_msm_gather_heavy(const uint32_t* offsets, const G1Xyzz* partial, G1Xyzz* buckets,
                                                           const uint32_t* heavy_list, const uint32_t* heavy_count, MsmGeom g) {
   extern __shared__ uint4 smraw[];
@@ -180,10 +259,8 @@ __global__ void __launch_bounds__(128) k_msm_gather_heavy(const uint32_t* offset
   for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
     const uint64_t key = heavy_list[h];
     const uint32_t off = offsets[key], cnt = offsets[key + 1] - off;
-    const uint64_t first = key + off / T, last = key + (off + cnt - 1) / T;
-    G1Xyzz acc = xyzz_identity();
-    for (uint64_t s = first + threadIdx.x; s <= last; s += blockDim.x) xyzz_add(acc, xyzz_load(partial + s));
-    G1Xyzz r = block_reduce_xyzz(acc, sm);
+    const uint64_t first = key + off / T, np = key + (off + cnt - 1) / T - first + 1;
+    G1Xyzz r = block_sum_partials(partial, first, 0, np, sm);
     if (threadIdx.x == 0) xyzz_store(buckets + key, r);
   }
 }
@@ -201,64 +278,108 @@ __global__ void __launch_bounds__(128) k_msm_gather_giant1(const uint32_t* offse
     const uint64_t first = key + off / T, np = key + (off + cnt - 1) / T - first + 1;
     const uint64_t per = (np + MSM_GIANT_SLICES - 1) / MSM_GIANT_SLICES;
     const uint64_t lo = (uint64_t)blockIdx.x * per, hi = lo + per < np ? lo + per : np;
-    G1Xyzz acc = xyzz_identity();
-    for (uint64_t s = lo + threadIdx.x; s < hi; s += blockDim.x) xyzz_add(acc, xyzz_load(partial + first + s));
-    G1Xyzz r = block_reduce_xyzz(acc, sm);
+    G1Xyzz r = block_sum_partials(partial, first, lo < np ? lo : np, hi, sm);
     if (threadIdx.x == 0) xyzz_store(hpart + (uint64_t)gi * MSM_GIANT_SLICES + blockIdx.x, r);
   }
 }
-// pass 2: fold the slices
-__global__ void __launch_bounds__(MSM_GIANT_SLICES) k_msm_gather_giant2(const G1Xyzz* hpart, G1Xyzz* buckets, const uint32_t* heavy_list,
-                                                                        const uint32_t* heavy_count, MsmGeom g) {
+// pass 2: fold the slices (one quad per slice)
+__global__ void __launch_bounds__(MSM_GIANT_SLICES * 4) k_msm_gather_giant2(const G1Xyzz* hpart, G1Xyzz* buckets, const uint32_t* heavy_list,
+                                                                            const uint32_t* heavy_count, MsmGeom g) {
   extern __shared__ uint4 smraw[];
   G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smraw);
   const uint32_t ng = min(heavy_count[1], (uint32_t)MSM_GIANT_CAP);
   for (uint32_t gi = blockIdx.x; gi < ng; gi += gridDim.x) {
-    G1Xyzz r = block_reduce_xyzz(xyzz_load(hpart + (uint64_t)gi * MSM_GIANT_SLICES + threadIdx.x), sm);
+    G1Xyzz r = block_reduce_quads(xyzz_load(hpart + (uint64_t)gi * MSM_GIANT_SLICES + (threadIdx.x >> 2)), sm);
     if (threadIdx.x == 0) xyzz_store(buckets + heavy_list[g.nbtot() + gi], r);
   }
 }
 
-// Level 1: P[set][t][chunk] = sum of buckets b of the chunk whose index has bit t set.  grid = (c, nchunks, nsets)
-// A chunk is the aligned range b in [ch * 1024, ch * 1024 + 1024); the buckets with bit t set are ENUMERATED (the j-th one
-// directly), not filtered: every lane adds in every iteration, where a filter would leave half of each warp idle and
-// double the dependent chain.  b = NB = 2^(c-1), the one bucket outside the aligned ranges, has only the top bit.
-#define RED_LOG 10
-#define RED_CHUNK (1u << RED_LOG)
-__global__ void __launch_bounds__(64) k_msm_reduce1(const G1Xyzz* buckets, G1Xyzz* P, MsmGeom g, uint32_t nchunks) {
+// ---- sum_b b * S_b as c bit-plane sums U_t = sum of the buckets whose index has bit t set, WORK-EFFICIENTLY -------------------
+// A binary tree over the bucket indices b in [0, NB) (b = 0 is an empty slot; NB = 2^(c-1) itself is handled at the end).  A
+// node of level t covers 2^t consecutive indices and carries (U_0 .. U_{t-1}, S): the bit-plane sums restricted to its range
+// and the plain sum.  Merging the siblings L (bit t clear) and R (bit t set):
+//        U_i = L.U_i + R.U_i  (i < t),     U_t = R.S,     S = L.S + R.S
+// i.e. t + 1 additions per merge, about 2 per bucket over the whole tree (the per-plane tree reductions it replaces took
+// c / 2 = 7.5), all additions of one level independent, depth c - 1.  One CTA merges `m` levels of 2^m sibling nodes through
+// shared memory (ping-pong), one output point per QUAD of lanes and step (xyzz_add_quad: the chain of dependent additions is
+// what this phase costs, so four lanes share each addition); the host chains launches until one node per bucket set is
+// left, and the last launch writes U_0 .. U_{c-2} and U_{c-1} = S_NB where the host epilogue expects them.
+// Node layout in memory: [U_0 .. U_{t-1}, S], t + 1 points.
+template <bool QUAD>
+__global__ void __launch_bounds__(256, 2) k_msm_tree(const G1Xyzz* in, G1Xyzz* out, const G1Xyzz* buckets, G1Xyzz* U, uint32_t t0, uint32_t m,
+                                                           uint32_t nodes_in, uint32_t NB, uint32_t c) {
   extern __shared__ uint4 smraw[];
-  G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smraw);
-  const uint32_t t = blockIdx.x, ch = blockIdx.y;
-  const uint64_t set = blockIdx.z;
-  const G1Xyzz* bk = buckets + set * g.NB;     // bucket b lives at bk[b - 1]
-  G1Xyzz acc = xyzz_identity();
-  const uint32_t lo = ch * RED_CHUNK;
-  if (t < RED_LOG) {
-    for (uint32_t j = threadIdx.x; j < RED_CHUNK / 2; j += blockDim.x) {
-      const uint32_t b = lo + (((j >> t) << (t + 1)) | (1u << t) | (j & ((1u << t) - 1)));
-      if (b < g.NB) xyzz_add(acc, xyzz_load(bk + (b - 1)));
+  G1Xyzz* buf0 = reinterpret_cast<G1Xyzz*>(smraw);
+  const uint32_t grp = blockIdx.x, groups = nodes_in >> m;
+  const uint64_t set = blockIdx.y;
+  const uint32_t nloc = 1u << m, P0 = t0 + 1;
+  const bool leaf = t0 == 0;
+  const G1Xyzz* bk = buckets + set * NB;           // bucket b lives at bk[b - 1]
+  const G1Xyzz* src_g = in + ((uint64_t)set * nodes_in + (uint64_t)grp * nloc) * P0;
+  const uint32_t leaf0 = grp * nloc;               // first bucket index of this CTA (leaf launch)
+  // buffers: a level with `nodes` input nodes of P points produces nodes / 2 nodes of P + 1 points
+  const uint32_t cap0 = (nloc >> 1) * (P0 + 1);    // largest output level is the first one
+  G1Xyzz* buf1 = buf0 + cap0;
+  G1Xyzz* cur = nullptr;                            // level input (nullptr: read the launch input from global memory)
+  G1Xyzz* nxt = buf0;
+  uint32_t nodes = nloc, P = P0;
+  for (uint32_t lvl = 0; lvl < m; ++lvl) {
+    const uint32_t T = P - 1, Pout = P + 1, nout = nodes >> 1;
+    const bool last = lvl + 1 == m;
+    // (a) the T + 1 sums of every merge: one per quad of lanes (QUAD: xyzz_add_quad, whole warps stay together) or per lane
+    const uint32_t total = nout * P, nslots = QUAD ? blockDim.x >> 2 : blockDim.x;
+    for (uint32_t base = 0; base < total; base += nslots) {
+      const uint32_t o = base + (QUAD ? threadIdx.x >> 2 : threadIdx.x);
+      const bool valid = o < total;
+      const uint32_t j = valid ? o / P : 0, ii = valid ? o - j * P : 0;
+      const uint32_t i = ii < T ? ii : T + 1;            // output slot: U_ii, or S behind U_T
+      G1Xyzz l = xyzz_identity(), r = xyzz_identity();
+      const uint32_t li = (2 * j) * P + ii, ri = (2 * j + 1) * P + ii;   // input slot ii of both children (ii == T: their S)
+      if (!valid) {
+      } else if (cur) {
+        l = xyzz_load(cur + li); r = xyzz_load(cur + ri);
+      } else if (leaf) {      // P = 1: the node is the bucket itself
+        const uint32_t b0 = leaf0 + 2 * j, b1 = b0 + 1;
+        if (b0) l = xyzz_load(bk + (b0 - 1));
+        r = xyzz_load(bk + (b1 - 1));
+      } else {
+        l = xyzz_load(src_g + li); r = xyzz_load(src_g + ri);
+      }
+      if (QUAD) xyzz_add_quad(l, r);
+      else xyzz_add(l, r);
+      if (!valid || (QUAD && (threadIdx.x & 3) != 0)) continue;    // the four lanes of a quad hold the same sum: one of them stores it
+      if (!last) xyzz_store(nxt + (uint64_t)j * Pout + i, l);
+      else if (groups > 1) xyzz_store(out + ((uint64_t)set * groups + grp) * Pout + i, l);
+      else if (i < T) xyzz_store(U + set * c + i, l);     // the root: U_0 .. U_{c-3} here, U_{c-2} below; its S is not needed
     }
-  } else {
-    // whole chunks qualify or not: the two CTAs of a chunk pair (ch with / without bit t) take half of the qualifying chunk each
-    const uint32_t bit = 1u << (t - RED_LOG);
-    const uint32_t base = (ch | bit) * RED_CHUNK + ((ch & bit) ? RED_CHUNK / 2 : 0);
-    for (uint32_t j = threadIdx.x; j < RED_CHUNK / 2; j += blockDim.x)
-      if (base + j < g.NB) xyzz_add(acc, xyzz_load(bk + (base + j - 1)));
+    // (b) U_T = R.S: a copy
+    for (uint32_t j = threadIdx.x; j < nout; j += blockDim.x) {
+      G1Xyzz r;
+      const uint32_t ri = (2 * j + 1) * P + T;
+      if (cur) r = xyzz_load(cur + ri);
+      else if (leaf) r = xyzz_load(bk + (leaf0 + 2 * j));   // bucket index leaf0 + 2 j + 1
+      else r = xyzz_load(src_g + ri);
+      if (!last) xyzz_store(nxt + (uint64_t)j * Pout + T, r);
+      else if (groups > 1) xyzz_store(out + ((uint64_t)set * groups + grp) * Pout + T, r);
+      else xyzz_store(U + set * c + T, r);
+    }
+    __syncthreads();
+    cur = nxt; nxt = (nxt == buf0) ? buf1 : buf0;
+    nodes = nout; P = Pout;
   }
-  if (ch == 0 && threadIdx.x == 0 && t == g.c - 1) xyzz_add(acc, xyzz_load(bk + (g.NB - 1)));
-  G1Xyzz r = block_reduce_xyzz(acc, sm);
-  if (threadIdx.x == 0) xyzz_store(P + (set * g.c + t) * nchunks + ch, r);
+  if (groups == 1 && grp == 0 && threadIdx.x == 0) xyzz_store(U + set * c + (c - 1), xyzz_load(bk + (NB - 1)));   // b = NB: top bit only
 }
-// Level 2: U[set][t] = sum over chunks.  grid = (c, nsets), one warp
-__global__ void __launch_bounds__(32) k_msm_reduce2(const G1Xyzz* P, G1Xyzz* U, MsmGeom g, uint32_t nchunks) {
-  extern __shared__ uint4 smraw[];
-  G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smraw);
-  const uint64_t idx = (uint64_t)blockIdx.y * g.c + blockIdx.x;
-  const G1Xyzz* p = P + idx * nchunks;
-  G1Xyzz acc = xyzz_identity();
-  for (uint32_t c = threadIdx.x; c < nchunks; c += 32) xyzz_add(acc, xyzz_load(p + c));
-  G1Xyzz r = block_reduce_xyzz(acc, sm);
-  if (threadIdx.x == 0) xyzz_store(U + idx, r);
+// levels one launch can merge: input (2^m nodes of t0 + 1 points) is read from global memory; the two shared buffers hold the
+// outputs of the first and second level
+static uint32_t tree_levels(uint32_t t0, uint32_t remaining, size_t smem_cap) {
+  uint32_t m = 1;
+  while (m < remaining && m < 7) {
+    const uint32_t mm = m + 1;
+    const size_t pts = (size_t)(1u << (mm - 1)) * (t0 + 2) + (mm > 1 ? (size_t)(1u << (mm - 2)) * (t0 + 3) : 0);
+    if (pts * sizeof(G1Xyzz) > smem_cap) break;
+    m = mm;
+  }
+  return m;
 }
 
 // ---- host-side epilogue: Horner over bit sums and windows (a few hundred point ops) -------------
@@ -289,11 +410,12 @@ uint32_t msm_pick_c(const zkc_ctx* ctx, uint64_t n, bool precomputed) {
   if (const int v = precomputed ? ctx->tune.msm_c_pre : ctx->tune.msm_c) { const int W = (255 + v - 1) / v; return (uint32_t)((255 + W - 1) / W); }
   uint32_t lg = 0;
   while ((1ull << (lg + 1)) <= n) ++lg;
-  // measured on B200: shared-bucket (precomputed) layout wants ~4-8 partials per bucket for the
-  // gather phase: c = lg-2 up to 2^18, lg-3 at 2^19, lg-4 from 2^20; the per-window layout uses lg-4 throughout
+  // measured on B200 (tools/sweep_c.py, round 2: the bucket back end costs about two additions per bucket now): shared-bucket
+  // (precomputed) layout c = lg-1 up to 2^17, lg-2 at 2^18, lg-3 from 2^19; the per-window layout uses lg-4 throughout
   int c = (int)lg - 4;
-  if (precomputed && lg <= 18) c = (int)lg - 2;
-  else if (precomputed && lg == 19) c = (int)lg - 3;
+  if (precomputed && lg <= 17) c = (int)lg - 1;
+  else if (precomputed && lg == 18) c = (int)lg - 2;
+  else if (precomputed) c = (int)lg - 3;
   c = std::max(3, std::min(20, c));
   const int W = (255 + c - 1) / c;
   return (uint32_t)((255 + W - 1) / W);   // same number of windows, evenly filled (see msm_geom)
@@ -309,7 +431,7 @@ MsmGeom msm_geom(const zkc_ctx* ctx, uint64_t n, uint32_t ncols, uint32_t c, boo
   // 0.99 of the IMAD.WIDE peak) but multiply the partials the gather phase must fold; 32 / 64 minimise the sum
   uint32_t T = e >= (1ull << 26) ? 64 : 32;
   if (ctx->tune.msm_T) T = (uint32_t)ctx->tune.msm_T;
-  while (T > 4 && e / T < 148ull * 512) T >>= 1;
+  while (T > 4 && e / T < MSM_MIN_THREADS) T >>= 1;
   g.T = T;
   return g;
 }
@@ -330,7 +452,7 @@ static int msm_kernels(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, c
   const size_t o_counts = carve(nbt * 4), o_offsets = carve((nbt + 1) * 4), o_cursor = carve(nbt * 4), o_heavyc = carve(8),
                o_heavy = carve((nbt + MSM_GIANT_CAP) * 4), o_hpart = carve((size_t)MSM_GIANT_CAP * MSM_GIANT_SLICES * sizeof(G1Xyzz)), o_dig = carve(em * 4), o_pt = carve(em * 4), o_key = carve(em * 4),
                o_part = carve(nslots * sizeof(G1Xyzz)), o_bk = carve(nbt * sizeof(G1Xyzz)),
-               o_redp = carve((size_t)nc * g.sets * g.c * ((g.NB + 1023) / 1024) * sizeof(G1Xyzz));
+               o_redp = carve((size_t)2 * nc * g.sets * (g.NB / 16 + g.c + 8) * sizeof(G1Xyzz));   // two node arrays of the reduction tree
   char* base;
   ZKC_TRY(scratch_reserve(ctx, SCR_MSM, o, (void**)&base));
   uint32_t* counts = (uint32_t*)(base + o_counts); uint32_t* offsets = (uint32_t*)(base + o_offsets);
@@ -355,30 +477,52 @@ static int msm_kernels(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, c
     k_msm_accum<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(bases, ent_pt, ent_key, offsets, partial, g);
     ZKC_LAUNCH_CHECK(ctx); }
   {
-    // group width from the expected number of partials per bucket (entries per bucket / T)
+    // quads per bucket from the expected number of partials per bucket (entries per bucket / T)
     const double avg_partials = (double)g.W * (double)n / (double)g.NB / (double)g.sets / (double)g.T + 1.0;
     uint32_t logG = 0;
-    while (logG < 5 && (double)(1u << logG) * 3.0 < avg_partials) ++logG;
+    while (logG < 3 && (double)(1u << logG) * 3.0 < avg_partials) ++logG;
     { ProfScope _p(ctx, "msm.gather");
-      const uint64_t nthr = nbt << logG;
-      k_msm_gather<<<(unsigned)((nthr + 127) / 128), 128, 0, st>>>(offsets, partial, buckets, heavy, heavyc, g, logG);
+      const uint64_t nslots = nbt << logG;
+      if (nslots * 4 <= (uint64_t)ctx->sm_count * 256) {     // room for four lanes per addition (latency-bound batch)
+        k_msm_gather<<<(unsigned)((nslots * 4 + 127) / 128), 128, 0, st>>>(offsets, partial, buckets, heavy, heavyc, g, logG);
+      } else {
+        k_msm_gather_plain<<<(unsigned)((nslots + 127) / 128), 128, 0, st>>>(offsets, partial, buckets, heavy, heavyc, g, logG);
+      }
       ZKC_LAUNCH_CHECK(ctx); }
     { ProfScope _p(ctx, "msm.gather_heavy");
-      k_msm_gather_heavy<<<ctx->sm_count * 4, 128, 128 * sizeof(G1Xyzz), st>>>(offsets, partial, buckets, heavy, heavyc, g);
+      k_msm_gather_heavy<<<ctx->sm_count * 4, 128, 8 * sizeof(G1Xyzz), st>>>(offsets, partial, buckets, heavy, heavyc, g);
       ZKC_LAUNCH_CHECK(ctx);
-      k_msm_gather_giant1<<<dim3(MSM_GIANT_SLICES, 16), 128, 128 * sizeof(G1Xyzz), st>>>(offsets, partial, hpart, heavy, heavyc, g);
+      k_msm_gather_giant1<<<dim3(MSM_GIANT_SLICES, 32), 128, 8 * sizeof(G1Xyzz), st>>>(offsets, partial, hpart, heavy, heavyc, g);
       ZKC_LAUNCH_CHECK(ctx);
-      k_msm_gather_giant2<<<64, MSM_GIANT_SLICES, MSM_GIANT_SLICES * sizeof(G1Xyzz), st>>>(hpart, buckets, heavy, heavyc, g);
+      k_msm_gather_giant2<<<64, MSM_GIANT_SLICES * 4, 8 * sizeof(G1Xyzz), st>>>(hpart, buckets, heavy, heavyc, g);
       ZKC_LAUNCH_CHECK(ctx); }
   }
   {
     ProfScope _p(ctx, "msm.reduce");
-    const uint32_t nchunks = (g.NB + RED_CHUNK - 1) / RED_CHUNK;
-    dim3 g1(g.c, nchunks, nc * g.sets), g2(g.c, nc * g.sets);
-    k_msm_reduce1<<<g1, 64, 64 * sizeof(G1Xyzz), st>>>(buckets, redp, g, nchunks);
-    ZKC_LAUNCH_CHECK(ctx);
-    k_msm_reduce2<<<g2, 32, 32 * sizeof(G1Xyzz), st>>>(redp, U, g, nchunks);
-    ZKC_LAUNCH_CHECK(ctx);
+    const uint32_t nsets = nc * g.sets;
+    G1Xyzz* node[2] = {redp, redp + (size_t)nsets * (g.NB / 16 + g.c + 8)};
+    uint32_t t0 = 0, nodes = g.NB, which = 0;      // NB = 2^(c-1) leaves: c - 1 levels
+    const G1Xyzz* in = nullptr;
+    while (nodes > 1) {
+      const uint32_t remaining = g.c - 1 - t0;
+      const uint32_t m = tree_levels(t0, remaining, 48 * 1024);
+      const size_t pts = (size_t)(1u << (m - 1)) * (t0 + 2) + (m > 1 ? (size_t)(1u << (m - 2)) * (t0 + 3) : 0);
+      // Four lanes per addition (xyzz_add_quad) while the launch leaves the machine mostly idle — the chain of dependent additions
+      // is what it costs then —, one lane per addition when there are enough merges to fill it (many columns: throughput-bound).
+      const uint32_t first = (1u << (m - 1)) * (t0 + 1);           // additions of the first, widest level of one CTA
+      const uint64_t ctas = (uint64_t)(nodes >> m) * nsets;
+      const bool quad = ctas * std::min<uint32_t>(first, 64) * 4 <= (uint64_t)ctx->sm_count * 512;
+      if (quad) {
+        const uint32_t threads = first <= 16 ? 64 : first <= 32 ? 128 : 256;
+        k_msm_tree<true><<<dim3(nodes >> m, nsets), threads, pts * sizeof(G1Xyzz), st>>>(in, node[which], buckets, U, t0, m, nodes, g.NB, g.c);
+      } else {
+        const uint32_t threads = first <= 32 ? 32 : first <= 64 ? 64 : 128;
+        k_msm_tree<false><<<dim3(nodes >> m, nsets), threads, pts * sizeof(G1Xyzz), st>>>(in, node[which], buckets, U, t0, m, nodes, g.NB, g.c);
+      }
+      ZKC_LAUNCH_CHECK(ctx);
+      in = node[which]; which ^= 1;
+      t0 += m; nodes >>= m;
+    }
   }
   ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(total_out, offsets + nbt, 4, cudaMemcpyDeviceToDevice, st));
   return ZKC_OK;
