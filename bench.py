@@ -44,6 +44,11 @@ WORKLOADS = {
     "agg_k20": dict(k=20, gate_cols=17, shape="base_fast", desc="aggregation shape reduced to k=20"),
     "sha_k15": dict(k=15, gate_cols=112, shape="sha_bit", desc="SHA256-bit shape reduced to k=15"),
 }
+# BASELINE config 4: the four independent proofs of a 3-certificate chain (/root/reference/src/tests/x509_aggregation.rs:34-57,
+# src/bin/cli.rs:385-390), with the single-GPU time and the non-scaling share of each shape measured on this pool's B200s
+# (profiles/r02_*): what the scheduler (dist.plan_chain) cuts the GPUs into teams with
+CHAIN4 = ["rsa_k17", "sha_k19", "rsa_k17", "sha_k19"]
+CHAIN_EST = {"rsa_k17": (0.0107, 0.75), "sha_k19": (0.122, 0.13)}
 ORACLE_MAX_K = {"base": 17, "base_fast": 17, "sha_bit": 15}   # real-size oracle proofs that finish within ~10 s on the box's cores
 FQMUL_PER_MADD = 10      # XYZZ mixed add: 8M + 2S
 IMADW_PER_FQMUL = 128    # 64 (a*b) + 64 (m*p) IMAD.WIDE per Montgomery product
@@ -353,13 +358,91 @@ def throughput(env, w, K, nctx):
     return {"contexts": nctx, "proofs": nctx * K, "wall_s": dt, "proofs_per_s": nctx * K / dt, "ms_per_proof_amortised": dt / (nctx * K) * 1e3}
 
 
+def run_chain(env, args):
+    """BASELINE config 4: wall-clock of the whole 4-proof chain on N GPUs.  The GPUs are cut into teams by the scheduler; each
+    team proves its share of the chain one proof after the other, every proof spread over the team (zkc_team_*).  Parity:
+    every team proof is compared byte for byte with the same proof made by one GPU alone."""
+    import torch
+    import torch.distributed as dist
+    pkg, ctx, world, rank = env.pkg, env.ctx, env.world, env.rank
+    jobs = [(name,) + CHAIN_EST[name] for name in CHAIN4]
+    teams, est = pkg.dist.plan_chain(jobs, world)
+    groups = [dist.new_group(list(range(f, f + sz))) if (world > 1 and sz > 1) else None for f, sz, _ in teams]   # same order on every rank
+    mine = pkg.dist.team_of(teams, rank)
+    first, size, js = teams[mine]
+    if size > 1:
+        ctx.team_init(groups[mine])
+    ws = {}
+    for j in js:
+        wl = WORKLOADS[CHAIN4[j]]
+        ws[j] = pkg.workload.build(ctx, wl["k"], wl["gate_cols"], seed=100 + j, shape=wl.get("shape", "base"))
+    W, K = max(args.warmup, 1), args.steps
+    seed_of = lambda j, i: pkg.seed_from_u64(7000 + 100 * j + i)
+
+    def chain_once(i):
+        return {j: pkg.create_proof(ws[j].pk, ws[j].advice_dev, ws[j].instances, seed_of(j, i)) for j in js}
+    for i in range(W):
+        chain_once(i)
+    total_ms, wall, proofs = 0.0, 0.0, None
+    for i in range(K):
+        env.flush.zero_()
+        env.barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        proofs = chain_once(W + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = env.max_over_ranks(e0.elapsed_time(e1))
+        env.barrier()
+        wall += time.perf_counter() - t0
+        total_ms += ms
+    launches = ctx.launches
+    # parity: the same proofs by this GPU alone (untimed), and their single-GPU times for the "one proof per GPU" comparison
+    if size > 1:
+        ctx.team_leave()
+    single_ms = {}
+    ok = True
+    if rank == first:
+        for j in js:
+            env.flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            pkg.create_proof(ws[j].pk, ws[j].advice_dev, ws[j].instances, seed_of(j, 0))
+            e0.record()
+            alone = pkg.create_proof(ws[j].pk, ws[j].advice_dev, ws[j].instances, seed_of(j, W + K - 1))
+            e1.record()
+            torch.cuda.synchronize()
+            single_ms[j] = e0.elapsed_time(e1)
+            ok = ok and alone == proofs[j]
+    gathered = pkg.dist.gather_objects({"ok": ok, "single_ms": single_ms, "proofs": {j: len(p) for j, p in (proofs or {}).items()} if rank == first else {}})
+    if rank == 0:
+        single = {}
+        for part in gathered:
+            single.update(part["single_ms"])
+        all_ok = all(part["ok"] for part in gathered)
+        naive = max(single.values()) if world >= len(CHAIN4) else None
+        line = {"metric": "chain4_wall_s", "value": total_ms / K / 1e3, "unit": "s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": total_ms / K, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u256 (BN254 Fr/Fq Montgomery, exact integer)", "data": "synthetic",
+                "config": {"workload": "chain4", "desc": "3-certificate chain: 2 x RSA k=17 + 2 x SHA256-bit k=19 proofs (BASELINE config 4), witnesses resident",
+                           "jobs": CHAIN4, "teams": [{"first_rank": f, "gpus": sz, "jobs": [CHAIN4[j] for j in jj]} for f, sz, jj in teams],
+                           "scheduler_estimate_s": est, "l2": "flushed between steps (256 MiB memset, untimed)",
+                           "parity": "every team proof == the same proof by one GPU alone: %s" % all_ok},
+                "single_gpu_ms_per_proof": {"%d:%s" % (j, CHAIN4[j]): round(v, 3) for j, v in sorted(single.items())},
+                "one_proof_per_gpu_ms": naive, "sum_of_single_gpu_ms": sum(single.values()),
+                "host_wall_s_per_chain": wall / K, "gpu_launches": int(launches)}
+        assert all_ok, "a team proof differs from the single-GPU proof"
+        print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="rsa_k17", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="rsa_k17", choices=sorted(WORKLOADS) + ["chain4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip other_workloads / throughput (N = 1) and the team record (N > 1)")
     ap.add_argument("--extras-budget-s", type=float, default=240.0, help="wall-clock budget for the extra records; what does not fit is reported as skipped")
@@ -367,7 +450,13 @@ def main():
                     help="N > 1: the HEADLINE is ONE proof spread over the N GPUs (MSM by point range, transforms by column, h(X) by row block; "
                          "strong scaling) instead of N independent proofs (default, weak scaling)")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    if args.workload == "chain4" and args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"metric": "chain4_wall_s", "value": None, "unit": "s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+                              "warmup": args.warmup, "higher_is_better": False, "config": {"workload": "chain4"},
+                              "unavailable": "the restated CPU oracle needs minutes per SHA256 k=19 proof; no scaled number is reported"}))
+        return 0
+    wl = WORKLOADS.get(args.workload)
     if args.impl == "reference":
         return run_reference(args, wl)
 
@@ -404,6 +493,11 @@ def main():
         return float(t.item())
     env.barrier, env.max_over_ranks = barrier, max_over_ranks
 
+    if args.workload == "chain4":
+        rc = run_chain(env, args)
+        if world > 1:
+            dist.destroy_process_group()
+        return rc
     team = args.team and world > 1
     if team:
         ctx.team_init()      # every rank proves the SAME certificate together (zkc_team_init: NCCL over NVLink); joined before

@@ -424,20 +424,61 @@ class ProvingKey:
     cs: circuit.ConstraintSystem; fixed / sigma: (num_columns * n, 4) Montgomery Lagrange columns
     (pk.fixed_values, pk.permutation.permutations); transcript_repr: (1, 4) Montgomery."""
 
-    def __init__(self, params, cs, fixed, sigma, transcript_repr, zeta_choice=0):
+    def __init__(self, params, cs, fixed, sigma, transcript_repr, zeta_choice=0, copies=None, file_bytes=None, num_selectors=0,
+                 file_format="unchecked"):
+        """keygen_pk from the Lagrange columns: fixed + sigma (zkc_pk_load), fixed + copy constraints (`copies`: (m, 4) uint32
+        rows (left column, left row, right column, right row) over cs.permutation's columns; zkc_keygen_pk assembles the
+        permutation), or the bytes of a `.pk` file (zkc_pk_read; file_format "raw" = SerdeFormat::RawBytes, checked)."""
         self.params, self.cs, self.ctx = params, cs, params.ctx
         n = cs.n
         blob = cs.serialize()
-        fixed = _np(fixed, 4) if cs.num_fixed else np.zeros((0, 4), dtype=np.uint64)
-        sigma = _np(sigma, 4) if cs.permutation else np.zeros((0, 4), dtype=np.uint64)
-        assert fixed.shape[0] == cs.num_fixed * n and sigma.shape[0] == len(cs.permutation) * n
         tr = _np(transcript_repr, 4)
         self._h = C.c_void_p()
-        self.ctx.check(lib().zkc_pk_load(self.ctx._h, params._h, blob, C.c_size_t(len(blob)), _hp(fixed), _hp(sigma), _hp(tr),
-                                         C.c_int(zeta_choice), C.byref(self._h)))
+        if file_bytes is not None:
+            raw = np.frombuffer(file_bytes, dtype=np.uint8)
+            self.ctx.check(lib().zkc_pk_read(self.ctx._h, params._h, blob, C.c_size_t(len(blob)), _hp(raw), C.c_size_t(raw.size), C.c_uint32(num_selectors),
+                                             C.c_int({"raw": 0, "unchecked": 1}[file_format]), _hp(tr), C.c_int(zeta_choice), C.byref(self._h)))
+        else:
+            fixed = _np(fixed, 4) if cs.num_fixed else np.zeros((0, 4), dtype=np.uint64)
+            assert fixed.shape[0] == cs.num_fixed * n
+            if copies is not None:
+                cp = np.ascontiguousarray(np.asarray(copies, dtype=np.uint32).reshape(-1, 4))
+                self.ctx.check(lib().zkc_keygen_pk(self.ctx._h, params._h, blob, C.c_size_t(len(blob)), _hp(fixed), _hp(cp), C.c_size_t(cp.shape[0]),
+                                                   _hp(tr), C.c_int(zeta_choice), C.byref(self._h)))
+            else:
+                sigma = _np(sigma, 4) if cs.permutation else np.zeros((0, 4), dtype=np.uint64)
+                assert sigma.shape[0] == len(cs.permutation) * n
+                self.ctx.check(lib().zkc_pk_load(self.ctx._h, params._h, blob, C.c_size_t(len(blob)), _hp(fixed), _hp(sigma), _hp(tr),
+                                                 C.c_int(zeta_choice), C.byref(self._h)))
         info = (C.c_uint32 * 8)()
         lib().zkc_pk_info(self._h, info)
         self.k, self.extended_k, self.degree, self.blinding_factors, self.num_sets, self.num_lookups = list(info)[:6]
+
+    @classmethod
+    def keygen(cls, params, cs, fixed, copies, transcript_repr, zeta_choice=0):
+        """keygen_pk as gen_pk reaches it: fixed columns + the copy constraints synthesis recorded"""
+        return cls(params, cs, fixed, None, transcript_repr, zeta_choice, copies=copies)
+
+    @classmethod
+    def read(cls, params, cs, data, transcript_repr, num_selectors=0, file_format="unchecked", zeta_choice=0):
+        """ProvingKey::read (`*.pk`, SerdeFormat::RawBytesUnchecked by default, as read_pk uses)"""
+        return cls(params, cs, None, None, transcript_repr, zeta_choice, file_bytes=data, num_selectors=num_selectors, file_format=file_format)
+
+    def write(self, selectors=None, be=True):
+        """ProvingKey::write -> bytes.  selectors: (num_selectors, ceil(n / 8)) uint8 bit-packed activations (vk.selectors) or None"""
+        ns = 0 if selectors is None else int(selectors.shape[0])
+        lib().zkc_pk_file_size.restype = C.c_size_t
+        size = lib().zkc_pk_file_size(self._h, C.c_uint32(ns))
+        out = np.zeros(size, dtype=np.uint8)
+        sel = None if selectors is None else _hp(np.ascontiguousarray(selectors, dtype=np.uint8))
+        self.ctx.check(lib().zkc_pk_write(self.ctx._h, self._h, sel, C.c_uint32(ns), C.c_int(1 if be else 0), _hp(out), C.c_size_t(size)))
+        return out.tobytes()
+
+    def sigma(self):
+        """pk.permutation.permutations: (n_perm_columns * n, 4) Montgomery Lagrange columns"""
+        out = np.zeros((len(self.cs.permutation) * self.cs.n, 4), dtype=np.uint64)
+        self.ctx.check(lib().zkc_pk_get_sigma(self.ctx._h, self._h, _hp(out)))
+        return out
 
     def __del__(self):
         try:
@@ -577,6 +618,49 @@ class RandomPolySpec:
             c.kind, c.rng_kind, c.first_word = 1, (0 if rng == "chacha20" else 1), int(first_word)
             c.seed[:] = list(seed)
         self._c = c
+
+
+# ---- keygen helpers (host only) -------------------------------------------------------------------------------------
+def keygen_permutation_mapping(k, num_columns, copies):
+    """permutation::keygen::Assembly over the copy list ((m, 4): left col, left row, right col, right row): flat mapping
+    [col * n + row] -> col' * n + row' (uint64)"""
+    cp = np.ascontiguousarray(np.asarray(copies, dtype=np.uint32).reshape(-1, 4))
+    out = np.zeros(num_columns << k, dtype=np.uint64)
+    st = lib().zkc_keygen_permutation_mapping(C.c_uint32(k), C.c_uint32(num_columns), _hp(cp), C.c_size_t(cp.shape[0]), _hp(out))
+    if st != 0:
+        raise ZkcError(st, "zkc_keygen_permutation_mapping")
+    return out
+
+
+def compress_selectors(k, activations, max_degrees, max_degree):
+    """ConstraintSystem::compress_selectors.  activations: (num_selectors, n) 0/1; returns (combination_of, root_of,
+    combination_len, columns) with columns (num_combinations, n) uint32"""
+    act = np.ascontiguousarray(activations, dtype=np.uint8)
+    S, n = act.shape
+    assert n == 1 << k
+    md = np.ascontiguousarray(max_degrees, dtype=np.uint32)
+    comb, root, clen = (np.zeros(S, dtype=np.uint32) for _ in range(3))
+    cols = np.zeros((max(S, 1), n), dtype=np.uint32)
+    ncomb = C.c_uint32(0)
+    st = lib().zkc_keygen_compress_selectors(C.c_uint32(k), C.c_uint32(S), _hp(act), _hp(md), C.c_uint32(max_degree), _hp(comb), _hp(root),
+                                             _hp(clen), _hp(cols), C.byref(ncomb))
+    if st != 0:
+        raise ZkcError(st, "zkc_keygen_compress_selectors")
+    return comb, root, clen, cols[:ncomb.value].copy()
+
+
+class PkFileLayout(C.Structure):
+    _fields_ = [(nm, C.c_uint64) for nm in ("k_off", "num_fixed_off", "fixed_commitments_off", "perm_commitments_off", "selectors_off", "l0_off",
+                                            "l_last_off", "l_active_row_off", "fixed_values_off", "fixed_polys_off", "fixed_cosets_off",
+                                            "perm_values_off", "perm_polys_off", "perm_cosets_off", "total")]
+
+
+def pk_file_layout(k, extended_k, num_fixed, num_perm, num_selectors=0):
+    L = PkFileLayout()
+    st = lib().zkc_pk_file_layout(C.c_uint32(k), C.c_uint32(extended_k), C.c_uint32(num_fixed), C.c_uint32(num_perm), C.c_uint32(num_selectors), C.byref(L))
+    if st != 0:
+        raise ZkcError(st, "zkc_pk_file_layout")
+    return L
 
 
 # ---- ParamsKZG files (host only) -----------------------------------------------------------------------------------

@@ -108,10 +108,48 @@ extern "C" void zkc_pk_free(zkc_pk* pk) {
   delete pk;
 }
 
+namespace {
+// where the Lagrange columns of a key come from: one contiguous host / device array, or per-column host pointers (a `.pk`
+// file: every column sits behind its own length prefix), or — sigma only — a permutation mapping to expand on the device
+struct ColumnSource {
+  const zkc_fr* contiguous = nullptr; bool on_device = false;
+  const uint8_t* file = nullptr; uint64_t first_off = 0, col_stride = 0;   // column c at file + first_off + c * col_stride
+  const uint64_t* mapping = nullptr;                                        // sigma: host mapping[col * n + row] = col' * n + row'
+  bool present() const { return contiguous || file || mapping; }
+};
+// sigma_col[row] = DELTA^col' * omega^row' through the permutation mapping (permutation::keygen::Assembly::build_pk)
+__global__ void k_sigma_from_mapping(const uint64_t* mapping, const Fr* delta_pows, const Fr* omega_pows, Fr* sigma, uint64_t n, uint64_t total) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const uint64_t m = mapping[i];
+  fe_store(sigma + i, fe_mul(fe_load(delta_pows + m / n), fe_load_nc(omega_pows + m % n)));
+}
+int upload_columns(zkc_ctx* ctx, Fr* dst, const ColumnSource& src, uint32_t ncols, uint64_t n) {
+  cudaStream_t st = ctx->stream;
+  if (src.contiguous) {
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src.contiguous, (size_t)ncols * n * sizeof(Fr), src.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  } else {
+    for (uint32_t c = 0; c < ncols; ++c)
+      ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(dst + (size_t)c * n, src.file + src.first_off + (uint64_t)c * src.col_stride, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  }
+  return ZKC_OK;
+}
+int pk_build(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs_len, const ColumnSource& fixed, const ColumnSource& sigma,
+             const zkc_fr* transcript_repr, int zeta_choice, zkc_pk** out);
+}  // namespace
+
 extern "C" int zkc_pk_load(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs_len, const zkc_fr* fixed,
                            const zkc_fr* sigma, const zkc_fr* transcript_repr, int zeta_choice, zkc_pk** out) {
   if (!ctx || !srs || !cs_blob || !transcript_repr || !out) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: null argument");
   CtxLock lock(ctx);
+  ColumnSource f, s;
+  f.contiguous = fixed; s.contiguous = sigma;
+  return pk_build(ctx, srs, cs_blob, cs_len, f, s, transcript_repr, zeta_choice, out);
+}
+
+namespace {
+int pk_build(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs_len, const ColumnSource& fixed, const ColumnSource& sigma,
+             const zkc_fr* transcript_repr, int zeta_choice, zkc_pk** out) {
   std::unique_ptr<zkc_pk, void (*)(zkc_pk*)> pk(new zkc_pk(), zkc_pk_free);
   pk->ctx = ctx; pk->srs = srs;
   Cs& cs = pk->cs;
@@ -125,7 +163,7 @@ extern "C" int zkc_pk_load(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_b
   if (n < cs.blinding_factors + 3) return set_err(ctx, ZKC_ERR_NOT_ENOUGH_ROWS, "zkc_pk_load: not enough rows for the blinding factors");
   if (cs.chunk_len > PERM_MAX_CHUNK) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: permutation chunk longer than PERM_MAX_CHUNK");
   if (cs.nsets() > PERM_MAX_SETS) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: too many permutation sets");
-  if ((cs.num_fixed && !fixed) || (nperm && !sigma)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: missing fixed / sigma columns");
+  if ((cs.num_fixed && !fixed.present()) || (nperm && !sigma.present())) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_load: missing fixed / sigma columns");
   ZKC_TRY(zkc_domain_create(ctx, cs.degree, cs.k, zeta_choice, &pk->dom));
   zkc_domain_info di;
   zkc_domain_get_info(pk->dom, &di);
@@ -140,14 +178,36 @@ extern "C" int zkc_pk_load(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_b
   ZKC_TRY(dev_alloc(ctx, P, &P->sigma_values, (size_t)S * n)); ZKC_TRY(dev_alloc(ctx, P, &P->sigma_polys, (size_t)S * n));
   ZKC_TRY(dev_alloc(ctx, P, &P->sigma_cosets, (size_t)S * en));
   cudaStream_t st = ctx->stream;
+  // omega^i (needed first when the sigma columns are expanded from a permutation mapping)
+  ZKC_TRY(dev_alloc(ctx, P, &P->omega_pows, n));
+  {
+    Fr omega; memcpy(omega.v, &di.omega, 32);
+    ZKC_TRY(fr_powers(ctx, P->omega_pows, n, omega, fe_one<FrP>()));
+  }
   if (F) {
-    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(P->fixed_values, fixed, (size_t)F * n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    ZKC_TRY(upload_columns(ctx, P->fixed_values, fixed, F, n));
     ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(P->fixed_polys, P->fixed_values, (size_t)F * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     ZKC_TRY(dom_lagrange_to_coeff(ctx, P->dom, P->fixed_polys, F));
     ZKC_TRY(dom_coeff_to_extended(ctx, P->dom, P->fixed_polys, n, P->fixed_cosets, F));
   }
+  if (S && sigma.mapping) {
+    // DELTA^c on the host (a handful of products), the n * S gathers on the device
+    std::vector<Fr> dp(S);
+    Fr d = fe_one<FrP>();
+    const Fr DELTA = fr_from_raw_words(FR_DELTA_RAW);
+    for (uint32_t c = 0; c < S; ++c) { dp[c] = d; d = fe_mul(d, DELTA); }
+    struct DevTmp { void* p = nullptr; ~DevTmp() { if (p) cudaFree(p); } } map_h, dp_h;
+    ZKC_CUDA_TRY(ctx, cudaMalloc(&map_h.p, (size_t)S * n * sizeof(uint64_t)));
+    ZKC_CUDA_TRY(ctx, cudaMalloc(&dp_h.p, (size_t)S * sizeof(Fr)));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(map_h.p, sigma.mapping, (size_t)S * n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(dp_h.p, dp.data(), (size_t)S * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    k_sigma_from_mapping<<<(unsigned)(((uint64_t)S * n + 255) / 256), 256, 0, st>>>((const uint64_t*)map_h.p, (const Fr*)dp_h.p, P->omega_pows, P->sigma_values, n, (uint64_t)S * n);
+    ctx->launches++;
+    ZKC_CUDA_TRY(ctx, cudaGetLastError());
+    ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));   // the temporaries are released when this block ends
+  }
   if (S) {
-    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(P->sigma_values, sigma, (size_t)S * n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (!sigma.mapping) ZKC_TRY(upload_columns(ctx, P->sigma_values, sigma, S, n));
     ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(P->sigma_polys, P->sigma_values, (size_t)S * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     ZKC_TRY(dom_lagrange_to_coeff(ctx, P->dom, P->sigma_polys, S));
     ZKC_TRY(dom_coeff_to_extended(ctx, P->dom, P->sigma_polys, n, P->sigma_cosets, S));
@@ -176,12 +236,6 @@ extern "C" int zkc_pk_load(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_b
     cudaStreamSynchronize(st);   // the temporaries are released when this block ends
     ZKC_TRY(s1);
   }
-  // omega^i
-  ZKC_TRY(dev_alloc(ctx, P, &P->omega_pows, n));
-  {
-    Fr omega; memcpy(omega.v, &di.omega, 32);
-    ZKC_TRY(fr_powers(ctx, P->omega_pows, n, omega, fe_one<FrP>()));
-  }
   // programs, query tables, pointer tables
   ZKC_TRY(upload_program(ctx, P, cs.gates, P->gates));
   P->lookups.resize(cs.lookups.size());
@@ -209,6 +263,103 @@ extern "C" int zkc_pk_load(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_b
   if (F) ZKC_TRY(commit_points(ctx, srs, 1, P->fixed_values, n, F, P->fixed_comm));
   if (S) ZKC_TRY(commit_points(ctx, srs, 1, P->sigma_values, n, S, P->sigma_comm));
   ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  *out = pk.release();
+  return ZKC_OK;
+}
+}  // namespace
+
+// keygen_pk from the fixed columns and the copy constraints synthesis recorded (gen_pk: /root/reference/src/helpers.rs:213,265)
+extern "C" int zkc_keygen_pk(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs_len, const zkc_fr* fixed, const uint32_t* copies,
+                             size_t num_copies, const zkc_fr* transcript_repr, int zeta_choice, zkc_pk** out) {
+  if (!ctx || !srs || !cs_blob || !transcript_repr || !out || (num_copies && !copies)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_keygen_pk: null argument");
+  CtxLock lock(ctx);
+  Cs cs;
+  std::string perr;
+  if (!zkc::host::parse_cs(cs_blob, cs_len, cs, perr)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_keygen_pk: " + perr);
+  std::vector<uint64_t> mapping(cs.perm.size() * cs.n());
+  const int st = zkc_keygen_permutation_mapping(cs.k, (uint32_t)cs.perm.size(), copies, num_copies, mapping.data());
+  if (st != ZKC_OK) return set_err(ctx, st, "zkc_keygen_pk: copy constraint outside the permutation columns / rows");
+  ColumnSource f, s;
+  f.contiguous = fixed; s.mapping = mapping.data();
+  return pk_build(ctx, srs, cs_blob, cs_len, f, s, transcript_repr, zeta_choice, out);
+}
+
+extern "C" int zkc_pk_get_sigma(zkc_ctx* ctx, const zkc_pk* pk, zkc_fr* sigma_out) {
+  if (!ctx || !pk || (!pk->cs.perm.empty() && !sigma_out)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_get_sigma: null argument");
+  CtxLock lock(ctx);
+  if (!pk->cs.perm.empty()) {
+    ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(sigma_out, pk->sigma_values, pk->cs.perm.size() * pk->cs.n() * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return ZKC_OK;
+}
+
+// ---- ProvingKey files (layout: csrc/host/keygen.cpp) --------------------------------------------------------------------------
+extern "C" size_t zkc_pk_file_size(const zkc_pk* pk, uint32_t num_selectors) {
+  zkc_pk_file_layout_t L;
+  if (!pk || zkc_pk_file_layout(pk->cs.k, pk->ext_k, pk->cs.num_fixed, (uint32_t)pk->cs.perm.size(), num_selectors, &L) != ZKC_OK) return 0;
+  return (size_t)L.total;
+}
+
+extern "C" int zkc_pk_write(zkc_ctx* ctx, const zkc_pk* pk, const uint8_t* selectors, uint32_t num_selectors, int be, uint8_t* out, size_t cap) {
+  if (!ctx || !pk || !out || (num_selectors && !selectors)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_write: null argument");
+  CtxLock lock(ctx);
+  const Cs& cs = pk->cs;
+  const uint32_t F = cs.num_fixed, S = (uint32_t)cs.perm.size();
+  const uint64_t n = cs.n(), en = 1ull << pk->ext_k;
+  zkc_pk_file_layout_t L;
+  if (zkc_pk_file_layout(cs.k, pk->ext_k, F, S, num_selectors, &L) != ZKC_OK || cap < L.total) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_write: buffer too small");
+  ZKC_TRY(zkc_pk_file_write_headers(out, cap, cs.k, pk->ext_k, F, S, num_selectors, be));
+  if (F) memcpy(out + L.fixed_commitments_off, pk->fixed_comm.data(), (size_t)F * 64);
+  if (S) memcpy(out + L.perm_commitments_off, pk->sigma_comm.data(), (size_t)S * 64);
+  if (num_selectors) memcpy(out + L.selectors_off, selectors, (size_t)num_selectors * ((n + 7) / 8));
+  cudaStream_t st = ctx->stream;
+  auto d2h = [&](uint64_t off, const Fr* src, uint64_t len) { return cudaMemcpyAsync(out + off, src, len * sizeof(Fr), cudaMemcpyDeviceToHost, st); };
+  ZKC_CUDA_TRY(ctx, d2h(L.l0_off + 4, pk->l0, en)); ZKC_CUDA_TRY(ctx, d2h(L.l_last_off + 4, pk->l_last, en)); ZKC_CUDA_TRY(ctx, d2h(L.l_active_row_off + 4, pk->l_active, en));
+  auto slice = [&](uint64_t off, const Fr* base, uint32_t count, uint64_t len) -> int {
+    for (uint32_t c = 0; c < count; ++c) ZKC_CUDA_TRY(ctx, d2h(off + 4 + (uint64_t)c * (4 + 32 * len) + 4, base + (size_t)c * len, len));
+    return ZKC_OK;
+  };
+  ZKC_TRY(slice(L.fixed_values_off, pk->fixed_values, F, n)); ZKC_TRY(slice(L.fixed_polys_off, pk->fixed_polys, F, n)); ZKC_TRY(slice(L.fixed_cosets_off, pk->fixed_cosets, F, en));
+  ZKC_TRY(slice(L.perm_values_off, pk->sigma_values, S, n)); ZKC_TRY(slice(L.perm_polys_off, pk->sigma_polys, S, n)); ZKC_TRY(slice(L.perm_cosets_off, pk->sigma_cosets, S, en));
+  ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return ZKC_OK;
+}
+
+extern "C" int zkc_pk_read(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs_len, const uint8_t* file, size_t file_len,
+                           uint32_t num_selectors, int format, const zkc_fr* transcript_repr, int zeta_choice, zkc_pk** out) {
+  if (!ctx || !srs || !cs_blob || !file || !transcript_repr || !out || format < 0 || format > 1) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_read: bad argument");
+  CtxLock lock(ctx);
+  Cs cs;
+  std::string perr;
+  if (!zkc::host::parse_cs(cs_blob, cs_len, cs, perr)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_read: " + perr);
+  const uint32_t F = cs.num_fixed, S = (uint32_t)cs.perm.size();
+  const uint64_t n = cs.n();
+  // extended_k follows from the constraint system's degree (EvaluationDomain::new)
+  uint32_t ext_k = cs.k;
+  while ((1ull << ext_k) < n * (uint64_t)(cs.degree - 1)) ++ext_k;
+  int be = 1;
+  if (zkc_pk_file_check(file, file_len, cs.k, ext_k, F, S, num_selectors, -1, &be) != ZKC_OK)
+    return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_read: the file does not have the shape of a ProvingKey for this constraint system");
+  zkc_pk_file_layout_t L;
+  zkc_pk_file_layout(cs.k, ext_k, F, S, num_selectors, &L);
+  ColumnSource f, s;
+  f.file = file; f.first_off = L.fixed_values_off + 8; f.col_stride = 4 + 32 * n;
+  s.file = file; s.first_off = L.perm_values_off + 8; s.col_stride = 4 + 32 * n;
+  if (format == 0) {   // SerdeFormat::RawBytes: every scalar canonical
+    for (uint32_t c = 0; c < F; ++c) if (!zkc_fr_column_is_canonical((const zkc_fr*)(file + f.first_off + (uint64_t)c * f.col_stride), n)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_read: non-canonical field element in fixed_values");
+    for (uint32_t c = 0; c < S; ++c) if (!zkc_fr_column_is_canonical((const zkc_fr*)(file + s.first_off + (uint64_t)c * s.col_stride), n)) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_read: non-canonical field element in the permutation columns");
+  }
+  std::unique_ptr<zkc_pk, void (*)(zkc_pk*)> pk(nullptr, zkc_pk_free);
+  {
+    zkc_pk* raw = nullptr;
+    ZKC_TRY(pk_build(ctx, srs, cs_blob, cs_len, f, s, transcript_repr, zeta_choice, &raw));
+    pk.reset(raw);
+  }
+  if (format == 0) {   // the commitments in the file must be the commitments of the columns in the file
+    if ((F && memcmp(file + L.fixed_commitments_off, pk->fixed_comm.data(), (size_t)F * 64)) || (S && memcmp(file + L.perm_commitments_off, pk->sigma_comm.data(), (size_t)S * 64)))
+      return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_pk_read: the verifying key's commitments do not match the columns");
+  }
   *out = pk.release();
   return ZKC_OK;
 }

@@ -51,6 +51,61 @@ def prove_chain(jobs, prove_fn, group=None):
     return [merged[i] for i in range(len(jobs))]
 
 
+# ---- certificate-chain scheduler (BASELINE config 4) ----------------------------------------------------------------
+# The chain's proofs are independent (2 x RSA k=17 + 2 x SHA256 k=19 for a 3-certificate chain:
+# /root/reference/src/tests/x509_aggregation.rs:34-57, src/bin/cli.rs:385-390) but very unequal: one SHA proof costs about
+# ten RSA proofs.  With more GPUs than proofs, or unequal proofs, "one proof per GPU" leaves most GPUs idle, so the GPUs are
+# partitioned into TEAMS (zkc_team_*: one create_proof spread over the team) and the proofs are dealt to the teams.
+def team_time(t1, g, serial_frac):
+    """estimated time of a proof that takes t1 on one GPU when a team of g proves it (Amdahl with the measured
+    non-scaling share: Fiat-Shamir-serial bucket phases, replicated scans, exchanges)"""
+    return t1 * (serial_frac + (1.0 - serial_frac) / g)
+
+
+def plan_chain(jobs, world):
+    """jobs: [(name, t1_seconds, serial_frac)], world: number of GPUs.  Returns (teams, makespan): teams = list of
+    (first_rank, size, [job indices in run order]); every rank belongs to exactly one team.  Exhaustive over the ways to cut
+    `world` GPUs into at most len(jobs) contiguous teams (non-increasing sizes), longest-processing-time dealing of the jobs
+    per cut; the search space is tiny (world <= 8, a handful of jobs)."""
+    njobs = len(jobs)
+    order = sorted(range(njobs), key=lambda i: -jobs[i][1])
+
+    def cuts(total, parts, cap):
+        if parts == 0:
+            if total == 0:
+                yield []
+            return
+        for first in range(min(cap, total - (parts - 1)), 0, -1):
+            for rest in cuts(total - first, parts - 1, first):
+                yield [first] + rest
+    best = None
+    for nteams in range(1, min(njobs, world) + 1):
+        for sizes in cuts(world, nteams, world):
+            load = [0.0] * nteams
+            deal = [[] for _ in range(nteams)]
+            for j in order:
+                # the team that would finish this job first
+                t = min(range(nteams), key=lambda q: (load[q] + team_time(jobs[j][1], sizes[q], jobs[j][2]), q))
+                load[t] += team_time(jobs[j][1], sizes[t], jobs[j][2])
+                deal[t].append(j)
+            span = max(load)
+            if best is None or span < best[0] - 1e-12:
+                best = (span, sizes, deal)
+    span, sizes, deal = best
+    teams, first = [], 0
+    for size, js in zip(sizes, deal):
+        teams.append((first, size, js))
+        first += size
+    return teams, span
+
+
+def team_of(teams, rank):
+    for idx, (first, size, js) in enumerate(teams):
+        if first <= rank < first + size:
+            return idx
+    raise ValueError("rank outside the plan")
+
+
 def sum_partials(local_point, add_fn, group=None):
     """point-sharded MSM epilogue: gather one partial sum per rank and fold them with `add_fn`"""
     parts = gather_objects(local_point, group)

@@ -3,7 +3,7 @@ using only the product library — what bench.py, smoke() and the multi-GPU driv
 
 Off the timed path: this is the work `gen_srs` + `gen_pk` + witness synthesis do in the reference
 (/root/reference/src/helpers.rs:201-216, 236-266).  Montgomery conversion, the sigma table and the
-SRS are produced on the device; torch is only the allocator/indexer here.
+SRS are produced on the device; torch is only the allocator here.
 """
 import numpy as np
 
@@ -61,22 +61,12 @@ def build(ctx, k, num_gate_cols, seed=0, circ=None, params=None, shape="base"):
         fixed = to_mont_dev(ctx, flat(w.circ.fixed))
         w.advice_dev = to_mont_dev(ctx, flat(w.circ.advice))
     w.instances = [to_host(to_mont_dev(ctx, c)) if len(c) else np.zeros((0, 4), dtype=np.uint64) for c in w.circ.instances]
-    # sigma_col[row] = DELTA^col' * omega^row' gathered through the permutation mapping
-    m = len(cs.permutation)
-    if isinstance(w.circ.copies, np.ndarray):
-        mapping = synth.build_permutation_mapping_fast(cs, w.circ.copies)
-    else:
-        mapping = synth.build_permutation_mapping(cs, w.circ.copies)
-    dom = api.EvaluationDomain(cs.degree(), k, ctx=ctx)
-    table = torch.empty((m * n, 4), dtype=torch.int64, device="cuda:%d" % ctx.device)
-    dpow = to_host(to_mont_dev(ctx, [pow(synth.DELTA, c, R_MOD) for c in range(m)]))
-    for c in range(m):
-        ctx.powers_dev(table[c * n:(c + 1) * n], dom.omega, dpow[c:c + 1])
-    ctx.sync()
-    sigma = table[torch.from_numpy(mapping).cuda(ctx.device)]
+    # keygen_pk behind the C ABI (zkc_keygen_pk): the permutation is assembled from the copy constraints on the host (C++), the
+    # sigma columns DELTA^col' * omega^row' are expanded on the device, then polys / cosets / vk commitments as for any key
     tr = to_host(to_mont_dev(ctx, [w.circ.transcript_repr()]))
     w.transcript_repr = tr          # (1, 4) Montgomery: vk.transcript_repr, also what verify_proof absorbs first
-    w.pk = api.ProvingKey(params, cs, to_host(fixed), to_host(sigma), tr)
+    copies = np.asarray(w.circ.copies, dtype=np.uint32).reshape(-1, 4)
+    w.pk = api.ProvingKey.keygen(params, cs, to_host(fixed), copies, tr)
     # pinned host copy of the witness for the end-to-end (host-buffer) path
     w.advice_pinned = w.advice_dev.cpu().pin_memory()
     w.advice_host = w.advice_pinned.numpy().view(np.uint64)

@@ -177,6 +177,48 @@ int zkc_pk_get_commitments(zkc_ctx* ctx, const zkc_pk* pk, zkc_g1_affine* fixed_
 /* out[8] = k, extended_k, cs.degree(), blinding_factors, #permutation sets, #lookups, #fixed, #permutation columns */
 int zkc_pk_info(const zkc_pk* pk, uint32_t* out);
 
+/* ---- keygen: what gen_pk does around the commitments (/root/reference/src/helpers.rs:213,265) --------------
+ * permutation::keygen::Assembly: replays the copy constraints (4 x u32 each: left column, left row, right column, right row;
+ * columns index cs.permutation's column list) in order and returns the cycle structure, mapping[col * n + row] = col' * n + row'
+ * (sigma_col[row] = DELTA^col' * omega^row').  Host only.  Out-of-range cells: ZKC_ERR_BOUNDS_FAILURE. */
+int zkc_keygen_permutation_mapping(uint32_t k, uint32_t num_columns, const uint32_t* copies, size_t num_copies, uint64_t* mapping_out);
+/* ConstraintSystem::compress_selectors: activations = num_selectors columns of n bytes (0 / 1), max_degrees[s] = largest gate
+ * degree the selector multiplies (0 = in no gate), max_degree = cs.degree().  Greedy upstream order.  combination_of[s] = fixed
+ * column the selector lands in, root_of[s] = the value j >= 1 that column holds on the selector's rows, combination_len[s] = L:
+ * the substitution is q * prod_{i = 1..L, i != j} (i - q).  columns_out: up to num_selectors columns of n u32.  Host only. */
+int zkc_keygen_compress_selectors(uint32_t k, uint32_t num_selectors, const uint8_t* activations, const uint32_t* max_degrees,
+                                  uint32_t max_degree, uint32_t* combination_of, uint32_t* root_of, uint32_t* combination_len,
+                                  uint32_t* columns_out, uint32_t* num_combinations);
+/* keygen_pk from what synthesis leaves behind: the fixed columns (selectors already substituted) and the copy constraints.
+ * The permutation is assembled on the host, the sigma columns are built on the device, the rest is zkc_pk_load. */
+int zkc_keygen_pk(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs_len, const zkc_fr* fixed /* num_fixed * n */,
+                  const uint32_t* copies, size_t num_copies, const zkc_fr* transcript_repr, int zeta_choice, zkc_pk** out);
+/* pk.permutation.permutations (the sigma columns, Lagrange basis) back on the host: n_perm_columns * n */
+int zkc_pk_get_sigma(zkc_ctx* ctx, const zkc_pk* pk, zkc_fr* sigma_out);
+
+/* ---- ProvingKey files: `*.pk` as snark-verifier-sdk's gen_pk writes and read_pk reads them with
+ * SerdeFormat::RawBytesUnchecked (/root/reference/src/bin/cli.rs:247,312,335,362,455).  Layout as recalled from
+ * ProvingKey::write (SURVEY OPEN-8, unpinned): see csrc/host/keygen.cpp.  Offsets of every section: */
+typedef struct {
+  uint64_t k_off, num_fixed_off, fixed_commitments_off, perm_commitments_off, selectors_off, l0_off, l_last_off, l_active_row_off,
+           fixed_values_off, fixed_polys_off, fixed_cosets_off, perm_values_off, perm_polys_off, perm_cosets_off, total;
+} zkc_pk_file_layout_t;
+int zkc_pk_file_layout(uint32_t k, uint32_t extended_k, uint32_t num_fixed, uint32_t num_perm, uint32_t num_selectors, zkc_pk_file_layout_t* out);
+int zkc_pk_file_write_headers(uint8_t* file, size_t cap, uint32_t k, uint32_t extended_k, uint32_t num_fixed, uint32_t num_perm,
+                              uint32_t num_selectors, int be);
+int zkc_pk_file_check(const uint8_t* file, size_t len, uint32_t k, uint32_t extended_k, uint32_t num_fixed, uint32_t num_perm,
+                      uint32_t num_selectors, int be /* -1 = detect */, int* be_out);
+int zkc_fr_column_is_canonical(const zkc_fr* col, size_t n);
+/* ProvingKey::write: every section of the resident key into `out` (size from zkc_pk_file_size).  selectors: num_selectors
+ * bit-packed activation columns (vk.selectors), may be NULL with num_selectors = 0.  be: 1 = big-endian counts (this revision). */
+size_t zkc_pk_file_size(const zkc_pk* pk, uint32_t num_selectors);
+int zkc_pk_write(zkc_ctx* ctx, const zkc_pk* pk, const uint8_t* selectors, uint32_t num_selectors, int be, uint8_t* out, size_t cap);
+/* ProvingKey::read: fixed_values and permutations stream from the file into the device, everything else is rebuilt there.
+ * format: 0 = RawBytes (scalars checked canonical, commitments checked on the curve and against the rebuilt ones),
+ * 1 = RawBytesUnchecked (trusted).  The constraint system comes from the circuit, as upstream (`read::<_, ConcreteCircuit>`). */
+int zkc_pk_read(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs_len, const uint8_t* file, size_t file_len,
+                uint32_t num_selectors, int format, const zkc_fr* transcript_repr, int zeta_choice, zkc_pk** out);
+
 typedef struct {
   int transcript;       /* 0 = Blake2bWrite<_, _, Challenge255>, 1 = Keccak256Write (halo2_proofs::transcript);
                            2 = snark-verifier EvmTranscript (gen_evm_proof_shplonk, cli.rs:519): Keccak-256 sponge over

@@ -341,3 +341,29 @@ def test_c_client_links_and_runs_host_entry_points(tmp_path):
     args = [exe] + (["--gpu"] if torch.cuda.is_available() else [])
     out = subprocess.run(args, capture_output=True, text=True)
     assert out.returncode == 0 and "cabi_host ok" in out.stdout, out.stderr
+
+
+def test_chain_scheduler_plans():
+    """dist.plan_chain (BASELINE config 4): every GPU in exactly one team, every proof dealt exactly once, and the plans for the
+    3-certificate chain (2 x RSA k=17 + 2 x SHA k=19) put the SHA proofs on the larger teams instead of one proof per GPU"""
+    d = pkg().dist
+    jobs = [("rsa", 0.0107, 0.75), ("sha", 0.122, 0.13), ("rsa", 0.0107, 0.75), ("sha", 0.122, 0.13)]
+    for world in range(1, 9):
+        teams, span = d.plan_chain(jobs, world)
+        ranks = [r for f, s, _ in teams for r in range(f, f + s)]
+        assert ranks == list(range(world))
+        assert sorted(j for _, _, js in teams for j in js) == [0, 1, 2, 3]
+        loads = [sum(d.team_time(jobs[j][1], s, jobs[j][2]) for j in js) for _, s, js in teams]
+        assert abs(max(loads) - span) < 1e-12
+        assert all(d.team_of(teams, r) == i for i, (f, s, _) in enumerate(teams) for r in range(f, f + s))
+        if world >= 2:
+            # never worse than one proof per GPU / round robin
+            naive = max(sum(jobs[j][1] for j in range(r, 4, min(world, 4))) for r in range(min(world, 4)))
+            assert span <= naive + 1e-12
+    teams8, span8 = d.plan_chain(jobs, 8)
+    assert [s for _, s, _ in teams8] == [4, 4] and all(sorted(jobs[j][0] for j in js) == ["rsa", "sha"] for _, _, js in teams8)
+    teams4, _ = d.plan_chain(jobs, 4)
+    assert [s for _, s, _ in teams4] == [2, 2]
+    # equal jobs, as many GPUs as jobs: one each
+    teams, _ = d.plan_chain([("a", 1.0, 0.5)] * 4, 4)
+    assert [s for _, s, _ in teams] == [1, 1, 1, 1]
