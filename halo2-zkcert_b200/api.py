@@ -163,7 +163,7 @@ class Context:
 
     # ---- field vectors -------------------------------------------------------------------
     def field_vec_op_dev(self, field, op, a, b, out):
-        ops = {"add": 0, "sub": 1, "mul": 2, "inv": 3, "from_canonical": 4, "to_canonical": 5, "neg": 6}
+        ops = {"add": 0, "sub": 1, "mul": 2, "inv": 3, "from_canonical": 4, "to_canonical": 5, "neg": 6, "square": 7}
         n = a.shape[0]
         self.check(lib().zkc_field_vec_op_dev(self._h, C.c_int(0 if field == "fr" else 1), C.c_int(ops[op]), _dp(a),
                                               None if b is None else _dp(b), _dp(out), C.c_size_t(n)))

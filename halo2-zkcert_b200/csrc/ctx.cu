@@ -9,7 +9,7 @@ namespace {
 int env_int(const char* name, int lo, int hi) { const char* e = getenv(name); if (!e) return 0; const int x = atoi(e); return x >= lo && x <= hi ? x : 0; }
 void tunables_from_env(Tunables& v) {
   v.msm_c = env_int("ZKC_MSM_C", 3, 20); v.msm_c_pre = env_int("ZKC_MSM_C_PRE", 3, 20); v.msm_T = env_int("ZKC_MSM_T", 4, 128);
-  v.ntt_two_pass_max = env_int("ZKC_NTT_TWO_PASS_MAX", 12, 22);
+  v.ntt_two_pass_max = env_int("ZKC_NTT_TWO_PASS_MAX", 12, 22); v.msm_accum_occ = env_int("ZKC_MSM_ACCUM_OCC", 3, 4);
   if (const char* e = getenv("ZKC_STAGE_MIN_BYTES")) v.stage_min_bytes = (size_t)strtoull(e, nullptr, 10);
   v.team_poison = getenv("ZKC_TEAM_POISON") != nullptr;
 }
@@ -23,6 +23,7 @@ extern "C" int zkc_ctx_set_tunable(zkc_ctx* c, const char* name, int64_t value) 
   if (n == "msm_c") t.msm_c = (int)value;
   else if (n == "msm_c_pre") t.msm_c_pre = (int)value;
   else if (n == "msm_T") t.msm_T = (int)value;
+  else if (n == "msm_accum_occ") t.msm_accum_occ = (int)value;
   else if (n == "ntt_two_pass_max") t.ntt_two_pass_max = (int)value;
   else if (n == "stage_min_bytes") t.stage_min_bytes = value < 0 ? ((size_t)4 << 20) : (size_t)value;
   else if (n == "team_poison") t.team_poison = value != 0;
@@ -212,6 +213,7 @@ __global__ void k_vec_op(int op, const Fe<P>* a, const Fe<P>* b, Fe<P>* out, siz
     case ZKC_OP_FROM_CANONICAL: r = fe_from_canonical(x); break;
     case ZKC_OP_TO_CANONICAL: r = fe_to_canonical(x); break;
     case ZKC_OP_NEG: r = fe_neg(x); break;
+    case ZKC_OP_SQUARE: r = fe_sqr(x); break;
     default: r = x;
   }
   fe_store(out + i, r);
@@ -295,7 +297,7 @@ extern "C" int zkc_batch_invert_assigned_dev(zkc_ctx* ctx, const zkc_fr* num, co
 extern "C" int zkc_field_vec_op_dev(zkc_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n) {
   if (!ctx || !a || !out) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_field_vec_op_dev: null argument");
   if ((op == ZKC_OP_ADD || op == ZKC_OP_SUB || op == ZKC_OP_MUL) && !b) return set_err(ctx, ZKC_ERR_BAD_ARG, "binary op needs b");
-  if (op < 0 || op > ZKC_OP_NEG) return set_err(ctx, ZKC_ERR_BAD_ARG, "unknown op");
+  if (op < 0 || op > ZKC_OP_SQUARE) return set_err(ctx, ZKC_ERR_BAD_ARG, "unknown op");
   CtxLock lock(ctx);
   if (field == 0 && op == ZKC_OP_INV) return fr_batch_invert(ctx, (const Fr*)a, (Fr*)out, n);
   if (field == 0) return vec_op_impl<FrP>(ctx, op, (const Fr*)a, (const Fr*)b, (Fr*)out, n);

@@ -225,6 +225,168 @@ template <class P> ZKC_D Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
   return r;
 }
 
+
+// ---- dedicated squaring: 100 instead of 128 wide multiplies --------------------------------------------------------------------
+// a^2 = 2 * sum_{i<j} a_i a_j B^(i+j) + sum_i a_i^2 B^(2i)  (B = 2^32): the 28 cross products are accumulated once on the same
+// even / odd aligned 64-bit columns as fe_mul (a_i a_j lands on E[(i+j)/2] or O[(i+j-1)/2]), merged and doubled with plain
+// adds, the 8 squares sit on the even columns without overlapping; the low half of the 512-bit square is then cancelled by
+// the same eight rows of m * p as in fe_mul (64 multiplies) and the high half is added at the end.  Where a chain's carry can
+// reach one accumulator further than its last product a carry-only step follows; the chain extents are those of a worst-case
+// (all-ones limbs) simulation in which no carry is lost (the partial sums are monotone in the limbs).
+#define ZKC_SQ_MAC1(a0, x0, m) asm("mad.wide.u32 %0,%1,%2,%0;" : "+l"(a0) : "r"(x0), "r"(m))
+#define ZKC_SQ_MAC1C(a0, c1, x0, m)                                                         \
+  asm("{\n\t.reg .u64 t;\n\t"                                                                \
+      "mul.wide.u32 t,%2,%3;\n\tadd.cc.u64 %0,%0,t;\n\taddc.u64 %1,%1,0;\n\t}"               \
+      : "+l"(a0), "+l"(c1) : "r"(x0), "r"(m))
+#define ZKC_SQ_MAC2(a0, a1, x0, x1, m)                                                      \
+  asm("{\n\t.reg .u64 t;\n\t"                                                                \
+      "mul.wide.u32 t,%2,%4;\n\tadd.cc.u64 %0,%0,t;\n\t"                                     \
+      "mul.wide.u32 t,%3,%4;\n\taddc.u64 %1,%1,t;\n\t}"                                      \
+      : "+l"(a0), "+l"(a1) : "r"(x0), "r"(x1), "r"(m))
+#define ZKC_SQ_MAC2C(a0, a1, c2, x0, x1, m)                                                 \
+  asm("{\n\t.reg .u64 t;\n\t"                                                                \
+      "mul.wide.u32 t,%3,%5;\n\tadd.cc.u64 %0,%0,t;\n\t"                                     \
+      "mul.wide.u32 t,%4,%5;\n\taddc.cc.u64 %1,%1,t;\n\taddc.u64 %2,%2,0;\n\t}"              \
+      : "+l"(a0), "+l"(a1), "+l"(c2) : "r"(x0), "r"(x1), "r"(m))
+#define ZKC_SQ_MAC3(a0, a1, a2, x0, x1, x2, m)                                              \
+  asm("{\n\t.reg .u64 t;\n\t"                                                                \
+      "mul.wide.u32 t,%3,%6;\n\tadd.cc.u64 %0,%0,t;\n\t"                                     \
+      "mul.wide.u32 t,%4,%6;\n\taddc.cc.u64 %1,%1,t;\n\t"                                    \
+      "mul.wide.u32 t,%5,%6;\n\taddc.u64 %2,%2,t;\n\t}"                                      \
+      : "+l"(a0), "+l"(a1), "+l"(a2) : "r"(x0), "r"(x1), "r"(x2), "r"(m))
+#define ZKC_SQ_MAC3C(a0, a1, a2, c3, x0, x1, x2, m)                                         \
+  asm("{\n\t.reg .u64 t;\n\t"                                                                \
+      "mul.wide.u32 t,%4,%7;\n\tadd.cc.u64 %0,%0,t;\n\t"                                     \
+      "mul.wide.u32 t,%5,%7;\n\taddc.cc.u64 %1,%1,t;\n\t"                                    \
+      "mul.wide.u32 t,%6,%7;\n\taddc.cc.u64 %2,%2,t;\n\taddc.u64 %3,%3,0;\n\t}"              \
+      : "+l"(a0), "+l"(a1), "+l"(a2), "+l"(c3) : "r"(x0), "r"(x1), "r"(x2), "r"(m))
+
+template <class P> ZKC_D Fe<P> fe_sqr(const Fe<P>& a) {
+  const uint32_t a0 = a.v[0], a1 = a.v[1], a2 = a.v[2], a3 = a.v[3], a4 = a.v[4], a5 = a.v[5], a6 = a.v[6], a7 = a.v[7];
+  // cross products, row i = a_i * (a_j, j > i): even columns E1..E6, odd columns O0..O6
+  u64 E1 = (u64)a0 * a2, E2 = (u64)a0 * a4, E3 = (u64)a0 * a6, E4 = 0, E5 = 0, E6 = 0;
+  u64 O0 = (u64)a0 * a1, O1 = (u64)a0 * a3, O2 = (u64)a0 * a5, O3 = (u64)a0 * a7, O4 = 0, O5 = 0, O6 = 0;
+  ZKC_SQ_MAC3(E2, E3, E4, a3, a5, a7, a1);       ZKC_SQ_MAC3C(O1, O2, O3, O4, a2, a4, a6, a1);
+  ZKC_SQ_MAC2C(E3, E4, E5, a4, a6, a2);          ZKC_SQ_MAC3(O2, O3, O4, a3, a5, a7, a2);
+  ZKC_SQ_MAC2(E4, E5, a5, a7, a3);               ZKC_SQ_MAC2C(O3, O4, O5, a4, a6, a3);
+  ZKC_SQ_MAC1C(E5, E6, a6, a4);                  ZKC_SQ_MAC2(O4, O5, a5, a7, a4);
+  ZKC_SQ_MAC1(E6, a7, a5);                       ZKC_SQ_MAC1C(O5, O6, a6, a5);
+  ZKC_SQ_MAC1(O6, a7, a6);
+  // c = E + (O << 32) as 16 limbs (c0 = 0): c[k] = E-limb k + O-limb k
+  uint32_t c[16];
+  c[0] = 0; c[1] = (uint32_t)O0;
+  asm("add.cc.u32 %0,%14,%15;\n\t"
+      "addc.cc.u32 %1,%16,%17;\n\t"
+      "addc.cc.u32 %2,%18,%19;\n\t"
+      "addc.cc.u32 %3,%20,%21;\n\t"
+      "addc.cc.u32 %4,%22,%23;\n\t"
+      "addc.cc.u32 %5,%24,%25;\n\t"
+      "addc.cc.u32 %6,%26,%27;\n\t"
+      "addc.cc.u32 %7,%28,%29;\n\t"
+      "addc.cc.u32 %8,%30,%31;\n\t"
+      "addc.cc.u32 %9,%32,%33;\n\t"
+      "addc.cc.u32 %10,%34,%35;\n\t"
+      "addc.cc.u32 %11,%36,%37;\n\t"
+      "addc.cc.u32 %12,%38,0;\n\t"
+      "addc.u32 %13,0,0;"
+      : "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]), "=r"(c[8]), "=r"(c[9]), "=r"(c[10]), "=r"(c[11]),
+        "=r"(c[12]), "=r"(c[13]), "=r"(c[14]), "=r"(c[15])
+      : "r"((uint32_t)E1), "r"((uint32_t)(O0 >> 32)), "r"((uint32_t)(E1 >> 32)), "r"((uint32_t)O1),
+        "r"((uint32_t)E2), "r"((uint32_t)(O1 >> 32)), "r"((uint32_t)(E2 >> 32)), "r"((uint32_t)O2),
+        "r"((uint32_t)E3), "r"((uint32_t)(O2 >> 32)), "r"((uint32_t)(E3 >> 32)), "r"((uint32_t)O3),
+        "r"((uint32_t)E4), "r"((uint32_t)(O3 >> 32)), "r"((uint32_t)(E4 >> 32)), "r"((uint32_t)O4),
+        "r"((uint32_t)E5), "r"((uint32_t)(O4 >> 32)), "r"((uint32_t)(E5 >> 32)), "r"((uint32_t)O5),
+        "r"((uint32_t)E6), "r"((uint32_t)(O5 >> 32)), "r"((uint32_t)(E6 >> 32)), "r"((uint32_t)O6),
+        "r"((uint32_t)(O6 >> 32)));
+  // t = 2 c + squares (a_i^2 on limbs 2i, 2i + 1)
+  const u64 S0 = (u64)a0 * a0, S1 = (u64)a1 * a1, S2 = (u64)a2 * a2, S3 = (u64)a3 * a3, S4 = (u64)a4 * a4, S5 = (u64)a5 * a5,
+            S6 = (u64)a6 * a6, S7 = (u64)a7 * a7;
+  uint32_t t[16];
+  asm("add.cc.u32 %0,%15,%15;\n\t"
+      "addc.cc.u32 %1,%16,%16;\n\t"
+      "addc.cc.u32 %2,%17,%17;\n\t"
+      "addc.cc.u32 %3,%18,%18;\n\t"
+      "addc.cc.u32 %4,%19,%19;\n\t"
+      "addc.cc.u32 %5,%20,%20;\n\t"
+      "addc.cc.u32 %6,%21,%21;\n\t"
+      "addc.cc.u32 %7,%22,%22;\n\t"
+      "addc.cc.u32 %8,%23,%23;\n\t"
+      "addc.cc.u32 %9,%24,%24;\n\t"
+      "addc.cc.u32 %10,%25,%25;\n\t"
+      "addc.cc.u32 %11,%26,%26;\n\t"
+      "addc.cc.u32 %12,%27,%27;\n\t"
+      "addc.cc.u32 %13,%28,%28;\n\t"
+      "addc.u32 %14,%29,%29;"
+      : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]), "=r"(t[9]), "=r"(t[10]),
+        "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+      : "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7]), "r"(c[8]), "r"(c[9]), "r"(c[10]), "r"(c[11]),
+        "r"(c[12]), "r"(c[13]), "r"(c[14]), "r"(c[15]));
+  t[0] = (uint32_t)S0;
+  asm("add.cc.u32 %0,%0,%15;\n\t"
+      "addc.cc.u32 %1,%1,%16;\n\t"
+      "addc.cc.u32 %2,%2,%17;\n\t"
+      "addc.cc.u32 %3,%3,%18;\n\t"
+      "addc.cc.u32 %4,%4,%19;\n\t"
+      "addc.cc.u32 %5,%5,%20;\n\t"
+      "addc.cc.u32 %6,%6,%21;\n\t"
+      "addc.cc.u32 %7,%7,%22;\n\t"
+      "addc.cc.u32 %8,%8,%23;\n\t"
+      "addc.cc.u32 %9,%9,%24;\n\t"
+      "addc.cc.u32 %10,%10,%25;\n\t"
+      "addc.cc.u32 %11,%11,%26;\n\t"
+      "addc.cc.u32 %12,%12,%27;\n\t"
+      "addc.cc.u32 %13,%13,%28;\n\t"
+      "addc.u32 %14,%14,%29;"
+      : "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(t[9]), "+r"(t[10]),
+        "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+      : "r"((uint32_t)(S0 >> 32)), "r"((uint32_t)S1), "r"((uint32_t)(S1 >> 32)), "r"((uint32_t)S2), "r"((uint32_t)(S2 >> 32)),
+        "r"((uint32_t)S3), "r"((uint32_t)(S3 >> 32)), "r"((uint32_t)S4), "r"((uint32_t)(S4 >> 32)), "r"((uint32_t)S5),
+        "r"((uint32_t)(S5 >> 32)), "r"((uint32_t)S6), "r"((uint32_t)(S6 >> 32)), "r"((uint32_t)S7), "r"((uint32_t)(S7 >> 32)));
+  // Montgomery reduction of the low half: fe_mul's rows without their a * b_i part
+  u64 e0 = ((u64)t[1] << 32) | t[0], e1 = ((u64)t[3] << 32) | t[2], e2 = ((u64)t[5] << 32) | t[4], e3 = ((u64)t[7] << 32) | t[6];
+  u64 o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+  uint32_t pend = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint32_t top = 0;
+    const uint32_t m = ((uint32_t)e0 + pend) * P::INV;
+    ZKC_CHAIN4_CO(e0, e1, e2, e3, top, P::M(0), P::M(2), P::M(4), P::M(6), m);
+    ZKC_CHAIN4_CI(o0, o1, o2, o3, P::M(1), P::M(3), P::M(5), P::M(7), m, pend);
+    const uint32_t np = (uint32_t)(e0 >> 32);
+    const u64 n0 = o0, n1 = o1, n2 = o2, n3 = o3;
+    o0 = e1; o1 = e2; o2 = e3; o3 = (u64)top;
+    e0 = n0; e1 = n1; e2 = n2; e3 = n3;
+    pend = np;
+  }
+  Fe<P> r;
+  asm("add.cc.u32 %0,%8,%16;\n\t"
+      "addc.cc.u32 %1,%9,%17;\n\t"
+      "addc.cc.u32 %2,%10,%18;\n\t"
+      "addc.cc.u32 %3,%11,%19;\n\t"
+      "addc.cc.u32 %4,%12,%20;\n\t"
+      "addc.cc.u32 %5,%13,%21;\n\t"
+      "addc.cc.u32 %6,%14,%22;\n\t"
+      "addc.u32 %7,%15,%23;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+      : "r"((uint32_t)e0), "r"((uint32_t)(e0 >> 32)), "r"((uint32_t)e1), "r"((uint32_t)(e1 >> 32)), "r"((uint32_t)e2),
+        "r"((uint32_t)(e2 >> 32)), "r"((uint32_t)e3), "r"((uint32_t)(e3 >> 32)),
+        "r"(pend), "r"((uint32_t)o0), "r"((uint32_t)(o0 >> 32)), "r"((uint32_t)o1), "r"((uint32_t)(o1 >> 32)),
+        "r"((uint32_t)o2), "r"((uint32_t)(o2 >> 32)), "r"((uint32_t)o3));
+  // + the high half of the square: the sum stays below 2p (the reduced low half is <= p, the high half < p^2 / 2^256 < p / 5)
+  asm("add.cc.u32 %0,%0,%8;\n\t"
+      "addc.cc.u32 %1,%1,%9;\n\t"
+      "addc.cc.u32 %2,%2,%10;\n\t"
+      "addc.cc.u32 %3,%3,%11;\n\t"
+      "addc.cc.u32 %4,%4,%12;\n\t"
+      "addc.cc.u32 %5,%5,%13;\n\t"
+      "addc.cc.u32 %6,%6,%14;\n\t"
+      "addc.u32 %7,%7,%15;"
+      : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7])
+      : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]));
+  reduce_once<P>(r.v);
+  return r;
+}
+
 #else  // ---- host path (unit tests of logic layered above the field ops; never the product path) ----
 
 template <class P> inline bool geq_mod(const uint32_t* a) {
@@ -275,9 +437,9 @@ template <class P> inline Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
   if (t[4] || geq_mod<P>(r.v)) sub_mod_inplace<P>(r.v);
   return r;
 }
+template <class P> inline Fe<P> fe_sqr(const Fe<P>& a) { return fe_mul(a, a); }
 #endif
 
-template <class P> ZKC_HD Fe<P> fe_sqr(const Fe<P>& a) { return fe_mul(a, a); }
 template <class P> ZKC_HD Fe<P> fe_neg(const Fe<P>& a) { return fe_sub(fe_zero<P>(), a); }
 template <class P> ZKC_HD Fe<P> fe_dbl(const Fe<P>& a) { return fe_add(a, a); }
 template <class P> ZKC_HD Fe<P> fe_from_canonical(const Fe<P>& a) { return fe_mul(a, fe_r2<P>()); }

@@ -99,7 +99,8 @@ __device__ __forceinline__ G1Xyzz xyzz_shfl_xor(const G1Xyzz& p, int mask) {
   return r;
 }
 
-__global__ void __launch_bounds__(128) k_msm_accum(const G1Affine* bases, const uint32_t* ent_pt, const uint32_t* ent_key,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_accum(const G1Affine* bases, const uint32_t* ent_pt, const uint32_t* ent_key,
                                                    const uint32_t* offsets, G1Xyzz* partial, MsmGeom g) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t E = offsets[g.nbtot()];
@@ -474,7 +475,8 @@ static int msm_kernels(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, c
     k_msm_scatter<<<(unsigned)((em + 255) / 256), 256, 0, st>>>(dig, cursor, ent_pt, ent_key, g);
     ZKC_LAUNCH_CHECK(ctx); }
   { ProfScope _p(ctx, "msm.accum");
-    k_msm_accum<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(bases, ent_pt, ent_key, offsets, partial, g);
+    if (ctx->tune.msm_accum_occ == 3) k_msm_accum<3><<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(bases, ent_pt, ent_key, offsets, partial, g);
+    else k_msm_accum<4><<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(bases, ent_pt, ent_key, offsets, partial, g);
     ZKC_LAUNCH_CHECK(ctx); }
   {
     // quads per bucket from the expected number of partials per bucket (entries per bucket / T)

@@ -97,7 +97,7 @@ int zkc_d2h(zkc_ctx* ctx, void* hptr, const void* dptr, size_t bytes);
 /* ---- field vectors: halo2curves Fr/Fq arithmetic ---------------------------- */
 typedef enum {
   ZKC_OP_ADD = 0, ZKC_OP_SUB = 1, ZKC_OP_MUL = 2, ZKC_OP_INV = 3 /* batch_invert; 0 -> 0 */,
-  ZKC_OP_FROM_CANONICAL = 4, ZKC_OP_TO_CANONICAL = 5, ZKC_OP_NEG = 6
+  ZKC_OP_FROM_CANONICAL = 4, ZKC_OP_TO_CANONICAL = 5, ZKC_OP_NEG = 6, ZKC_OP_SQUARE = 7 /* Field::square */
 } zkc_vec_op;
 /* field: 0 = Fr, 1 = Fq.  out[i] = a[i] (op) b[i]; b may be NULL for unary ops.  Device pointers. */
 int zkc_field_vec_op_dev(zkc_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);

@@ -125,6 +125,30 @@ def test_field_vec_ops():
             assert np.array_equal(to_host(out), orc.field_op(field, op, a)), (field, op)
 
 
+def test_field_square_edge_values():
+    """dedicated squaring (ff.cuh fe_sqr: 36 + 64 wide multiplies) == a * a, on random and carry-heavy inputs, both fields"""
+    import torch
+    ctx = gpu_ctx()
+    P = {"fr": pyref.R_MOD, "fq": pyref.P_MOD}
+    for field in ("fr", "fq"):
+        p = P[field]
+        edge = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, (1 << 253) - 1, (1 << 253), ((1 << 254) - 1) % p,
+                0xFFFFFFFF, (1 << 32), (1 << 224) - 1, int("f" * 56, 16) % p, int("ffffffff00000000" * 4, 16) % p,
+                int("00000000ffffffff" * 4, 16) % p, p - (1 << 32), p - (1 << 128)]
+        # the kernel sees MONTGOMERY words: feed raw limb patterns directly too (every limb all-ones below p is impossible, so
+        # use the largest raw values: p - 1, p - 2^32k, and words with all-ones low limbs)
+        raw = np.zeros((len(edge), 4), dtype=np.uint64)
+        for i, v in enumerate(edge):
+            for l in range(4):
+                raw[i, l] = (v >> (64 * l)) & 0xFFFFFFFFFFFFFFFF
+        a = np.concatenate([raw, random_fr_mont(20000, 9) if field == "fr" else orc.field_op("fq", "from_canonical", random_fr_mont(20000, 9))])
+        ta = to_dev(a)
+        out = torch.empty_like(ta)
+        ctx.field_vec_op_dev(field, "square", ta, None, out)
+        ctx.sync()
+        assert np.array_equal(to_host(out), orc.field_op(field, "mul", a, a)), field
+
+
 def test_batch_invert_assigned():
     import torch
     ctx = gpu_ctx()
