@@ -302,6 +302,15 @@ class EvaluationDomain:
         self.ctx.check(lib().zkc_coeff_to_extended_dev(self.ctx._h, self._h, _dp(src), _dp(dst), C.c_uint32(ncols)))
         return dst
 
+    def coeff_to_extended_classes_dev(self, src, dst, ncols, c0, c1):
+        """classes [c0, c1) of the extended coset, class-major (the residue-class split of team proving)"""
+        self.ctx.check(lib().zkc_coeff_to_extended_classes_dev(self.ctx._h, self._h, _dp(src), _dp(dst), C.c_uint32(ncols), C.c_uint32(c0), C.c_uint32(c1)))
+        return dst
+
+    def extended_classes_to_natural_dev(self, src, dst):
+        self.ctx.check(lib().zkc_extended_classes_to_natural_dev(self.ctx._h, self._h, _dp(src), _dp(dst)))
+        return dst
+
     def extended_to_coeff_dev(self, t, ncols=1):
         self.ctx.check(lib().zkc_extended_to_coeff_dev(self.ctx._h, self._h, _dp(t), C.c_uint32(ncols)))
         return t

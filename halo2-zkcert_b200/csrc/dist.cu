@@ -70,17 +70,6 @@ NcclComm comm_of(const zkc_ctx* ctx) { return (NcclComm)ctx->team_comm[ctx->side
 
 }  // namespace
 
-std::vector<Segment> halo_segments(uint64_t en, uint64_t lo, uint64_t hi, uint64_t halo_lo, uint64_t halo_hi) {
-  std::vector<Segment> out;
-  if (hi <= lo) return out;
-  if ((hi - lo) + halo_lo + halo_hi >= en) { out.push_back({0, en}); return out; }
-  // the cyclic interval [lo - halo_lo, hi + halo_hi) has length < en: at most one wrap
-  const uint64_t start = (lo + en - halo_lo % en) % en, len = (hi - lo) + halo_lo + halo_hi;
-  if (start + len <= en) out.push_back({start, len});
-  else { out.push_back({0, start + len - en}); out.push_back({start, en - start}); }
-  return out;
-}
-
 std::vector<int> team_ranks(const zkc_ctx* ctx) {
   std::vector<int> r;
   if (ctx->team_emulate) for (int i = 0; i < ctx->team_world; ++i) r.push_back(i);
@@ -109,39 +98,6 @@ int team_bcast_cols(zkc_ctx* ctx, Fr* base, uint64_t stride, uint64_t len, uint3
     }
   }
   ZKC_NCCL_TRY(ctx, nccl().GroupEnd());
-  return ZKC_OK;
-}
-
-int team_scatter_rows(zkc_ctx* ctx, Fr* base, uint64_t en, uint32_t ncols, uint64_t halo_lo, uint64_t halo_hi) {
-  if (!real_comm(ctx) || !ncols) return ZKC_OK;
-  ProfScope _p(ctx, "team.scatter_rows");
-  const int me = ctx->team_rank, W = ctx->team_world;
-  // one NCCL group per chunk of columns (every owner sends at once: full NVSwitch bisection), bounded op count per group
-  const uint32_t block = (ncols + (uint32_t)W - 1) / (uint32_t)W, CH = 16;
-  for (uint32_t j0 = 0; j0 < block; j0 += CH) {
-    ZKC_NCCL_TRY(ctx, nccl().GroupStart());
-    int rc = 0;
-    for (int owner = 0; owner < W && rc == 0; ++owner) {
-      uint32_t c0, c1;
-      team_cols(ctx, ncols, owner, &c0, &c1);
-      const uint32_t ca = std::min(c1, c0 + j0), cb = std::min(c1, c0 + j0 + CH);
-      for (int dst = 0; dst < W && rc == 0; ++dst) {
-        if (dst == owner || (me != owner && me != dst)) continue;
-        uint64_t lo, hi;
-        shard_range(en, W, dst, &lo, &hi);
-        const std::vector<Segment> segs = halo_segments(en, lo, hi, halo_lo, halo_hi);
-        for (uint32_t c = ca; c < cb && rc == 0; ++c)
-          for (const Segment& s : segs) {
-            Fr* p = base + (uint64_t)c * en + s.lo;
-            rc = me == owner ? nccl().Send(p, s.len * sizeof(Fr), kNcclUint8, dst, comm_of(ctx), ctx->stream)
-                             : nccl().Recv(p, s.len * sizeof(Fr), kNcclUint8, owner, comm_of(ctx), ctx->stream);
-            if (rc != 0) break;
-          }
-      }
-    }
-    if (rc != 0) { nccl().GroupEnd(); return nccl_fail(ctx, "ncclSend/ncclRecv", rc); }
-    ZKC_NCCL_TRY(ctx, nccl().GroupEnd());
-  }
   return ZKC_OK;
 }
 
@@ -262,12 +218,13 @@ extern "C" int zkc_team_shard_range(uint64_t total, int world, int rank, uint64_
   shard_range(total, world, rank, lo, hi);
   return ZKC_OK;
 }
-extern "C" int zkc_team_row_segments(uint64_t rows, int world, int rank, uint64_t halo_lo, uint64_t halo_hi, uint64_t out_lo_len[4], int* nseg) {
-  if (world < 1 || rank < 0 || rank >= world || !out_lo_len || !nseg || rows == 0) return ZKC_ERR_BAD_ARG;
+// residue classes [c0, c1) of the extended coset that `rank`'s row block of the class-major extended domain touches
+// (prover.cu: the classes the rank transforms from the replicated coefficient forms)
+extern "C" int zkc_team_classes(uint32_t k, uint32_t extended_k, int world, int rank, uint32_t* c0, uint32_t* c1) {
+  if (world < 1 || rank < 0 || rank >= world || !c0 || !c1 || extended_k < k || extended_k > 27) return ZKC_ERR_BAD_ARG;
   uint64_t lo, hi;
-  shard_range(rows, world, rank, &lo, &hi);
-  const std::vector<Segment> segs = halo_segments(rows, lo, hi, halo_lo, halo_hi);
-  *nseg = (int)segs.size();
-  for (size_t i = 0; i < segs.size() && i < 2; ++i) { out_lo_len[2 * i] = segs[i].lo; out_lo_len[2 * i + 1] = segs[i].len; }
+  shard_range(1ull << extended_k, world, rank, &lo, &hi);
+  if (hi == lo) { *c0 = *c1 = 0; return ZKC_OK; }
+  *c0 = (uint32_t)(lo >> k); *c1 = (uint32_t)((hi - 1) >> k) + 1;
   return ZKC_OK;
 }

@@ -3,11 +3,12 @@
 // device work is partitioned:
 //   * MSM / commitments  by POINT RANGE   — the split best_multiexp makes across CPU threads; the only
 //                                           exchange is an all-gather of the c bit-plane sums per column
-//   * column transforms  by COLUMN        — lagrange_to_coeff / coeff_to_extended of independent columns;
-//                                           the owner broadcasts the coefficient form and sends every
-//                                           rank its row slice (+ rotation halo) of the extended coset
-//   * h(X) evaluation    by EXTENDED ROW  — contiguous row blocks with a halo of max|rotation| rows, then an
-//                                           all-gather of the quotient values
+//   * lagrange_to_coeff  by COLUMN        — the owner broadcasts the coefficient form
+//   * coeff_to_extended  by RESIDUE CLASS — the extended coset splits into 2^(extended_k - k) cosets of the size-n
+//                                           subgroup (ntt.cu, dom_coeff_to_classes); a rank transforms the classes its
+//                                           row block touches from the replicated coefficient forms: no exchange
+//   * h(X) evaluation    by EXTENDED ROW  — contiguous blocks of the class-major extended coset (rotations stay inside a
+//                                           class), then an all-gather of the quotient values
 // The collectives are NCCL over NVLink/NVSwitch, issued on the stream the kernels run on.  libnccl is
 // bound at run time (dlopen), so the library loads on hosts without it.
 // ZKC_TEAM_EMULATE=W runs the W shards of every partitioned step one after the other on ONE GPU with the
@@ -26,9 +27,6 @@ inline void shard_range(uint64_t total, int world, int rank, uint64_t* lo, uint6
   *hi = *lo + base + ((uint64_t)rank < rem ? 1 : 0);
 }
 
-// rows of a length-`en` cyclic column that the owner of rows [lo, hi) reads with rotations in [-halo_lo, +halo_hi]
-std::vector<Segment> halo_segments(uint64_t en, uint64_t lo, uint64_t hi, uint64_t halo_lo, uint64_t halo_hi);
-
 // ranks whose shards this process computes: {rank} normally, {0..world) under ZKC_TEAM_EMULATE
 std::vector<int> team_ranks(const zkc_ctx* ctx);
 inline bool team_active(const zkc_ctx* ctx) { return ctx->team_world > 1; }
@@ -37,8 +35,6 @@ inline bool team_active(const zkc_ctx* ctx) { return ctx->team_world > 1; }
 int team_allgather(zkc_ctx* ctx, void* buf, size_t bytes_per_rank);
 // column c of base[ncols][stride] (first `len` elements) is broadcast from the rank that owns it
 int team_bcast_cols(zkc_ctx* ctx, Fr* base, uint64_t stride, uint64_t len, uint32_t ncols);
-// the owner of column c sends rank d the rows rank d's row block needs (block + halo); rows elsewhere stay undefined
-int team_scatter_rows(zkc_ctx* ctx, Fr* base, uint64_t en, uint32_t ncols, uint64_t halo_lo, uint64_t halo_hi);
 // in-place all-gather of the row blocks of one length-en column
 int team_allgather_rows(zkc_ctx* ctx, Fr* col, uint64_t en);
 // in-place all-gather of a flat array split with shard_range(total, world, r)

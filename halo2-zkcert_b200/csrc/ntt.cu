@@ -31,7 +31,12 @@ struct NttPass {
   uint32_t logB;          // strided pass: inner stride
   uint32_t logN1, logN2;  // last pass: rows A = N1*N2, output index = k1 + N1*k2 + A*kp
   int inverse, pre, post;
-  Fr pre1, pre2;          // in[i] *= pre^(i mod 3)
+  Fr pre1, pre2;          // pre == 1: in[i] *= pre^(i mod 3)
+  // residue classes of the extended coset (dom_coeff_to_classes): blockIdx.y = column * cls_div + class slot.  The first pass
+  // reads column y / cls_div and multiplies element g by pre_tab[class * N + g] (pre == 2); the last pass writes to
+  // dst + column * dst_stride + class * N.  cls_div == 0: plain batches (blockIdx.y = column on both sides).
+  uint32_t src_cls_div, dst_cls_div, cls0;
+  const Fr* pre_tab;
   Fr post0, post1, post2; // out[i] *= post[i mod 3]
 };
 
@@ -55,6 +60,23 @@ __device__ __forceinline__ void butterfly_dif(uint4* lo, uint4* hi, uint32_t i0,
   lo[i1] = fe_lo(diff); hi[i1] = fe_hi(diff);
 }
 
+__device__ __forceinline__ const Fr* pass_src(const NttPass& p) {
+  return p.src + (uint64_t)(p.src_cls_div ? blockIdx.y / p.src_cls_div : blockIdx.y) * p.src_stride;
+}
+__device__ __forceinline__ Fr* pass_dst(const NttPass& p) {
+  if (!p.dst_cls_div) return p.dst + (uint64_t)blockIdx.y * p.dst_stride;
+  return p.dst + (uint64_t)(blockIdx.y / p.dst_cls_div) * p.dst_stride + ((uint64_t)(p.cls0 + blockIdx.y % p.dst_cls_div) << p.log_n);
+}
+__device__ __forceinline__ Fr pass_pre(const NttPass& p, Fr x, uint64_t g) {
+  if (p.pre == 1) {
+    const uint32_t m = (uint32_t)(g % 3);
+    if (m == 1) x = fe_mul(x, p.pre1); else if (m == 2) x = fe_mul(x, p.pre2);
+  } else if (p.pre == 2) {
+    x = fe_mul(x, fe_load_nc(p.pre_tab + ((uint64_t)(p.cls0 + blockIdx.y % p.src_cls_div) << p.log_n) + g));
+  }
+  return x;
+}
+
 #define NTT_THREADS 256
 #define NTT_PLANE_PAD 4  // uint4 units: offsets the high plane by 64 B so paired accesses hit distinct banks
 
@@ -63,8 +85,8 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_strided(NttPass p) {
   const uint32_t L = 1u << p.s, C = 1u << p.logC, T = L << p.logC;
   uint4* lo = sm;
   uint4* hi = sm + T + NTT_PLANE_PAD;
-  const Fr* src = p.src + (uint64_t)blockIdx.y * p.src_stride;
-  Fr* dst = p.dst + (uint64_t)blockIdx.y * p.dst_stride;
+  const Fr* src = pass_src(p);
+  Fr* dst = pass_dst(p);
   const uint32_t tiles_per_a = 1u << (p.logB - p.logC);
   const uint64_t a = blockIdx.x >> (p.logB - p.logC);
   const uint64_t b0 = (uint64_t)(blockIdx.x & (tiles_per_a - 1)) << p.logC;
@@ -76,10 +98,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_strided(NttPass p) {
     Fr x = fe_zero<FrP>();
     if (g < p.n_in) {
       x = fe_load(src + g);
-      if (p.pre) {
-        const uint32_t m = (uint32_t)(g % 3);
-        if (m == 1) x = fe_mul(x, p.pre1); else if (m == 2) x = fe_mul(x, p.pre2);
-      }
+      if (p.pre) x = pass_pre(p, x, g);
     }
     lo[e] = fe_lo(x); hi[e] = fe_hi(x);
   }
@@ -114,8 +133,8 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_last(NttPass p) {
   const uint32_t pitch = L + (C > 1 ? 1u : 0u);
   uint4* lo = sm;
   uint4* hi = sm + pitch * C + NTT_PLANE_PAD;
-  const Fr* src = p.src + (uint64_t)blockIdx.y * p.src_stride;
-  Fr* dst = p.dst + (uint64_t)blockIdx.y * p.dst_stride;
+  const Fr* src = pass_src(p);
+  Fr* dst = pass_dst(p);
   const uint64_t N2 = 1ull << p.logN2;
   const uint64_t kb = blockIdx.x >> p.logN2, k2 = blockIdx.x & (N2 - 1);
 
@@ -126,10 +145,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_last(NttPass p) {
     Fr x = fe_zero<FrP>();
     if (g < p.n_in) {
       x = fe_load(src + g);
-      if (p.pre) {
-        const uint32_t m = (uint32_t)(g % 3);
-        if (m == 1) x = fe_mul(x, p.pre1); else if (m == 2) x = fe_mul(x, p.pre2);
-      }
+      if (p.pre) x = pass_pre(p, x, g);
     }
     lo[c * pitch + i] = fe_lo(x); hi[c * pitch + i] = fe_hi(x);
   }
@@ -177,6 +193,44 @@ __global__ void k_scale_periodic(Fr* a, const Fr* t, uint32_t mask, uint64_t row
   fe_store(a + i, fe_mul(fe_load(a + i), fe_load_nc(t + (i & mask))));
 }
 
+// pre[c * n + i] = zeta^(i mod 3) * w^(c * i)  (w = extended_omega): the coefficient scaling that turns a size-n transform into
+// the evaluations on residue class c of the extended coset.  Each thread fills a run of 64 entries of one class.
+__global__ void k_class_pre(Fr* pre, Fr w_ext, Fr zeta, uint32_t log_n, uint32_t ncls) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t runs = 1ull << (log_n > 6 ? log_n - 6 : 0), n = 1ull << log_n;
+  if (t >= runs * ncls) return;
+  const uint64_t c = t / runs, start = (t % runs) * 64;
+  const Fr wc = fe_pow_u64(w_ext, c);
+  Fr cur = fe_pow_u64(wc, start);
+  const Fr z1 = zeta, z2 = fe_sqr(zeta);
+  const uint64_t end = start + 64 < n ? start + 64 : n;
+  for (uint64_t i = start; i < end; ++i) {
+    const uint32_t m = (uint32_t)(i % 3);
+    fe_store(pre + c * n + i, m == 0 ? cur : fe_mul(cur, m == 1 ? z1 : z2));
+    cur = fe_mul(cur, wc);
+  }
+}
+// class-major <-> natural order of extended-coset rows: natural row c + 2^e * m  <->  class-major row c * n + m
+__global__ void k_classes_to_natural(const Fr* cm, Fr* nat, uint32_t log_n, uint32_t e, uint64_t rows) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // natural index: coalesced stores
+  if (i >= rows) return;
+  const uint64_t c = i & ((1ull << e) - 1), m = i >> e;
+  fe_store(nat + i, fe_load(cm + (c << log_n) + m));
+}
+__global__ void k_natural_to_classes(const Fr* nat, Fr* cm, uint32_t log_n, uint32_t e, uint64_t rows) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // class-major index
+  if (i >= rows) return;
+  const uint64_t c = i >> log_n, m = i & ((1ull << log_n) - 1);
+  fe_store(cm + i, fe_load(nat + c + (m << e)));
+}
+// class-major rows [row0, row0 + cnt): a[i] *= t[class of i]
+__global__ void k_scale_by_class(Fr* a, const Fr* t, uint32_t log_n, uint64_t row0, uint64_t cnt) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= cnt) return;
+  const uint64_t i = row0 + tid;
+  fe_store(a + i, fe_mul(fe_load(a + i), fe_load_nc(t + (i >> log_n))));
+}
+
 static int get_twiddles(zkc_ctx* ctx, uint32_t log_n, const Fr** out) {
   auto it = ctx->twiddles.find(log_n);
   if (it != ctx->twiddles.end()) { *out = it->second; return ZKC_OK; }
@@ -201,6 +255,10 @@ struct NttOpts {
   uint64_t n_in = 0;      // 0 = full
   int pre = 0; Fr pre1, pre2;
   int post = 0; Fr post0, post1, post2;
+  // residue-class batches: every source column is transformed once per class in [cls0, cls0 + ncls), pre-scaled by
+  // pre_tab[class * N + i]; class c of column j lands at dst + j * dst_stride + c * N
+  uint32_t ncls = 0, cls0 = 0;
+  const Fr* pre_tab = nullptr;
 };
 
 static const uint32_t LOG_TILE = 11;  // 2^11 elements = 64 KiB of shared memory per CTA
@@ -221,7 +279,7 @@ static int launch_pass(zkc_ctx* ctx, bool last, const NttPass& p, uint32_t grid_
     // field products of this pass (the roofline numerator of bench.py): N/2 per butterfly stage, N inter-pass twiddles after a
     // strided pass, N for a fused post-scaling, ~2/3 n_in for the coset pre-scaling
     const uint64_t N = 1ull << p.log_n;
-    ctx->stats["ntt.muls"] += (uint64_t)ncols * ((N >> 1) * p.s + (last ? 0 : N) + (p.post ? N : 0) + (p.pre ? (p.n_in * 2) / 3 : 0));
+    ctx->stats["ntt.muls"] += (uint64_t)ncols * ((N >> 1) * p.s + (last ? 0 : N) + (p.post ? N : 0) + (p.pre == 1 ? (p.n_in * 2) / 3 : (p.pre == 2 ? p.n_in : 0)));
     ctx->stats["ntt.bytes"] += (uint64_t)ncols * (std::min<uint64_t>(p.n_in, N) + N) * sizeof(Fr);   // read the valid inputs, write N
   }
   ProfScope _p(ctx, last ? "ntt.last" : "ntt.strided");
@@ -244,18 +302,21 @@ int ntt_run(zkc_ctx* ctx, const Fr* src, uint64_t src_stride, Fr* dst, uint64_t 
   }
   if (log_n > 27) return set_err(ctx, ZKC_ERR_BAD_ARG, "ntt: log_n > 27 unsupported");
   const uint64_t N = 1ull << log_n;
+  const uint32_t mult = o.ncls ? o.ncls : 1;   // transforms per source column
   const Fr* tw;
   ZKC_TRY(get_twiddles(ctx, log_n, &tw));
   NttPass base{};
   base.tw = tw; base.log_n = log_n; base.inverse = o.inverse;
   base.n_in = N;
-  auto first = [&](NttPass& p) { p.src = src; p.src_stride = src_stride; p.n_in = o.n_in ? o.n_in : N; p.pre = o.pre; p.pre1 = o.pre1; p.pre2 = o.pre2; };
-  auto final_ = [&](NttPass& p) { p.dst = dst; p.dst_stride = dst_stride; p.post = o.post; p.post0 = o.post0; p.post1 = o.post1; p.post2 = o.post2; };
+  auto first = [&](NttPass& p) { p.src = src; p.src_stride = src_stride; p.n_in = o.n_in ? o.n_in : N; p.pre = o.pre; p.pre1 = o.pre1; p.pre2 = o.pre2;
+                            p.src_cls_div = o.ncls; p.cls0 = o.cls0; p.pre_tab = o.pre_tab; };
+  auto final_ = [&](NttPass& p) { p.dst = dst; p.dst_stride = dst_stride; p.post = o.post; p.post0 = o.post0; p.post1 = o.post1; p.post2 = o.post2;
+                             p.dst_cls_div = o.ncls; p.cls0 = o.cls0; };
 
   if (log_n <= LOG_TILE) {
     NttPass p = base; first(p); final_(p);
     p.s = log_n; p.logC = 0; p.logN1 = 0; p.logN2 = 0;
-    return launch_pass(ctx, true, p, 1, ncols);
+    return launch_pass(ctx, true, p, 1, ncols * mult);
   }
   // Two passes up to 2^two_pass_max, three above.  A pass boundary costs one twiddle product per element and one trip
   // through HBM; a tile is 2^11 elements, so two passes of a 2^22 transform read single 32-byte elements at large
@@ -263,12 +324,12 @@ int ntt_run(zkc_ctx* ctx, const Fr* src, uint64_t src_stride, Fr* dst, uint64_t 
   uint32_t two_pass_max = NTT_TWO_PASS_MAX;
   if (const int v = ctx->tune.ntt_two_pass_max) { if (v <= 2 * (int)LOG_TILE) two_pass_max = (uint32_t)v; }
   // bound the scratch: process columns in chunks of <= 1 GiB
-  uint32_t chunk = (uint32_t)std::max<uint64_t>(1, (1ull << 30) / (N * sizeof(Fr)));
+  uint32_t chunk = (uint32_t)std::max<uint64_t>(1, (1ull << 30) / (N * sizeof(Fr) * mult));
   if (chunk > ncols) chunk = ncols;
   Fr* tmp;
-  ZKC_TRY(scratch_reserve(ctx, SCR_NTT, (size_t)chunk * N * sizeof(Fr), (void**)&tmp));
+  ZKC_TRY(scratch_reserve(ctx, SCR_NTT, (size_t)chunk * mult * N * sizeof(Fr), (void**)&tmp));
   for (uint32_t c0 = 0; c0 < ncols; c0 += chunk) {
-    const uint32_t nc = std::min(chunk, ncols - c0);
+    const uint32_t nc = std::min(chunk, ncols - c0) * mult;   // grid.y of this chunk
     const Fr* csrc = src + (uint64_t)c0 * src_stride;
     Fr* cdst = dst + (uint64_t)c0 * dst_stride;
     if (log_n <= two_pass_max) {
@@ -306,6 +367,7 @@ struct zkc_domain {
   int zeta_choice;
   Fr omega, omega_inv, extended_omega, extended_omega_inv, g_coset, g_coset_inv, ifft_divisor, extended_ifft_divisor;
   Fr* t_inv_dev = nullptr;  // 2^(extended_k - k) inverted vanishing evaluations
+  Fr* class_pre = nullptr;  // [class][i < n]: zeta^(i mod 3) * extended_omega^(class * i), built on first use (dom_coeff_to_classes)
 };
 
 static inline void fr_to_abi(const Fr& f, zkc_fr* o) { memcpy(o, f.v, 32); }
@@ -345,6 +407,7 @@ extern "C" int zkc_domain_create(zkc_ctx* ctx, uint32_t j, uint32_t k, int zeta_
 extern "C" void zkc_domain_free(zkc_domain* d) {
   if (!d) return;
   if (d->t_inv_dev) cudaFree(d->t_inv_dev);
+  if (d->class_pre) cudaFree(d->class_pre);
   delete d;
 }
 
@@ -386,6 +449,58 @@ int dom_extended_to_coeff(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint32_t nco
     for (uint32_t c = 0; c < ncols; ++c)
       ZKC_CUDA_TRY(ctx, cudaMemsetAsync(a + (uint64_t)c * en + keep, 0, (en - keep) * sizeof(Fr), ctx->stream));
   }
+  return ZKC_OK;
+}
+// ---- residue classes of the extended coset --------------------------------------------------------------------------------------
+// The extended coset { zeta * w_ext^r } splits into 2^e classes r = c + 2^e * m (e = extended_k - k), and class c is the coset
+// (zeta * w_ext^c) * <omega> of the size-n subgroup: p on class c is ONE size-n transform of the coefficients scaled by
+// zeta^(i mod 3) * w_ext^(c i).  This is the four-step decomposition of the size-2^extended_k transform with N1 = n, N2 = 2^e,
+// specialised to an input whose upper (2^e - 1) n coefficients are zero: the N2-point column transforms have one non-zero input
+// each (nothing to compute), the twiddle step is the pre-scaling, and the N1-point row transforms are the classes.  Rotations by
+// omega stay inside a class (row m -> m + 1), so h(X) is evaluated class by class and a team of GPUs needs no exchange of coset
+// rows at all: rank j transforms the classes its row block touches from the (replicated) coefficient forms.
+// CLASS-MAJOR layout: class c of a column occupies [c * n, (c + 1) * n).
+int dom_class_pre(zkc_ctx* ctx, const zkc_domain* d, const Fr** out) {
+  zkc_domain* dm = const_cast<zkc_domain*>(d);
+  if (!dm->class_pre) {
+    const uint32_t ncls = 1u << (d->extended_k - d->k);
+    Fr* p;
+    ZKC_CUDA_TRY(ctx, cudaMalloc(&p, (sizeof(Fr) << d->k) * ncls));
+    const uint64_t threads = (1ull << (d->k > 6 ? d->k - 6 : 0)) * ncls;
+    k_class_pre<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(p, d->extended_omega, d->g_coset, d->k, ncls);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // shared by both streams of the ctx
+    if (e != cudaSuccess) { cudaFree(p); return set_err(ctx, ZKC_ERR_CUDA, std::string("dom_class_pre: ") + cudaGetErrorString(e)); }
+    dm->class_pre = p;
+  }
+  *out = dm->class_pre;
+  return ZKC_OK;
+}
+// classes [c0, c1) of `ncols` coefficient-form columns (stride in_stride) -> out (column stride 2^extended_k, class-major)
+int dom_coeff_to_classes(zkc_ctx* ctx, const zkc_domain* d, const Fr* in, uint64_t in_stride, Fr* out, uint32_t ncols, uint32_t c0, uint32_t c1) {
+  if (c1 <= c0 || !ncols) return ZKC_OK;
+  NttOpts o; o.pre = 2; o.ncls = c1 - c0; o.cls0 = c0;
+  ZKC_TRY(dom_class_pre(ctx, d, &o.pre_tab));
+  return ntt_run(ctx, in, in_stride, out, 1ull << d->extended_k, d->k, ncols, o);
+}
+int dom_classes_to_natural(zkc_ctx* ctx, const zkc_domain* d, const Fr* cm, Fr* nat) {
+  const uint64_t en = 1ull << d->extended_k;
+  k_classes_to_natural<<<(unsigned)((en + 255) / 256), 256, 0, ctx->stream>>>(cm, nat, d->k, d->extended_k - d->k, en);
+  ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+int dom_natural_to_classes(zkc_ctx* ctx, const zkc_domain* d, const Fr* nat, Fr* cm) {
+  const uint64_t en = 1ull << d->extended_k;
+  k_natural_to_classes<<<(unsigned)((en + 255) / 256), 256, 0, ctx->stream>>>(nat, cm, d->k, d->extended_k - d->k, en);
+  ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+// division by X^n - 1 on class-major rows [row0, row0 + cnt): the vanishing polynomial is constant on a class
+int dom_divide_by_vanishing_classes(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint64_t row0, uint64_t cnt) {
+  if (cnt == 0) return ZKC_OK;
+  k_scale_by_class<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(a, d->t_inv_dev, d->k, row0, cnt);
+  ZKC_LAUNCH_CHECK(ctx);
   return ZKC_OK;
 }
 int dom_divide_by_vanishing(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint64_t row0, uint64_t cnt) {   // rows [row0, row0 + cnt)
@@ -443,6 +558,16 @@ extern "C" int zkc_coeff_to_lagrange_dev(zkc_ctx* ctx, const zkc_domain* d, zkc_
 extern "C" int zkc_coeff_to_extended_dev(zkc_ctx* ctx, const zkc_domain* d, const zkc_fr* in, zkc_fr* out, uint32_t ncols) {
   if (!ctx || !d || !in || !out) return set_err(ctx, ZKC_ERR_BAD_ARG, "null argument");
   CtxLock lock(ctx); return dom_coeff_to_extended(ctx, d, (const Fr*)in, 1ull << d->k, (Fr*)out, ncols);
+}
+extern "C" int zkc_coeff_to_extended_classes_dev(zkc_ctx* ctx, const zkc_domain* d, const zkc_fr* in, zkc_fr* out, uint32_t ncols, uint32_t c0,
+                                                 uint32_t c1) {
+  if (!ctx || !d || !in || !out) return set_err(ctx, ZKC_ERR_BAD_ARG, "null argument");
+  if (c0 > c1 || c1 > (1u << (d->extended_k - d->k))) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_coeff_to_extended_classes_dev: class range outside [0, 2^(extended_k - k)]");
+  CtxLock lock(ctx); return dom_coeff_to_classes(ctx, d, (const Fr*)in, 1ull << d->k, (Fr*)out, ncols, c0, c1);
+}
+extern "C" int zkc_extended_classes_to_natural_dev(zkc_ctx* ctx, const zkc_domain* d, const zkc_fr* cm, zkc_fr* nat) {
+  if (!ctx || !d || !cm || !nat || cm == nat) return set_err(ctx, ZKC_ERR_BAD_ARG, "zkc_extended_classes_to_natural_dev: null or aliased argument");
+  CtxLock lock(ctx); return dom_classes_to_natural(ctx, d, (const Fr*)cm, (Fr*)nat);
 }
 extern "C" int zkc_extended_to_coeff_dev(zkc_ctx* ctx, const zkc_domain* d, zkc_fr* a, uint32_t ncols) {
   if (!ctx || !d || !a) return set_err(ctx, ZKC_ERR_BAD_ARG, "null argument");

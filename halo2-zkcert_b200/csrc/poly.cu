@@ -502,7 +502,9 @@ __global__ void __launch_bounds__(128) k_eval_program(const uint32_t* words, uin
         const uint32_t col = op == 1 ? q.aq_col[arg] : (op == 2 ? q.fq_col[arg] : q.iq_col[arg]);
         const int32_t rot = op == 1 ? q.aq_rot[arg] : (op == 2 ? q.fq_rot[arg] : q.iq_rot[arg]);
         const Fr* colp = op == 1 ? q.advice[col] : (op == 2 ? q.fixed[col] : q.instance[col]);
-        const uint64_t idx = (i + rows + (int64_t)rot * (int64_t)rot_scale) & (rows - 1);   // rows is a power of two
+        // rows (a power of two) is the cyclic length: the column itself (Lagrange values), or one residue class of the
+        // class-major extended coset, in which case i >= rows selects the class and rotations stay inside it
+        const uint64_t idx = (i & ~(rows - 1)) | ((i + rows + (int64_t)rot * (int64_t)rot_scale) & (rows - 1));
         stack[sp++] = fe_load(colp + idx);
         break;
       }

@@ -25,6 +25,9 @@ int dom_lagrange_to_coeff(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint32_t nco
 int dom_coeff_to_extended(zkc_ctx* ctx, const zkc_domain* d, const Fr* in, uint64_t in_stride, Fr* out, uint32_t ncols);
 int dom_extended_to_coeff(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint32_t ncols);
 int dom_divide_by_vanishing(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint64_t row0, uint64_t cnt);
+int dom_coeff_to_classes(zkc_ctx* ctx, const zkc_domain* d, const Fr* in, uint64_t in_stride, Fr* out, uint32_t ncols, uint32_t c0, uint32_t c1);
+int dom_classes_to_natural(zkc_ctx* ctx, const zkc_domain* d, const Fr* cm, Fr* nat);
+int dom_divide_by_vanishing_classes(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint64_t row0, uint64_t cnt);
 int srs_commit_dev(zkc_ctx* ctx, const zkc_srs* s, int basis, const Fr* polys, uint64_t len, uint32_t ncols, zkc_g1* out);
 }  // namespace zkc
 
@@ -169,6 +172,7 @@ int pk_build(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs
   zkc_domain_get_info(pk->dom, &di);
   pk->ext_k = di.extended_k;
   const uint64_t en = 1ull << pk->ext_k;
+  const uint32_t ncls = 1u << (pk->ext_k - cs.k);   // every extended coset of the key is kept CLASS-MAJOR (ntt.cu, dom_coeff_to_classes)
   memcpy(pk->transcript_repr.v, transcript_repr, 32);
   zkc_pk* P = pk.get();
   const uint32_t F = cs.num_fixed, S = nperm;
@@ -188,7 +192,7 @@ int pk_build(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs
     ZKC_TRY(upload_columns(ctx, P->fixed_values, fixed, F, n));
     ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(P->fixed_polys, P->fixed_values, (size_t)F * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     ZKC_TRY(dom_lagrange_to_coeff(ctx, P->dom, P->fixed_polys, F));
-    ZKC_TRY(dom_coeff_to_extended(ctx, P->dom, P->fixed_polys, n, P->fixed_cosets, F));
+    ZKC_TRY(dom_coeff_to_classes(ctx, P->dom, P->fixed_polys, n, P->fixed_cosets, F, 0, ncls));
   }
   if (S && sigma.mapping) {
     // DELTA^c on the host (a handful of products), the n * S gathers on the device
@@ -210,7 +214,7 @@ int pk_build(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs
     if (!sigma.mapping) ZKC_TRY(upload_columns(ctx, P->sigma_values, sigma, S, n));
     ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(P->sigma_polys, P->sigma_values, (size_t)S * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     ZKC_TRY(dom_lagrange_to_coeff(ctx, P->dom, P->sigma_polys, S));
-    ZKC_TRY(dom_coeff_to_extended(ctx, P->dom, P->sigma_polys, n, P->sigma_cosets, S));
+    ZKC_TRY(dom_coeff_to_classes(ctx, P->dom, P->sigma_polys, n, P->sigma_cosets, S, 0, ncls));
   }
   // l0, l_last, l_blind -> cosets; l_active = 1 - l_last - l_blind
   {
@@ -229,9 +233,9 @@ int pk_build(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs
     ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(tmp + 2 * n + (n - bf), ones.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, st));
     ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     int s1 = dom_lagrange_to_coeff(ctx, P->dom, tmp, 3);
-    if (s1 == ZKC_OK) s1 = dom_coeff_to_extended(ctx, P->dom, tmp, n, P->l0, 1);
-    if (s1 == ZKC_OK) s1 = dom_coeff_to_extended(ctx, P->dom, tmp + n, n, P->l_last, 1);
-    if (s1 == ZKC_OK) s1 = dom_coeff_to_extended(ctx, P->dom, tmp + 2 * n, n, lb, 1);
+    if (s1 == ZKC_OK) s1 = dom_coeff_to_classes(ctx, P->dom, tmp, n, P->l0, 1, 0, ncls);
+    if (s1 == ZKC_OK) s1 = dom_coeff_to_classes(ctx, P->dom, tmp + n, n, P->l_last, 1, 0, ncls);
+    if (s1 == ZKC_OK) s1 = dom_coeff_to_classes(ctx, P->dom, tmp + 2 * n, n, lb, 1, 0, ncls);
     if (s1 == ZKC_OK) { k_l_active<<<(unsigned)((en + 255) / 256), 256, 0, st>>>(P->l_last, lb, P->l_active, en); ctx->launches++; }
     cudaStreamSynchronize(st);   // the temporaries are released when this block ends
     ZKC_TRY(s1);
@@ -315,9 +319,21 @@ extern "C" int zkc_pk_write(zkc_ctx* ctx, const zkc_pk* pk, const uint8_t* selec
   if (num_selectors) memcpy(out + L.selectors_off, selectors, (size_t)num_selectors * ((n + 7) / 8));
   cudaStream_t st = ctx->stream;
   auto d2h = [&](uint64_t off, const Fr* src, uint64_t len) { return cudaMemcpyAsync(out + off, src, len * sizeof(Fr), cudaMemcpyDeviceToHost, st); };
-  ZKC_CUDA_TRY(ctx, d2h(L.l0_off + 4, pk->l0, en)); ZKC_CUDA_TRY(ctx, d2h(L.l_last_off + 4, pk->l_last, en)); ZKC_CUDA_TRY(ctx, d2h(L.l_active_row_off + 4, pk->l_active, en));
+  // the key keeps its extended cosets class-major; the file holds them in upstream's natural order
+  Fr* nat;
+  ZKC_TRY(scratch_reserve(ctx, SCR_MISC3, en * sizeof(Fr), (void**)&nat));
+  auto coset_out = [&](uint64_t off, const Fr* cm) -> int {
+    ZKC_TRY(dom_classes_to_natural(ctx, pk->dom, cm, nat));
+    ZKC_CUDA_TRY(ctx, d2h(off, nat, en));
+    ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));   // `nat` is reused by the next column
+    return ZKC_OK;
+  };
+  ZKC_TRY(coset_out(L.l0_off + 4, pk->l0)); ZKC_TRY(coset_out(L.l_last_off + 4, pk->l_last)); ZKC_TRY(coset_out(L.l_active_row_off + 4, pk->l_active));
   auto slice = [&](uint64_t off, const Fr* base, uint32_t count, uint64_t len) -> int {
-    for (uint32_t c = 0; c < count; ++c) ZKC_CUDA_TRY(ctx, d2h(off + 4 + (uint64_t)c * (4 + 32 * len) + 4, base + (size_t)c * len, len));
+    for (uint32_t c = 0; c < count; ++c) {
+      const uint64_t o = off + 4 + (uint64_t)c * (4 + 32 * len) + 4;
+      if (len == en) ZKC_TRY(coset_out(o, base + (size_t)c * len)); else ZKC_CUDA_TRY(ctx, d2h(o, base + (size_t)c * len, len));
+    }
     return ZKC_OK;
   };
   ZKC_TRY(slice(L.fixed_values_off, pk->fixed_values, F, n)); ZKC_TRY(slice(L.fixed_polys_off, pk->fixed_polys, F, n)); ZKC_TRY(slice(L.fixed_cosets_off, pk->fixed_cosets, F, en));
@@ -484,10 +500,10 @@ struct zkc_prover {
   int stage = 0;
   // shape
   uint64_t n = 0, en = 0, U = 0;
-  uint32_t bf = 0, A = 0, I = 0, L = 0, Pn = 0, rot_scale = 1, q = 0;
+  uint32_t bf = 0, A = 0, I = 0, L = 0, Pn = 0, q = 0;
   bool team = false;
-  uint64_t halo_lo = 0, halo_hi = 0;   // rows of rotation reach on the extended coset, before / after a row block
-  std::vector<Segment> my_rows;        // row blocks of the extended coset this process evaluates
+  std::vector<Segment> my_rows;        // row blocks of the (class-major) extended coset this process evaluates
+  std::vector<std::pair<uint32_t, uint32_t>> my_classes;   // residue classes [first, second) those blocks touch
   Fr omega, omega_inv, zeta, ONE, ZERO, DELTA;
   // columns
   Fr *inst_values = nullptr, *inst_polys = nullptr, *adv_values = nullptr, *adv_polys = nullptr;
@@ -533,16 +549,10 @@ struct zkc_prover {
     team_advance(ctx, ncols);
     return ZKC_OK;
   }
-  // coefficient form -> extended coset; team: the owner sends every rank the rows its block reads (block + rotation halo)
+  // coefficient form -> extended coset, CLASS-MAJOR (ntt.cu: residue classes of the extended coset).  Team: every rank holds the
+  // coefficient forms, so it transforms the classes its row block touches itself — no coset row ever crosses a link.
   int to_extended(const Fr* polys, Fr* cosets, uint32_t ncols) {
-    if (!team) return dom_coeff_to_extended(ctx, pk->dom, polys, n, cosets, ncols);
-    for (int r : team_ranks(ctx)) {
-      uint32_t c0, c1;
-      team_cols(ctx, ncols, r, &c0, &c1);
-      if (c1 > c0) ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, polys + (size_t)c0 * n, n, cosets + (size_t)c0 * en, c1 - c0));
-    }
-    ZKC_TRY(team_scatter_rows(ctx, cosets, en, ncols, halo_lo, halo_hi));
-    team_advance(ctx, ncols);
+    for (const auto& cr : my_classes) ZKC_TRY(dom_coeff_to_classes(ctx, pk->dom, polys, n, cosets, ncols, cr.first, cr.second));
     return ZKC_OK;
   }
   const Fr* column_ptr(uint32_t kind, uint32_t idx, bool coset) const {
@@ -624,20 +634,22 @@ int zkc_prover::begin(const zkc_fr* advice, int advice_on_device, const zkc_fr* 
   const Cs& cs = pk->cs;
   n = cs.n(); en = 1ull << pk->ext_k; U = cs.usable();
   bf = cs.blinding_factors; A = cs.num_advice; I = cs.num_instance; L = (uint32_t)cs.lookups.size(); Pn = cs.nsets();
-  rot_scale = 1u << (pk->ext_k - cs.k); q = cs.degree - 1;
+  q = cs.degree - 1;
   cudaStream_t st = ctx->stream;
   // Team proving (dist.cuh): the same driver runs on every rank; MSMs split by point range, column transforms by column,
   // h(X) by extended-row block.  Collectives are issued on the stream of the kernels they depend on (one communicator per
   // stream), in the same host order on every rank, so the column exchanges of the side stream hide under the MSM phases.
   team = team_active(ctx);
   if (team) ctx->team_rot = 0;
-  {
-    int64_t rmin = -(int64_t)(bf + 1), rmax = 1;   // z(omega X), z(omega^-(bf+1) X), a'(omega^-1 X)
-    for (auto* v : {&cs.aq, &cs.fq, &cs.iq}) for (auto& qq : *v) { rmin = std::min<int64_t>(rmin, qq.second); rmax = std::max<int64_t>(rmax, qq.second); }
-    halo_lo = (uint64_t)(-rmin) * rot_scale; halo_hi = (uint64_t)rmax * rot_scale;
-  }
+  // h(X) is evaluated on the class-major extended coset: a rank's row block [lo, hi) of the flat class-major index touches the
+  // classes lo / n .. (hi - 1) / n, and every rotation of a row stays inside its class
   if (!team) my_rows.push_back({0, en});
   else for (int r : team_ranks(ctx)) { uint64_t lo, hi; shard_range(en, ctx->team_world, r, &lo, &hi); if (hi > lo) my_rows.push_back({lo, hi - lo}); }
+  for (const Segment& rb : my_rows) {
+    const uint32_t c0 = (uint32_t)(rb.lo / n), c1 = (uint32_t)((rb.lo + rb.len - 1) / n) + 1;
+    if (!my_classes.empty() && my_classes.back().second >= c0) my_classes.back().second = std::max(my_classes.back().second, c1);
+    else my_classes.push_back({c0, c1});
+  }
   zkc_domain_info di;
   zkc_domain_get_info(pk->dom, &di);
   memcpy(omega.v, &di.omega, 32); memcpy(omega_inv.v, &di.omega_inv, 32); memcpy(zeta.v, &di.g_coset, 32);
@@ -732,7 +744,7 @@ int zkc_prover::begin(const zkc_fr* advice, int advice_on_device, const zkc_fr* 
       ZKC_TRY(to_coeff(adv_polys, A));
       ZKC_TRY(to_extended(adv_polys, adv_cosets, A));
     }
-    if (I) ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, inst_polys, n, inst_cosets, I));
+    if (I) ZKC_TRY(to_extended(inst_polys, inst_cosets, I));
   }
   out.clear();
   if (A && staged.empty()) {
@@ -910,38 +922,41 @@ int zkc_prover::vanishing(const RandomSpec* rs, G1Affine* out) {
 int zkc_prover::quotient(const Fr& y_, std::vector<G1Affine>& out) {
   y = y_;
   cudaStream_t st = ctx->stream;
-  ZKC_TRY(pool.get(&hval, en)); ZKC_TRY(pool.get(&lk_comp_cosets, (size_t)2 * en));
+  Fr* hcm;   // h on the class-major extended coset
+  ZKC_TRY(pool.get(&hval, en)); ZKC_TRY(pool.get(&hcm, en)); ZKC_TRY(pool.get(&lk_comp_cosets, (size_t)2 * en));
   side_join(ctx);   // every coset produced on the side stream is complete from here on
   {
     ProfScope _p(ctx, "prove.quotient");
     const Fr* tw_ext = nullptr;
     if (Pn) ZKC_TRY(ntt_twiddles(ctx, pk->ext_k, &tw_ext));
+    // class-major rows: the cyclic length every kernel sees is n (one residue class), rotations are not scaled
     for (const Segment& rb : my_rows) {
       const uint64_t r0 = rb.lo, rc = rb.len;
-      ZKC_TRY(eval_program(ctx, pk->gates, qext, hval, en, rot_scale, y, 0, r0, rc));
+      ZKC_TRY(eval_program(ctx, pk->gates, qext, hcm, n, 1, y, 0, r0, rc));
       if (Pn) {
         PermFixedArgs fa; fa.nsets = Pn;
         for (uint32_t s = 0; s < Pn; ++s) fa.z[s] = pz_cosets + (size_t)s * en;
-        const int64_t last_off = -(int64_t)(bf + 1) * rot_scale;
-        k_quot_perm_fixed<<<grid_for(rc, 128), 128, 0, st>>>(hval, fa, pk->l0, pk->l_last, y, en, last_off, r0, rc); ZKC_LAUNCH_CHECK(ctx);
+        const int64_t last_off = -(int64_t)(bf + 1);
+        k_quot_perm_fixed<<<grid_for(rc, 128), 128, 0, st>>>(hcm, fa, pk->l0, pk->l_last, y, n, last_off, r0, rc); ZKC_LAUNCH_CHECK(ctx);
         for (uint32_t s = 0; s < Pn; ++s) {
-          k_quot_perm_set<<<grid_for(rc, 128), 128, 0, st>>>(hval, perm_args(s, true), pz_cosets + (size_t)s * en, pk->l_active, tw_ext, pk->ext_k, beta,
-                                                              gamma, y, en, rot_scale, r0, rc);
+          k_quot_perm_set<<<grid_for(rc, 128), 128, 0, st>>>(hcm, perm_args(s, true), pz_cosets + (size_t)s * en, pk->l_active, tw_ext, pk->ext_k,
+                                                              pk->cs.k, beta, gamma, y, r0, rc);
           ZKC_LAUNCH_CHECK(ctx);
         }
       }
       for (uint32_t l = 0; l < L; ++l) {
         Fr* zc = lk_cosets + (size_t)3 * l * en; Fr* ac = zc + en; Fr* sc = ac + en;
-        ZKC_TRY(eval_program(ctx, pk->lookups[l].first, qext, lk_comp_cosets, en, rot_scale, theta, 0, r0, rc));
-        ZKC_TRY(eval_program(ctx, pk->lookups[l].second, qext, lk_comp_cosets + en, en, rot_scale, theta, 0, r0, rc));
-        k_quot_lookup<<<grid_for(rc, 128), 128, 0, st>>>(hval, zc, ac, sc, lk_comp_cosets, lk_comp_cosets + en, pk->l0, pk->l_last, pk->l_active, beta,
-                                                          gamma, y, en, rot_scale, r0, rc);
+        ZKC_TRY(eval_program(ctx, pk->lookups[l].first, qext, lk_comp_cosets, n, 1, theta, 0, r0, rc));
+        ZKC_TRY(eval_program(ctx, pk->lookups[l].second, qext, lk_comp_cosets + en, n, 1, theta, 0, r0, rc));
+        k_quot_lookup<<<grid_for(rc, 128), 128, 0, st>>>(hcm, zc, ac, sc, lk_comp_cosets, lk_comp_cosets + en, pk->l0, pk->l_last, pk->l_active, beta,
+                                                          gamma, y, n, r0, rc);
         ZKC_LAUNCH_CHECK(ctx);
       }
-      ZKC_TRY(dom_divide_by_vanishing(ctx, pk->dom, hval, r0, rc));
+      ZKC_TRY(dom_divide_by_vanishing_classes(ctx, pk->dom, hcm, r0, rc));
     }
-    //     ... (team: every rank needs the whole quotient) and back to coefficients
-    if (team) ZKC_TRY(team_allgather_rows(ctx, hval, en));
+    //     ... (team: every rank needs the whole quotient), natural row order, and back to coefficients
+    if (team) ZKC_TRY(team_allgather_rows(ctx, hcm, en));
+    ZKC_TRY(dom_classes_to_natural(ctx, pk->dom, hcm, hval));
     ZKC_TRY(dom_extended_to_coeff(ctx, pk->dom, hval, 1));
   }
   ZKC_TRY(commit_points(ctx, pk->srs, 0, hval, n, q, out));

@@ -191,7 +191,9 @@ __global__ void k_lookup_finish(const Fr* canon, const Fr* tail, Fr* out, uint64
 #define PERM_MAX_SETS 32
 struct PermFixedArgs { const Fr* z[PERM_MAX_SETS]; uint32_t nsets; };
 // value = value*y + l0*(1 - z_0);  value*y + l_last*(z_l^2 - z_l);  for s >= 1: value*y + l0*(z_s - z_{s-1}[i + last_rot])
-// (all h(X) kernels: `rows` is the size of the extended domain, [row0, row0 + cnt) the row block this launch evaluates)
+// (all h(X) kernels work on the CLASS-MAJOR extended coset (ntt.cu, dom_coeff_to_classes): `rows` = n is the length of one residue
+//  class, row i belongs to class i / rows, a rotation moves inside the class; [row0, row0 + cnt) is the block this launch evaluates)
+__device__ __forceinline__ uint64_t class_rot(uint64_t i, uint64_t rows, int64_t off) { return (i & ~(rows - 1)) | ((i + rows + off) & (rows - 1)); }
 __global__ void k_quot_perm_fixed(Fr* value, PermFixedArgs a, const Fr* l0, const Fr* l_last, Fr y, uint64_t rows, int64_t last_off, uint64_t row0,
                                   uint64_t cnt) {
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,7 +205,7 @@ __global__ void k_quot_perm_fixed(Fr* value, PermFixedArgs a, const Fr* l0, cons
   v = fe_add(fe_mul(v, y), fe_mul(fe_sub(fe_one<FrP>(), z0), L0));
   const Fr zl = fe_load(a.z[a.nsets - 1] + i);
   v = fe_add(fe_mul(v, y), fe_mul(fe_sub(fe_sqr(zl), zl), LL));
-  const uint64_t r = (i + rows + last_off) & (rows - 1);
+  const uint64_t r = class_rot(i, rows, last_off);
   for (uint32_t s = 1; s < a.nsets; ++s) {
     const Fr d = fe_sub(fe_load(a.z[s] + i), fe_load(a.z[s - 1] + r));
     v = fe_add(fe_mul(v, y), fe_mul(d, L0));
@@ -211,16 +213,17 @@ __global__ void k_quot_perm_fixed(Fr* value, PermFixedArgs a, const Fr* l0, cons
   fe_store(value + i, v);
 }
 // value = value*y + l_active * ( z(wX) prod (v + beta sigma + gamma) - z(X) prod (v + delta_beta_t X + gamma) )
-// X = zeta * w_ext^i is folded into delta_beta (zeta) and the twiddle table (w_ext^i).
-__global__ void k_quot_perm_set(Fr* value, PermSetArgs a, const Fr* z, const Fr* l_active, const Fr* tw_ext, uint32_t ext_k, Fr beta,
-                                Fr gamma, Fr y, uint64_t rows, uint32_t rot_scale, uint64_t row0, uint64_t cnt) {
+// X = zeta * w_ext^r is folded into delta_beta (zeta) and the twiddle table (w_ext^r), r = class + 2^e * (row inside the class).
+__global__ void k_quot_perm_set(Fr* value, PermSetArgs a, const Fr* z, const Fr* l_active, const Fr* tw_ext, uint32_t ext_k, uint32_t log_rows,
+                                Fr beta, Fr gamma, Fr y, uint64_t row0, uint64_t cnt) {
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= cnt) return;
   const uint64_t i = row0 + tid;
-  const uint64_t half = rows >> 1;
-  Fr w = fe_load_nc(tw_ext + (i >= half ? i - half : i));
-  if (i >= half) w = fe_neg(w);
-  Fr left = fe_load(z + ((i + rot_scale) & (rows - 1)));
+  const uint64_t rows = 1ull << log_rows, half = 1ull << (ext_k - 1);
+  const uint64_t r = (i >> log_rows) + ((i & (rows - 1)) << (ext_k - log_rows));
+  Fr w = fe_load_nc(tw_ext + (r >= half ? r - half : r));
+  if (r >= half) w = fe_neg(w);
+  Fr left = fe_load(z + class_rot(i, rows, 1));
   Fr right = fe_load(z + i);
   for (uint32_t t = 0; t < a.m; ++t) {
     const Fr v = fe_load(a.cols[t] + i);
@@ -232,15 +235,14 @@ __global__ void k_quot_perm_set(Fr* value, PermSetArgs a, const Fr* z, const Fr*
 }
 // the five lookup terms (A.7 / evaluation.rs order)
 __global__ void k_quot_lookup(Fr* value, const Fr* zc, const Fr* ac, const Fr* sc, const Fr* comp_in, const Fr* comp_tab, const Fr* l0,
-                              const Fr* l_last, const Fr* l_active, Fr beta, Fr gamma, Fr y, uint64_t rows, uint32_t rot_scale, uint64_t row0,
-                              uint64_t cnt) {
+                              const Fr* l_last, const Fr* l_active, Fr beta, Fr gamma, Fr y, uint64_t rows, uint64_t row0, uint64_t cnt) {
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= cnt) return;
   const uint64_t i = row0 + tid;
   Fr v = fe_load(value + i);
   const Fr L0 = fe_load(l0 + i), LL = fe_load(l_last + i), LA = fe_load(l_active + i);
-  const Fr z = fe_load(zc + i), zn = fe_load(zc + ((i + rot_scale) & (rows - 1)));
-  const Fr ap = fe_load(ac + i), sp = fe_load(sc + i), apm = fe_load(ac + ((i + rows - rot_scale) & (rows - 1)));
+  const Fr z = fe_load(zc + i), zn = fe_load(zc + class_rot(i, rows, 1));
+  const Fr ap = fe_load(ac + i), sp = fe_load(sc + i), apm = fe_load(ac + class_rot(i, rows, -1));
   const Fr table_value = fe_mul(fe_add(fe_load(comp_in + i), beta), fe_add(fe_load(comp_tab + i), gamma));
   const Fr a_minus_s = fe_sub(ap, sp);
   v = fe_add(fe_mul(v, y), fe_mul(fe_sub(fe_one<FrP>(), z), L0));

@@ -136,6 +136,14 @@ int zkc_coeff_to_lagrange_dev(zkc_ctx* ctx, const zkc_domain* dom, zkc_fr* a_dev
 int zkc_coeff_to_extended_dev(zkc_ctx* ctx, const zkc_domain* dom, const zkc_fr* coeffs_dev, zkc_fr* out_dev, uint32_t ncols);
 int zkc_extended_to_coeff_dev(zkc_ctx* ctx, const zkc_domain* dom, zkc_fr* a_dev, uint32_t ncols);
 int zkc_divide_by_vanishing_dev(zkc_ctx* ctx, const zkc_domain* dom, zkc_fr* a_dev);
+/* coeff_to_extended by RESIDUE CLASS (the split team proving uses): the extended coset zeta * <w_ext> is the union of
+ * the 2^(extended_k - k) cosets (zeta * w_ext^c) * <omega>; class c of a column is ONE size-n transform and holds the rows
+ * c + 2^(extended_k - k) * m of zkc_coeff_to_extended's output at out[c * n + m] (class-major).  Transforms classes [c0, c1) of
+ * ncols columns (input stride n, output stride 2^extended_k); the other classes of `out_dev` are left untouched.
+ * zkc_extended_classes_to_natural_dev reorders one class-major column into zkc_coeff_to_extended's row order. */
+int zkc_coeff_to_extended_classes_dev(zkc_ctx* ctx, const zkc_domain* dom, const zkc_fr* coeffs_dev, zkc_fr* out_dev, uint32_t ncols,
+                                      uint32_t c0, uint32_t c1);
+int zkc_extended_classes_to_natural_dev(zkc_ctx* ctx, const zkc_domain* dom, const zkc_fr* class_major_dev, zkc_fr* natural_dev);
 
 /* ---- best_multiexp / ParamsKZG ------------------------------------------ */
 /* best_multiexp(coeffs, bases) -> G1 (normalised Jacobian).  Host pointers. */
@@ -356,11 +364,11 @@ int zkc_team_init(zkc_ctx* ctx, int rank, int world, const uint8_t id[ZKC_TEAM_I
 int zkc_team_emulate(zkc_ctx* ctx, int world);
 int zkc_team_leave(zkc_ctx* ctx);
 int zkc_team_info(const zkc_ctx* ctx, int* rank, int* world, int* emulated);
-/* the partition arithmetic (host only): contiguous share [lo, hi) of `total` items for `rank`; and the <= 2 row segments
- * {lo, len} of a cyclic column of `rows` rows that `rank` reads when evaluating its row block with rotations reaching
- * halo_lo rows back and halo_hi rows forward */
+/* the partition arithmetic (host only): contiguous share [lo, hi) of `total` items for `rank`; and the residue classes
+ * [c0, c1) of the extended coset (class c = rows c + 2^(extended_k - k) * m, a coset of the size-n subgroup) that `rank`
+ * transforms and evaluates: the classes its share of the class-major extended domain touches */
 int zkc_team_shard_range(uint64_t total, int world, int rank, uint64_t* lo, uint64_t* hi);
-int zkc_team_row_segments(uint64_t rows, int world, int rank, uint64_t halo_lo, uint64_t halo_hi, uint64_t out_lo_len[4], int* nseg);
+int zkc_team_classes(uint32_t k, uint32_t extended_k, int world, int rank, uint32_t* c0, uint32_t* c1);
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,40 @@ def test_domain_conversions(j, k):
     assert np.array_equal(to_host(t), orc.divide_by_vanishing(j, k, e))
 
 
+@pytest.mark.parametrize("j,k,ncols", [(4, 4, 2), (4, 9, 3), (3, 13, 2), (4, 15, 2), (4, 17, 3), (5, 14, 1), (9, 10, 2), (2, 8, 2)])
+def test_coeff_to_extended_by_residue_class(j, k, ncols):
+    """The class split of the extended coset (ntt.cu dom_coeff_to_classes; what team proving shards by): class c of a column is
+    one size-n transform and equals rows c, c + 2^e, c + 2 * 2^e, ... of the oracle's coeff_to_extended; classes outside
+    [c0, c1) are left untouched; the natural-order permutation gives the oracle's column back."""
+    import torch
+    ctx = gpu_ctx()
+    dom = pkg().EvaluationDomain(j, k, ctx=ctx)
+    n, en = 1 << k, 1 << dom.extended_k
+    ncls = en // n
+    a = random_fr_mont(n * ncols, 700 + k)
+    want = [orc.coeff_to_extended(j, k, a[c * n:(c + 1) * n]) for c in range(ncols)]
+    src = to_dev(a)
+    for c0, c1 in sorted({(0, ncls), (0, 1), (ncls - 1, ncls), (ncls // 2, ncls)}):
+        dst = torch.full((en * ncols, 4), -1, dtype=torch.int64, device="cuda")
+        dom.coeff_to_extended_classes_dev(src, dst, ncols, c0, c1)
+        ctx.sync()
+        got = to_host(dst)
+        for col in range(ncols):
+            for c in range(ncls):
+                blk = got[col * en + c * n: col * en + (c + 1) * n]
+                if c0 <= c < c1:
+                    assert np.array_equal(blk, want[col][c::ncls]), (col, c)
+                else:
+                    assert (blk == np.uint64(0xFFFFFFFFFFFFFFFF)).all(), (col, c)
+    nat = torch.empty((en, 4), dtype=torch.int64, device="cuda")
+    dom.extended_classes_to_natural_dev(dst[en * (ncols - 1):], nat)   # last loop iteration transformed a suffix of the classes only
+    dst = torch.empty((en * ncols, 4), dtype=torch.int64, device="cuda")
+    dom.coeff_to_extended_classes_dev(src, dst, ncols, 0, ncls)
+    dom.extended_classes_to_natural_dev(dst[en * (ncols - 1):], nat)
+    ctx.sync()
+    assert np.array_equal(to_host(nat), want[ncols - 1])
+
+
 def test_domain_batched_dev_full_size():
     """BASELINE config-1 shape: k=17, extended 2^19, a few columns; round trip + spot parity."""
     ctx = gpu_ctx()

@@ -223,8 +223,8 @@ def test_g1_sum_host_epilogue():
 
 
 def test_team_partition_arithmetic():
-    """zkc_team_shard_range / zkc_team_row_segments (dist.cu): blocks tile the range; the segments a rank receives
-    cover exactly the rows its block reads under every rotation in [-halo_lo, +halo_hi] (cyclic)."""
+    """zkc_team_shard_range / zkc_team_classes (dist.cu): blocks tile the range; a rank's residue classes are the ones its
+    block of the class-major extended domain overlaps (rotations never leave a class, so that is all it has to transform)."""
     import ctypes as C
     L = pkg().lib()
     for total, world in [(10, 3), (7, 8), (1 << 12, 4), (0, 2), (5, 5)]:
@@ -235,20 +235,18 @@ def test_team_partition_arithmetic():
             assert lo.value == prev and hi.value - lo.value in (total // world, total // world + 1)
             prev = hi.value
         assert prev == total
-    for rows, world, hl, hh in [(64, 2, 28, 12), (64, 4, 28, 12), (256, 3, 28, 12), (1 << 10, 8, 40, 4), (32, 2, 28, 12), (16, 4, 0, 0)]:
+    # residue classes: every class is covered, a rank's classes are exactly those its class-major row block overlaps
+    for k, ek, world in [(10, 12, 2), (10, 12, 4), (10, 12, 8), (10, 12, 3), (8, 11, 5), (6, 6, 2), (12, 13, 1)]:
+        n, en, seen = 1 << k, 1 << ek, set()
         for r in range(world):
-            lo, hi = C.c_uint64(), C.c_uint64()
-            L.zkc_team_shard_range(C.c_uint64(rows), world, r, C.byref(lo), C.byref(hi))
-            out, nseg = (C.c_uint64 * 4)(), C.c_int()
-            assert L.zkc_team_row_segments(C.c_uint64(rows), world, r, C.c_uint64(hl), C.c_uint64(hh), out, C.byref(nseg)) == 0
-            got = set()
-            for i in range(nseg.value):
-                assert out[2 * i] + out[2 * i + 1] <= rows
-                seg = set(range(out[2 * i], out[2 * i] + out[2 * i + 1]))
-                assert not (got & seg)
-                got |= seg
-            want = {(i + d) % rows for i in range(lo.value, hi.value) for d in range(-hl, hh + 1)}
-            assert got == want if len(want) < rows else got == set(range(rows))
+            lo, hi, c0, c1 = C.c_uint64(), C.c_uint64(), C.c_uint32(), C.c_uint32()
+            L.zkc_team_shard_range(C.c_uint64(en), world, r, C.byref(lo), C.byref(hi))
+            assert L.zkc_team_classes(k, ek, world, r, C.byref(c0), C.byref(c1)) == 0
+            want = {i // n for i in range(lo.value, hi.value)}
+            assert set(range(c0.value, c1.value)) == want
+            seen |= want
+        assert seen == set(range(en // n))
+    assert L.zkc_team_classes(12, 10, 2, 0, C.byref(C.c_uint32()), C.byref(C.c_uint32())) != 0
     assert L.zkc_team_shard_range(C.c_uint64(4), 2, 2, None, None) != 0
 
 
