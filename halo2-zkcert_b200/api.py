@@ -99,7 +99,7 @@ class Context:
 
     def set_tunable(self, name, value):
         """debug / sweep override on this ctx (zkc_ctx_set_tunable): msm_c, msm_c_pre, msm_T, ntt_two_pass_max,
-        stage_min_bytes (-1 = default), team_poison"""
+        stage_min_bytes (-1 = default), team_poison, team_commit_by_column, msm_accum_occ"""
         self.check(lib().zkc_ctx_set_tunable(self._h, name.encode(), C.c_int64(int(value))))
 
     @property

@@ -12,6 +12,7 @@ void tunables_from_env(Tunables& v) {
   v.ntt_two_pass_max = env_int("ZKC_NTT_TWO_PASS_MAX", 12, 22); v.msm_accum_occ = env_int("ZKC_MSM_ACCUM_OCC", 3, 4);
   if (const char* e = getenv("ZKC_STAGE_MIN_BYTES")) v.stage_min_bytes = (size_t)strtoull(e, nullptr, 10);
   v.team_poison = getenv("ZKC_TEAM_POISON") != nullptr;
+  v.team_commit_by_column = getenv("ZKC_TEAM_COMMIT_BY_COLUMN") != nullptr;
 }
 }  // namespace
 
@@ -27,6 +28,7 @@ extern "C" int zkc_ctx_set_tunable(zkc_ctx* c, const char* name, int64_t value) 
   else if (n == "ntt_two_pass_max") t.ntt_two_pass_max = (int)value;
   else if (n == "stage_min_bytes") t.stage_min_bytes = value < 0 ? ((size_t)4 << 20) : (size_t)value;
   else if (n == "team_poison") t.team_poison = value != 0;
+  else if (n == "team_commit_by_column") t.team_commit_by_column = value != 0;
   else return set_err(c, ZKC_ERR_BAD_ARG, "zkc_ctx_set_tunable: unknown name " + n);
   return ZKC_OK;
 }

@@ -101,6 +101,19 @@ int team_bcast_cols(zkc_ctx* ctx, Fr* base, uint64_t stride, uint64_t len, uint3
   return ZKC_OK;
 }
 
+int team_exchange(zkc_ctx* ctx, const std::vector<TeamXfer>& ops, const char* what) {
+  if (!real_comm(ctx) || ops.empty()) return ZKC_OK;
+  ProfScope _p(ctx, what);
+  ZKC_NCCL_TRY(ctx, nccl().GroupStart());
+  for (const TeamXfer& x : ops) {
+    const int rc = x.send ? nccl().Send(x.p, x.bytes, kNcclUint8, x.peer, comm_of(ctx), ctx->stream)
+                          : nccl().Recv(x.p, x.bytes, kNcclUint8, x.peer, comm_of(ctx), ctx->stream);
+    if (rc != 0) { nccl().GroupEnd(); return nccl_fail(ctx, "ncclSend/ncclRecv", rc); }
+  }
+  ZKC_NCCL_TRY(ctx, nccl().GroupEnd());
+  return ZKC_OK;
+}
+
 int team_allgather_rows(zkc_ctx* ctx, Fr* col, uint64_t en) {
   if (!real_comm(ctx)) return ZKC_OK;
   ProfScope _p(ctx, "team.allgather_rows");

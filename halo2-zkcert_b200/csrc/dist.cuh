@@ -35,6 +35,9 @@ inline bool team_active(const zkc_ctx* ctx) { return ctx->team_world > 1; }
 int team_allgather(zkc_ctx* ctx, void* buf, size_t bytes_per_rank);
 // column c of base[ncols][stride] (first `len` elements) is broadcast from the rank that owns it
 int team_bcast_cols(zkc_ctx* ctx, Fr* base, uint64_t stride, uint64_t len, uint32_t ncols);
+// point-to-point transfers of one step, issued as ONE NCCL group (every send has its matching receive in the peer's group)
+struct TeamXfer { int peer; bool send; void* p; size_t bytes; };
+int team_exchange(zkc_ctx* ctx, const std::vector<TeamXfer>& ops, const char* what);
 // in-place all-gather of the row blocks of one length-en column
 int team_allgather_rows(zkc_ctx* ctx, Fr* col, uint64_t en);
 // in-place all-gather of a flat array split with shard_range(total, world, r)

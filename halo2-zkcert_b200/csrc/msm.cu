@@ -535,12 +535,27 @@ int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t
                 int result_slot, bool team) {
   team = team && team_active(ctx) && n >= (uint64_t)ctx->team_world;
   const int shards = team ? ctx->team_world : 1;
+  // Two ways to share a batch of commitments: by POINT RANGE (default: every rank walks 1/world of every column, the
+  // split best_multiexp makes across threads) or, for batches of at least `world` columns and on request (tunable
+  // team_commit_by_column), by COLUMN: rank r commits columns shard_range(nc, world, r) whole.  The column split runs the
+  // bucket phases of nc / world bucket sets per rank instead of nc, but its accumulate work is only balanced when world divides nc.
+  const bool by_column = team && ctx->tune.team_commit_by_column && nc >= (uint32_t)shards;
   const MsmGeom g0 = msm_geom(ctx, n, nc, c, precomputed);
-  const size_t ubytes = (size_t)nc * g0.sets * g0.c * sizeof(G1Xyzz), slot_bytes = (ubytes + 4 + 255) & ~(size_t)255;   // U, then the digit count
+  const uint32_t slot_cols = by_column ? (nc + (uint32_t)shards - 1) / (uint32_t)shards : nc;
+  const size_t ubytes = (size_t)slot_cols * g0.sets * g0.c * sizeof(G1Xyzz), slot_bytes = (ubytes + 4 + 255) & ~(size_t)255;   // U, then the digit count
   char* dU;
   ZKC_TRY(scratch_reserve(ctx, SCR_MSM2, slot_bytes * shards, (void**)&dU));
   if (!team) {
     ZKC_TRY(msm_kernels(ctx, scalars, bases, g0, (G1Xyzz*)dU, (uint32_t*)(dU + ubytes)));
+  } else if (by_column) {
+    for (int r : team_ranks(ctx)) {
+      uint64_t a, b;
+      shard_range(nc, shards, r, &a, &b);
+      char* slot = dU + (size_t)r * slot_bytes;
+      ZKC_TRY(msm_kernels(ctx, scalars + a * n, bases, msm_geom(ctx, n, (uint32_t)(b - a), c, precomputed), (G1Xyzz*)slot, (uint32_t*)(slot + ubytes)));
+    }
+    ProfScope _p(ctx, "team.msm_allgather");
+    ZKC_TRY(team_allgather(ctx, dU, slot_bytes));
   } else {
     // point-range shards: rank r walks points [lo, hi) of every column against the same slice of every window table
     for (int r : team_ranks(ctx)) {
@@ -559,7 +574,7 @@ int msm_enqueue(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t
   ZKC_CUDA_TRY(ctx, cudaMemcpyAsync(hU, dU, slot_bytes * shards, cudaMemcpyDeviceToHost, ctx->stream));
   cudaEvent_t ev = result_slot ? ctx->ev_msm_side : ctx->ev_msm_main;
   ZKC_CUDA_TRY(ctx, cudaEventRecord(ev, ctx->stream));
-  pend->g = g0; pend->nc = nc; pend->n = n; pend->hU = hU; pend->ubytes = ubytes; pend->shards = shards; pend->done = ev; pend->active = true;
+  pend->g = g0; pend->nc = nc; pend->n = n; pend->hU = hU; pend->ubytes = ubytes; pend->shards = shards; pend->by_column = by_column; pend->done = ev; pend->active = true;
   return ZKC_OK;
 }
 
@@ -578,6 +593,15 @@ int msm_finish(zkc_ctx* ctx, MsmPending* pend, zkc_g1* out) {
     if (ctx->team_emulate || pend->shards == 1 || r == ctx->team_rank) madds += e;    // this GPU's own work
   }
   ctx->stats["msm.madds"] += madds; ctx->stats["msm.points"] += pend->n * pend->nc;
+  if (pend->by_column) {
+    for (int r = 0; r < pend->shards; ++r) {
+      uint64_t a, b;
+      shard_range(pend->nc, pend->shards, r, &a, &b);
+      const G1Xyzz* Ur = (const G1Xyzz*)((const char*)pend->hU + (size_t)r * slot_bytes);
+      for (uint64_t col = a; col < b; ++col) xyzz_to_abi(host_combine(Ur + (size_t)(col - a) * per_col, pend->g), out + col);
+    }
+    return ZKC_OK;
+  }
   if (pend->shards > 1) {
     sum.assign(U, U + per_col * pend->nc);
     for (int r = 1; r < pend->shards; ++r) {

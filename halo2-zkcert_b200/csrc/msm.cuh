@@ -28,6 +28,7 @@ struct MsmPending {
   void* hU = nullptr;
   size_t ubytes = 0;   // bytes of bit-plane sums per shard
   int shards = 1;      // team proving: one block of `ubytes` per rank, summed on the host
+  bool by_column = false;   // team proving, column split: rank r's block holds the sums of ITS columns (shard_range(nc, shards, r))
   cudaEvent_t done = nullptr;
   bool active = false;
 };

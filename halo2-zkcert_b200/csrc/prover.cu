@@ -552,7 +552,38 @@ struct zkc_prover {
   // coefficient form -> extended coset, CLASS-MAJOR (ntt.cu: residue classes of the extended coset).  Team: every rank holds the
   // coefficient forms, so it transforms the classes its row block touches itself — no coset row ever crosses a link.
   int to_extended(const Fr* polys, Fr* cosets, uint32_t ncols) {
-    for (const auto& cr : my_classes) ZKC_TRY(dom_coeff_to_classes(ctx, pk->dom, polys, n, cosets, ncols, cr.first, cr.second));
+    if (!team || ctx->team_emulate) {
+      for (const auto& cr : my_classes) ZKC_TRY(dom_coeff_to_classes(ctx, pk->dom, polys, n, cosets, ncols, cr.first, cr.second));
+      return ZKC_OK;
+    }
+    // A class that lies inside one rank's row block is transformed there, all columns.  Where g > 1 row blocks share a class
+    // (more ranks than classes, or a world size that does not divide them) those g ranks deal its columns among themselves,
+    // each transforms its share and hands the class blocks (n rows, contiguous) to the other g - 1: large point-to-point
+    // messages inside a small group instead of g-fold redundant transforms.
+    const int W = ctx->team_world, me = ctx->team_rank;
+    std::vector<TeamXfer> xf;
+    for (const auto& cr : my_classes)
+      for (uint32_t c = cr.first; c < cr.second; ++c) {
+        std::vector<int> mem;
+        for (int r = 0; r < W; ++r) {
+          uint64_t lo, hi;
+          shard_range(en, W, r, &lo, &hi);
+          if (hi > lo && lo < (uint64_t)(c + 1) * n && hi > (uint64_t)c * n) mem.push_back(r);
+        }
+        const int g = (int)mem.size();
+        for (int t = 0; t < g; ++t) {
+          uint64_t a, b;
+          shard_range(ncols, g, (t + ctx->team_rot) % g, &a, &b);
+          if (mem[t] == me && b > a) ZKC_TRY(dom_coeff_to_classes(ctx, pk->dom, polys + a * n, n, cosets + a * en, (uint32_t)(b - a), c, c + 1));
+          for (uint64_t col = a; col < b; ++col) {
+            Fr* blk = cosets + col * en + (uint64_t)c * n;
+            if (mem[t] == me) { for (int o = 0; o < g; ++o) if (mem[o] != me) xf.push_back({mem[o], true, blk, n * sizeof(Fr)}); }
+            else xf.push_back({mem[t], false, blk, n * sizeof(Fr)});
+          }
+        }
+      }
+    ZKC_TRY(team_exchange(ctx, xf, "team.class_exchange"));
+    team_advance(ctx, ncols);
     return ZKC_OK;
   }
   const Fr* column_ptr(uint32_t kind, uint32_t idx, bool coset) const {

@@ -9,8 +9,11 @@ GPUs, gloo in the CPU tests).
 
 ONE proof spread over several GPUs (MSM by point range, transforms by column, h(X) by row block) is not
 orchestrated from here: it lives inside the library (`csrc/dist.cu`, `zkc_team_*`, `Context.team_init`),
-where the collectives run on the streams of the kernels they depend on.  The helpers below remain the
-operator-level building blocks (sharded MSM, four-step NTT) and the proof-chain distributor.
+where the collectives run on the streams of the kernels they depend on.  The helpers below are the
+proof-chain distributor / scheduler and the operator-level sharded MSM.  There is no NTT here: the size-2^extended_k coset
+transforms are split by residue class inside the library (csrc/ntt.cu, dom_coeff_to_classes — the four-step decomposition
+N1 = n, N2 = 2^(extended_k - k) of a zero-padded input, in which the exchange step disappears), natively and without a
+transpose; the eager-torch four-step operator of round 1 was removed.
 """
 import torch.distributed as dist
 
@@ -126,103 +129,3 @@ def msm_point_sharded(ctx, scalars_local, bases_local, n_local, group=None):
     parts = gather_objects(local.tobytes(), group)
     pts = np.frombuffer(b"".join(parts), dtype=np.uint64).reshape(-1, 12)
     return api.g1_sum(pts)
-
-
-# ---- four-step NTT with all-to-all transposes (k >= 20) --------------------------------
-class GpuNttOps:
-    """local pieces of the distributed NTT on one GPU, built from the single-GPU C ABI"""
-
-    def __init__(self, ctx):
-        self.ctx = ctx
-        self._tw = {}
-
-    def fft_rows(self, t, log_len, inverse):
-        """t: [rows, 2^log_len, 4] int64 CUDA, contiguous; in-place NTT of every row"""
-        rows = t.shape[0]
-        dom = self._dom(log_len)
-        omega = dom.omega_inv if inverse else dom.omega
-        self.ctx.fft_dev(t.view(-1, 4), omega, log_len, rows)
-        return t
-
-    def _dom(self, log_len):
-        from . import api
-        key = ("dom", log_len)
-        if key not in self._tw:
-            self._tw[key] = api.EvaluationDomain(2, log_len, ctx=self.ctx)
-        return self._tw[key]
-
-    def twiddles(self, row0, nrows, length, log_n, inverse):
-        """T[r][c] = w_N^((row0 + r) * c), w_N the canonical 2^log_n-th root (or its inverse); cached"""
-        import torch
-        key = ("tw", row0, nrows, length, log_n, inverse)
-        if key not in self._tw:
-            dom = self._dom(log_n)
-            w = dom.omega_inv if inverse else dom.omega
-            from .workload import to_mont_dev, to_host
-            one = to_host(to_mont_dev(self.ctx, [1]))
-            dev = "cuda:%d" % self.ctx.device
-            bases = torch.empty((row0 + nrows, 4), dtype=torch.int64, device=dev)
-            self.ctx.powers_dev(bases, w, one)            # w^i, i < row0 + nrows
-            bases_h = to_host(bases)
-            T = torch.empty((nrows, length, 4), dtype=torch.int64, device=dev)
-            for r in range(nrows):
-                self.ctx.powers_dev(T[r], bases_h[row0 + r:row0 + r + 1], one)
-            self.ctx.sync()
-            self._tw[key] = T
-        return self._tw[key]
-
-    def mul(self, a, b):
-        import torch
-        out = torch.empty_like(a)
-        self.ctx.field_vec_op_dev("fr", "mul", a.reshape(-1, 4), b.reshape(-1, 4), out.view(-1, 4))
-        return out
-
-    def scale(self, a, s_mont):
-        import torch
-        b = torch.from_numpy(s_mont.view("int64")).to(a.device).expand(a.numel() // 4, 4).contiguous()
-        return self.mul(a, b.view(a.shape))
-
-
-def _all_to_all(t, group):
-    import torch
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return t
-    out = torch.empty_like(t)
-    dist.all_to_all_single(out, t.contiguous(), group=group)
-    return out
-
-
-def ntt_four_step(x_local, log_n, inverse, ops, group=None):
-    """Distributed size-2^log_n NTT over G ranks; natural order in and out, rank g holding the contiguous
-    block [g N/G, (g+1) N/G) (x_local: [N/G, 4] int64 on the ops' device).
-
-    N = N1 * N2 with n = n1*N2 + n2 and k = k1 + N1*k2:
-      transpose (all-to-all)  -> rank holds a block of columns n2, all n1
-      local NTT over n1 (length N1) for each owned column, times w_N^(n2*k1)
-      transpose (all-to-all)  -> rank holds a block of k1, all n2
-      local NTT over n2 (length N2) for each owned k1
-      transpose (all-to-all)  -> natural order: rank holds a block of k2, all k1
-    The inverse transform applies the same steps with w^-1; scaling by 1/N is the caller's."""
-    G = dist.get_world_size(group) if dist.is_initialized() else 1
-    g = dist.get_rank(group) if dist.is_initialized() else 0
-    N = 1 << log_n
-    l1 = (log_n + 1) // 2
-    l2 = log_n - l1
-    N1, N2 = 1 << l1, 1 << l2
-    assert N1 % G == 0 and N2 % G == 0 and x_local.shape[0] == N // G
-    r1, c2 = N1 // G, N2 // G
-    # local rows n1 in block g: [r1][N2] -> send column block j to rank j
-    a = x_local.view(r1, G, c2, 4).permute(1, 0, 2, 3).contiguous()          # [G][r1][c2]
-    a = _all_to_all(a.view(G * r1 * c2, 4), group).view(G * r1, c2, 4)       # [N1][c2]: all n1, my columns
-    cols = a.permute(1, 0, 2).contiguous()                                   # [c2][N1]
-    cols = ops.fft_rows(cols, l1, inverse)                                   # Y[n2][k1]
-    cols = ops.mul(cols, ops.twiddles(g * c2, c2, N1, log_n, inverse))
-    # now distribute by k1: [c2][G][r1] -> rank j gets k1 block j
-    b = cols.view(c2, G, r1, 4).permute(1, 0, 2, 3).contiguous()             # [G][c2][r1]
-    b = _all_to_all(b.view(G * c2 * r1, 4), group).view(G * c2, r1, 4)       # [N2][r1]: all n2, my k1
-    rows = b.permute(1, 0, 2).contiguous()                                   # [r1][N2]
-    rows = ops.fft_rows(rows, l2, inverse)                                   # X[k1][k2], k = k1 + N1*k2
-    # natural order: rank j owns k2 block j, all k1 -> [G][r1][c2] -> all-to-all -> [N1][c2] -> [c2][N1]
-    c = rows.view(r1, G, c2, 4).permute(1, 0, 2, 3).contiguous()
-    c = _all_to_all(c.view(G * r1 * c2, 4), group).view(G * r1, c2, 4)       # [k1 all][my k2]
-    return c.permute(1, 0, 2).contiguous().view(N // G, 4)                   # index = k2_local*N1 + k1

@@ -43,6 +43,32 @@ def test_emulated_team_proof_equals_single_gpu_and_oracle(team_ctx, world, maker
         assert team == plonk.create_proof(opk, advice, circ.instances, pyref.ChaChaRng(seed, 20), transcript, multiopen)
 
 
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_emulated_team_commitments_by_column(team_ctx, world):
+    """SURVEY 8e row 5 (per-column commitments dealt to the GPUs): with `team_commit_by_column` a batch of at least `world`
+    commitments is split by column (rank r commits its columns whole) instead of by point range — same points, same proof;
+    batches with fewer columns than ranks keep the point-range split."""
+    p = pkg()
+    circ = p.synth.make_sha_bit_circuit(9, 48, 3, blocks=4, seed=2)      # 51 advice columns: 17 / 17 / 17 and 13 / 13 / 13 / 12
+    opk, advice = oracle_setup(circ)
+    params, gpk = gpu_setup(circ, opk)
+    inst = [orc.fr_from_ints(c) for c in circ.instances]
+    seed = pyref.seed_from_u64(40 + world)
+    single = p.create_proof(gpk, np.concatenate(advice), inst, seed)
+    from tests.util import to_dev
+    cols = to_dev(np.concatenate(advice[:7]))
+    want = params.commit_dev(cols, 1 << 9, 7, basis=1)
+    team_ctx.team_emulate(world)
+    team_ctx.set_tunable("team_commit_by_column", 1)
+    try:
+        assert p.create_proof(gpk, np.concatenate(advice), inst, seed) == single
+        assert np.array_equal(params.commit_dev(cols, 1 << 9, 7, basis=1), want)
+    finally:
+        team_ctx.set_tunable("team_commit_by_column", 0)
+        team_ctx.team_emulate(1)
+    assert single == plonk.create_proof(opk, advice, circ.instances, pyref.ChaChaRng(seed, 20))
+
+
 def test_emulated_team_keygen_and_commit(team_ctx):
     """pk_load (vk commitments) and ParamsKZG.commit under a team context: point-range shards sum to the same points"""
     p = pkg()

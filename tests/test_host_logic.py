@@ -126,83 +126,6 @@ def test_sharding_helpers_gloo_world2():
     assert [r[3] for r in res] == [(0, 5), (5, 10)]
 
 
-# ---- distributed four-step NTT + point-sharded MSM epilogue, world_size 2 over gloo, oracle as the local engine ----
-class _CpuNttOps:
-    """oracle-backed stand-in for dist.GpuNttOps so the exchange logic runs on CPU tensors"""
-
-    def fft_rows(self, t, log_len, inverse):
-        import torch
-        from oracle import orc
-        from tests import pyref
-        w = pyref.omega_for(log_len)
-        if inverse:
-            w = pow(w, -1, R_MOD)
-        W = orc.fr_from_ints([w])
-        rows = [orc.best_fft(t[r].numpy().view(np.uint64), W, log_len, 1) for r in range(t.shape[0])]
-        return torch.from_numpy(np.stack(rows).view(np.int64))
-
-    def twiddles(self, row0, nrows, length, log_n, inverse):
-        import torch
-        from oracle import orc
-        from tests import pyref
-        w = pyref.omega_for(log_n)
-        if inverse:
-            w = pow(w, -1, R_MOD)
-        vals = [pow(w, (row0 + r) * c, R_MOD) for r in range(nrows) for c in range(length)]
-        return torch.from_numpy(orc.fr_from_ints(vals).view(np.int64)).view(nrows, length, 4)
-
-    def mul(self, a, b):
-        import torch
-        from oracle import orc
-        out = orc.vec_vec("mul", a.reshape(-1, 4).numpy().view(np.uint64), b.reshape(-1, 4).numpy().view(np.uint64))
-        return torch.from_numpy(out.view(np.int64)).view(a.shape)
-
-
-def _ntt_worker(rank, world, port, q, log_n):
-    import torch
-    import torch.distributed as dist
-    from oracle import orc
-    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    d = pkg().dist
-    N = 1 << log_n
-    rng = np.random.default_rng(5)
-    full = orc.fr_from_ints([int(v) for v in rng.integers(0, 1 << 62, size=N)])
-    lo, hi = d.shard_range(N, world, rank)
-    out = {}
-    for inverse in (0, 1):
-        res = d.ntt_four_step(torch.from_numpy(full[lo:hi].view(np.int64)).clone(), log_n, inverse, _CpuNttOps())
-        out[inverse] = res.numpy().view(np.uint64).copy()
-    q.put((rank, out))
-    dist.destroy_process_group()
-
-
-def test_four_step_ntt_gloo_world2_matches_best_fft():
-    import torch.multiprocessing as mp
-    from oracle import orc
-    from tests import pyref
-    log_n = 8
-    N = 1 << log_n
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 31500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_ntt_worker, args=(r, 2, port, q, log_n)) for r in range(2)]
-    for pr in procs:
-        pr.start()
-    res = dict(q.get(timeout=180) for _ in procs)
-    for pr in procs:
-        pr.join(timeout=60)
-    rng = np.random.default_rng(5)
-    full = orc.fr_from_ints([int(v) for v in rng.integers(0, 1 << 62, size=N)])
-    for inverse in (0, 1):
-        w = pyref.omega_for(log_n)
-        if inverse:
-            w = pow(w, -1, R_MOD)
-        want = orc.best_fft(full, orc.fr_from_ints([w]), log_n)
-        got = np.concatenate([res[0][inverse], res[1][inverse]])
-        assert np.array_equal(got, want), inverse
-
-
 def test_g1_sum_host_epilogue():
     """zkc_g1_sum is host-only: the point-sharded MSM epilogue can be checked without a GPU."""
     from oracle import orc
