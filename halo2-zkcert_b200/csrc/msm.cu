@@ -627,10 +627,16 @@ int msm_run(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, uint64_t n, 
     return ZKC_OK;
   }
   if (n >= (1ull << 31) / 32) return set_err(ctx, ZKC_ERR_BAD_ARG, "msm: n too large");
-  // bound memory: process columns in chunks
-  MsmGeom g1 = msm_geom(ctx, n, 1, c, precomputed);
+  // bound memory: process columns in chunks sized by what ONE GPU holds — a team rank walks n / world points of every column
+  // (point-range split) or all n points of its own columns (column split)
+  team = team && team_active(ctx) && n >= (uint64_t)ctx->team_world;
+  const uint32_t world = team ? (uint32_t)ctx->team_world : 1;
+  const bool by_column = team && ctx->tune.team_commit_by_column && ncols >= world;
+  const uint64_t n_rank = team && !by_column ? (n + world - 1) / world : n;
+  MsmGeom g1 = msm_geom(ctx, n_rank, 1, c, precomputed);
   const uint64_t per_col = g1.emax() * 12 + g1.nbtot() * (128 + 12) + (g1.nbtot() + g1.emax() / g1.T + 1) * 128;
   uint32_t chunk = (uint32_t)std::max<uint64_t>(1, (3ull << 30) / per_col);
+  if (by_column) chunk *= world;   // columns per batch: every rank takes at most chunk / world of them
   chunk = std::min(chunk, ncols);
   for (uint32_t c0 = 0; c0 < ncols; c0 += chunk) {
     const uint32_t nc = std::min(chunk, ncols - c0);

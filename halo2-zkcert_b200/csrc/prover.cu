@@ -504,6 +504,7 @@ struct zkc_prover {
   bool team = false;
   std::vector<Segment> my_rows;        // row blocks of the (class-major) extended coset this process evaluates
   std::vector<std::pair<uint32_t, uint32_t>> my_classes;   // residue classes [first, second) those blocks touch
+  uint64_t halo_lo = 0, halo_hi = 0;   // rotation reach inside a class: rows read before / after a row
   Fr omega, omega_inv, zeta, ONE, ZERO, DELTA;
   // columns
   Fr *inst_values = nullptr, *inst_polys = nullptr, *adv_values = nullptr, *adv_polys = nullptr;
@@ -575,10 +576,33 @@ struct zkc_prover {
           uint64_t a, b;
           shard_range(ncols, g, (t + ctx->team_rot) % g, &a, &b);
           if (mem[t] == me && b > a) ZKC_TRY(dom_coeff_to_classes(ctx, pk->dom, polys + a * n, n, cosets + a * en, (uint32_t)(b - a), c, c + 1));
+          // rows of class c that member o evaluates, widened by the rotation reach (cyclic inside the class): <= 2 segments
+          auto rows_of = [&](int o, Segment seg[2]) -> int {
+            uint64_t lo, hi;
+            shard_range(en, W, mem[o], &lo, &hi);
+            const uint64_t ra = std::max<uint64_t>(lo, (uint64_t)c * n) - (uint64_t)c * n, rb = std::min<uint64_t>(hi, (uint64_t)(c + 1) * n) - (uint64_t)c * n;
+            const uint64_t len = (rb - ra) + halo_lo + halo_hi;
+            if (len >= n) { seg[0] = {0, n}; return 1; }
+            const uint64_t start = (ra + n - halo_lo % n) % n;
+            if (start + len <= n) { seg[0] = {start, len}; return 1; }
+            seg[0] = {0, start + len - n}; seg[1] = {start, n - start};
+            return 2;
+          };
           for (uint64_t col = a; col < b; ++col) {
             Fr* blk = cosets + col * en + (uint64_t)c * n;
-            if (mem[t] == me) { for (int o = 0; o < g; ++o) if (mem[o] != me) xf.push_back({mem[o], true, blk, n * sizeof(Fr)}); }
-            else xf.push_back({mem[t], false, blk, n * sizeof(Fr)});
+            Segment seg[2];
+            if (mem[t] == me) {
+              for (int o = 0; o < g; ++o) {
+                if (mem[o] == me) continue;
+                const int ns = rows_of(o, seg);
+                for (int q2 = 0; q2 < ns; ++q2) xf.push_back({mem[o], true, blk + seg[q2].lo, seg[q2].len * sizeof(Fr)});
+              }
+            } else {
+              int self = 0;
+              while (mem[self] != me) ++self;
+              const int ns = rows_of(self, seg);
+              for (int q2 = 0; q2 < ns; ++q2) xf.push_back({mem[t], false, blk + seg[q2].lo, seg[q2].len * sizeof(Fr)});
+            }
           }
         }
       }
@@ -672,6 +696,11 @@ int zkc_prover::begin(const zkc_fr* advice, int advice_on_device, const zkc_fr* 
   // stream), in the same host order on every rank, so the column exchanges of the side stream hide under the MSM phases.
   team = team_active(ctx);
   if (team) ctx->team_rot = 0;
+  {
+    int64_t rmin = -(int64_t)(bf + 1), rmax = 1;   // z(omega X), z(omega^-(bf+1) X), a'(omega^-1 X)
+    for (auto* v : {&cs.aq, &cs.fq, &cs.iq}) for (auto& qq : *v) { rmin = std::min<int64_t>(rmin, qq.second); rmax = std::max<int64_t>(rmax, qq.second); }
+    halo_lo = (uint64_t)(-rmin); halo_hi = (uint64_t)rmax;
+  }
   // h(X) is evaluated on the class-major extended coset: a rank's row block [lo, hi) of the flat class-major index touches the
   // classes lo / n .. (hi - 1) / n, and every rotation of a row stays inside its class
   if (!team) my_rows.push_back({0, en});
