@@ -231,12 +231,13 @@ extern "C" int zkc_team_shard_range(uint64_t total, int world, int rank, uint64_
   shard_range(total, world, rank, lo, hi);
   return ZKC_OK;
 }
-// residue classes [c0, c1) of the extended coset that `rank`'s row block of the class-major extended domain touches
-// (prover.cu: the classes the rank transforms from the replicated coefficient forms)
-extern "C" int zkc_team_classes(uint32_t k, uint32_t extended_k, int world, int rank, uint32_t* c0, uint32_t* c1) {
-  if (world < 1 || rank < 0 || rank >= world || !c0 || !c1 || extended_k < k || extended_k > 27) return ZKC_ERR_BAD_ARG;
+// residue classes [c0, c1) of the extended coset that `rank`'s row block of the class-major extended domain touches; only the
+// first `num_classes` = degree - 1 classes are evaluated (prover.cu: the classes the rank transforms from the replicated
+// coefficient forms)
+extern "C" int zkc_team_classes(uint32_t k, uint32_t num_classes, int world, int rank, uint32_t* c0, uint32_t* c1) {
+  if (world < 1 || rank < 0 || rank >= world || !c0 || !c1 || k > 27 || num_classes < 1 || num_classes > 256) return ZKC_ERR_BAD_ARG;
   uint64_t lo, hi;
-  shard_range(1ull << extended_k, world, rank, &lo, &hi);
+  shard_range((uint64_t)num_classes << k, world, rank, &lo, &hi);
   if (hi == lo) { *c0 = *c1 = 0; return ZKC_OK; }
   *c0 = (uint32_t)(lo >> k); *c1 = (uint32_t)((hi - 1) >> k) + 1;
   return ZKC_OK;

@@ -37,6 +37,7 @@ struct NttPass {
   // dst + column * dst_stride + class * N.  cls_div == 0: plain batches (blockIdx.y = column on both sides).
   uint32_t src_cls_div, dst_cls_div, cls0;
   const Fr* pre_tab;
+  const Fr* post_tab;     // post == 2: out[o] *= post_tab[(cls0 + blockIdx.y) * N + o]
   Fr post0, post1, post2; // out[i] *= post[i mod 3]
 };
 
@@ -169,9 +170,11 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_last(NttPass p) {
     const uint32_t pos = __brev(kp) >> (32 - p.s);
     Fr x = fe_from_halves<FrP>(lo[c * pitch + pos], hi[c * pitch + pos]);
     const uint64_t o = ((kb << p.logC) + c) + (k2 << p.logN1) + ((uint64_t)kp << logA);
-    if (p.post) {
+    if (p.post == 1) {
       const uint32_t m = (uint32_t)(o % 3);
       x = fe_mul(x, m == 0 ? p.post0 : (m == 1 ? p.post1 : p.post2));
+    } else if (p.post == 2) {   // per-transform table: transform blockIdx.y is residue class cls0 + blockIdx.y
+      x = fe_mul(x, fe_load_nc(p.post_tab + ((uint64_t)(p.cls0 + blockIdx.y) << p.log_n) + o));
     }
     fe_store(dst + o, x);
   }
@@ -193,15 +196,15 @@ __global__ void k_scale_periodic(Fr* a, const Fr* t, uint32_t mask, uint64_t row
   fe_store(a + i, fe_mul(fe_load(a + i), fe_load_nc(t + (i & mask))));
 }
 
-// pre[c * n + i] = zeta^(i mod 3) * w^(c * i)  (w = extended_omega): the coefficient scaling that turns a size-n transform into
+// pre[c * n + i] = scale * zeta^(i mod 3) * w^(c * i)  (w = extended_omega, scale = 1; or their inverses and scale = 1/n): the coefficient scaling that turns a size-n transform into
 // the evaluations on residue class c of the extended coset.  Each thread fills a run of 64 entries of one class.
-__global__ void k_class_pre(Fr* pre, Fr w_ext, Fr zeta, uint32_t log_n, uint32_t ncls) {
+__global__ void k_class_pre(Fr* pre, Fr w_ext, Fr zeta, Fr scale, uint32_t log_n, uint32_t ncls) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t runs = 1ull << (log_n > 6 ? log_n - 6 : 0), n = 1ull << log_n;
   if (t >= runs * ncls) return;
   const uint64_t c = t / runs, start = (t % runs) * 64;
   const Fr wc = fe_pow_u64(w_ext, c);
-  Fr cur = fe_pow_u64(wc, start);
+  Fr cur = fe_mul(fe_pow_u64(wc, start), scale);
   const Fr z1 = zeta, z2 = fe_sqr(zeta);
   const uint64_t end = start + 64 < n ? start + 64 : n;
   for (uint64_t i = start; i < end; ++i) {
@@ -259,6 +262,7 @@ struct NttOpts {
   // pre_tab[class * N + i]; class c of column j lands at dst + j * dst_stride + c * N
   uint32_t ncls = 0, cls0 = 0;
   const Fr* pre_tab = nullptr;
+  const Fr* post_tab = nullptr;   // post == 2 (plain batches: transform y is class cls0 + y)
 };
 
 static const uint32_t LOG_TILE = 11;  // 2^11 elements = 64 KiB of shared memory per CTA
@@ -311,7 +315,7 @@ int ntt_run(zkc_ctx* ctx, const Fr* src, uint64_t src_stride, Fr* dst, uint64_t 
   auto first = [&](NttPass& p) { p.src = src; p.src_stride = src_stride; p.n_in = o.n_in ? o.n_in : N; p.pre = o.pre; p.pre1 = o.pre1; p.pre2 = o.pre2;
                             p.src_cls_div = o.ncls; p.cls0 = o.cls0; p.pre_tab = o.pre_tab; };
   auto final_ = [&](NttPass& p) { p.dst = dst; p.dst_stride = dst_stride; p.post = o.post; p.post0 = o.post0; p.post1 = o.post1; p.post2 = o.post2;
-                             p.dst_cls_div = o.ncls; p.cls0 = o.cls0; };
+                             p.dst_cls_div = o.ncls; p.cls0 = o.cls0; p.post_tab = o.post_tab; };
 
   if (log_n <= LOG_TILE) {
     NttPass p = base; first(p); final_(p);
@@ -368,6 +372,8 @@ struct zkc_domain {
   Fr omega, omega_inv, extended_omega, extended_omega_inv, g_coset, g_coset_inv, ifft_divisor, extended_ifft_divisor;
   Fr* t_inv_dev = nullptr;  // 2^(extended_k - k) inverted vanishing evaluations
   Fr* class_pre = nullptr;  // [class][i < n]: zeta^(i mod 3) * extended_omega^(class * i), built on first use (dom_coeff_to_classes)
+  Fr* class_post = nullptr; // [class < j - 1][i < n]: (zeta * extended_omega^class)^-i / n (dom_classes_to_pieces)
+  Fr* mix_dev = nullptr;    // (j - 1)^2 inverse Vandermonde entries of dom_classes_to_pieces
 };
 
 static inline void fr_to_abi(const Fr& f, zkc_fr* o) { memcpy(o, f.v, 32); }
@@ -408,6 +414,8 @@ extern "C" void zkc_domain_free(zkc_domain* d) {
   if (!d) return;
   if (d->t_inv_dev) cudaFree(d->t_inv_dev);
   if (d->class_pre) cudaFree(d->class_pre);
+  if (d->class_post) cudaFree(d->class_post);
+  if (d->mix_dev) cudaFree(d->mix_dev);
   delete d;
 }
 
@@ -467,7 +475,7 @@ int dom_class_pre(zkc_ctx* ctx, const zkc_domain* d, const Fr** out) {
     Fr* p;
     ZKC_CUDA_TRY(ctx, cudaMalloc(&p, (sizeof(Fr) << d->k) * ncls));
     const uint64_t threads = (1ull << (d->k > 6 ? d->k - 6 : 0)) * ncls;
-    k_class_pre<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(p, d->extended_omega, d->g_coset, d->k, ncls);
+    k_class_pre<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(p, d->extended_omega, d->g_coset, fe_one<FrP>(), d->k, ncls);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // shared by both streams of the ctx
@@ -494,6 +502,83 @@ int dom_natural_to_classes(zkc_ctx* ctx, const zkc_domain* d, const Fr* nat, Fr*
   const uint64_t en = 1ull << d->extended_k;
   k_natural_to_classes<<<(unsigned)((en + 255) / 256), 256, 0, ctx->stream>>>(nat, cm, d->k, d->extended_k - d->k, en);
   ZKC_LAUNCH_CHECK(ctx);
+  return ZKC_OK;
+}
+// ---- the way back: h(X) from its values on q = j - 1 residue classes ----------------------------------------------------------
+// h has fewer than q n coefficients: h = sum_{i1 < q} X^(n i1) H_i1 with deg H_i1 < n (the pieces that get committed).  On class c
+// X^n is the constant tau_c = (zeta w_ext^c)^n, so h restricted to class c is the degree < n polynomial g_c = sum_i1 tau_c^i1 H_i1:
+// q classes determine h (upstream evaluates on all 2^e >= q of them only because its FFT wants a power of two).  So:
+//   g_c   = coset-iNTT of class c     (size-n inverse transform, then (zeta w_ext^c)^-i / n: the fused post table)
+//   H_i1  = sum_c (V^-1)[i1][c] g_c   (V[c][i1] = tau_c^i1: a q x q Vandermonde matrix, inverted once on the host)
+// — exact, so the pieces are upstream's extended_to_coeff output coefficient for coefficient.
+#define MIX_MAX_Q 8
+__global__ void k_mix_classes(const Fr* g, Fr* out, const Fr* minv, uint32_t q, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr v[MIX_MAX_Q];
+  for (uint32_t c = 0; c < q; ++c) v[c] = fe_load(g + (uint64_t)c * n + i);
+  for (uint32_t p = 0; p < q; ++p) {
+    Fr acc = fe_mul(v[0], fe_load_nc(minv + p * q));
+    for (uint32_t c = 1; c < q; ++c) acc = fe_add(acc, fe_mul(v[c], fe_load_nc(minv + p * q + c)));
+    fe_store(out + (uint64_t)p * n + i, acc);
+  }
+}
+static int dom_pieces_setup(zkc_ctx* ctx, const zkc_domain* d) {
+  zkc_domain* dm = const_cast<zkc_domain*>(d);
+  if (dm->class_post) return ZKC_OK;
+  const uint32_t q = d->j - 1;
+  if (q > MIX_MAX_Q || q > (1u << (d->extended_k - d->k))) return set_err(ctx, ZKC_ERR_BAD_ARG, "dom_classes_to_pieces: degree too large");
+  // inverse of V[c][p] = tau_c^p by Gauss-Jordan over Fr (q <= 8)
+  const uint64_t n = 1ull << d->k;
+  std::vector<Fr> a((size_t)q * 2 * q);
+  Fr zc = d->g_coset;
+  for (uint32_t c = 0; c < q; ++c) {
+    const Fr tau = fe_pow_u64(zc, n);
+    Fr pw = fe_one<FrP>();
+    for (uint32_t p = 0; p < q; ++p) { a[(size_t)c * 2 * q + p] = pw; a[(size_t)c * 2 * q + q + p] = p == c ? fe_one<FrP>() : fe_zero<FrP>(); pw = fe_mul(pw, tau); }
+    zc = fe_mul(zc, d->extended_omega);
+  }
+  for (uint32_t col = 0; col < q; ++col) {
+    uint32_t piv = col;
+    while (piv < q && fe_is_zero(a[(size_t)piv * 2 * q + col])) ++piv;
+    if (piv == q) return set_err(ctx, ZKC_ERR_BAD_ARG, "dom_classes_to_pieces: singular class matrix");
+    if (piv != col) for (uint32_t t = 0; t < 2 * q; ++t) std::swap(a[(size_t)piv * 2 * q + t], a[(size_t)col * 2 * q + t]);
+    const Fr inv = fe_inv(a[(size_t)col * 2 * q + col]);
+    for (uint32_t t = 0; t < 2 * q; ++t) a[(size_t)col * 2 * q + t] = fe_mul(a[(size_t)col * 2 * q + t], inv);
+    for (uint32_t r = 0; r < q; ++r) {
+      if (r == col) continue;
+      const Fr f = a[(size_t)r * 2 * q + col];
+      if (fe_is_zero(f)) continue;
+      for (uint32_t t = 0; t < 2 * q; ++t) a[(size_t)r * 2 * q + t] = fe_sub(a[(size_t)r * 2 * q + t], fe_mul(f, a[(size_t)col * 2 * q + t]));
+    }
+  }
+  std::vector<Fr> minv((size_t)q * q);
+  for (uint32_t p = 0; p < q; ++p) for (uint32_t c = 0; c < q; ++c) minv[(size_t)p * q + c] = a[(size_t)p * 2 * q + q + c];
+  Fr *mix = nullptr, *post = nullptr;
+  ZKC_CUDA_TRY(ctx, cudaMalloc(&mix, minv.size() * sizeof(Fr)));
+  cudaError_t e = cudaMemcpy(mix, minv.data(), minv.size() * sizeof(Fr), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&post, (sizeof(Fr) << d->k) * q);
+  if (e == cudaSuccess) {
+    const uint64_t threads = (1ull << (d->k > 6 ? d->k - 6 : 0)) * q;
+    k_class_pre<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(post, d->extended_omega_inv, d->g_coset_inv, d->ifft_divisor, d->k, q);
+    ctx->launches++;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  if (e != cudaSuccess) { cudaFree(mix); if (post) cudaFree(post); return set_err(ctx, ZKC_ERR_CUDA, std::string("dom_classes_to_pieces: ") + cudaGetErrorString(e)); }
+  dm->mix_dev = mix; dm->class_post = post;
+  return ZKC_OK;
+}
+// values of h on classes 0 .. q-1 (class-major, `vals`: q * n, destroyed) -> the q pieces of h in coefficient form (`out`: q * n)
+int dom_classes_to_pieces(zkc_ctx* ctx, const zkc_domain* d, Fr* vals, Fr* out) {
+  ZKC_TRY(dom_pieces_setup(ctx, d));
+  const uint32_t q = d->j - 1;
+  const uint64_t n = 1ull << d->k;
+  NttOpts o; o.inverse = 1; o.post = 2; o.post_tab = d->class_post;
+  ZKC_TRY(ntt_run(ctx, vals, n, vals, n, d->k, q, o));
+  k_mix_classes<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(vals, out, d->mix_dev, q, n);
+  ZKC_LAUNCH_CHECK(ctx);
+  ctx->stats["ntt.muls"] += (uint64_t)q * q * n;
   return ZKC_OK;
 }
 // division by X^n - 1 on class-major rows [row0, row0 + cnt): the vanishing polynomial is constant on a class

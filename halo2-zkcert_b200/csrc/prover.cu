@@ -27,6 +27,7 @@ int dom_extended_to_coeff(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint32_t nco
 int dom_divide_by_vanishing(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint64_t row0, uint64_t cnt);
 int dom_coeff_to_classes(zkc_ctx* ctx, const zkc_domain* d, const Fr* in, uint64_t in_stride, Fr* out, uint32_t ncols, uint32_t c0, uint32_t c1);
 int dom_classes_to_natural(zkc_ctx* ctx, const zkc_domain* d, const Fr* cm, Fr* nat);
+int dom_classes_to_pieces(zkc_ctx* ctx, const zkc_domain* d, Fr* vals, Fr* out);
 int dom_divide_by_vanishing_classes(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint64_t row0, uint64_t cnt);
 int srs_commit_dev(zkc_ctx* ctx, const zkc_srs* s, int basis, const Fr* polys, uint64_t len, uint32_t ncols, zkc_g1* out);
 }  // namespace zkc
@@ -55,6 +56,7 @@ struct zkc_pk {
   Fr *fixed_values = nullptr, *fixed_polys = nullptr, *fixed_cosets = nullptr;
   Fr *sigma_values = nullptr, *sigma_polys = nullptr, *sigma_cosets = nullptr;
   Fr *l0 = nullptr, *l_last = nullptr, *l_active = nullptr, *omega_pows = nullptr;
+  Fr* l_polys = nullptr;   // l_0, l_last, l_blind in coefficient form (3 n): ProvingKey::write re-derives the natural-order cosets from them
   // programs + query tables
   DevProgram gates;
   std::vector<std::pair<DevProgram, DevProgram>> lookups;
@@ -172,7 +174,9 @@ int pk_build(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs
   zkc_domain_get_info(pk->dom, &di);
   pk->ext_k = di.extended_k;
   const uint64_t en = 1ull << pk->ext_k;
-  const uint32_t ncls = 1u << (pk->ext_k - cs.k);   // every extended coset of the key is kept CLASS-MAJOR (ntt.cu, dom_coeff_to_classes)
+  // every extended coset of the key is kept CLASS-MAJOR (ntt.cu, dom_coeff_to_classes), and only the degree - 1 residue classes
+  // that determine h(X) are ever evaluated (dom_classes_to_pieces): the remaining 2^e - (degree - 1) class blocks stay unused
+  const uint32_t ncls = cs.degree - 1;
   memcpy(pk->transcript_repr.v, transcript_repr, 32);
   zkc_pk* P = pk.get();
   const uint32_t F = cs.num_fixed, S = nperm;
@@ -219,10 +223,10 @@ int pk_build(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs
   // l0, l_last, l_blind -> cosets; l_active = 1 - l_last - l_blind
   {
     ZKC_TRY(dev_alloc(ctx, P, &P->l0, en)); ZKC_TRY(dev_alloc(ctx, P, &P->l_last, en)); ZKC_TRY(dev_alloc(ctx, P, &P->l_active, en));
-    struct DevTmp { void* p = nullptr; ~DevTmp() { if (p) cudaFree(p); } } tmp_h, lb_h;   // freed on every exit path
-    ZKC_CUDA_TRY(ctx, cudaMalloc(&tmp_h.p, 3 * n * sizeof(Fr)));
+    struct DevTmp { void* p = nullptr; ~DevTmp() { if (p) cudaFree(p); } } lb_h;   // freed on every exit path
+    ZKC_TRY(dev_alloc(ctx, P, &P->l_polys, 3 * n));
     ZKC_CUDA_TRY(ctx, cudaMalloc(&lb_h.p, en * sizeof(Fr)));
-    Fr* tmp = (Fr*)tmp_h.p;   // three Lagrange columns: l0, l_last, l_blind
+    Fr* tmp = P->l_polys;   // three Lagrange columns: l0, l_last, l_blind
     Fr* lb = (Fr*)lb_h.p;
     ZKC_CUDA_TRY(ctx, cudaMemsetAsync(tmp, 0, 3 * n * sizeof(Fr), st));
     const Fr one = fe_one<FrP>();
@@ -236,7 +240,7 @@ int pk_build(zkc_ctx* ctx, const zkc_srs* srs, const uint8_t* cs_blob, size_t cs
     if (s1 == ZKC_OK) s1 = dom_coeff_to_classes(ctx, P->dom, tmp, n, P->l0, 1, 0, ncls);
     if (s1 == ZKC_OK) s1 = dom_coeff_to_classes(ctx, P->dom, tmp + n, n, P->l_last, 1, 0, ncls);
     if (s1 == ZKC_OK) s1 = dom_coeff_to_classes(ctx, P->dom, tmp + 2 * n, n, lb, 1, 0, ncls);
-    if (s1 == ZKC_OK) { k_l_active<<<(unsigned)((en + 255) / 256), 256, 0, st>>>(P->l_last, lb, P->l_active, en); ctx->launches++; }
+    if (s1 == ZKC_OK) { k_l_active<<<(unsigned)(((uint64_t)ncls * n + 255) / 256), 256, 0, st>>>(P->l_last, lb, P->l_active, (uint64_t)ncls * n); ctx->launches++; }
     cudaStreamSynchronize(st);   // the temporaries are released when this block ends
     ZKC_TRY(s1);
   }
@@ -319,25 +323,34 @@ extern "C" int zkc_pk_write(zkc_ctx* ctx, const zkc_pk* pk, const uint8_t* selec
   if (num_selectors) memcpy(out + L.selectors_off, selectors, (size_t)num_selectors * ((n + 7) / 8));
   cudaStream_t st = ctx->stream;
   auto d2h = [&](uint64_t off, const Fr* src, uint64_t len) { return cudaMemcpyAsync(out + off, src, len * sizeof(Fr), cudaMemcpyDeviceToHost, st); };
-  // the key keeps its extended cosets class-major; the file holds them in upstream's natural order
+  // the key keeps only the residue classes of its extended cosets that h(X) needs, class-major; the file holds whole cosets in
+  // upstream's natural order, so they are re-derived here from the coefficient forms (off the proving path)
   Fr* nat;
-  ZKC_TRY(scratch_reserve(ctx, SCR_MISC3, en * sizeof(Fr), (void**)&nat));
-  auto coset_out = [&](uint64_t off, const Fr* cm) -> int {
-    ZKC_TRY(dom_classes_to_natural(ctx, pk->dom, cm, nat));
+  ZKC_TRY(scratch_reserve(ctx, SCR_MISC3, 2 * en * sizeof(Fr), (void**)&nat));
+  auto coset_out = [&](uint64_t off, const Fr* poly) -> int {
+    ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, poly, n, nat, 1));
     ZKC_CUDA_TRY(ctx, d2h(off, nat, en));
     ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));   // `nat` is reused by the next column
     return ZKC_OK;
   };
-  ZKC_TRY(coset_out(L.l0_off + 4, pk->l0)); ZKC_TRY(coset_out(L.l_last_off + 4, pk->l_last)); ZKC_TRY(coset_out(L.l_active_row_off + 4, pk->l_active));
+  ZKC_TRY(coset_out(L.l0_off + 4, pk->l_polys)); ZKC_TRY(coset_out(L.l_last_off + 4, pk->l_polys + n));
+  {
+    ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, pk->l_polys + n, n, nat, 1));
+    ZKC_TRY(dom_coeff_to_extended(ctx, pk->dom, pk->l_polys + 2 * n, n, nat + en, 1));
+    k_l_active<<<(unsigned)((en + 255) / 256), 256, 0, st>>>(nat, nat + en, nat, en); ZKC_LAUNCH_CHECK(ctx);
+    ZKC_CUDA_TRY(ctx, d2h(L.l_active_row_off + 4, nat, en));
+    ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  }
   auto slice = [&](uint64_t off, const Fr* base, uint32_t count, uint64_t len) -> int {
-    for (uint32_t c = 0; c < count; ++c) {
-      const uint64_t o = off + 4 + (uint64_t)c * (4 + 32 * len) + 4;
-      if (len == en) ZKC_TRY(coset_out(o, base + (size_t)c * len)); else ZKC_CUDA_TRY(ctx, d2h(o, base + (size_t)c * len, len));
-    }
+    for (uint32_t c = 0; c < count; ++c) ZKC_CUDA_TRY(ctx, d2h(off + 4 + (uint64_t)c * (4 + 32 * len) + 4, base + (size_t)c * len, len));
     return ZKC_OK;
   };
-  ZKC_TRY(slice(L.fixed_values_off, pk->fixed_values, F, n)); ZKC_TRY(slice(L.fixed_polys_off, pk->fixed_polys, F, n)); ZKC_TRY(slice(L.fixed_cosets_off, pk->fixed_cosets, F, en));
-  ZKC_TRY(slice(L.perm_values_off, pk->sigma_values, S, n)); ZKC_TRY(slice(L.perm_polys_off, pk->sigma_polys, S, n)); ZKC_TRY(slice(L.perm_cosets_off, pk->sigma_cosets, S, en));
+  auto cosets = [&](uint64_t off, const Fr* polys, uint32_t count) -> int {
+    for (uint32_t c = 0; c < count; ++c) ZKC_TRY(coset_out(off + 4 + (uint64_t)c * (4 + 32 * en) + 4, polys + (size_t)c * n));
+    return ZKC_OK;
+  };
+  ZKC_TRY(slice(L.fixed_values_off, pk->fixed_values, F, n)); ZKC_TRY(slice(L.fixed_polys_off, pk->fixed_polys, F, n)); ZKC_TRY(cosets(L.fixed_cosets_off, pk->fixed_polys, F));
+  ZKC_TRY(slice(L.perm_values_off, pk->sigma_values, S, n)); ZKC_TRY(slice(L.perm_polys_off, pk->sigma_polys, S, n)); ZKC_TRY(cosets(L.perm_cosets_off, pk->sigma_polys, S));
   ZKC_CUDA_TRY(ctx, cudaStreamSynchronize(st));
   return ZKC_OK;
 }
@@ -499,7 +512,7 @@ struct zkc_prover {
   Pool pool;
   int stage = 0;
   // shape
-  uint64_t n = 0, en = 0, U = 0;
+  uint64_t n = 0, en = 0, hn = 0, U = 0;   // hn: rows of the class-major extended coset that are evaluated (degree - 1 classes)
   uint32_t bf = 0, A = 0, I = 0, L = 0, Pn = 0, q = 0;
   bool team = false;
   std::vector<Segment> my_rows;        // row blocks of the (class-major) extended coset this process evaluates
@@ -568,7 +581,7 @@ struct zkc_prover {
         std::vector<int> mem;
         for (int r = 0; r < W; ++r) {
           uint64_t lo, hi;
-          shard_range(en, W, r, &lo, &hi);
+          shard_range(hn, W, r, &lo, &hi);
           if (hi > lo && lo < (uint64_t)(c + 1) * n && hi > (uint64_t)c * n) mem.push_back(r);
         }
         const int g = (int)mem.size();
@@ -579,7 +592,7 @@ struct zkc_prover {
           // rows of class c that member o evaluates, widened by the rotation reach (cyclic inside the class): <= 2 segments
           auto rows_of = [&](int o, Segment seg[2]) -> int {
             uint64_t lo, hi;
-            shard_range(en, W, mem[o], &lo, &hi);
+            shard_range(hn, W, mem[o], &lo, &hi);
             const uint64_t ra = std::max<uint64_t>(lo, (uint64_t)c * n) - (uint64_t)c * n, rb = std::min<uint64_t>(hi, (uint64_t)(c + 1) * n) - (uint64_t)c * n;
             const uint64_t len = (rb - ra) + halo_lo + halo_hi;
             if (len >= n) { seg[0] = {0, n}; return 1; }
@@ -703,8 +716,11 @@ int zkc_prover::begin(const zkc_fr* advice, int advice_on_device, const zkc_fr* 
   }
   // h(X) is evaluated on the class-major extended coset: a rank's row block [lo, hi) of the flat class-major index touches the
   // classes lo / n .. (hi - 1) / n, and every rotation of a row stays inside its class
-  if (!team) my_rows.push_back({0, en});
-  else for (int r : team_ranks(ctx)) { uint64_t lo, hi; shard_range(en, ctx->team_world, r, &lo, &hi); if (hi > lo) my_rows.push_back({lo, hi - lo}); }
+  // Only q = degree - 1 of the 2^e classes are evaluated: h has fewer than q n coefficients, so q classes determine it
+  // (ntt.cu, dom_classes_to_pieces) — a quarter less extended-domain work at degree 4, half at degree 5.
+  hn = (uint64_t)q * n;
+  if (!team) my_rows.push_back({0, hn});
+  else for (int r : team_ranks(ctx)) { uint64_t lo, hi; shard_range(hn, ctx->team_world, r, &lo, &hi); if (hi > lo) my_rows.push_back({lo, hi - lo}); }
   for (const Segment& rb : my_rows) {
     const uint32_t c0 = (uint32_t)(rb.lo / n), c1 = (uint32_t)((rb.lo + rb.len - 1) / n) + 1;
     if (!my_classes.empty() && my_classes.back().second >= c0) my_classes.back().second = std::max(my_classes.back().second, c1);
@@ -1014,10 +1030,9 @@ int zkc_prover::quotient(const Fr& y_, std::vector<G1Affine>& out) {
       }
       ZKC_TRY(dom_divide_by_vanishing_classes(ctx, pk->dom, hcm, r0, rc));
     }
-    //     ... (team: every rank needs the whole quotient), natural row order, and back to coefficients
-    if (team) ZKC_TRY(team_allgather_rows(ctx, hcm, en));
-    ZKC_TRY(dom_classes_to_natural(ctx, pk->dom, hcm, hval));
-    ZKC_TRY(dom_extended_to_coeff(ctx, pk->dom, hval, 1));
+    //     ... (team: every rank needs the whole quotient) and back to the coefficient forms of the q pieces
+    if (team) ZKC_TRY(team_allgather_rows(ctx, hcm, hn));
+    ZKC_TRY(dom_classes_to_pieces(ctx, pk->dom, hcm, hval));
   }
   ZKC_TRY(commit_points(ctx, pk->srs, 0, hval, n, q, out));
   stage = ST_EVALS;

@@ -366,9 +366,10 @@ int zkc_team_leave(zkc_ctx* ctx);
 int zkc_team_info(const zkc_ctx* ctx, int* rank, int* world, int* emulated);
 /* the partition arithmetic (host only): contiguous share [lo, hi) of `total` items for `rank`; and the residue classes
  * [c0, c1) of the extended coset (class c = rows c + 2^(extended_k - k) * m, a coset of the size-n subgroup) that `rank`
- * transforms and evaluates: the classes its share of the class-major extended domain touches */
+ * transforms and evaluates: the classes its share of the num_classes * 2^k evaluated rows touches (num_classes = degree - 1:
+ * h(X) has fewer than (degree - 1) n coefficients, so that many classes determine it) */
 int zkc_team_shard_range(uint64_t total, int world, int rank, uint64_t* lo, uint64_t* hi);
-int zkc_team_classes(uint32_t k, uint32_t extended_k, int world, int rank, uint32_t* c0, uint32_t* c1);
+int zkc_team_classes(uint32_t k, uint32_t num_classes, int world, int rank, uint32_t* c0, uint32_t* c1);
 
 #ifdef __cplusplus
 }

@@ -159,17 +159,17 @@ def test_team_partition_arithmetic():
             prev = hi.value
         assert prev == total
     # residue classes: every class is covered, a rank's classes are exactly those its class-major row block overlaps
-    for k, ek, world in [(10, 12, 2), (10, 12, 4), (10, 12, 8), (10, 12, 3), (8, 11, 5), (6, 6, 2), (12, 13, 1)]:
-        n, en, seen = 1 << k, 1 << ek, set()
+    for k, ncls, world in [(10, 4, 2), (10, 3, 4), (10, 3, 8), (10, 4, 3), (8, 7, 5), (6, 1, 2), (12, 2, 1)]:
+        n, seen = 1 << k, set()
         for r in range(world):
             lo, hi, c0, c1 = C.c_uint64(), C.c_uint64(), C.c_uint32(), C.c_uint32()
-            L.zkc_team_shard_range(C.c_uint64(en), world, r, C.byref(lo), C.byref(hi))
-            assert L.zkc_team_classes(k, ek, world, r, C.byref(c0), C.byref(c1)) == 0
+            L.zkc_team_shard_range(C.c_uint64(ncls * n), world, r, C.byref(lo), C.byref(hi))
+            assert L.zkc_team_classes(k, ncls, world, r, C.byref(c0), C.byref(c1)) == 0
             want = {i // n for i in range(lo.value, hi.value)}
             assert set(range(c0.value, c1.value)) == want
             seen |= want
-        assert seen == set(range(en // n))
-    assert L.zkc_team_classes(12, 10, 2, 0, C.byref(C.c_uint32()), C.byref(C.c_uint32())) != 0
+        assert seen == set(range(ncls))
+    assert L.zkc_team_classes(12, 0, 2, 0, C.byref(C.c_uint32()), C.byref(C.c_uint32())) != 0
     assert L.zkc_team_shard_range(C.c_uint64(4), 2, 2, None, None) != 0
 
 
