@@ -25,6 +25,7 @@ struct Tunables {
   int msm_c = 0, msm_c_pre = 0, msm_T = 0, ntt_two_pass_max = 0;   // 0 = library default
   int msm_accum_occ = 0;                      // k_msm_accum CTAs per SM: 3 = no register cap (134), else 4 (128 registers)
   size_t stage_min_bytes = (size_t)4 << 20;   // host witnesses at least this large are uploaded in stages on a copy stream
+  bool no_program_factoring = false;         // keys loaded while set keep the gate / lookup programs as parsed (host/cs.h optimize_program off)
   bool team_commit_by_column = false;         // team proving: batches of >= world commitments are dealt by column instead of by point range
   bool team_poison = false;                   // team proving: rows a rank never receives are filled with 0xff
 };

@@ -13,6 +13,7 @@ void tunables_from_env(Tunables& v) {
   if (const char* e = getenv("ZKC_STAGE_MIN_BYTES")) v.stage_min_bytes = (size_t)strtoull(e, nullptr, 10);
   v.team_poison = getenv("ZKC_TEAM_POISON") != nullptr;
   v.team_commit_by_column = getenv("ZKC_TEAM_COMMIT_BY_COLUMN") != nullptr;
+  v.no_program_factoring = getenv("ZKC_NO_PROGRAM_FACTORING") != nullptr;
 }
 }  // namespace
 
@@ -28,6 +29,7 @@ extern "C" int zkc_ctx_set_tunable(zkc_ctx* c, const char* name, int64_t value) 
   else if (n == "ntt_two_pass_max") t.ntt_two_pass_max = (int)value;
   else if (n == "stage_min_bytes") t.stage_min_bytes = value < 0 ? ((size_t)4 << 20) : (size_t)value;
   else if (n == "team_poison") t.team_poison = value != 0;
+  else if (n == "no_program_factoring") t.no_program_factoring = value != 0;
   else if (n == "team_commit_by_column") t.team_commit_by_column = value != 0;
   else return set_err(c, ZKC_ERR_BAD_ARG, "zkc_ctx_set_tunable: unknown name " + n);
   return ZKC_OK;

@@ -72,6 +72,65 @@ inline bool parse_program(Reader& r, uint32_t nexprs, HostProgram& out) {
 }
 
 
+// ---- device-side program optimisation: a shared leading factor is taken out of a run of expressions --------------------------------
+// Gates come as `selector * constraint` (Constraints::with_selector, or q.clone() * expr by hand), and consecutive constraints
+// usually share the selector.  The interpreter folds expressions with Horner in `mult`: acc = acc * mult + e_i.  For a run of
+// L >= 3 expressions e_i = S * r_i with the same leaf S (a fixed / advice / instance query):
+//      acc' = acc * mult^L + S * (sum_i r_i mult^(L - i))
+// — exact field algebra, so the value is bit-identical, with L - 2 fewer products per row.  Emitted as
+//      GROUP_BEGIN (9)           saved = acc; acc = 0
+//      r_1 END r_2 END ... r_L END
+//      S  GROUP_END (10, slot)   acc = saved * pow[slot] + S * acc        (pow[slot] = mult^L, filled per launch)
+// Only the device copy is rewritten; the verifier and the degree analysis keep the original stream.
+inline bool complete_expr(const std::vector<uint32_t>& w, size_t a, size_t b) {   // pairs [a, b) leave exactly one value, never underflow
+  int d = 0;
+  for (size_t i = a; i < b; ++i) {
+    const uint32_t op = w[2 * i];
+    if (op <= 3) ++d;
+    else if (op == 4 || op == 7) { if (d < 1) return false; }
+    else if (op == 5 || op == 6) { if (d < 2) return false; --d; }
+    else return false;
+  }
+  return d == 1;
+}
+struct OptimizedProgram { std::vector<uint32_t> words; std::vector<uint32_t> pow_len; };
+inline OptimizedProgram optimize_program(const HostProgram& h, uint32_t max_slots = 8) {
+  struct Poly { size_t a, b; bool fact; uint32_t lop, larg; size_t ra, rb; };   // pairs [a, b) without the END; rest = [ra, rb)
+  const std::vector<uint32_t>& w = h.words;
+  std::vector<Poly> polys;
+  size_t start = 0;
+  for (size_t i = 0; i < w.size() / 2; ++i) {
+    if (w[2 * i] != 8) continue;
+    Poly p{start, i, false, 0, 0, 0, 0};
+    if (i >= start + 3 && w[2 * (i - 1)] == 6) {
+      const uint32_t f = w[2 * start], l = w[2 * (i - 2)];
+      if (f >= 1 && f <= 3 && complete_expr(w, start + 1, i - 1)) { p.fact = true; p.lop = f; p.larg = w[2 * start + 1]; p.ra = start + 1; p.rb = i - 1; }
+      else if (l >= 1 && l <= 3 && complete_expr(w, start, i - 2)) { p.fact = true; p.lop = l; p.larg = w[2 * (i - 2) + 1]; p.ra = start; p.rb = i - 2; }
+    }
+    polys.push_back(p);
+    start = i + 1;
+  }
+  OptimizedProgram out;
+  auto copy = [&](size_t a, size_t b) { out.words.insert(out.words.end(), w.begin() + 2 * a, w.begin() + 2 * b); };
+  for (size_t i = 0; i < polys.size();) {
+    size_t j = i + 1;
+    if (polys[i].fact) while (j < polys.size() && polys[j].fact && polys[j].lop == polys[i].lop && polys[j].larg == polys[i].larg) ++j;
+    const uint32_t L = (uint32_t)(j - i);
+    int slot = -1;
+    if (polys[i].fact && L >= 3) {
+      for (size_t s = 0; s < out.pow_len.size(); ++s) if (out.pow_len[s] == L) slot = (int)s;
+      if (slot < 0 && out.pow_len.size() < max_slots) { out.pow_len.push_back(L); slot = (int)out.pow_len.size() - 1; }
+    }
+    if (slot < 0) { for (size_t t = i; t < j; ++t) { copy(polys[t].a, polys[t].b); out.words.push_back(8); out.words.push_back(0); } i = j; continue; }
+    out.words.push_back(9); out.words.push_back(0);
+    for (size_t t = i; t < j; ++t) { copy(polys[t].ra, polys[t].rb); out.words.push_back(8); out.words.push_back(0); }
+    out.words.push_back(polys[i].lop); out.words.push_back(polys[i].larg);
+    out.words.push_back(10); out.words.push_back((uint32_t)slot);
+    i = j;
+  }
+  return out;
+}
+
 // Parses the whole blob and fills the derived numbers.  Returns false with a message on malformed input.
 inline bool parse_cs(const uint8_t* cs_blob, size_t cs_len, Cs& cs, std::string& err) {
   Reader r{cs_blob, cs_len};

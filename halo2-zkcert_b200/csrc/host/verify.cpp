@@ -405,3 +405,48 @@ extern "C" int zkc_verify(const uint8_t* cs_blob, size_t cs_len, const zkc_g1_af
 #undef RD_POINT
 #undef RD_SCALAR
 }
+
+// Host fold of the gate program exactly as the device interpreter folds it (acc = acc * mult + e, poly::eval_program), over
+// given query values — with the stream as parsed (`factored` = 0) or with the factored stream the device runs (host/cs.h
+// optimize_program).  Test hook for the program optimiser: both must give the same field element.  No device work.
+extern "C" int zkc_host_fold_gates(const uint8_t* cs_blob, size_t cs_len, const zkc_fr* advice_q, const zkc_fr* fixed_q, const zkc_fr* instance_q,
+                                   const zkc_fr* mult, int factored, zkc_fr* out, uint32_t* groups) {
+  if (!cs_blob || !mult || !out) return ZKC_ERR_BAD_ARG;
+  zkc::host::Cs cs;
+  std::string err;
+  if (!zkc::host::parse_cs(cs_blob, cs_len, cs, err)) return ZKC_ERR_BAD_ARG;
+  if ((cs.aq.size() && !advice_q) || (cs.fq.size() && !fixed_q) || (cs.iq.size() && !instance_q)) return ZKC_ERR_BAD_ARG;
+  std::vector<uint32_t> words = cs.gates.words;
+  std::vector<Fr> pows;
+  Fr m; memcpy(m.v, mult, 32);
+  uint32_t ngroups = 0;
+  if (factored) {
+    const zkc::host::OptimizedProgram opt = zkc::host::optimize_program(cs.gates);
+    words = opt.words;
+    for (uint32_t L : opt.pow_len) pows.push_back(fe_pow_u64(m, L));
+  }
+  auto val = [](const zkc_fr* base, uint32_t i) { Fr f; memcpy(f.v, base + i, 32); return f; };
+  std::vector<Fr> st;
+  Fr acc = fe_zero<FrP>(), saved = fe_zero<FrP>();
+  for (size_t i = 0; i < words.size(); i += 2) {
+    const uint32_t op = words[i], arg = words[i + 1];
+    switch (op) {
+      case 0: st.push_back(cs.gates.consts[arg]); break;
+      case 1: st.push_back(val(advice_q, arg)); break;
+      case 2: st.push_back(val(fixed_q, arg)); break;
+      case 3: st.push_back(val(instance_q, arg)); break;
+      case 4: st.back() = fe_neg(st.back()); break;
+      case 5: { Fr b = st.back(); st.pop_back(); st.back() = fe_add(st.back(), b); break; }
+      case 6: { Fr b = st.back(); st.pop_back(); st.back() = fe_mul(st.back(), b); break; }
+      case 7: st.back() = fe_mul(st.back(), cs.gates.consts[arg]); break;
+      case 8: acc = fe_add(fe_mul(acc, m), st.back()); st.pop_back(); break;
+      case 9: saved = acc; acc = fe_zero<FrP>(); ++ngroups; break;
+      case 10: acc = fe_add(fe_mul(saved, pows[arg]), fe_mul(st.back(), acc)); st.pop_back(); break;
+      default: return ZKC_ERR_BAD_ARG;
+    }
+  }
+  if (!st.empty()) return ZKC_ERR_BAD_ARG;
+  memcpy(out, acc.v, 32);
+  if (groups) *groups = ngroups;
+  return ZKC_OK;
+}

@@ -486,14 +486,18 @@ int fr_eval_batch(zkc_ctx* ctx, const std::vector<const Fr*>& polys, uint64_t n,
 
 // ---- constraint-system program interpreter ---------------------------------------------------------------------
 #define PROG_STACK 12
+struct ProgPows { Fr p[8]; };   // mult^L for the factored groups of the program (host/cs.h optimize_program)
+template <bool GROUPS>   // GROUPS: the stream holds factored runs (ops 9 / 10); programs without any run the leaner instantiation
 __global__ void __launch_bounds__(128) k_eval_program(const uint32_t* words, uint32_t npairs, const Fr* consts, DevQueries q, Fr* out,
-                                                      uint64_t rows, uint32_t rot_scale, Fr mult, int accumulate, uint64_t row0, uint64_t cnt) {
+                                                      uint64_t rows, uint32_t rot_scale, Fr mult, ProgPows pows, int accumulate, uint64_t row0,
+                                                      uint64_t cnt) {
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= cnt) return;
   const uint64_t i = row0 + tid;
   Fr stack[PROG_STACK];
   int sp = 0;
   Fr acc = accumulate ? fe_load(out + i) : fe_zero<FrP>();
+  Fr saved = fe_zero<FrP>();
   for (uint32_t pc = 0; pc < npairs; ++pc) {
     const uint32_t op = words[2 * pc], arg = words[2 * pc + 1];
     switch (op) {
@@ -512,6 +516,16 @@ __global__ void __launch_bounds__(128) k_eval_program(const uint32_t* words, uin
       case 5: stack[sp - 2] = fe_add(stack[sp - 2], stack[sp - 1]); --sp; break;
       case 6: stack[sp - 2] = fe_mul(stack[sp - 2], stack[sp - 1]); --sp; break;
       case 7: stack[sp - 1] = fe_mul(stack[sp - 1], fe_load_nc(consts + arg)); break;
+      case 9: if (GROUPS) { saved = acc; acc = fe_zero<FrP>(); } break;                             // GROUP_BEGIN
+      case 10: if (GROUPS) {                                                                                    // GROUP_END
+        Fr pw;   // static indices: a dynamically indexed kernel parameter would be copied to local memory by every thread
+        switch (arg & 7) {
+          case 0: pw = pows.p[0]; break; case 1: pw = pows.p[1]; break; case 2: pw = pows.p[2]; break; case 3: pw = pows.p[3]; break;
+          case 4: pw = pows.p[4]; break; case 5: pw = pows.p[5]; break; case 6: pw = pows.p[6]; break; default: pw = pows.p[7]; break;
+        }
+        acc = fe_add(fe_mul(saved, pw), fe_mul(stack[--sp], acc));
+        break;
+      }
       default: acc = fe_add(fe_mul(acc, mult), stack[--sp]); break;   // OP_END
     }
   }
@@ -526,8 +540,12 @@ int eval_program(zkc_ctx* ctx, const DevProgram& prog, const DevQueries& q, Fr* 
     if (!accumulate) ZKC_CUDA_TRY(ctx, cudaMemsetAsync(out + row0, 0, cnt * sizeof(Fr), ctx->stream));
     return ZKC_OK;
   }
-  k_eval_program<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(prog.words, prog.npairs, prog.consts, q, out, rows, rot_scale, mult,
-                                                                          accumulate, row0, cnt);
+  ProgPows pows;
+  for (uint32_t s = 0; s < 8; ++s) pows.p[s] = s < prog.npows ? fe_pow_u64(mult, prog.pow_len[s]) : fe_zero<FrP>();
+  if (prog.npows) k_eval_program<true><<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(prog.words, prog.npairs, prog.consts, q, out, rows, rot_scale,
+                                                                                                mult, pows, accumulate, row0, cnt);
+  else k_eval_program<false><<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(prog.words, prog.npairs, prog.consts, q, out, rows, rot_scale,
+                                                                                      mult, pows, accumulate, row0, cnt);
   ZKC_LAUNCH_CHECK(ctx);
   return ZKC_OK;
 }

@@ -12,6 +12,9 @@ struct DevProgram {
   Fr* consts = nullptr;        // Montgomery
   uint32_t nconsts = 0;
   uint32_t nexprs = 0;
+  // factored groups (host/cs.h optimize_program): run lengths whose power of `mult` the GROUP_END op needs, by slot
+  uint32_t npows = 0;
+  uint32_t pow_len[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 // query tables + column pointer tables for one evaluation domain (Lagrange rows or extended coset)

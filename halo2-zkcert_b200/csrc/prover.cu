@@ -70,10 +70,14 @@ struct zkc_pk {
 namespace {
 
 int upload_program(zkc_ctx* ctx, zkc_pk* pk, const HostProgram& h, DevProgram& d) {
-  d.npairs = (uint32_t)(h.words.size() / 2); d.nconsts = (uint32_t)h.consts.size(); d.nexprs = h.nexprs;
+  // the device runs the factored stream (host/cs.h optimize_program: shared selectors taken out of runs of constraints)
+  const zkc::host::OptimizedProgram opt = zkc::host::optimize_program(h, ctx->tune.no_program_factoring ? 0 : 8);
+  d.npairs = (uint32_t)(opt.words.size() / 2); d.nconsts = (uint32_t)h.consts.size(); d.nexprs = h.nexprs;
+  d.npows = (uint32_t)opt.pow_len.size();
+  for (uint32_t s = 0; s < d.npows; ++s) d.pow_len[s] = opt.pow_len[s];
   if (d.npairs) {
-    ZKC_CUDA_TRY(ctx, cudaMalloc(&d.words, h.words.size() * 4)); pk->owned.push_back(d.words);
-    ZKC_CUDA_TRY(ctx, cudaMemcpy(d.words, h.words.data(), h.words.size() * 4, cudaMemcpyHostToDevice));
+    ZKC_CUDA_TRY(ctx, cudaMalloc(&d.words, opt.words.size() * 4)); pk->owned.push_back(d.words);
+    ZKC_CUDA_TRY(ctx, cudaMemcpy(d.words, opt.words.data(), opt.words.size() * 4, cudaMemcpyHostToDevice));
   }
   if (d.nconsts) {
     ZKC_CUDA_TRY(ctx, cudaMalloc(&d.consts, h.consts.size() * sizeof(Fr))); pk->owned.push_back(d.consts);

@@ -340,6 +340,12 @@ int zkc_verify(const uint8_t* cs_blob, size_t cs_len, const zkc_g1_affine* fixed
 int zkc_g2_generator(zkc_g2_affine* out);
 int zkc_g2_mul(const zkc_g2_affine* p, const zkc_fr* scalar, zkc_g2_affine* out);
 int zkc_pairing_check(const zkc_g1_affine* g1s, const zkc_g2_affine* g2s, size_t npairs, int* is_one);
+/* Test hook for the device program optimiser (csrc/host/cs.h optimize_program: a selector shared by a run of constraints is
+ * taken out of the run): the Horner fold acc = acc * mult + e_i of the gate expressions over given query values (one zkc_fr
+ * per advice / fixed / instance query, Montgomery), with the stream as parsed (factored = 0) or as the device runs it
+ * (factored = 1; *groups = number of factored runs).  Both give the same field element.  Host only. */
+int zkc_host_fold_gates(const uint8_t* cs_blob, size_t cs_len, const zkc_fr* advice_q, const zkc_fr* fixed_q, const zkc_fr* instance_q,
+                        const zkc_fr* mult, int factored, zkc_fr* out, uint32_t* groups);
 
 /* ---- ParamsKZG files (host only) ------------------------------------------------------------------------------------------
  * `kzg_bn254_{k}.srs` as ParamsKZG::write / read lay it out in SerdeFormat::RawBytes[Unchecked] (SURVEY OPEN-8):

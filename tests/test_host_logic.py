@@ -288,3 +288,76 @@ def test_chain_scheduler_plans():
     # equal jobs, as many GPUs as jobs: one each
     teams, _ = d.plan_chain([("a", 1.0, 0.5)] * 4, 4)
     assert [s for _, s, _ in teams] == [1, 1, 1, 1]
+
+
+def pyref_mod():
+    from tests import pyref
+    return pyref.R_MOD
+
+
+def test_gate_program_factoring_is_exact():
+    """csrc/host/cs.h optimize_program (the stream the device interpreter runs): a leaf shared by a run of >= 3 constraints is
+    taken out of the run.  The Horner fold over random query values equals the fold of the stream as parsed, for left and
+    right factors, runs broken by other selectors / unfactorable forms / short runs, and many distinct run lengths."""
+    import ctypes as C
+    import random
+    p = pkg()
+    from oracle import orc
+    cir = p.circuit
+    rnd = random.Random(7)
+    A = lambda i: ("advice", i)
+    F = lambda i: ("fixed", i)
+    I = lambda i: ("instance", i)
+    P = lambda a, b: ("product", a, b)
+    S = lambda a, b: ("sum", a, b)
+    N = lambda a: ("neg", a)
+    K = lambda v: ("const", v)
+
+    def body(t):
+        return [S(P(A(0), A(1)), N(A(2))), P(A(3), S(K(1), N(A(3)))), ("scaled", S(A(1), A(2)), 5 + t), S(P(P(A(0), A(2)), A(3)), K(t)), A(2)][t % 5]
+
+    def check(polys, want_groups):
+        naq, nfq, niq = 4, 3, 1
+        cs = cir.ConstraintSystem(6, 4, 3, 1, [(c, 0) for c in range(naq)], [(c, 0) for c in range(nfq)], [(0, 0)], [polys], [], [])
+        blob = cs.serialize()
+        vals = lambda m: orc.fr_from_ints([rnd.randrange(pyref_mod()) for _ in range(m)])
+        aq, fq, iq, mult = vals(naq), vals(nfq), vals(niq), vals(1)
+        got = []
+        for factored in (0, 1):
+            out = np.zeros((1, 4), dtype=np.uint64)
+            groups = C.c_uint32(99)
+            rc = p.lib().zkc_host_fold_gates(blob, C.c_size_t(len(blob)), aq.ctypes.data_as(C.c_void_p), fq.ctypes.data_as(C.c_void_p),
+                                             iq.ctypes.data_as(C.c_void_p), mult.ctypes.data_as(C.c_void_p), factored, out.ctypes.data_as(C.c_void_p),
+                                             C.byref(groups))
+            assert rc == 0
+            got.append((out.copy(), groups.value))
+        assert np.array_equal(got[0][0], got[1][0])
+        assert got[0][1] == 0 and got[1][1] == want_groups, got[1][1]
+        # and the value is the plain big-integer fold
+        R = pyref_mod()
+        env = {"advice": orc.fr_to_ints(aq), "fixed": orc.fr_to_ints(fq), "instance": orc.fr_to_ints(iq)}
+
+        def ev(e):
+            t = e[0]
+            if t == "const": return e[1] % R
+            if t in env: return env[t][e[1]]
+            if t == "neg": return (-ev(e[1])) % R
+            if t == "sum": return (ev(e[1]) + ev(e[2])) % R
+            if t == "product": return ev(e[1]) * ev(e[2]) % R
+            return ev(e[1]) * e[2] % R
+        acc, m = 0, orc.fr_to_ints(mult)[0]
+        for e in polys:
+            acc = (acc * m + ev(e)) % R
+        assert orc.fr_to_ints(got[1][0])[0] == acc
+
+    check([P(F(0), body(t)) for t in range(7)], 1)                                             # one run, selector on the left
+    check([P(body(t), F(1)) for t in range(5)], 1)                                             # ... on the right
+    check([P(F(0), body(0)), P(F(0), body(1))], 0)                                             # too short
+    check([P(F(0), body(t)) for t in range(3)] + [P(F(1), body(t)) for t in range(4)] + [body(2)] + [P(F(0), body(t)) for t in range(3)], 3)
+    check([P(F(0), body(t)) for t in range(3)] + [S(F(0), body(1))] + [P(A(1), body(t)) for t in range(6)] + [P(I(0), body(3))], 2)
+    check([P(F(0), P(F(0), body(t))) for t in range(4)], 1)                                    # nested: only the outer factor goes
+    runs = []
+    for L in range(3, 13):                                                                     # ten distinct lengths: two runs stay unfactored
+        runs += [P(F(L % 3), body(t)) for t in range(L)] + [K(L)]
+    check(runs, 8)
+    check([P(S(F(0), K(1)), body(t)) for t in range(4)], 0)                                    # the shared factor is not a leaf
