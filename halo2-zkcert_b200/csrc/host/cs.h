@@ -128,6 +128,33 @@ inline OptimizedProgram optimize_program(const HostProgram& h, uint32_t max_slot
     out.words.push_back(10); out.words.push_back((uint32_t)slot);
     i = j;
   }
+  if (max_slots == 0) return out;   // optimisation off: the stream as parsed
+  // Peephole pass: an operand that is pushed only to be consumed by the next operation is folded into it, so the interpreter
+  // (whose stack beyond the top value lives in local memory) neither stores nor reloads it:
+  //   leaf MUL -> MUL_leaf (11 + kind)    leaf ADD -> ADD_leaf (14 + kind)    leaf NEG ADD -> SUB_leaf (17 + kind)
+  //   NEG ADD  -> SUB (20)                const ADD -> ADD_CONST (21)         const MUL -> SCALE (7)
+  // (kind = 0 advice, 1 fixed, 2 instance).  Same field operations in the same order: nothing changes but the bookkeeping.
+  std::vector<uint32_t> pp;
+  const std::vector<uint32_t>& v = out.words;
+  const size_t np = v.size() / 2;
+  auto op_at = [&](size_t i) { return i < np ? v[2 * i] : 0xffffffffu; };
+  for (size_t i = 0; i < np;) {
+    const uint32_t op = v[2 * i], arg = v[2 * i + 1];
+    // a fused operand needs a value underneath it: never at the start of an expression (there the leaf is the left operand)
+    const bool has_below = i > 0 && v[2 * (i - 1)] != 8 && v[2 * (i - 1)] != 9 && v[2 * (i - 1)] != 10;
+    if (op >= 1 && op <= 3 && has_below) {
+      if (op_at(i + 1) == 6) { pp.push_back(11 + (op - 1)); pp.push_back(arg); i += 2; continue; }
+      if (op_at(i + 1) == 5) { pp.push_back(14 + (op - 1)); pp.push_back(arg); i += 2; continue; }
+      if (op_at(i + 1) == 4 && op_at(i + 2) == 5) { pp.push_back(17 + (op - 1)); pp.push_back(arg); i += 3; continue; }
+    }
+    if (op == 0 && has_below) {
+      if (op_at(i + 1) == 5) { pp.push_back(21); pp.push_back(arg); i += 2; continue; }
+      if (op_at(i + 1) == 6) { pp.push_back(7); pp.push_back(arg); i += 2; continue; }
+    }
+    if (op == 4 && op_at(i + 1) == 5) { pp.push_back(20); pp.push_back(0); i += 2; continue; }
+    pp.push_back(op); pp.push_back(arg); ++i;
+  }
+  out.words.swap(pp);
   return out;
 }
 

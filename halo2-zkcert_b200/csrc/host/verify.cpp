@@ -442,6 +442,11 @@ extern "C" int zkc_host_fold_gates(const uint8_t* cs_blob, size_t cs_len, const 
       case 8: acc = fe_add(fe_mul(acc, m), st.back()); st.pop_back(); break;
       case 9: saved = acc; acc = fe_zero<FrP>(); ++ngroups; break;
       case 10: acc = fe_add(fe_mul(saved, pows[arg]), fe_mul(st.back(), acc)); st.pop_back(); break;
+      case 11: case 12: case 13: st.back() = fe_mul(st.back(), val(op == 11 ? advice_q : (op == 12 ? fixed_q : instance_q), arg)); break;
+      case 14: case 15: case 16: st.back() = fe_add(st.back(), val(op == 14 ? advice_q : (op == 15 ? fixed_q : instance_q), arg)); break;
+      case 17: case 18: case 19: st.back() = fe_sub(st.back(), val(op == 17 ? advice_q : (op == 18 ? fixed_q : instance_q), arg)); break;
+      case 20: { Fr b = st.back(); st.pop_back(); st.back() = fe_sub(st.back(), b); break; }
+      case 21: st.back() = fe_add(st.back(), cs.gates.consts[arg]); break;
       default: return ZKC_ERR_BAD_ARG;
     }
   }

@@ -494,39 +494,48 @@ __global__ void __launch_bounds__(128) k_eval_program(const uint32_t* words, uin
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= cnt) return;
   const uint64_t i = row0 + tid;
+  // The top of the evaluation stack lives in registers (t0); only the values underneath it go to the local-memory array.  With
+  // the operand-fused opcodes of host/cs.h optimize_program most operations never touch that array.
   Fr stack[PROG_STACK];
-  int sp = 0;
+  Fr t0 = fe_zero<FrP>();
+  int sp = 0;    // live values: t0 (when sp > 0) and stack[0 .. sp - 1)
   Fr acc = accumulate ? fe_load(out + i) : fe_zero<FrP>();
   Fr saved = fe_zero<FrP>();
+  auto column = [&](uint32_t kind, uint32_t arg) -> Fr {   // kind: 0 advice, 1 fixed, 2 instance
+    const uint32_t col = kind == 0 ? q.aq_col[arg] : (kind == 1 ? q.fq_col[arg] : q.iq_col[arg]);
+    const int32_t rot = kind == 0 ? q.aq_rot[arg] : (kind == 1 ? q.fq_rot[arg] : q.iq_rot[arg]);
+    const Fr* colp = kind == 0 ? q.advice[col] : (kind == 1 ? q.fixed[col] : q.instance[col]);
+    // rows (a power of two) is the cyclic length: the column itself (Lagrange values), or one residue class of the
+    // class-major extended coset, in which case i >= rows selects the class and rotations stay inside it
+    const uint64_t idx = (i & ~(rows - 1)) | ((i + rows + (int64_t)rot * (int64_t)rot_scale) & (rows - 1));
+    return fe_load(colp + idx);
+  };
   for (uint32_t pc = 0; pc < npairs; ++pc) {
     const uint32_t op = words[2 * pc], arg = words[2 * pc + 1];
     switch (op) {
-      case 0: stack[sp++] = fe_load_nc(consts + arg); break;
-      case 1: case 2: case 3: {
-        const uint32_t col = op == 1 ? q.aq_col[arg] : (op == 2 ? q.fq_col[arg] : q.iq_col[arg]);
-        const int32_t rot = op == 1 ? q.aq_rot[arg] : (op == 2 ? q.fq_rot[arg] : q.iq_rot[arg]);
-        const Fr* colp = op == 1 ? q.advice[col] : (op == 2 ? q.fixed[col] : q.instance[col]);
-        // rows (a power of two) is the cyclic length: the column itself (Lagrange values), or one residue class of the
-        // class-major extended coset, in which case i >= rows selects the class and rotations stay inside it
-        const uint64_t idx = (i & ~(rows - 1)) | ((i + rows + (int64_t)rot * (int64_t)rot_scale) & (rows - 1));
-        stack[sp++] = fe_load(colp + idx);
-        break;
-      }
-      case 4: stack[sp - 1] = fe_neg(stack[sp - 1]); break;
-      case 5: stack[sp - 2] = fe_add(stack[sp - 2], stack[sp - 1]); --sp; break;
-      case 6: stack[sp - 2] = fe_mul(stack[sp - 2], stack[sp - 1]); --sp; break;
-      case 7: stack[sp - 1] = fe_mul(stack[sp - 1], fe_load_nc(consts + arg)); break;
+      case 0: if (sp) stack[sp - 1] = t0; t0 = fe_load_nc(consts + arg); ++sp; break;
+      case 1: case 2: case 3: if (sp) stack[sp - 1] = t0; t0 = column(op - 1, arg); ++sp; break;
+      case 4: t0 = fe_neg(t0); break;
+      case 5: t0 = fe_add(stack[sp - 2], t0); --sp; break;
+      case 6: t0 = fe_mul(stack[sp - 2], t0); --sp; break;
+      case 7: t0 = fe_mul(t0, fe_load_nc(consts + arg)); break;
       case 9: if (GROUPS) { saved = acc; acc = fe_zero<FrP>(); } break;                             // GROUP_BEGIN
-      case 10: if (GROUPS) {                                                                                    // GROUP_END
+      case 10: if (GROUPS) {                                                                        // GROUP_END
         Fr pw;   // static indices: a dynamically indexed kernel parameter would be copied to local memory by every thread
         switch (arg & 7) {
           case 0: pw = pows.p[0]; break; case 1: pw = pows.p[1]; break; case 2: pw = pows.p[2]; break; case 3: pw = pows.p[3]; break;
           case 4: pw = pows.p[4]; break; case 5: pw = pows.p[5]; break; case 6: pw = pows.p[6]; break; default: pw = pows.p[7]; break;
         }
-        acc = fe_add(fe_mul(saved, pw), fe_mul(stack[--sp], acc));
+        acc = fe_add(fe_mul(saved, pw), fe_mul(t0, acc));
+        sp = 0;
         break;
       }
-      default: acc = fe_add(fe_mul(acc, mult), stack[--sp]); break;   // OP_END
+      case 11: case 12: case 13: t0 = fe_mul(t0, column(op - 11, arg)); break;                      // operand-fused forms
+      case 14: case 15: case 16: t0 = fe_add(t0, column(op - 14, arg)); break;
+      case 17: case 18: case 19: t0 = fe_sub(t0, column(op - 17, arg)); break;
+      case 20: t0 = fe_sub(stack[sp - 2], t0); --sp; break;
+      case 21: t0 = fe_add(t0, fe_load_nc(consts + arg)); break;
+      default: acc = fe_add(fe_mul(acc, mult), t0); sp = 0; break;   // OP_END
     }
   }
   fe_store(out + i, acc);
