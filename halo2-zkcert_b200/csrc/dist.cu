@@ -101,6 +101,19 @@ int team_bcast_cols(zkc_ctx* ctx, Fr* base, uint64_t stride, uint64_t len, uint3
   return ZKC_OK;
 }
 
+int team_bcast_blocks(zkc_ctx* ctx, Fr* base, uint64_t len, uint32_t nblocks) {
+  if (!real_comm(ctx) || !nblocks || !len) return ZKC_OK;
+  ProfScope _p(ctx, "team.bcast_cols");
+  ZKC_NCCL_TRY(ctx, nccl().GroupStart());
+  for (uint32_t b = 0; b < nblocks; ++b) {
+    Fr* p = base + (uint64_t)b * len;
+    int rc = nccl().Broadcast(p, p, len * sizeof(Fr), kNcclUint8, (int)(b % (uint32_t)ctx->team_world), comm_of(ctx), ctx->stream);
+    if (rc != 0) { nccl().GroupEnd(); return nccl_fail(ctx, "ncclBroadcast", rc); }
+  }
+  ZKC_NCCL_TRY(ctx, nccl().GroupEnd());
+  return ZKC_OK;
+}
+
 int team_exchange(zkc_ctx* ctx, const std::vector<TeamXfer>& ops, const char* what) {
   if (!real_comm(ctx) || ops.empty()) return ZKC_OK;
   ProfScope _p(ctx, what);

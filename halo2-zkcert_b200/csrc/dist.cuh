@@ -35,6 +35,8 @@ inline bool team_active(const zkc_ctx* ctx) { return ctx->team_world > 1; }
 int team_allgather(zkc_ctx* ctx, void* buf, size_t bytes_per_rank);
 // column c of base[ncols][stride] (first `len` elements) is broadcast from the rank that owns it
 int team_bcast_cols(zkc_ctx* ctx, Fr* base, uint64_t stride, uint64_t len, uint32_t ncols);
+// block b of base[nblocks][len] is broadcast from rank b mod world
+int team_bcast_blocks(zkc_ctx* ctx, Fr* base, uint64_t len, uint32_t nblocks);
 // point-to-point transfers of one step, issued as ONE NCCL group (every send has its matching receive in the peer's group)
 struct TeamXfer { int peer; bool send; void* p; size_t bytes; };
 int team_exchange(zkc_ctx* ctx, const std::vector<TeamXfer>& ops, const char* what);

@@ -569,17 +569,27 @@ static int dom_pieces_setup(zkc_ctx* ctx, const zkc_domain* d) {
   dm->mix_dev = mix; dm->class_post = post;
   return ZKC_OK;
 }
-// values of h on classes 0 .. q-1 (class-major, `vals`: q * n, destroyed) -> the q pieces of h in coefficient form (`out`: q * n)
-int dom_classes_to_pieces(zkc_ctx* ctx, const zkc_domain* d, Fr* vals, Fr* out) {
+// values of h on classes 0 .. q-1 (class-major, `vals`: q * n, destroyed) -> the q pieces of h in coefficient form (`out`: q * n),
+// in two steps so that a team can deal the classes: g_c for classes [c0, c1) in place, then the mix over all q classes
+int dom_classes_inverse(zkc_ctx* ctx, const zkc_domain* d, Fr* vals, uint32_t c0, uint32_t c1) {
+  ZKC_TRY(dom_pieces_setup(ctx, d));
+  if (c1 <= c0) return ZKC_OK;
+  const uint64_t n = 1ull << d->k;
+  NttOpts o; o.inverse = 1; o.post = 2; o.post_tab = d->class_post; o.cls0 = c0;
+  return ntt_run(ctx, vals + (uint64_t)c0 * n, n, vals + (uint64_t)c0 * n, n, d->k, c1 - c0, o);
+}
+int dom_classes_mix(zkc_ctx* ctx, const zkc_domain* d, const Fr* g, Fr* out) {
   ZKC_TRY(dom_pieces_setup(ctx, d));
   const uint32_t q = d->j - 1;
   const uint64_t n = 1ull << d->k;
-  NttOpts o; o.inverse = 1; o.post = 2; o.post_tab = d->class_post;
-  ZKC_TRY(ntt_run(ctx, vals, n, vals, n, d->k, q, o));
-  k_mix_classes<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(vals, out, d->mix_dev, q, n);
+  k_mix_classes<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(g, out, d->mix_dev, q, n);
   ZKC_LAUNCH_CHECK(ctx);
   ctx->stats["ntt.muls"] += (uint64_t)q * q * n;
   return ZKC_OK;
+}
+int dom_classes_to_pieces(zkc_ctx* ctx, const zkc_domain* d, Fr* vals, Fr* out) {
+  ZKC_TRY(dom_classes_inverse(ctx, d, vals, 0, d->j - 1));
+  return dom_classes_mix(ctx, d, vals, out);
 }
 // division by X^n - 1 on class-major rows [row0, row0 + cnt): the vanishing polynomial is constant on a class
 int dom_divide_by_vanishing_classes(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint64_t row0, uint64_t cnt) {

@@ -28,6 +28,8 @@ int dom_divide_by_vanishing(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint64_t r
 int dom_coeff_to_classes(zkc_ctx* ctx, const zkc_domain* d, const Fr* in, uint64_t in_stride, Fr* out, uint32_t ncols, uint32_t c0, uint32_t c1);
 int dom_classes_to_natural(zkc_ctx* ctx, const zkc_domain* d, const Fr* cm, Fr* nat);
 int dom_classes_to_pieces(zkc_ctx* ctx, const zkc_domain* d, Fr* vals, Fr* out);
+int dom_classes_inverse(zkc_ctx* ctx, const zkc_domain* d, Fr* vals, uint32_t c0, uint32_t c1);
+int dom_classes_mix(zkc_ctx* ctx, const zkc_domain* d, const Fr* g, Fr* out);
 int dom_divide_by_vanishing_classes(zkc_ctx* ctx, const zkc_domain* d, Fr* a, uint64_t row0, uint64_t cnt);
 int srs_commit_dev(zkc_ctx* ctx, const zkc_srs* s, int basis, const Fr* polys, uint64_t len, uint32_t ncols, zkc_g1* out);
 }  // namespace zkc
@@ -1035,8 +1037,17 @@ int zkc_prover::quotient(const Fr& y_, std::vector<G1Affine>& out) {
       ZKC_TRY(dom_divide_by_vanishing_classes(ctx, pk->dom, hcm, r0, rc));
     }
     //     ... (team: every rank needs the whole quotient) and back to the coefficient forms of the q pieces
-    if (team) ZKC_TRY(team_allgather_rows(ctx, hcm, hn));
-    ZKC_TRY(dom_classes_to_pieces(ctx, pk->dom, hcm, hval));
+    if (!team) {
+      ZKC_TRY(dom_classes_to_pieces(ctx, pk->dom, hcm, hval));
+    } else {
+      // the way back is the four-step transform with its exchange: every rank gathers the class values, the per-class inverse
+      // transforms are dealt to the ranks (class c to rank c mod world) and broadcast, the q x q mix is replicated
+      ZKC_TRY(team_allgather_rows(ctx, hcm, hn));
+      for (int r : team_ranks(ctx))
+        for (uint32_t c = (uint32_t)r; c < q; c += (uint32_t)ctx->team_world) ZKC_TRY(dom_classes_inverse(ctx, pk->dom, hcm, c, c + 1));
+      ZKC_TRY(team_bcast_blocks(ctx, hcm, n, q));
+      ZKC_TRY(dom_classes_mix(ctx, pk->dom, hcm, hval));
+    }
   }
   ZKC_TRY(commit_points(ctx, pk->srs, 0, hval, n, q, out));
   stage = ST_EVALS;
