@@ -585,15 +585,21 @@ struct zkc_prover {
     for (const auto& cr : my_classes)
       for (uint32_t c = cr.first; c < cr.second; ++c) {
         std::vector<int> mem;
+        std::vector<uint64_t> cum(1, 0);   // rows of class c owned by the members before member t
         for (int r = 0; r < W; ++r) {
           uint64_t lo, hi;
           shard_range(hn, W, r, &lo, &hi);
-          if (hi > lo && lo < (uint64_t)(c + 1) * n && hi > (uint64_t)c * n) mem.push_back(r);
+          if (hi > lo && lo < (uint64_t)(c + 1) * n && hi > (uint64_t)c * n) {
+            mem.push_back(r);
+            cum.push_back(cum.back() + std::min<uint64_t>(hi, (uint64_t)(c + 1) * n) - std::max<uint64_t>(lo, (uint64_t)c * n));
+          }
         }
         const int g = (int)mem.size();
+        // columns in proportion to the rows each member owns (so every rank transforms its fair share of class blocks whatever
+        // way the row blocks cut the classes); the offset moves single-column batches from member to member
+        const uint64_t off = ((uint64_t)ctx->team_rot * n / (uint64_t)W) % n;
         for (int t = 0; t < g; ++t) {
-          uint64_t a, b;
-          shard_range(ncols, g, (t + ctx->team_rot) % g, &a, &b);
+          const uint64_t a = ((uint64_t)ncols * cum[t] + (t ? off : 0)) / n, b = t + 1 == g ? ncols : ((uint64_t)ncols * cum[t + 1] + off) / n;
           if (mem[t] == me && b > a) ZKC_TRY(dom_coeff_to_classes(ctx, pk->dom, polys + a * n, n, cosets + a * en, (uint32_t)(b - a), c, c + 1));
           // rows of class c that member o evaluates, widened by the rotation reach (cyclic inside the class): <= 2 segments
           auto rows_of = [&](int o, Segment seg[2]) -> int {
