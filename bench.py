@@ -48,7 +48,7 @@ WORKLOADS = {
 # src/bin/cli.rs:385-390), with the single-GPU time and the non-scaling share of each shape measured on this pool's B200s
 # (profiles/r02_*): what the scheduler (dist.plan_chain) cuts the GPUs into teams with
 CHAIN4 = ["rsa_k17", "sha_k19", "rsa_k17", "sha_k19"]
-CHAIN_EST = {"rsa_k17": (0.0107, 0.75), "sha_k19": (0.122, 0.13)}
+CHAIN_EST = {"rsa_k17": (0.0104, 0.75), "sha_k19": (0.0953, 0.15)}
 ORACLE_MAX_K = {"base": 17, "base_fast": 17, "sha_bit": 15}   # real-size oracle proofs that finish within ~10 s on the box's cores
 FQMUL_PER_MADD = 10      # XYZZ mixed add: 8M + 2S
 IMADW_PER_FQMUL = 128    # 64 (a*b) + 64 (m*p) IMAD.WIDE per Montgomery product

@@ -13,6 +13,7 @@
 // falls between the two alignments is carried as a 32-bit `pend` word whose only effect is a
 // carry-in bit into the next odd chain.  16 IMAD.WIDE + ~5 other instructions per row.
 #pragma once
+#include <cstring>
 #include <cstdint>
 
 #if defined(__CUDACC__)
@@ -387,8 +388,28 @@ template <class P> ZKC_D Fe<P> fe_sqr(const Fe<P>& a) {
   return r;
 }
 
-#else  // ---- host path (unit tests of logic layered above the field ops; never the product path) ----
+#else  // ---- host path: 4 x 64-bit limbs (the 8 x u32 limbs are the same bytes on a little-endian host) ----
+// Used by everything the host keeps: MSM epilogues (Horner over the bit-plane sums, normalisation), the driver's transcript
+// scalars, keygen pieces, zkc_verify.  Never a fallback for device work.
 
+template <class P> struct HostMod {
+  static constexpr uint64_t m(int i) { return (uint64_t)P::M(2 * i) | ((uint64_t)P::M(2 * i + 1) << 32); }
+  static constexpr uint64_t inv64() {   // -M^-1 mod 2^64 from the 32-bit constant by one Newton step
+    uint64_t ninv = (uint64_t)0 - (uint64_t)P::INV;      // M^-1 mod 2^32
+    ninv = ninv * (2 - m(0) * ninv);                      // M^-1 mod 2^64
+    return (uint64_t)0 - ninv;
+  }
+};
+template <class P> inline void fe_to_u64(const Fe<P>& a, uint64_t t[4]) { memcpy(t, a.v, 32); }
+template <class P> inline Fe<P> fe_from_u64(const uint64_t t[4]) { Fe<P> r; memcpy(r.v, t, 32); return r; }
+// t (4 limbs + carry word `hi`) -> t - M when t >= M
+template <class P> inline void host_reduce_once(uint64_t t[4], uint64_t hi) {
+  typedef unsigned __int128 u128;
+  uint64_t d[4];
+  u128 bw = 0;
+  for (int i = 0; i < 4; ++i) { const u128 x = (u128)t[i] - HostMod<P>::m(i) - (uint64_t)bw; d[i] = (uint64_t)x; bw = (x >> 64) & 1; }
+  if (hi || !bw) { t[0] = d[0]; t[1] = d[1]; t[2] = d[2]; t[3] = d[3]; }
+}
 template <class P> inline bool geq_mod(const uint32_t* a) {
   for (int i = 7; i >= 0; --i) { if (a[i] > P::M(i)) return true; if (a[i] < P::M(i)) return false; }
   return true;
@@ -398,31 +419,30 @@ template <class P> inline void sub_mod_inplace(uint32_t* a) {
   for (int i = 0; i < 8; ++i) { int64_t d = (int64_t)a[i] - P::M(i) + bw; a[i] = (uint32_t)d; bw = d >> 32; }
 }
 template <class P> inline Fe<P> fe_add(const Fe<P>& a, const Fe<P>& b) {
-  Fe<P> r; u64 c = 0;
-  for (int i = 0; i < 8; ++i) { c += (u64)a.v[i] + b.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
-  if (geq_mod<P>(r.v)) sub_mod_inplace<P>(r.v);
-  return r;
+  typedef unsigned __int128 u128;
+  uint64_t A[4], B[4], t[4];
+  fe_to_u64(a, A); fe_to_u64(b, B);
+  u128 c = 0;
+  for (int i = 0; i < 4; ++i) { c += (u128)A[i] + B[i]; t[i] = (uint64_t)c; c >>= 64; }
+  host_reduce_once<P>(t, (uint64_t)c);
+  return fe_from_u64<P>(t);
 }
 template <class P> inline Fe<P> fe_sub(const Fe<P>& a, const Fe<P>& b) {
-  Fe<P> r; int64_t bw = 0;
-  for (int i = 0; i < 8; ++i) { int64_t d = (int64_t)a.v[i] - b.v[i] + bw; r.v[i] = (uint32_t)d; bw = d >> 32; }
-  if (bw) { u64 c = 0; for (int i = 0; i < 8; ++i) { c += (u64)r.v[i] + P::M(i); r.v[i] = (uint32_t)c; c >>= 32; } }
-  return r;
+  typedef unsigned __int128 u128;
+  uint64_t A[4], B[4], t[4];
+  fe_to_u64(a, A); fe_to_u64(b, B);
+  u128 bw = 0;
+  for (int i = 0; i < 4; ++i) { const u128 x = (u128)A[i] - B[i] - (uint64_t)bw; t[i] = (uint64_t)x; bw = (x >> 64) & 1; }
+  if (bw) { u128 c = 0; for (int i = 0; i < 4; ++i) { c += (u128)t[i] + HostMod<P>::m(i); t[i] = (uint64_t)c; c >>= 64; } }
+  return fe_from_u64<P>(t);
 }
-// host product: 4 x 64-bit CIOS with 128-bit accumulators (the 8 x u32 limbs are the same bytes)
+// host product: 4 x 64-bit CIOS with 128-bit accumulators
 template <class P> inline Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
   typedef unsigned __int128 u128;
-  uint64_t A[4], B[4], M[4], t[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = 0; i < 4; ++i) {
-    A[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
-    B[i] = (uint64_t)b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32);
-    M[i] = (uint64_t)P::M(2 * i) | ((uint64_t)P::M(2 * i + 1) << 32);
-  }
-  // -M^-1 mod 2^64 from the 32-bit constant by one Newton step
-  const uint64_t inv32 = P::INV;
-  uint64_t ninv = (uint64_t)0 - inv32;                 // M^-1 mod 2^32 (as 64-bit)
-  ninv = ninv * (2 - M[0] * ninv);                     // now M^-1 mod 2^64
-  const uint64_t inv64 = (uint64_t)0 - ninv;
+  uint64_t A[4], B[4], t[6] = {0, 0, 0, 0, 0, 0};
+  fe_to_u64(a, A); fe_to_u64(b, B);
+  constexpr uint64_t M0 = HostMod<P>::m(0), M1 = HostMod<P>::m(1), M2 = HostMod<P>::m(2), M3 = HostMod<P>::m(3), inv64 = HostMod<P>::inv64();
+  const uint64_t M[4] = {M0, M1, M2, M3};
   for (int i = 0; i < 4; ++i) {
     u128 c = 0;
     for (int j = 0; j < 4; ++j) { c += (u128)A[j] * B[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
@@ -432,10 +452,8 @@ template <class P> inline Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
     for (int j = 1; j < 4; ++j) { c += (u128)m * M[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
     c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64); t[5] = 0;
   }
-  Fe<P> r;
-  for (int i = 0; i < 4; ++i) { r.v[2 * i] = (uint32_t)t[i]; r.v[2 * i + 1] = (uint32_t)(t[i] >> 32); }
-  if (t[4] || geq_mod<P>(r.v)) sub_mod_inplace<P>(r.v);
-  return r;
+  host_reduce_once<P>(t, t[4]);
+  return fe_from_u64<P>(t);
 }
 template <class P> inline Fe<P> fe_sqr(const Fe<P>& a) { return fe_mul(a, a); }
 #endif
