@@ -110,7 +110,6 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accum(const G1Affine* bases, 
   const uint64_t p1 = !active ? p0 : (p0 + T < E ? p0 + T : E);
   G1Xyzz acc = xyzz_identity();
   uint32_t cur = 0xffffffffu;
-  bool single = true;     // the thread's whole range lies in one bucket
   if (active) {
     cur = ent_key[p0];
     // software pipeline: the next entry's base point is requested before the current mixed add is issued
@@ -121,21 +120,42 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accum(const G1Affine* bases, 
       const uint32_t e_cur = e;
       const G1Affine q_cur = q;
       if (p + 1 < p1) { e = ent_pt[p + 1]; q = affine_load_nc(bases + (e & 0x7fffffffu)); }
-      if (k != cur) { xyzz_store(partial + cur + t, acc); acc = xyzz_identity(); cur = k; single = false; }
+      if (k != cur) { xyzz_store(partial + cur + t, acc); acc = xyzz_identity(); cur = k; }
       if (!affine_is_identity(q_cur)) xyzz_madd(acc, q_cur, (e_cur >> 31) != 0);
     }
   }
-  // A warp that sits entirely inside ONE bucket (bit / byte valued witness columns and the top window of range-checked
-  // cells pile thousands of entries on a few buckets) folds its 32 partials with a shuffle tree and leaves the identity in
-  // the other 31 slots, so such a bucket hands 32x fewer non-trivial partials to the bucket-sum kernels: their dependent
-  // chain is what costs there, and adding the identity is free.
+  // A warp-wide convergence point before the final store: with it ptxas fits the loop into 126 registers without spilling,
+  // without it the same code takes 128 + 80 bytes of spills (four CTAs per SM either way; checked with -Xptxas -v).
   const uint32_t k0 = __shfl_sync(0xffffffffu, cur, 0);
-  if (__all_sync(0xffffffffu, active && single && cur == k0)) {
-#pragma unroll 1
-    for (int d = 16; d > 0; d >>= 1) { const G1Xyzz o = xyzz_shfl_xor(acc, d); xyzz_add(acc, o); }
-    if (threadIdx.x & 31) acc = xyzz_identity();
-  }
+  if (k0 == 0xfffffffeu) acc = xyzz_identity();   // never true: bucket keys are < 2^31
   if (active) xyzz_store(partial + cur + t, acc);
+}
+
+// A warp of accumulate threads that sits entirely inside ONE bucket (bit / byte valued witness columns and the top window of
+// range-checked cells pile thousands of entries on a few buckets) folds its 32 partials with a shuffle tree and leaves the
+// identity in the other 31 slots, so such a bucket hands 32x fewer non-trivial partials to the bucket-sum kernels: their dependent
+// chain is what costs there, and adding the identity is free.  A kernel of its own: inside k_msm_accum the 32 extra live
+// registers of the shuffled operand pushed the accumulate loop over the 128 registers that four CTAs per SM allow.
+__global__ void __launch_bounds__(128) k_msm_fold(const uint32_t* ent_key, const uint32_t* offsets, G1Xyzz* partial, MsmGeom g) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t E = offsets[g.nbtot()];
+  const uint32_t T = msm_T(g, E);
+  const uint64_t p0 = t * T;
+  const bool active = p0 < E;
+  uint32_t cur = 0xffffffffu;
+  bool single = false;
+  if (active) {
+    const uint64_t p1 = p0 + T < E ? p0 + T : E;
+    cur = ent_key[p1 - 1];
+    single = ent_key[p0] == cur;       // the thread's whole range lies in one bucket: one partial, at slot cur + t
+  }
+  const uint32_t k0 = __shfl_sync(0xffffffffu, cur, 0);
+  if (!__all_sync(0xffffffffu, active && single && cur == k0)) return;
+  G1Xyzz acc = xyzz_load(partial + cur + t);
+#pragma unroll 1
+  for (int d = 16; d > 0; d >>= 1) { const G1Xyzz o = xyzz_shfl_xor(acc, d); xyzz_add(acc, o); }
+  if (threadIdx.x & 31) acc = xyzz_identity();
+  xyzz_store(partial + cur + t, acc);
 }
 
 // ---- bucket sums: the partials of a bucket are folded by QUADS of lanes (xyzz_add_quad: this phase is a chain of dependent
@@ -477,6 +497,8 @@ static int msm_kernels(zkc_ctx* ctx, const Fr* scalars, const G1Affine* bases, c
   { ProfScope _p(ctx, "msm.accum");
     if (ctx->tune.msm_accum_occ == 3) k_msm_accum<3><<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(bases, ent_pt, ent_key, offsets, partial, g);
     else k_msm_accum<4><<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(bases, ent_pt, ent_key, offsets, partial, g);
+    ZKC_LAUNCH_CHECK(ctx);
+    k_msm_fold<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(ent_key, offsets, partial, g);
     ZKC_LAUNCH_CHECK(ctx); }
   {
     // quads per bucket from the expected number of partials per bucket (entries per bucket / T)
