@@ -91,9 +91,13 @@ int team_bcast_cols(zkc_ctx* ctx, Fr* base, uint64_t stride, uint64_t len, uint3
   for (int r = 0; r < ctx->team_world; ++r) {
     uint32_t c0, c1;
     team_cols(ctx, ncols, r, &c0, &c1);
-    for (uint32_t c = c0; c < c1; ++c) {
+    if (c1 <= c0) continue;
+    // an owner's columns are adjacent: when they are also dense (stride == len) they travel as ONE message — a 512 MB
+    // message moves at twice the rate of eight 64 MB ones (profiles/r02_p2p_2gpu.json)
+    const uint32_t per = stride == len ? c1 - c0 : 1;
+    for (uint32_t c = c0; c < c1; c += per) {
       Fr* p = base + (uint64_t)c * stride;
-      int rc = nccl().Broadcast(p, p, len * sizeof(Fr), kNcclUint8, r, comm_of(ctx), ctx->stream);
+      int rc = nccl().Broadcast(p, p, (size_t)per * len * sizeof(Fr), kNcclUint8, r, comm_of(ctx), ctx->stream);
       if (rc != 0) { nccl().GroupEnd(); return nccl_fail(ctx, "ncclBroadcast", rc); }
     }
   }

@@ -581,7 +581,10 @@ struct zkc_prover {
     // each transforms its share and hands the class blocks (n rows, contiguous) to the other g - 1: large point-to-point
     // messages inside a small group instead of g-fold redundant transforms.
     const int W = ctx->team_world, me = ctx->team_rank;
-    std::vector<TeamXfer> xf;
+    // what travels: rows [p, p + len) of `cols` consecutive columns (column stride en), per peer and direction, in an order
+    // both sides derive alike (class, then segment)
+    struct Piece { Fr* p; uint64_t len; uint32_t cols; };
+    std::vector<std::vector<Piece>> snd(W), rcv(W);
     for (const auto& cr : my_classes)
       for (uint32_t c = cr.first; c < cr.second; ++c) {
         std::vector<int> mem;
@@ -595,43 +598,73 @@ struct zkc_prover {
           }
         }
         const int g = (int)mem.size();
+        // rows of class c that member o evaluates, widened by the rotation reach (cyclic inside the class): <= 2 segments
+        auto rows_of = [&](int o, Segment seg[2]) -> int {
+          const uint64_t ra = cum[o], len = (cum[o + 1] - cum[o]) + halo_lo + halo_hi;
+          if (len >= n) { seg[0] = {0, n}; return 1; }
+          const uint64_t start = (ra + n - halo_lo % n) % n;
+          if (start + len <= n) { seg[0] = {start, len}; return 1; }
+          seg[0] = {0, start + len - n}; seg[1] = {start, n - start};
+          return 2;
+        };
+        int self = 0;
+        while (mem[self] != me) ++self;
         // columns in proportion to the rows each member owns (so every rank transforms its fair share of class blocks whatever
         // way the row blocks cut the classes); the offset moves single-column batches from member to member
         const uint64_t off = ((uint64_t)ctx->team_rot * n / (uint64_t)W) % n;
         for (int t = 0; t < g; ++t) {
           const uint64_t a = ((uint64_t)ncols * cum[t] + (t ? off : 0)) / n, b = t + 1 == g ? ncols : ((uint64_t)ncols * cum[t + 1] + off) / n;
-          if (mem[t] == me && b > a) ZKC_TRY(dom_coeff_to_classes(ctx, pk->dom, polys + a * n, n, cosets + a * en, (uint32_t)(b - a), c, c + 1));
-          // rows of class c that member o evaluates, widened by the rotation reach (cyclic inside the class): <= 2 segments
-          auto rows_of = [&](int o, Segment seg[2]) -> int {
-            uint64_t lo, hi;
-            shard_range(hn, W, mem[o], &lo, &hi);
-            const uint64_t ra = std::max<uint64_t>(lo, (uint64_t)c * n) - (uint64_t)c * n, rb = std::min<uint64_t>(hi, (uint64_t)(c + 1) * n) - (uint64_t)c * n;
-            const uint64_t len = (rb - ra) + halo_lo + halo_hi;
-            if (len >= n) { seg[0] = {0, n}; return 1; }
-            const uint64_t start = (ra + n - halo_lo % n) % n;
-            if (start + len <= n) { seg[0] = {start, len}; return 1; }
-            seg[0] = {0, start + len - n}; seg[1] = {start, n - start};
-            return 2;
-          };
-          for (uint64_t col = a; col < b; ++col) {
-            Fr* blk = cosets + col * en + (uint64_t)c * n;
-            Segment seg[2];
-            if (mem[t] == me) {
-              for (int o = 0; o < g; ++o) {
-                if (mem[o] == me) continue;
-                const int ns = rows_of(o, seg);
-                for (int q2 = 0; q2 < ns; ++q2) xf.push_back({mem[o], true, blk + seg[q2].lo, seg[q2].len * sizeof(Fr)});
-              }
-            } else {
-              int self = 0;
-              while (mem[self] != me) ++self;
-              const int ns = rows_of(self, seg);
-              for (int q2 = 0; q2 < ns; ++q2) xf.push_back({mem[t], false, blk + seg[q2].lo, seg[q2].len * sizeof(Fr)});
+          if (b <= a) continue;
+          Fr* blk = cosets + a * en + (uint64_t)c * n;
+          Segment seg[2];
+          if (mem[t] == me) {
+            ZKC_TRY(dom_coeff_to_classes(ctx, pk->dom, polys + a * n, n, cosets + a * en, (uint32_t)(b - a), c, c + 1));
+            for (int o = 0; o < g; ++o) {
+              if (o == self) continue;
+              const int ns = rows_of(o, seg);
+              for (int q2 = 0; q2 < ns; ++q2) snd[mem[o]].push_back({blk + seg[q2].lo, seg[q2].len, (uint32_t)(b - a)});
             }
+          } else {
+            const int ns = rows_of(self, seg);
+            for (int q2 = 0; q2 < ns; ++q2) rcv[mem[t]].push_back({blk + seg[q2].lo, seg[q2].len, (uint32_t)(b - a)});
           }
         }
       }
-    ZKC_TRY(team_exchange(ctx, xf, "team.class_exchange"));
+    // One message per peer and direction: the pieces are packed into a staging buffer with strided device copies, because one
+    // large message moves at about twice the rate of the same bytes in column-sized ones (profiles/r02_p2p_2gpu.json).
+    auto volume = [](const std::vector<std::vector<Piece>>& v) { uint64_t e = 0; for (auto& l : v) for (auto& pc : l) e += pc.len * pc.cols; return e; };
+    const uint64_t nsend = volume(snd), nrecv = volume(rcv);
+    if (nsend + nrecv) {
+      ProfScope _p(ctx, "team.class_exchange");
+      Fr *ssend = nullptr, *srecv = nullptr;
+      ZKC_TRY(scratch_reserve(ctx, SCR_HOSTIO, std::max<uint64_t>(nsend, 1) * sizeof(Fr), (void**)&ssend));
+      ZKC_TRY(scratch_reserve(ctx, SCR_HOSTIO2, std::max<uint64_t>(nrecv, 1) * sizeof(Fr), (void**)&srecv));
+      cudaStream_t st = ctx->stream;
+      auto strided = [&](Fr* packed, Fr* rows, const Piece& pc, bool pack) -> int {
+        if (en * sizeof(Fr) < ((size_t)1 << 31)) {   // cudaMemcpy2D pitch limit (cudaDeviceProp::memPitch)
+          ZKC_CUDA_TRY(ctx, pack ? cudaMemcpy2DAsync(packed, pc.len * sizeof(Fr), rows, en * sizeof(Fr), pc.len * sizeof(Fr), pc.cols, cudaMemcpyDeviceToDevice, st)
+                                 : cudaMemcpy2DAsync(rows, en * sizeof(Fr), packed, pc.len * sizeof(Fr), pc.len * sizeof(Fr), pc.cols, cudaMemcpyDeviceToDevice, st));
+        } else {
+          for (uint32_t cc = 0; cc < pc.cols; ++cc)
+            ZKC_CUDA_TRY(ctx, pack ? cudaMemcpyAsync(packed + cc * pc.len, rows + (uint64_t)cc * en, pc.len * sizeof(Fr), cudaMemcpyDeviceToDevice, st)
+                                   : cudaMemcpyAsync(rows + (uint64_t)cc * en, packed + cc * pc.len, pc.len * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+        }
+        return ZKC_OK;
+      };
+      std::vector<TeamXfer> xf;
+      uint64_t so = 0, ro = 0;
+      for (int r = 0; r < W; ++r) {
+        const uint64_t s0 = so, r0 = ro;
+        for (const Piece& pc : snd[r]) { ZKC_TRY(strided(ssend + so, pc.p, pc, true)); so += pc.len * pc.cols; }
+        for (const Piece& pc : rcv[r]) ro += pc.len * pc.cols;
+        if (so > s0) xf.push_back({r, true, ssend + s0, (so - s0) * sizeof(Fr)});
+        if (ro > r0) xf.push_back({r, false, srecv + r0, (ro - r0) * sizeof(Fr)});
+      }
+      ZKC_TRY(team_exchange(ctx, xf, "team.class_exchange.nccl"));
+      ro = 0;
+      for (int r = 0; r < W; ++r)
+        for (const Piece& pc : rcv[r]) { ZKC_TRY(strided(srecv + ro, pc.p, pc, false)); ro += pc.len * pc.cols; }
+    }
     team_advance(ctx, ncols);
     return ZKC_OK;
   }
