@@ -1,7 +1,8 @@
 """Team proving on real GPUs (run under torchrun on a `gpurun --gpus N` box): ONE create_proof spread over N GPUs —
-MSM by point range, column transforms by column, h(X) by extended-row block, NCCL collectives between.
+MSM by point range, lagrange_to_coeff by column, coset transforms by residue class, h(X) by row block of the class-major
+extended coset, NCCL collectives between.
 
-  1. parity: for small circuits the team proof (with ZKC_TEAM_POISON=1: rows a rank never receives are 0xff) equals the
+  1. parity: for small circuits the team proof (with ZKC_TEAM_POISON=1: class blocks and rows a rank never computes or receives are 0xff) equals the
      single-GPU proof of the same context on every rank;
   2. timing: `WORKLOAD` (default agg_k20) single-GPU vs team, CUDA events, max over ranks, L2 flushed between proofs.
 Prints one JSON line from rank 0; exit code 1 on any mismatch."""
