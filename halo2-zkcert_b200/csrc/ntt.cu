@@ -155,7 +155,9 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_last(NttPass p) {
   for (uint32_t logh = p.s; logh-- > 0;) {
     const uint32_t h = 1u << logh;
     for (uint32_t bt = threadIdx.x; bt < (T >> 1); bt += NTT_THREADS) {
-      const uint32_t c = bt >> (p.s - 1), pr = bt & ((L >> 1) - 1);
+      // columns fastest: the 8 lanes of a quarter-warp touch 8 rows of odd pitch — distinct 16-byte banks at every stage (with
+      // the butterfly index fastest the last three stages, h < 8, were two-way conflicted) — and share one twiddle
+      const uint32_t c = bt & (C - 1), pr = bt >> p.logC;
       const uint32_t j = pr & (h - 1);
       const uint32_t i = ((pr - j) << 1) | j;
       const uint32_t i0 = c * pitch + i;

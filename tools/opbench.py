@@ -53,7 +53,7 @@ def timeit(fn, reps=5, warm=3):
 
 res = {"peaks": {"fr_mul_per_s": FE_MUL_PEAK, "imad_wide_per_s": IMADW_PEAK, "hbm_gbs": HBM}, "msm": {}, "ntt": {}}
 s = pkg.api.fr_random_stream(bytes(32), 1)
-for k in [int(x) for x in os.environ.get("KS", "15,17,19,22").split(",")]:
+for k in [int(x) for x in os.environ.get("KS", "15,17,19,22").split(",") if x]:
     n = 1 << k
     params = pkg.ParamsKZG.setup(k, s, ctx=ctx)
     for kind in ("uniform", "bits", "u16"):
