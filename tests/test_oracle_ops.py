@@ -207,3 +207,55 @@ def test_std_rng_chacha12_stream():
     want = [slow.fr_random() for _ in range(6)]
     assert orc.fr_to_ints(orc.ChaCha20Rng(seed, rounds=12).fr_random_bulk(6)) == want
     assert want != [pyref.ChaChaRng(seed, 20).fr_random() for _ in range(6)]
+
+
+def test_residue_class_identities_of_the_extended_coset():
+    """The algebra behind the class-major prover (csrc/ntt.cu dom_coeff_to_classes / dom_classes_to_pieces), checked on the
+    oracle's own transforms with Python integers in between — no GPU involved:
+      (1) rows c, c + 2^e, c + 2*2^e, ... of coeff_to_extended are ONE size-n transform of the coefficients scaled by
+          zeta^(i mod 3) * w_ext^(c i)  (the four-step split N1 = n, N2 = 2^e of a zero-padded input);
+      (2) a polynomial with fewer than q n coefficients is determined by its values on q classes: per-class coset iNTT, then the
+          inverse of the q x q Vandermonde matrix in tau_c = (zeta w_ext^c)^n gives extended_to_coeff's output piece by piece."""
+    import random
+    R = pyref.R_MOD
+    rnd = random.Random(11)
+    for j, k in [(4, 5), (5, 4), (3, 6)]:
+        d = orc.domain_constants(j, k)
+        ek = d["extended_k"]
+        n, en, e = 1 << k, 1 << ek, ek - k
+        w_ext, w, zeta = orc.fr_to_ints(d["extended_omega"])[0], orc.fr_to_ints(d["omega"])[0], orc.fr_to_ints(d["g_coset"])[0]
+        assert pow(w_ext, 1 << e, R) == w and pow(zeta, 3, R) == 1
+        # (1) forward
+        a = [rnd.randrange(R) for _ in range(n)]
+        ext = orc.fr_to_ints(orc.coeff_to_extended(j, k, orc.fr_from_ints(a)))
+        for c in range(1 << e):
+            scaled = [a[i] * pow(zeta, i % 3, R) * pow(w_ext, c * i, R) % R for i in range(n)]
+            cls = orc.fr_to_ints(orc.best_fft(orc.fr_from_ints(scaled), d["omega"], k))
+            assert cls == ext[c::1 << e], (j, k, c)
+        # (2) the way back from q = j - 1 classes
+        q = j - 1
+        h = [rnd.randrange(R) for _ in range(q * n)]
+        hs = [h[i] * pow(zeta, i % 3, R) % R for i in range(q * n)] + [0] * (en - q * n)
+        vals = orc.fr_to_ints(orc.best_fft(orc.fr_from_ints(hs), d["extended_omega"], ek))       # h on the whole extended coset
+        assert orc.fr_to_ints(orc.extended_to_coeff(j, k, orc.fr_from_ints(vals)))[:q * n] == h
+        ninv, g, tau = pow(n, -1, R), [], []
+        for c in range(q):
+            zc = zeta * pow(w_ext, c, R) % R
+            y = orc.fr_to_ints(orc.best_fft(orc.fr_from_ints(vals[c::1 << e]), d["omega_inv"], k))
+            g.append([y[i] * ninv * pow(zc, -i, R) % R for i in range(n)])
+            tau.append(pow(zc, n, R))
+        # solve V H = g with V[c][p] = tau_c^p (Gauss-Jordan over the field, per coefficient index all at once)
+        V = [[pow(tau[c], p, R) for p in range(q)] + [1 if p == c else 0 for p in range(q)] for c in range(q)]
+        for col in range(q):
+            piv = next(r for r in range(col, q) if V[r][col])
+            V[col], V[piv] = V[piv], V[col]
+            inv = pow(V[col][col], -1, R)
+            V[col] = [x * inv % R for x in V[col]]
+            for r in range(q):
+                if r != col and V[r][col]:
+                    f = V[r][col]
+                    V[r] = [(x - f * y) % R for x, y in zip(V[r], V[col])]
+        Minv = [row[q:] for row in V]
+        for p in range(q):
+            piece = [sum(Minv[p][c] * g[c][i] for c in range(q)) % R for i in range(n)]
+            assert piece == h[p * n:(p + 1) * n], (j, k, p)
