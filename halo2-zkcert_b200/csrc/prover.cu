@@ -570,7 +570,8 @@ struct zkc_prover {
     return ZKC_OK;
   }
   // coefficient form -> extended coset, CLASS-MAJOR (ntt.cu: residue classes of the extended coset).  Team: every rank holds the
-  // coefficient forms, so it transforms the classes its row block touches itself — no coset row ever crosses a link.
+  // coefficient forms, so it transforms the classes its row block touches itself; coset rows cross a link only where two row
+  // blocks share a class.
   int to_extended(const Fr* polys, Fr* cosets, uint32_t ncols) {
     if (!team || ctx->team_emulate) {
       for (const auto& cr : my_classes) ZKC_TRY(dom_coeff_to_classes(ctx, pk->dom, polys, n, cosets, ncols, cr.first, cr.second));
@@ -578,7 +579,7 @@ struct zkc_prover {
     }
     // A class that lies inside one rank's row block is transformed there, all columns.  Where g > 1 row blocks share a class
     // (more ranks than classes, or a world size that does not divide them) those g ranks deal its columns among themselves,
-    // each transforms its share and hands the class blocks (n rows, contiguous) to the other g - 1: large point-to-point
+    // each transforms its share and hands the rows the other g - 1 evaluate (+ rotation reach) to them: large point-to-point
     // messages inside a small group instead of g-fold redundant transforms.
     const int W = ctx->team_world, me = ctx->team_rank;
     // what travels: rows [p, p + len) of `cols` consecutive columns (column stride en), per peer and direction, in an order
