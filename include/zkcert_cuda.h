@@ -72,9 +72,10 @@ int zkc_ctx_sync(zkc_ctx* ctx);
  * stream underneath the latency-bound MSM phases.  on = 0 serialises everything on one stream (used when timing
  * individual kernels); results are identical either way. */
 int zkc_ctx_set_overlap(zkc_ctx* ctx, int on);
-/* Debug / sweep overrides on a live ctx: "msm_c", "msm_c_pre", "msm_T", "ntt_two_pass_max" (0 = library default),
- * "stage_min_bytes" (-1 = default), "team_poison".  The ZKC_* environment variables of the same names are read once, when the
- * ctx is created; nothing reads the environment on the proving path. */
+/* Debug / sweep overrides on a live ctx: "msm_c", "msm_c_pre", "msm_T", "ntt_two_pass_max", "msm_accum_occ" (0 = library default),
+ * "stage_min_bytes" (-1 = default), "team_poison", "team_commit_by_column" (team commitments dealt by column instead of by point
+ * range), "no_program_factoring" (keys loaded while set keep their gate programs as parsed).  The ZKC_* environment
+ * variables of the same names are read once, when the ctx is created; nothing reads the environment on the proving path. */
 int zkc_ctx_set_tunable(zkc_ctx* ctx, const char* name, int64_t value);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 uint64_t zkc_ctx_launch_count(const zkc_ctx* ctx);
